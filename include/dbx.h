@@ -1,0 +1,303 @@
+/*
+ * dbx.h — C-ABI of libdbx, the B200-native replacement for Databend's in-memory
+ * vectorised execution hot path (filter -> hash aggregate / hash join / top-k /
+ * vector distance).
+ *
+ * The reference has no FFI on this path: the boundary is a set of Rust traits.
+ * Every entry point below names the reference interface it replaces, so that a
+ * thin Rust `-sys` crate + shim `impl`s can forward the
+ * trait calls here unchanged:
+ *
+ *   Processor / Transform adaptors     src/query/pipeline/src/core/processor.rs:62-108
+ *                                      src/query/pipeline/transforms/src/processors/transforms/transform.rs:30-48
+ *                                      .../transform_accumulating.rs:30-37
+ *   DataBlock / BlockEntry / Column    src/query/expression/src/block.rs:49-60, values.rs:192-215
+ *   Buffer<T> / Bitmap                 src/common/column/src/buffer/immutable.rs:60-73, bitmap/immutable.rs
+ *   FilterExecutor / SelectExpr        src/query/expression/src/filter/filter_executor.rs:82-160,
+ *                                      filter/select_expr.rs:34-50
+ *   AggregateHashTable + transforms    src/query/expression/src/aggregate/aggregate_hashtable.rs:168-408,
+ *                                      service/.../aggregator/transform_aggregate_{partial,final}.rs
+ *   Join trait                         service/.../new_hash_join/join.rs:26-53
+ *   sort / TopN                        src/query/expression/src/kernels/sort.rs:91-111, top_n/
+ *   cosine_distance / l2_distance      src/common/vector/src/distance.rs:19-35,65-80
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types cross this boundary;
+ *   - every function returns a dbx_status (0 = ok); the message of the last failure
+ *     on a handle is read with dbx_last_error(handle) (NULL handle = thread-local
+ *     error of the failed create call).  Nothing aborts or throws across the ABI;
+ *   - a handle is thread-compatible (one caller at a time, may migrate between
+ *     threads), distinct handles are fully concurrent: each owns one CUDA stream;
+ *   - input blocks are borrowed for the duration of the call only;
+ *   - output blocks are owned by the library until dbx_block_release().
+ */
+#ifndef DBX_H_
+#define DBX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DBX_ABI_VERSION 1
+
+/* ---------------------------------------------------------------- status */
+typedef enum dbx_status {
+  DBX_OK = 0,
+  DBX_ERR_INVALID = 1,       /* bad argument / unsupported combination (ErrorCode::BadArguments at build time) */
+  DBX_ERR_CUDA = 2,          /* CUDA runtime failure (ErrorCode::Internal) */
+  DBX_ERR_BAD_ARGUMENTS = 3, /* per-row evaluation error, e.g. "Division by zero" (evaluator.rs:234-244) */
+  DBX_ERR_UNSUPPORTED = 4,   /* valid in the reference but not built here */
+  DBX_ERR_OOM = 5,
+  DBX_ERR_STATE = 6,         /* call order violated (push after finish, ...) */
+  DBX_ERR_NO_DEVICE = 7      /* no usable CUDA device: there is NO CPU fallback */
+} dbx_status;
+
+/* ------------------------------------------------------------- data types */
+/* NumberDataType subset (src/query/expression/src/types/number.rs) + Boolean + Vector(Float32) */
+typedef enum dbx_dtype {
+  DBX_BOOL = 0, /* bit-packed, LSB first (Bitmap) */
+  DBX_I8 = 1,
+  DBX_I16 = 2,
+  DBX_I32 = 3,
+  DBX_I64 = 4,
+  DBX_U8 = 5,
+  DBX_U16 = 6,
+  DBX_U32 = 7,
+  DBX_U64 = 8,
+  DBX_F32 = 9,
+  DBX_F64 = 10,
+  DBX_VEC_F32 = 11 /* VectorColumn::Float32((Buffer<F32>, dim)), flat row-major (types/vector.rs:377-380) */
+} dbx_dtype;
+
+typedef enum dbx_mem { DBX_MEM_HOST = 0, DBX_MEM_DEVICE = 1 } dbx_mem;
+
+/* A constant (BlockEntry::Const payload, or a literal in an expression). */
+typedef struct dbx_scalar {
+  int32_t dtype;
+  int32_t is_null;
+  union {
+    int64_t i64;
+    uint64_t u64;
+    double f64;
+  } v;
+} dbx_scalar;
+
+/* Column = Buffer<T> (+ optional validity Bitmap with a BIT offset, as left by
+ * Bitmap::slice).  `is_const` mirrors BlockEntry::Const(Scalar, DataType, n):
+ * the value is in `konst`, `data` is ignored and nothing is materialised. */
+typedef struct dbx_column {
+  int32_t dtype;               /* dbx_dtype */
+  int32_t mem;                 /* dbx_mem: where data/validity live */
+  int32_t is_const;
+  int32_t vec_dim;             /* DBX_VEC_F32 only */
+  int64_t len;                 /* rows */
+  const void* data;            /* T[len] (bool: bit-packed; vec: f32[len*vec_dim]) */
+  int64_t data_bit_offset;     /* DBX_BOOL only: bit offset of row 0 */
+  const uint8_t* validity;     /* NULL = no nulls; else LSB-first bitmap, 1 = valid */
+  int64_t validity_bit_offset;
+  int64_t null_count;          /* -1 = unknown */
+  dbx_scalar konst;
+} dbx_column;
+
+/* DataBlock{entries, num_rows, meta}.  `meta` carries BlockMetaInfo-like side
+ * channels that stay on the device (partial aggregate payloads, block.rs:370-440). */
+typedef struct dbx_block {
+  int64_t num_rows;
+  int32_t num_cols;
+  int32_t reserved;
+  dbx_column* cols;
+  void* meta;    /* opaque: dbx partial-payload reference, or NULL */
+  void* owner;   /* library-owned outputs: released by dbx_block_release */
+} dbx_block;
+
+/* ------------------------------------------------------------- predicates */
+/* Flattened SelectExpr tree in postfix order (filter/select_expr.rs:34-50):
+ *   And / Or                   -> DBX_PRED_AND / DBX_PRED_OR (pop n_children results)
+ *   Compare(op, lhs, rhs)      -> DBX_PRED_CMP with two operands
+ *   BooleanColumn              -> DBX_PRED_BOOLCOL (a DBX_BOOL column, NULL counts as false)
+ *   BooleanScalar              -> DBX_PRED_CONST
+ * Operands are column refs, literals, or `column <arith> literal` — the one level of
+ * scalar evaluation the configs need (modulo: arithmetic_modulo.rs:29-97).           */
+typedef enum dbx_cmp_op { DBX_EQ = 0, DBX_NE = 1, DBX_LT = 2, DBX_LE = 3, DBX_GT = 4, DBX_GE = 5 } dbx_cmp_op;
+typedef enum dbx_arith_op { DBX_ARITH_NONE = 0, DBX_ARITH_MODULO = 1 } dbx_arith_op;
+typedef enum dbx_pred_kind { DBX_PRED_CMP = 0, DBX_PRED_AND = 1, DBX_PRED_OR = 2, DBX_PRED_BOOLCOL = 3, DBX_PRED_CONST = 4 } dbx_pred_kind;
+
+typedef struct dbx_operand {
+  int32_t is_const;   /* 1: literal `c`; 0: column `col` (optionally `col <arith> c`) */
+  int32_t col;        /* column index in the pushed block */
+  int32_t arith;      /* dbx_arith_op applied as  col <arith> c */
+  int32_t reserved;
+  dbx_scalar c;
+} dbx_operand;
+
+typedef struct dbx_pred_node {
+  int32_t kind;       /* dbx_pred_kind */
+  int32_t cmp;        /* dbx_cmp_op          (DBX_PRED_CMP) */
+  int32_t n_children; /* operand count       (DBX_PRED_AND / DBX_PRED_OR), >= 2 */
+  int32_t value;      /* DBX_PRED_CONST: 0/1; DBX_PRED_BOOLCOL: column index */
+  dbx_operand lhs, rhs;
+} dbx_pred_node;
+
+#define DBX_MAX_PRED_NODES 16
+typedef struct dbx_predicate {
+  int32_t n_nodes;    /* 0 = no filter (all rows pass) */
+  int32_t reserved;
+  dbx_pred_node nodes[DBX_MAX_PRED_NODES];
+} dbx_predicate;
+
+/* ------------------------------------------------------------- aggregates */
+/* AggregateFunctionFactory names (aggregate_function_factory.rs:189-247); all are
+ * wrapped by the OrNull adaptor exactly as the factory does:  sum/avg/min/max return
+ * Nullable(T) (NULL iff no non-NULL input row), count returns plain UInt64.           */
+typedef enum dbx_agg_kind { DBX_AGG_SUM = 0, DBX_AGG_COUNT = 1, DBX_AGG_AVG = 2, DBX_AGG_MIN = 3, DBX_AGG_MAX = 4 } dbx_agg_kind;
+
+typedef struct dbx_agg_desc {
+  int32_t kind;     /* dbx_agg_kind */
+  int32_t arg_col;  /* argument column index in the pushed block; -1 = count(*) */
+} dbx_agg_desc;
+
+#define DBX_MAX_AGGS 8
+#define DBX_MAX_GROUP_COLS 4
+
+/* AggregatorParams (aggregator_params.rs:30-78) + the fused predicate. */
+typedef struct dbx_agg_params {
+  int32_t n_group_cols;                 /* 0 = no GROUP BY (transform_single_key.rs) */
+  int32_t group_cols[DBX_MAX_GROUP_COLS];
+  int32_t n_aggs;
+  dbx_agg_desc aggs[DBX_MAX_AGGS];
+  dbx_predicate filter;                 /* fused TransformFilter in front (n_nodes = 0: none) */
+  int64_t expected_groups;              /* cardinality hint, 0 = unknown (table grows on demand) */
+} dbx_agg_params;
+
+/* ----------------------------------------------------------------- top-k */
+/* SortColumnDescription{offset, asc, nulls_first} + LimitType::LimitRows(k)
+ * (kernels/sort.rs:41-63).  Order: OrderedFloat (NaN greatest, -0 == +0). */
+typedef struct dbx_topk_params {
+  int32_t key_col;
+  int32_t asc;
+  int32_t nulls_first;
+  int32_t reserved;
+  int64_t limit;
+} dbx_topk_params;
+
+/* ------------------------------------------------------------------ join */
+typedef enum dbx_join_kind { DBX_JOIN_INNER = 0 } dbx_join_kind;
+typedef struct dbx_join_params {
+  int32_t kind;          /* dbx_join_kind */
+  int32_t build_key_col; /* key column index in build blocks */
+  int32_t probe_key_col; /* key column index in probe blocks */
+  int32_t reserved;
+  int64_t expected_build_rows; /* hint; 0 = unknown */
+} dbx_join_params;
+
+/* -------------------------------------------------------- vector distance */
+typedef enum dbx_distance_kind { DBX_DIST_COSINE = 0, DBX_DIST_L2 = 1 } dbx_distance_kind;
+
+/* ----------------------------------------------------------- operator API */
+typedef enum dbx_op_kind {
+  DBX_OP_FILTER = 0,              /* TransformFilter (filters/filter_predicate.rs:35-104) */
+  DBX_OP_AGG_PARTIAL = 1,         /* [TransformFilter ->] TransformPartialAggregate / PartialSingleStateAggregator */
+  DBX_OP_AGG_FINAL = 2,           /* TransformFinalAggregate / FinalSingleStateAggregator */
+  DBX_OP_TOPK = 3,                /* TransformSortPartial+merge with LIMIT / TransformPartialTopN+FinalTopN */
+  DBX_OP_JOIN = 4                 /* Join trait: add_block / final_build / probe_block / final_probe */
+} dbx_op_kind;
+
+typedef struct dbx_op dbx_op; /* opaque operator handle */
+
+/* Library / device */
+int32_t dbx_abi_version(void);
+int32_t dbx_device_count(int32_t* n);                 /* DBX_ERR_NO_DEVICE when none */
+const char* dbx_last_error(const dbx_op* op);         /* op == NULL: error of the last failed create on this thread */
+
+/* Pinned host buffers (Buffer::from foreign allocation hook, buffer/mod.rs:26-48) */
+int32_t dbx_host_alloc(size_t bytes, void** out);
+int32_t dbx_host_free(void* p);
+int32_t dbx_host_register(void* p, size_t bytes);     /* pin caller-owned memory for direct DMA */
+int32_t dbx_host_unregister(void* p);
+
+/* Device buffers for device-resident pipelines (tests, bench, op->op hand-off) */
+int32_t dbx_device_alloc(int32_t device, size_t bytes, void** out);
+int32_t dbx_device_free(int32_t device, void* p);
+int32_t dbx_memcpy_h2d(int32_t device, void* dst, const void* src, size_t bytes);
+int32_t dbx_memcpy_d2h(int32_t device, void* dst, const void* src, size_t bytes);
+int32_t dbx_device_synchronize(int32_t device);
+
+/* Operator lifecycle.  `params` is the struct matching `kind`
+ * (FILTER: dbx_predicate, AGG_*: dbx_agg_params, TOPK: dbx_topk_params, JOIN: dbx_join_params).
+ * `input_types[n_input_cols]` are the dbx_dtype of the block columns that will be pushed
+ * (DataSchema of the upstream pipe); nullability is taken per block from `validity`. */
+int32_t dbx_op_create(int32_t kind, const void* params, const int32_t* input_types, int32_t n_input_cols,
+                      int32_t device, dbx_op** out);
+int32_t dbx_op_destroy(dbx_op* op);
+
+/* Transform::transform / AccumulatingTransform::transform / Join::add_block(build side) */
+int32_t dbx_op_push(dbx_op* op, const dbx_block* block);
+/* AccumulatingTransform::on_finish / Join::final_build */
+int32_t dbx_op_finish(dbx_op* op);
+/* Pull the next output block: *has_block = 0 when drained.  `out_mem` selects where the
+ * output columns live (host: pinned, zero-copy wrappable; device: stays in HBM). */
+int32_t dbx_op_pull(dbx_op* op, int32_t out_mem, dbx_block* out, int32_t* has_block);
+int32_t dbx_block_release(dbx_block* block);
+
+/* Join probe side: Join::probe_block(block) -> JoinStream::next()* ; output blocks are
+ * pulled with dbx_op_pull until drained.  Join::final_probe is a no-op for inner joins. */
+int32_t dbx_join_probe(dbx_op* op, const dbx_block* block);
+
+/* AGG_FINAL input: hand over a partial operator's device-resident payload
+ * (AggregateMeta::AggregatePayload, aggregate_meta.rs) without leaving HBM. */
+int32_t dbx_agg_final_merge_partial(dbx_op* final_op, dbx_op* partial_op);
+
+/* Multi-GPU exchange support for the partial->final shuffle (build_partition_bucket.rs:41-131,
+ * partitioned_payload.rs:44-57): scatter the finished partial's groups into `n_parts`
+ * owner-contiguous runs of fixed-width rows [key:8][state words...] in one device buffer.
+ * part_offsets[n_parts+1] is written on the HOST.  Rows are `row_bytes` wide. */
+int32_t dbx_agg_partial_partition(dbx_op* partial_op, int32_t n_parts, void** dev_rows, int64_t* part_offsets,
+                                  int32_t* row_bytes);
+/* AGG_FINAL: merge `n_rows` such rows (device memory, e.g. the all-to-all receive buffer). */
+int32_t dbx_agg_final_merge_rows(dbx_op* final_op, const void* dev_rows, int64_t n_rows);
+
+/* ScalarFunction::eval replacement for the vector distances (scalars/vector.rs:497-556):
+ * out[i] = distance(lhs[i], rhs[i]) row-wise, either side may be const.  f32 result. */
+int32_t dbx_eval_distance(int32_t kind, int32_t device, const dbx_column* lhs, const dbx_column* rhs,
+                          dbx_column* out /* caller-provided f32 buffer, mem as given */);
+
+/* Brute-force kNN: `ORDER BY cosine_distance(c, q) LIMIT k` for a batch of queries, i.e.
+ * the EvalScalar -> TopN pipeline of SURVEY 3.5 fused: tensor-core GEMM for candidate
+ * selection, exact fp32 re-evaluation of the returned distances.
+ * corpus: DBX_VEC_F32 [n, dim]; queries: DBX_VEC_F32 [nq, dim];
+ * out_idx[nq*k] (int64 row ids), out_dist[nq*k] (f32), ascending by distance (NaN last). */
+typedef struct dbx_knn dbx_knn;
+int32_t dbx_knn_create(int32_t kind, int32_t device, const dbx_column* corpus, dbx_knn** out);
+int32_t dbx_knn_search(dbx_knn* h, const dbx_column* queries, int32_t k, int32_t out_mem, int64_t* out_idx,
+                       float* out_dist);
+int32_t dbx_knn_destroy(dbx_knn* h);
+const char* dbx_knn_last_error(const dbx_knn* h);
+
+/* Deterministic synthetic column generator (counter-based: splitmix64(seed + row)),
+ * used by tests and bench so host oracle and device data agree bit-for-bit.
+ *   kind 0: int64 uniform in [0, a)            (mulhi(r, a))
+ *   kind 1: int64 uniform in [-2^31, 2^31)     (sign-extended high 32 bits)
+ *   kind 2: float64 = (double)(r >> (64-a))    integer-valued in [0, 2^a)
+ *   kind 3: float64 uniform [0,1) from 53 bits
+ *   kind 4: float32 ~ N(0,1) (Box-Muller on two 24-bit uniforms), len counts floats
+ *   kind 5: int64 unique permutation-ish key: row itself xor-shuffled (bijection on [0,2^a))
+ * `first_row` offsets the counter so shards generate their slice of one global column. */
+int32_t dbx_synth_fill(int32_t device, int32_t kind, uint64_t seed, int64_t a, int64_t first_row, int64_t len,
+                       void* dev_out);
+
+/* Instrumentation: number of kernel launches issued by the library on this thread's
+ * handles since process start (bench.py's gpu_launches). */
+int64_t dbx_kernel_launch_count(void);
+/* Device time (ms) of the dominant kernel of the last push on this handle, measured
+ * with CUDA events on the handle's stream (roofline.achieved in bench.py). */
+int32_t dbx_op_last_kernel_ms(dbx_op* op, float* ms);
+/* Stream of a handle as a cudaStream_t value (for external event timing). */
+int32_t dbx_op_stream(dbx_op* op, void** stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DBX_H_ */
