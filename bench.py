@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path: filter -> hash-aggregate.
+
+Workload (BASELINE.json configs[1]):
+    SELECT k, sum(v), count(v), avg(x) FROM t WHERE v % 3 = 0 GROUP BY k
+    t = 1e9 rows, k Int64 uniform [0,1e6), v Int64 uniform [-2^31,2^31), x Float64 integer-valued [0,2^20)
+    synthetic, counter-based generator (dbx_synth_fill / orc_synth_fill, seeds 42/43/44).
+
+One "step" = one full query over the 1e9-row batch: table reset, fused filter+partial
+aggregation, final merge, result materialisation.
+
+  value  rows/s with the three columns already resident in HBM (CUDA events on the operator's
+         stream; includes table re-initialisation and result finalisation, excludes nothing)
+  e2e    the same query through the public operator API with HOST (pinned) columns pushed in
+         blocks: host->device copies and the device->host copy of the result are inside the
+         timed region
+  roofline  the fused kernel alone: 24 algorithmic bytes per row / its CUDA-event duration
+            against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline  the CPU oracle (reference-algorithm restatement, OpenMP) on a bounded sample
+
+`--impl reference` times the CPU oracle on the host cores (the Rust reference cannot be
+built in this image: no cargo/rustc).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "rows/sec filter->hash-agg (sum,count,avg GROUP BY 1e6 int64 keys) over int64/float64 columns"
+SEEDS = (42, 43, 44)
+N_KEYS = 1_000_000
+BYTES_PER_ROW = 24.0  # three 8-byte columns, each read exactly once
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi during the timed region."""
+
+    def __init__(self, gpu_index=0):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for nm, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_query():
+    from databend_b200 import expr as E
+    from databend_b200.transforms import AggregatorParams
+    params = AggregatorParams([0], [("sum", 1), ("count", 1), ("avg", 2)])
+    filt = E.eq(E.col(1) % E.lit(3), E.lit(0))
+    return params, filt
+
+
+# ---------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """CPU arm: the oracle port on all host threads, each step a bounded sample of the workload."""
+    import numpy as np
+    from databend_b200.block import Column, DataBlock
+    from oracle import oracle as orc
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = orc.num_threads()
+    n = args.cpu_rows
+    params, filt = make_query()
+    k = orc.synth_fill(0, SEEDS[0], N_KEYS, 0, n)
+    v = orc.synth_fill(1, SEEDS[1], 0, 0, n)
+    x = orc.synth_fill(2, SEEDS[2], 20, 0, n)
+    blk = DataBlock([Column.from_data(k), Column.from_data(v), Column.from_data(x)])
+    cp = params.to_c(filt)
+    for _ in range(args.warmup):
+        orc.filter_group_agg(blk, cp, threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.filter_group_agg(blk, cp, threads=threads)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = n / dt
+    sample = f"{n} rows of the same synthetic columns per step (reference-algorithm CPU restatement in C/OpenMP; the Rust reference cannot be built here)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": {"workload": "filter+hash-agg sum/count/avg GROUP BY 1e6 int64 keys, WHERE v%3=0", "rows": n},
+        "cpu_baseline": {"value": val, "unit": "rows/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------- GPU arm
+def run_dbx(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from databend_b200 import abi, build, lib
+    from databend_b200.block import Column, DataBlock
+    from databend_b200.transforms import (DeviceBuffer, TransformFinalAggregate, TransformPartialAggregate)
+
+    build.build()
+    L = lib.load()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    lib.require_device()
+    dev = local_rank
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+
+    total_rows = args.rows
+    # strong scaling: the 1e9-row table is split into `world` contiguous row ranges
+    r_begin = total_rows * rank // world
+    r_end = total_rows * (rank + 1) // world
+    n = r_end - r_begin
+    params, filt = make_query()
+    types = [abi.I64, abi.I64, abi.F64]
+
+    bufs = [DeviceBuffer(n * 8, dev) for _ in range(3)]
+    lib.check(L.dbx_synth_fill(dev, 0, SEEDS[0], N_KEYS, r_begin, n, bufs[0].ptr))
+    lib.check(L.dbx_synth_fill(dev, 1, SEEDS[1], 0, r_begin, n, bufs[1].ptr))
+    lib.check(L.dbx_synth_fill(dev, 2, SEEDS[2], 20, r_begin, n, bufs[2].ptr))
+    dblock = DataBlock([Column.device(abi.I64, n, bufs[0].ptr), Column.device(abi.I64, n, bufs[1].ptr),
+                        Column.device(abi.F64, n, bufs[2].ptr)], n)
+
+    part = TransformPartialAggregate(params, types, filt, dev)
+    fin = TransformFinalAggregate(params, types, dev)
+    sp = C.c_void_p()
+    lib.check(L.dbx_op_stream(part.handle, C.byref(sp)))
+    part_stream = torch.cuda.ExternalStream(sp.value, device=dev)
+    lib.check(L.dbx_op_stream(fin.handle, C.byref(sp)))
+    fin_stream = torch.cuda.ExternalStream(sp.value, device=dev)
+
+    kernel_ms = []
+
+    def exchange_and_finish(out_mem):
+        """partial -> (N>1: hash-partition + one all-to-all) -> final -> result block"""
+        part.on_finish()
+        if world == 1:
+            fin.transform(part)
+        else:
+            rows_ptr = C.c_void_p()
+            offs = (C.c_int64 * (world + 1))()
+            rb = C.c_int32(0)
+            lib.check(L.dbx_agg_partial_partition(part.handle, world, C.byref(rows_ptr), offs, C.byref(rb)), part.handle)
+            row_bytes = rb.value
+            send_counts = [offs[i + 1] - offs[i] for i in range(world)]
+            sc = torch.tensor(send_counts, dtype=torch.int64, device=f"cuda:{dev}")
+            rc = torch.empty_like(sc)
+            dist.all_to_all_single(rc, sc)
+            recv_counts = rc.tolist()
+            total_send = offs[world]
+            send = torch.empty(max(total_send, 1) * row_bytes, dtype=torch.uint8, device=f"cuda:{dev}")
+            if total_send:
+                lib.check(L.dbx_memcpy_d2d(dev, send.data_ptr(), rows_ptr.value, total_send * row_bytes))
+            lib.check(L.dbx_device_free(dev, rows_ptr))
+            recv = torch.empty(max(sum(recv_counts), 1) * row_bytes, dtype=torch.uint8, device=f"cuda:{dev}")
+            dist.all_to_all_single(recv[: sum(recv_counts) * row_bytes], send[: total_send * row_bytes],
+                                   [c * row_bytes for c in recv_counts], [c * row_bytes for c in send_counts])
+            torch.cuda.current_stream().synchronize()
+            fin.merge_rows(recv.data_ptr(), sum(recv_counts))
+        return fin.on_finish(out_mem)
+
+    def step_device():
+        part.reset()
+        fin.reset()
+        part.transform(dblock)
+        kernel_ms.append(part.last_kernel_ms())
+        out = exchange_and_finish(abi.MEM_DEVICE)
+        rows_out = out[0].num_rows
+        L.dbx_block_release(C.byref(out[0]))
+        return rows_out
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        groups = step_device()
+    kernel_ms.clear()
+    barrier()
+    sampler = ClockSampler(dev)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.dbx_kernel_launch_count()
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    ev0.record(part_stream)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        groups = step_device()
+    ev1.record(fin_stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = L.dbx_kernel_launch_count() - launches0
+    step_ms = max(dev_ms, 0.0) / args.steps
+    t = torch.tensor([step_ms, wall * 1e3 / args.steps], dtype=torch.float64, device=f"cuda:{dev}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_ms, wall_ms = t.tolist()
+    k_ms = sum(kernel_ms) / max(1, len(kernel_ms))
+
+    # ---- e2e: host (pinned) columns pushed through the operator API, result pulled to the host
+    e2e = None
+    if not args.no_e2e:
+        e_rows = min(n, args.e2e_rows // world if args.e2e_rows else n)
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available
+            while e_rows * 24 > 0.5 * avail and e_rows > 1_000_000:
+                e_rows //= 2
+        except Exception:
+            pass
+        hp = []
+        for i in range(3):
+            p = C.c_void_p()
+            lib.check(L.dbx_host_alloc(e_rows * 8, C.byref(p)))
+            lib.check(L.dbx_memcpy_d2h(dev, p, bufs[i].ptr, e_rows * 8))
+            hp.append(p)
+        nd = [np.int64, np.int64, np.float64]
+        harr = [np.ctypeslib.as_array(C.cast(hp[i], C.POINTER(C.c_int64 if i < 2 else C.c_double)), shape=(e_rows,)) for i in range(3)]
+        hblock = DataBlock([Column.from_data(harr[0]), Column.from_data(harr[1]), Column.from_data(harr[2])], e_rows)
+        hblocks = hblock.split_by_rows(args.block_rows)
+
+        def step_host():
+            part.reset()
+            fin.reset()
+            for b in hblocks:
+                part.transform(b)
+            out = exchange_and_finish(abi.MEM_HOST)
+            return out[0]
+
+        res = None
+        for _ in range(max(1, args.warmup - 1)):
+            res = step_host()
+        barrier()
+        e_steps = max(1, min(args.steps, 3))
+        ev0.record(part_stream)
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            res = step_host()
+        ev1.record(fin_stream)
+        barrier()
+        e_wall_ms = (time.perf_counter() - t0) * 1e3 / e_steps
+        te = torch.tensor([e_wall_ms], dtype=torch.float64, device=f"cuda:{dev}")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e_wall_ms = te.item()
+        d2h = sum(c.data.nbytes for c in res.columns)
+        e2e = {"value": (e_rows * world) / (e_wall_ms * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": int(e_rows * 24),
+               "d2h_bytes_per_step": int(d2h), "rows": int(e_rows * world), "block_rows": args.block_rows,
+               "ms_per_step": e_wall_ms, "timing": "host wall clock around push..pull incl. stream sync, max over ranks"}
+        for p in hp:
+            L.dbx_host_free(p)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline on a bounded sample (rank 0, N=1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        from oracle import oracle as orc
+        threads = orc.num_threads()
+        cn = args.cpu_rows
+        k = orc.synth_fill(0, SEEDS[0], N_KEYS, 0, cn)
+        v = orc.synth_fill(1, SEEDS[1], 0, 0, cn)
+        x = orc.synth_fill(2, SEEDS[2], 20, 0, cn)
+        cblk = DataBlock([Column.from_data(k), Column.from_data(v), Column.from_data(x)])
+        cp = params.to_c(filt)
+        orc.filter_group_agg(cblk, cp, threads=threads)
+        t0 = time.perf_counter()
+        reps = 2
+        for _ in range(reps):
+            orc.filter_group_agg(cblk, cp, threads=threads)
+        cdt = (time.perf_counter() - t0) / reps
+        cpu = {"value": cn / cdt, "unit": "rows/s", "cores": threads, "kind": "port",
+               "sample": f"first {cn} rows of the same columns, reference-algorithm C/OpenMP restatement (oracle), {reps} reps"}
+
+    peak, peak_src = peaks()
+    achieved = BYTES_PER_ROW * n / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    line = {
+        "metric": METRIC, "value": total_rows / (step_ms * 1e-3), "unit": "rows/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "int64", "data": "synthetic",
+        "config": {"workload": "configs[1]: filter(v%3=0) + hash-agg sum(v),count(v),avg(x) GROUP BY k; 1e6 int64 keys",
+                   "rows": total_rows, "rows_per_gpu": n, "groups_out": int(groups) * (1 if world == 1 else world),
+                   "columns": "k:int64 v:int64 x:float64", "l2": "inputs (24 B/row x rows) far larger than the 126 MB L2",
+                   "timing": "CUDA events on the operators' stream, max over ranks; wall_ms_per_step alongside",
+                   "parallelism": f"row-range x{world}" + ("" if world == 1 else " + NCCL all-to-all of partial groups")},
+        "wall_ms_per_step": wall_ms, "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "filter_group_agg_kernel<3,false>", "kernel_ms": k_ms,
+                     "algorithmic_bytes_per_row": BYTES_PER_ROW, "peak_source": peak_src},
+        "cpu_baseline": cpu, "e2e": e2e,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="dbx", choices=["dbx", "reference"])
+    ap.add_argument("--rows", type=int, default=1_000_000_000)
+    ap.add_argument("--e2e-rows", type=int, default=0, help="0 = same as --rows")
+    ap.add_argument("--block-rows", type=int, default=1 << 22, help="rows per pushed host block in the e2e leg (max_block_size)")
+    ap.add_argument("--cpu-rows", type=int, default=50_000_000)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_dbx(args)
+
+
+if __name__ == "__main__":
+    main()

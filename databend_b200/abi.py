@@ -13,6 +13,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_BAD_ARGUMENTS, ERR_UNSUPPORTED, ERR_OOM, ERR_STAT
 # dbx_dtype
 BOOL, I8, I16, I32, I64, U8, U16, U32, U64, F32, F64, VEC_F32 = range(12)
 MEM_HOST, MEM_DEVICE = 0, 1
+NULLABLE = 0x100
 
 # dbx_cmp_op / dbx_arith_op / dbx_pred_kind
 EQ, NE, LT, LE, GT, GE = range(6)
@@ -131,8 +132,8 @@ class JoinParams(C.Structure):
 EXPORTS = [
     "dbx_abi_version", "dbx_device_count", "dbx_last_error",
     "dbx_host_alloc", "dbx_host_free", "dbx_host_register", "dbx_host_unregister",
-    "dbx_device_alloc", "dbx_device_free", "dbx_memcpy_h2d", "dbx_memcpy_d2h", "dbx_device_synchronize",
-    "dbx_op_create", "dbx_op_destroy", "dbx_op_push", "dbx_op_finish", "dbx_op_pull", "dbx_block_release",
+    "dbx_device_alloc", "dbx_device_free", "dbx_memcpy_h2d", "dbx_memcpy_d2h", "dbx_memcpy_d2d", "dbx_device_synchronize",
+    "dbx_op_create", "dbx_op_destroy", "dbx_op_push", "dbx_op_finish", "dbx_op_pull", "dbx_block_release", "dbx_op_reset", "dbx_op_synchronize",
     "dbx_join_probe", "dbx_agg_final_merge_partial", "dbx_agg_partial_partition", "dbx_agg_final_merge_rows",
     "dbx_eval_distance", "dbx_knn_create", "dbx_knn_search", "dbx_knn_destroy", "dbx_knn_last_error",
     "dbx_synth_fill", "dbx_kernel_launch_count", "dbx_op_last_kernel_ms", "dbx_op_stream",

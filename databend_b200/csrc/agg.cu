@@ -1,0 +1,931 @@
+// agg.cu — DBX_OP_AGG_PARTIAL / DBX_OP_AGG_FINAL: host side of the fused
+// [TransformFilter ->] TransformPartialAggregate -> TransformFinalAggregate path.
+//
+// Reference operators replaced (paths relative to /root/reference):
+//   TransformFilter                    src/query/pipeline/transforms/src/processors/transforms/filters/filter_predicate.rs:35-104
+//   TransformPartialAggregate          src/query/service/src/pipelines/processors/transforms/aggregator/transform_aggregate_partial.rs:117-304
+//   PartialSingleStateAggregator       .../aggregator/transform_single_key.rs:42-188
+//   TransformFinalAggregate            .../aggregator/transform_aggregate_final.rs:67-330
+//   FinalSingleStateAggregator         .../aggregator/transform_single_key.rs:190-279
+//   AggregateHashTable                 src/query/expression/src/aggregate/aggregate_hashtable.rs:168-408
+#include <algorithm>
+
+#include "agg_kernels.cuh"
+#include "runtime.h"
+
+namespace dbx {
+
+namespace {
+
+constexpr int64_t kChunkRows = 1LL << 28;        // rows per kernel launch (u32 overflow row ids)
+constexpr int64_t kDefaultTableBytes = 64 << 20; // default table = half of the 126 MB L2
+constexpr int kProbeLimit = 256;
+
+inline int grid_for_rows(int64_t n_rows) {
+  int64_t tiles = (n_rows + kTileRows - 1) / kTileRows;
+  int64_t g = (int64_t)kNumSMs * 8;  // 8 resident CTAs of 256 threads per SM = full occupancy
+  return (int)std::max<int64_t>(1, std::min(tiles, g));
+}
+inline int grid_for_entries(int64_t n) {
+  int64_t g = (n + 255) / 256;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(g, (int64_t)kNumSMs * 8));
+}
+
+// ---------------------------------------------------------------- plan
+struct AggPlan {
+  dbx_agg_params params;
+  int n_cols = 0;
+  int col_dtype[64];
+  bool col_nullable[64];
+
+  int n_slots = 0;
+  int slot_col[kMaxSlots];
+
+  int n_nodes = 0;
+  PredNodeDev nodes[DBX_MAX_PRED_NODES];
+  bool div_by_zero = false;
+
+  bool grouped = false;
+  int key_slot = -1, key_dtype = -1;
+  bool key_nullable = false;
+
+  int n_words = 0;
+  WordInit init;
+  WordKinds kinds;
+  int n_updates = 0;
+  UpdateDev upd[kMaxUpdates];
+  int stride_shift = 4;
+
+  FinalAgg fin[DBX_MAX_AGGS];  // out pointers filled at finalize time
+
+  int slot_of(int col, ErrorSink* err) {
+    for (int s = 0; s < n_slots; ++s)
+      if (slot_col[s] == col) return s;
+    if (n_slots == kMaxSlots) { err->set("operator reads more than 8 distinct columns"); return -1; }
+    slot_col[n_slots] = col;
+    return n_slots++;
+  }
+  int add_word(uint64_t init_v, int kind) {
+    init.w[n_words] = init_v;
+    kinds.op[n_words] = kind;
+    return n_words++;
+  }
+};
+
+// widened class of a column as loaded by load_slot: every integer type narrower than 64 bits is
+// exactly representable as i64.
+inline int loaded_class(int dtype) {
+  switch (dtype) {
+    case DBX_U64: return VC_UINT;
+    case DBX_F32: case DBX_F64: return VC_FLT;
+    default: return VC_INT;
+  }
+}
+inline int flip_cmp(int op) {
+  switch (op) {
+    case DBX_LT: return DBX_GT;
+    case DBX_LE: return DBX_GE;
+    case DBX_GT: return DBX_LT;
+    case DBX_GE: return DBX_LE;
+    default: return op;
+  }
+}
+inline double scalar_as_double(const dbx_scalar& s) {
+  int c = dtype_class(s.dtype);
+  return c == VC_FLT ? s.v.f64 : (c == VC_INT ? (double)s.v.i64 : (double)s.v.u64);
+}
+inline int cmp3_d(double a, double b) {
+  bool an = a != a, bn = b != b;
+  if (an || bn) return an == bn ? 0 : (an ? 1 : -1);
+  return a < b ? -1 : (a > b ? 1 : 0);
+}
+inline bool apply_cmp_host(int op, int c) {
+  switch (op) {
+    case DBX_EQ: return c == 0;
+    case DBX_NE: return c != 0;
+    case DBX_LT: return c < 0;
+    case DBX_LE: return c <= 0;
+    case DBX_GT: return c > 0;
+    default: return c >= 0;
+  }
+}
+
+int32_t lower_cmp(AggPlan* pl, const dbx_pred_node& in, PredNodeDev* out, ErrorSink* err) {
+  memset(out, 0, sizeof(*out));
+  out->kind = DBX_PRED_CMP;
+  out->r_slot = -1;
+  dbx_operand l = in.lhs, r = in.rhs;
+  int cmp = in.cmp;
+  if (l.is_const && r.is_const) {  // constant folding -> BooleanScalar
+    out->kind = DBX_PRED_CONST;
+    if (l.c.is_null || r.c.is_null) { out->value = 0; return DBX_OK; }
+    int cl = dtype_class(l.c.dtype), cr = dtype_class(r.c.dtype);
+    int c3;
+    if (cl == VC_FLT || cr == VC_FLT || cl != cr) c3 = cmp3_d(scalar_as_double(l.c), scalar_as_double(r.c));
+    else if (cl == VC_INT) c3 = l.c.v.i64 < r.c.v.i64 ? -1 : (l.c.v.i64 > r.c.v.i64 ? 1 : 0);
+    else c3 = l.c.v.u64 < r.c.v.u64 ? -1 : (l.c.v.u64 > r.c.v.u64 ? 1 : 0);
+    out->value = apply_cmp_host(cmp, c3);
+    return DBX_OK;
+  }
+  if (l.is_const) { std::swap(l, r); cmp = flip_cmp(cmp); }
+  if (l.col < 0 || l.col >= pl->n_cols) { err->set("predicate references a column outside the input schema"); return DBX_ERR_INVALID; }
+  if (!r.is_const && r.arith != DBX_ARITH_NONE) { err->set("arithmetic on the right-hand column of a comparison is not supported"); return DBX_ERR_UNSUPPORTED; }
+  int lcls = loaded_class(pl->col_dtype[l.col]);
+  out->l_slot = pl->slot_of(l.col, err);
+  if (out->l_slot < 0) return DBX_ERR_UNSUPPORTED;
+  out->cmp = cmp;
+  if (l.arith == DBX_ARITH_MODULO) {
+    if (l.c.is_null) { out->kind = DBX_PRED_CONST; out->value = 0; return DBX_OK; }  // x % NULL is NULL
+    int ccls = dtype_class(l.c.dtype);
+    if (lcls == VC_FLT || ccls == VC_FLT) {
+      if (lcls != VC_FLT) { err->set("integer column % float literal is not supported"); return DBX_ERR_UNSUPPORTED; }
+      double d = scalar_as_double(l.c);
+      if (d == 0.0) pl->div_by_zero = true;
+      out->mod_f = d;
+    } else {
+      uint64_t ad;
+      if (ccls == VC_INT) ad = l.c.v.i64 < 0 ? (uint64_t)0 - (uint64_t)l.c.v.i64 : (uint64_t)l.c.v.i64;
+      else ad = l.c.v.u64;
+      if (lcls == VC_UINT && ccls == VC_INT && l.c.v.i64 < 0) { err->set("UInt64 % negative literal is not supported"); return DBX_ERR_UNSUPPORTED; }
+      if (lcls == VC_INT && ccls == VC_UINT && l.c.v.u64 > (uint64_t)INT64_MAX) { err->set("Int64 % literal above i64::MAX is not supported"); return DBX_ERR_UNSUPPORTED; }
+      if (ad == 0) { pl->div_by_zero = true; ad = 1; }
+      out->mod = make_mod_magic(ad);
+    }
+    out->l_mod = 1;
+  } else if (l.arith != DBX_ARITH_NONE) {
+    err->set("unknown arithmetic op in predicate");
+    return DBX_ERR_INVALID;
+  }
+  if (!r.is_const) {
+    if (r.col < 0 || r.col >= pl->n_cols) { err->set("predicate references a column outside the input schema"); return DBX_ERR_INVALID; }
+    int rcls = loaded_class(pl->col_dtype[r.col]);
+    if (rcls != lcls) { err->set("comparison between columns of different numeric classes is not supported"); return DBX_ERR_UNSUPPORTED; }
+    out->r_slot = pl->slot_of(r.col, err);
+    if (out->r_slot < 0) return DBX_ERR_UNSUPPORTED;
+    out->cls = lcls;
+    return DBX_OK;
+  }
+  if (r.c.is_null) { out->kind = DBX_PRED_CONST; out->value = 0; return DBX_OK; }  // cmp with NULL is never true
+  int rcls = dtype_class(r.c.dtype);
+  if (lcls == VC_FLT) {
+    out->cls = VC_FLT;
+    out->r_const = scalar_bits(r.c, VC_FLT);
+  } else if (rcls == VC_FLT) {
+    err->set("integer column compared with a float literal is not supported");
+    return DBX_ERR_UNSUPPORTED;
+  } else if (lcls == VC_INT) {
+    out->cls = VC_INT;
+    if (rcls == VC_UINT && r.c.v.u64 > (uint64_t)INT64_MAX) {  // literal above every i64: fold, keep NULL handling
+      bool always = cmp == DBX_LT || cmp == DBX_LE || cmp == DBX_NE;
+      out->cmp = always ? DBX_LE : DBX_GT;
+      out->r_const = (uint64_t)INT64_MAX;
+    } else {
+      out->r_const = r.c.v.u64;
+    }
+  } else {
+    out->cls = VC_UINT;
+    if (rcls == VC_INT && r.c.v.i64 < 0) {  // literal below every u64
+      bool always = cmp == DBX_GT || cmp == DBX_GE || cmp == DBX_NE;
+      out->cmp = always ? DBX_GE : DBX_LT;
+      out->r_const = 0;
+    } else {
+      out->r_const = r.c.v.u64;
+    }
+  }
+  return DBX_OK;
+}
+
+int32_t lower_predicate(AggPlan* pl, const dbx_predicate& pred, ErrorSink* err) {
+  if (pred.n_nodes < 0 || pred.n_nodes > DBX_MAX_PRED_NODES) { err->set("predicate: bad node count"); return DBX_ERR_INVALID; }
+  pl->n_nodes = pred.n_nodes;
+  int depth = 0;
+  for (int i = 0; i < pred.n_nodes; ++i) {
+    const dbx_pred_node& in = pred.nodes[i];
+    PredNodeDev* out = &pl->nodes[i];
+    switch (in.kind) {
+      case DBX_PRED_CMP: DBX_TRY(lower_cmp(pl, in, out, err)); depth += 1; break;
+      case DBX_PRED_AND:
+      case DBX_PRED_OR:
+        memset(out, 0, sizeof(*out));
+        out->kind = in.kind;
+        out->n_children = in.n_children;
+        if (in.n_children < 2 || in.n_children > depth || in.n_children > 16) { err->set("predicate: malformed AND/OR"); return DBX_ERR_INVALID; }
+        depth -= in.n_children - 1;
+        break;
+      case DBX_PRED_BOOLCOL:
+        memset(out, 0, sizeof(*out));
+        out->kind = DBX_PRED_BOOLCOL;
+        if (in.value < 0 || in.value >= pl->n_cols || pl->col_dtype[in.value] != DBX_BOOL) { err->set("predicate: BooleanColumn must reference a Boolean column"); return DBX_ERR_INVALID; }
+        out->value = pl->slot_of(in.value, err);
+        if (out->value < 0) return DBX_ERR_UNSUPPORTED;
+        depth += 1;
+        break;
+      case DBX_PRED_CONST:
+        memset(out, 0, sizeof(*out));
+        out->kind = DBX_PRED_CONST;
+        out->value = in.value != 0;
+        depth += 1;
+        break;
+      default: err->set("predicate: unknown node kind"); return DBX_ERR_INVALID;
+    }
+    if (depth > 30) { err->set("predicate: expression too deep"); return DBX_ERR_UNSUPPORTED; }
+  }
+  if (pred.n_nodes && depth != 1) { err->set("predicate: postfix tree does not reduce to one value"); return DBX_ERR_INVALID; }
+  return DBX_OK;
+}
+
+int32_t build_plan(const dbx_agg_params* p, const int32_t* types, int32_t n_cols, AggPlan* pl, ErrorSink* err) {
+  if (n_cols < 0 || n_cols > 64) { err->set("too many input columns"); return DBX_ERR_INVALID; }
+  pl->params = *p;
+  pl->n_cols = n_cols;
+  for (int i = 0; i < n_cols; ++i) {
+    pl->col_dtype[i] = types[i] & 0xFF;
+    pl->col_nullable[i] = (types[i] & DBX_NULLABLE) != 0;
+  }
+  if (p->n_aggs < 0 || p->n_aggs > DBX_MAX_AGGS) { err->set("bad aggregate count"); return DBX_ERR_INVALID; }
+  if (p->n_group_cols < 0 || p->n_group_cols > DBX_MAX_GROUP_COLS) { err->set("bad group column count"); return DBX_ERR_INVALID; }
+  DBX_TRY(lower_predicate(pl, p->filter, err));
+
+  pl->grouped = p->n_group_cols > 0;
+  if (p->n_group_cols > 1) { err->set("multi-column GROUP BY keys are not built yet (SURVEY 8f.1)"); return DBX_ERR_UNSUPPORTED; }
+  if (pl->grouped) {
+    int kc = p->group_cols[0];
+    if (kc < 0 || kc >= n_cols) { err->set("group column outside the input schema"); return DBX_ERR_INVALID; }
+    int dt = pl->col_dtype[kc];
+    if (dtype_class(dt) == VC_FLT || dt == DBX_BOOL || dtype_size(dt) == 0) { err->set("GROUP BY key must be an integer column (float/bool keys not built yet)"); return DBX_ERR_UNSUPPORTED; }
+    pl->key_slot = pl->slot_of(kc, err);
+    if (pl->key_slot < 0) return DBX_ERR_UNSUPPORTED;
+    pl->key_dtype = dt;
+    pl->key_nullable = pl->col_nullable[kc];
+  }
+
+  // state words: word 0 = number of rows of the group (count(*), and the OrNull flag / avg
+  // divisor of every aggregate whose argument type is not Nullable)
+  memset(&pl->init, 0, sizeof(pl->init));
+  memset(&pl->kinds, 0, sizeof(pl->kinds));
+  pl->add_word(0, UPD_ADD_INT);
+  pl->upd[pl->n_updates++] = UpdateDev{UPD_INC, 0, 0, 0};
+  int cnt_word_of_col[64], acc_word_of_col[64];
+  for (int i = 0; i < 64; ++i) cnt_word_of_col[i] = acc_word_of_col[i] = -1;
+
+  for (int a = 0; a < p->n_aggs; ++a) {
+    const dbx_agg_desc& ad = p->aggs[a];
+    FinalAgg& fa = pl->fin[a];
+    memset(&fa, 0, sizeof(fa));
+    fa.kind = ad.kind;
+    fa.acc_word = -1;
+    if (ad.arg_col < 0) {
+      if (ad.kind != DBX_AGG_COUNT) { err->set("only count() may omit its argument"); return DBX_ERR_INVALID; }
+      fa.cnt_word = 0;
+      fa.arg_dtype = DBX_U64;
+      continue;
+    }
+    if (ad.arg_col >= n_cols) { err->set("aggregate argument outside the input schema"); return DBX_ERR_INVALID; }
+    int dt = pl->col_dtype[ad.arg_col];
+    if (dtype_size(dt) == 0) { err->set("aggregate argument must be a numeric column"); return DBX_ERR_UNSUPPORTED; }
+    fa.arg_dtype = dt;
+    int slot = pl->slot_of(ad.arg_col, err);
+    if (slot < 0) return DBX_ERR_UNSUPPORTED;
+    if (pl->n_words + 2 > kMaxWords || pl->n_updates + 2 > kMaxUpdates) { err->set("too many aggregate states"); return DBX_ERR_UNSUPPORTED; }
+    if (!pl->col_nullable[ad.arg_col]) {
+      fa.cnt_word = 0;
+    } else {
+      if (cnt_word_of_col[ad.arg_col] < 0) {
+        cnt_word_of_col[ad.arg_col] = pl->add_word(0, UPD_ADD_INT);
+        pl->upd[pl->n_updates++] = UpdateDev{UPD_INC_VALID, slot, cnt_word_of_col[ad.arg_col], 0};
+      }
+      fa.cnt_word = cnt_word_of_col[ad.arg_col];
+    }
+    int cls = loaded_class(dt);
+    switch (ad.kind) {
+      case DBX_AGG_COUNT: break;
+      case DBX_AGG_SUM:
+      case DBX_AGG_AVG:
+        if (acc_word_of_col[ad.arg_col] < 0) {
+          int op = cls == VC_FLT ? UPD_ADD_F64 : UPD_ADD_INT;
+          acc_word_of_col[ad.arg_col] = pl->add_word(0, op);
+          pl->upd[pl->n_updates++] = UpdateDev{op, slot, acc_word_of_col[ad.arg_col], 0};
+        }
+        fa.acc_word = acc_word_of_col[ad.arg_col];
+        break;
+      case DBX_AGG_MIN:
+      case DBX_AGG_MAX: {
+        bool mn = ad.kind == DBX_AGG_MIN;
+        int op = cls == VC_FLT ? (mn ? UPD_MIN_F64 : UPD_MAX_F64) : cls == VC_UINT ? (mn ? UPD_MIN_U64 : UPD_MAX_U64) : (mn ? UPD_MIN_S64 : UPD_MAX_S64);
+        uint64_t iv = op == UPD_MIN_S64 ? (uint64_t)INT64_MAX : op == UPD_MAX_S64 ? (uint64_t)INT64_MIN : (op == UPD_MIN_U64 || op == UPD_MIN_F64) ? ~0ULL : 0ULL;
+        fa.acc_word = pl->add_word(iv, op);
+        pl->upd[pl->n_updates++] = UpdateDev{op, slot, fa.acc_word, 0};
+        break;
+      }
+      default: err->set("unknown aggregate kind"); return DBX_ERR_INVALID;
+    }
+  }
+  if (pl->n_slots == 0) {  // e.g. count(*) without filter: still need a row source
+    if (n_cols == 0) { err->set("operator needs at least one input column"); return DBX_ERR_INVALID; }
+    pl->slot_of(0, err);
+  }
+  int bytes = 8 * (1 + pl->n_words);
+  pl->stride_shift = 4;
+  while ((1 << pl->stride_shift) < bytes) ++pl->stride_shift;
+  return DBX_OK;
+}
+
+// ---------------------------------------------------------------- device table
+struct DeviceTable {
+  DevBuf buf;
+  DevBuf counters;  // [0] n_groups, [1] n_overflow
+  int64_t cap = 0;
+  int stride_shift = 4;
+  int n_words = 0;
+
+  unsigned long long* n_groups() const { return (unsigned long long*)counters.p; }
+  unsigned long long* n_overflow() const { return (unsigned long long*)counters.p + 1; }
+
+  int32_t create(int64_t capacity, const AggPlan& pl, cudaStream_t stream, ErrorSink* err) {
+    cap = capacity;
+    stride_shift = pl.stride_shift;
+    n_words = pl.n_words;
+    DBX_CUDA_TRY(*err, buf.ensure((size_t)(cap + 2) << stride_shift));
+    DBX_CUDA_TRY(*err, counters.ensure(64));
+    return clear(pl, stream, err);
+  }
+  int32_t clear(const AggPlan& pl, cudaStream_t stream, ErrorSink* err) {
+    DBX_CUDA_TRY(*err, cudaMemsetAsync(counters.p, 0, 64, stream));
+    int64_t total_words = (cap + 2) << (stride_shift - 3);
+    int grid = (int)std::min<int64_t>((total_words + 255) / 256, (int64_t)kNumSMs * 16);
+    table_init_kernel<<<grid, 256, 0, stream>>>((uint8_t*)buf.p, cap + 2, stride_shift, n_words, pl.init);
+    count_launch();
+    DBX_CUDA_TRY(*err, cudaGetLastError());
+    if (!pl.grouped) {  // the single state is entry 0 and always exists
+      uint64_t zero = 0;
+      DBX_CUDA_TRY(*err, cudaMemcpyAsync(buf.p, &zero, 8, cudaMemcpyHostToDevice, stream));
+      unsigned long long one = 1;
+      DBX_CUDA_TRY(*err, cudaMemcpyAsync(counters.p, &one, 8, cudaMemcpyHostToDevice, stream));
+    }
+    return DBX_OK;
+  }
+  TableDev view(uint32_t* overflow_rows) const {
+    TableDev t;
+    t.base = (uint8_t*)buf.p;
+    t.cap = cap;
+    t.stride_shift = stride_shift;
+    t.n_words = n_words;
+    t.n_groups = n_groups();
+    t.n_overflow = n_overflow();
+    t.overflow_rows = overflow_rows;
+    t.probe_limit = (int32_t)std::min<int64_t>(kProbeLimit, cap);
+    t.pad = 0;
+    return t;
+  }
+};
+
+inline int64_t next_pow2(int64_t x) {
+  int64_t p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+}  // namespace
+
+// ================================================================ partial
+class AggPartialOp : public Op {
+ public:
+  AggPlan plan;
+  DeviceTable table;
+  Stager stager;
+  DevBuf ovf[2];
+  PinnedBuf host_counters;
+  int64_t groups_known = 0;    // exact group count at the last counter read
+  int64_t rows_since_read = 0; // rows pushed since (upper bound on new groups)
+  bool pulled = false;
+  int64_t rows_in = 0;
+  int64_t initial_cap = 0;
+  bool table_ready = false;
+
+  int32_t init(const dbx_agg_params* p, const int32_t* types, int32_t n, int dev) {
+    DBX_TRY(base_init(dev));
+    DBX_TRY(build_plan(p, types, n, &plan, &err));
+    DBX_TRY(stager.init(dev, stream, &err));
+    DBX_CUDA_TRY(err, host_counters.ensure(64));
+    int64_t cap;
+    if (!plan.grouped) cap = 1;
+    else if (p->expected_groups > 0) cap = next_pow2(std::max<int64_t>(2 * p->expected_groups, 1024));
+    else cap = std::max<int64_t>(1024, kDefaultTableBytes >> plan.stride_shift);
+    initial_cap = cap;
+    DBX_TRY(ensure_table());
+    return DBX_OK;
+  }
+
+  // (Re-)create or clear the table lazily: after a final operator adopted it, or after reset().
+  int32_t ensure_table() {
+    if (table_ready) return DBX_OK;
+    if (table.cap != initial_cap || !table.buf.p) DBX_TRY(table.create(initial_cap, plan, stream, &err));
+    else DBX_TRY(table.clear(plan, stream, &err));
+    table_ready = true;
+    groups_known = plan.grouped ? 0 : 1;
+    rows_since_read = 0;
+    return DBX_OK;
+  }
+
+  int32_t reset() override {
+    table_ready = false;
+    DBX_TRY(ensure_table());
+    groups_known = plan.grouped ? 0 : 1;
+    rows_since_read = 0;
+    pulled = false;
+    rows_in = 0;
+    return DBX_OK;
+  }
+
+  int32_t read_counters(unsigned long long* n_groups, unsigned long long* n_overflow) {
+    DBX_CUDA_TRY(err, cudaMemcpyAsync(host_counters.p, table.counters.p, 16, cudaMemcpyDeviceToHost, stream));
+    DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
+    *n_groups = ((unsigned long long*)host_counters.p)[0];
+    *n_overflow = ((unsigned long long*)host_counters.p)[1];
+    groups_known = (int64_t)*n_groups;
+    rows_since_read = 0;
+    return DBX_OK;
+  }
+
+  // resize (aggregate_hashtable.rs:463-489): rebuild into a larger table on the device
+  int32_t grow_to(int64_t new_cap) {
+    DeviceTable nt;
+    DBX_TRY(nt.create(new_cap, plan, stream, &err));
+    table_merge_kernel<<<grid_for_entries(table.cap + 2), 256, 0, stream>>>(table.view(nullptr), nt.view(nullptr), plan.kinds);
+    count_launch();
+    DBX_CUDA_TRY(err, cudaGetLastError());
+    DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));  // old table is freed below
+    std::swap(table.buf, nt.buf);
+    std::swap(table.counters, nt.counters);
+    table.cap = new_cap;
+    return DBX_OK;
+  }
+
+  template <bool INDIRECT>
+  int32_t launch_grouped(const AggKernelParams& kp) {
+    int grid = grid_for_rows(kp.n_rows);
+    switch (plan.n_slots) {
+      case 1: filter_group_agg_kernel<1, INDIRECT><<<grid, kBlock, 0, stream>>>(kp); break;
+      case 2: filter_group_agg_kernel<2, INDIRECT><<<grid, kBlock, 0, stream>>>(kp); break;
+      case 3: filter_group_agg_kernel<3, INDIRECT><<<grid, kBlock, 0, stream>>>(kp); break;
+      case 4: filter_group_agg_kernel<4, INDIRECT><<<grid, kBlock, 0, stream>>>(kp); break;
+      case 5: filter_group_agg_kernel<5, INDIRECT><<<grid, kBlock, 0, stream>>>(kp); break;
+      case 6: filter_group_agg_kernel<6, INDIRECT><<<grid, kBlock, 0, stream>>>(kp); break;
+      case 7: filter_group_agg_kernel<7, INDIRECT><<<grid, kBlock, 0, stream>>>(kp); break;
+      default: filter_group_agg_kernel<8, INDIRECT><<<grid, kBlock, 0, stream>>>(kp); break;
+    }
+    count_launch();
+    DBX_CUDA_TRY(err, cudaGetLastError());
+    return DBX_OK;
+  }
+  int32_t launch_single(const AggKernelParams& kp) {
+    int grid = std::min(grid_for_rows(kp.n_rows), kNumSMs * 4);
+    switch (plan.n_slots) {
+      case 1: filter_single_agg_kernel<1><<<grid, kBlock, 0, stream>>>(kp); break;
+      case 2: filter_single_agg_kernel<2><<<grid, kBlock, 0, stream>>>(kp); break;
+      case 3: filter_single_agg_kernel<3><<<grid, kBlock, 0, stream>>>(kp); break;
+      case 4: filter_single_agg_kernel<4><<<grid, kBlock, 0, stream>>>(kp); break;
+      case 5: filter_single_agg_kernel<5><<<grid, kBlock, 0, stream>>>(kp); break;
+      case 6: filter_single_agg_kernel<6><<<grid, kBlock, 0, stream>>>(kp); break;
+      case 7: filter_single_agg_kernel<7><<<grid, kBlock, 0, stream>>>(kp); break;
+      default: filter_single_agg_kernel<8><<<grid, kBlock, 0, stream>>>(kp); break;
+    }
+    count_launch();
+    DBX_CUDA_TRY(err, cudaGetLastError());
+    return DBX_OK;
+  }
+
+  void fill_params(AggKernelParams* kp, const DevCol* cols, int64_t row0, int64_t n) {
+    memset(kp, 0, sizeof(*kp));
+    for (int s = 0; s < plan.n_slots; ++s) {
+      DevCol c = cols[s];
+      if (!c.is_const) {
+        if (c.dtype == DBX_BOOL) c.dbit_off += row0;
+        else c.data = (const char*)c.data + row0 * dtype_size(c.dtype);
+        if (c.validity) c.vbit_off += row0;
+      }
+      kp->cols[s] = c;
+    }
+    memcpy(kp->nodes, plan.nodes, sizeof(PredNodeDev) * plan.n_nodes);
+    memcpy(kp->upd, plan.upd, sizeof(UpdateDev) * plan.n_updates);
+    kp->n_rows = n;
+    kp->n_slots = plan.n_slots;
+    kp->n_nodes = plan.n_nodes;
+    kp->n_updates = plan.n_updates;
+    kp->key_slot = plan.key_slot;
+    kp->key_nullable = plan.key_nullable;
+  }
+
+  int32_t push(const dbx_block* b) override {
+    if (b->num_cols != plan.n_cols) { err.set("push: block column count differs from the operator's input schema"); return DBX_ERR_INVALID; }
+    for (int i = 0; i < plan.n_cols; ++i) {
+      if (b->cols[i].dtype != plan.col_dtype[i]) { err.set("push: block column dtype differs from the operator's input schema"); return DBX_ERR_INVALID; }
+      if (b->cols[i].len != b->num_rows) { err.set("push: column length differs from num_rows"); return DBX_ERR_INVALID; }
+      if (b->cols[i].validity && !plan.col_nullable[i] && !b->cols[i].is_const) { err.set("push: validity bitmap on a column declared non-nullable"); return DBX_ERR_INVALID; }
+    }
+    const int64_t n = b->num_rows;
+    if (n == 0) return DBX_OK;
+    if (plan.div_by_zero) {  // rem_scalar: divisor literal 0 fails the whole block (arithmetic_modulo.rs:137-140)
+      err.set("Division by zero, during run expr: modulo (first failing row 0)");
+      return DBX_ERR_BAD_ARGUMENTS;
+    }
+    DBX_TRY(ensure_table());
+    DevCol cols[kMaxSlots];
+    DBX_TRY(stager.begin());
+    for (int s = 0; s < plan.n_slots; ++s) DBX_TRY(stager.stage(b->cols[plan.slot_col[s]], s, &cols[s]));
+    rows_in += n;
+
+    DBX_CUDA_TRY(err, cudaEventRecord(ev_k0, stream));
+    for (int64_t row0 = 0; row0 < n; row0 += kChunkRows) {
+      const int64_t m = std::min(kChunkRows, n - row0);
+      AggKernelParams kp;
+      fill_params(&kp, cols, row0, m);
+      if (!plan.grouped) {
+        kp.table = table.view(nullptr);
+        kp.single_state = (unsigned long long*)((uint8_t*)table.buf.p + 8);
+        DBX_TRY(launch_single(kp));
+        continue;
+      }
+      // Insertions are provably within the load-factor budget when even "every row is a new
+      // group" keeps the table at most half full: no overflow list, no host sync.
+      const bool safe = (groups_known + rows_since_read + m) * 2 <= table.cap;
+      if (safe) {
+        kp.table = table.view(nullptr);
+        DBX_TRY(launch_grouped<false>(kp));
+        rows_since_read += m;
+        continue;
+      }
+      DBX_CUDA_TRY(err, ovf[0].ensure((size_t)m * 4));
+      kp.table = table.view((uint32_t*)ovf[0].p);
+      DBX_TRY(launch_grouped<false>(kp));
+      unsigned long long ng = 0, no = 0;
+      DBX_TRY(read_counters(&ng, &no));
+      int cur = 0;
+      while (no > 0) {  // rows whose group did not fit: grow and replay just those rows
+        int64_t want = next_pow2(std::max<int64_t>(table.cap * 4, 2 * (int64_t)ng));
+        DBX_TRY(grow_to(want));
+        DBX_CUDA_TRY(err, cudaMemsetAsync(table.n_overflow(), 0, 8, stream));
+        DBX_CUDA_TRY(err, ovf[cur ^ 1].ensure((size_t)no * 4));
+        AggKernelParams kr;
+        fill_params(&kr, cols, row0, (int64_t)no);
+        kr.row_index = (const uint32_t*)ovf[cur].p;
+        kr.table = table.view((uint32_t*)ovf[cur ^ 1].p);
+        DBX_TRY(launch_grouped<true>(kr));
+        cur ^= 1;
+        DBX_TRY(read_counters(&ng, &no));
+      }
+      if ((int64_t)ng * 2 > table.cap) DBX_TRY(grow_to(next_pow2(4 * (int64_t)ng)));
+    }
+    DBX_CUDA_TRY(err, cudaEventRecord(ev_k1, stream));
+    timed = true;
+    DBX_TRY(stager.end());
+    return DBX_OK;
+  }
+
+  int32_t finish() override { return DBX_OK; }
+
+  // The partial emits one metadata-only block (AggregateMeta::AggregatePayload): the payload
+  // stays in HBM and is referenced through block.meta.
+  int32_t pull(int32_t, dbx_block* out, int32_t* has_block) override {
+    if (!finished) { err.set("pull before finish"); return DBX_ERR_STATE; }
+    if (pulled) { *has_block = 0; return DBX_OK; }
+    memset(out, 0, sizeof(*out));
+    out->meta = this;
+    *has_block = 1;
+    pulled = true;
+    return DBX_OK;
+  }
+
+  int32_t exact_groups(int64_t* n) {
+    unsigned long long ng, no;
+    DBX_TRY(ensure_table());
+    DBX_TRY(read_counters(&ng, &no));
+    if (no) { err.set("internal: rows were dropped by the partial table (overflow in safe mode)"); return DBX_ERR_CUDA; }
+    *n = (int64_t)ng;
+    return DBX_OK;
+  }
+};
+
+// ================================================================ final
+class AggFinalOp : public Op {
+ public:
+  AggPlan plan;
+  DeviceTable table;
+  bool has_table = false;
+  PinnedBuf host_counters;
+  std::unique_ptr<OwnedBlock> result_dev;  // finalized columns in HBM
+  int64_t result_rows = 0;
+  bool pulled = false;
+
+  int32_t init(const dbx_agg_params* p, const int32_t* types, int32_t n, int dev) {
+    DBX_TRY(base_init(dev));
+    DBX_TRY(build_plan(p, types, n, &plan, &err));
+    DBX_CUDA_TRY(err, host_counters.ensure(64));
+    return DBX_OK;
+  }
+  int32_t reset() override {
+    has_table = false;
+    result_dev.reset();
+    result_rows = 0;
+    pulled = false;
+    return DBX_OK;
+  }
+
+  int32_t read_groups(int64_t* ng, int64_t* no) {
+    DBX_CUDA_TRY(err, cudaMemcpyAsync(host_counters.p, table.counters.p, 16, cudaMemcpyDeviceToHost, stream));
+    DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
+    *ng = (int64_t)((unsigned long long*)host_counters.p)[0];
+    *no = (int64_t)((unsigned long long*)host_counters.p)[1];
+    return DBX_OK;
+  }
+
+  int32_t ensure_capacity(int64_t incoming) {
+    if (!has_table) {
+      int64_t cap = plan.grouped ? next_pow2(std::max<int64_t>(1024, 2 * incoming)) : 1;
+      DBX_TRY(table.create(cap, plan, stream, &err));
+      has_table = true;
+      return DBX_OK;
+    }
+    if (!plan.grouped) return DBX_OK;
+    int64_t ng, no;
+    DBX_TRY(read_groups(&ng, &no));
+    if ((ng + incoming) * 2 > table.cap) {
+      DeviceTable nt;
+      DBX_TRY(nt.create(next_pow2(2 * (ng + incoming)), plan, stream, &err));
+      table_merge_kernel<<<grid_for_entries(table.cap + 2), 256, 0, stream>>>(table.view(nullptr), nt.view(nullptr), plan.kinds);
+      count_launch();
+      DBX_CUDA_TRY(err, cudaGetLastError());
+      DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
+      std::swap(table.buf, nt.buf);
+      std::swap(table.counters, nt.counters);
+      table.cap = nt.cap;
+    }
+    return DBX_OK;
+  }
+
+  // combine_payload of one partial's table (AggregateMeta::AggregatePayload)
+  int32_t merge_partial(AggPartialOp* part) {
+    if (finished) { err.set("merge after finish"); return DBX_ERR_STATE; }
+    if (part->device != device) { err.set("partial and final operators live on different devices"); return DBX_ERR_INVALID; }
+    if (part->plan.n_words != plan.n_words || part->plan.stride_shift != plan.stride_shift || part->plan.grouped != plan.grouped ||
+        memcmp(&part->plan.kinds, &plan.kinds, sizeof(WordKinds)) != 0) {
+      err.set("partial and final operators were created with different aggregate parameters");
+      return DBX_ERR_INVALID;
+    }
+    {
+      int32_t st = part->ensure_table();
+      if (st != DBX_OK) { err.set(part->err.msg); return st; }
+    }
+    DBX_CUDA_TRY(err, cudaStreamSynchronize(part->stream));  // partial's kernels precede the merge
+    if (!has_table) {  // first partial: adopt its table (swap buffers), nothing to merge
+      unsigned long long ng = 0, no = 0;
+      int32_t st = part->read_counters(&ng, &no);
+      if (st != DBX_OK) { err.set(part->err.msg); return st; }
+      if (no) { err.set("internal: rows were dropped by the partial table (overflow in safe mode)"); return DBX_ERR_CUDA; }
+      std::swap(table.buf, part->table.buf);
+      std::swap(table.counters, part->table.counters);
+      std::swap(table.cap, part->table.cap);
+      table.stride_shift = part->table.stride_shift;
+      table.n_words = part->table.n_words;
+      has_table = true;
+      part->table_ready = false;  // whatever buffer it now holds is re-created / cleared lazily
+      return DBX_OK;
+    }
+    int64_t pg = 0;
+    {
+      int32_t st = part->exact_groups(&pg);
+      if (st != DBX_OK) { err.set(part->err.msg); return st; }
+    }
+    DBX_TRY(ensure_capacity(pg));
+    table_merge_kernel<<<grid_for_entries(part->table.cap + 2), 256, 0, stream>>>(part->table.view(nullptr), table.view(nullptr), plan.kinds);
+    count_launch();
+    DBX_CUDA_TRY(err, cudaGetLastError());
+    int64_t ng, no;
+    DBX_TRY(read_groups(&ng, &no));
+    if (no) { err.set("internal: final table overflow during merge"); return DBX_ERR_CUDA; }
+    return DBX_OK;
+  }
+
+  int32_t merge_rows(const void* dev_rows, int64_t n_rows) {
+    if (finished) { err.set("merge after finish"); return DBX_ERR_STATE; }
+    DBX_TRY(ensure_capacity(n_rows));
+    if (n_rows == 0) return DBX_OK;
+    rows_merge_kernel<<<grid_for_entries(n_rows), 256, 0, stream>>>((const uint64_t*)dev_rows, n_rows, table.view(nullptr), plan.kinds);
+    count_launch();
+    DBX_CUDA_TRY(err, cudaGetLastError());
+    int64_t ng, no;
+    DBX_TRY(read_groups(&ng, &no));
+    if (no) { err.set("internal: final table overflow during merge"); return DBX_ERR_CUDA; }
+    return DBX_OK;
+  }
+
+  // Final input port: blocks whose meta references a partial payload.
+  int32_t push(const dbx_block* b) override {
+    if (!b->meta) { err.set("AGG_FINAL consumes partial payload blocks (block.meta) or dbx_agg_final_merge_*"); return DBX_ERR_INVALID; }
+    return merge_partial(reinterpret_cast<AggPartialOp*>(b->meta));
+  }
+
+  static int result_dtype(const FinalAgg& fa) {
+    int cls = dtype_class(fa.arg_dtype);
+    switch (fa.kind) {
+      case DBX_AGG_COUNT: return DBX_U64;
+      case DBX_AGG_AVG: return DBX_F64;
+      case DBX_AGG_SUM: return cls == VC_FLT ? DBX_F64 : (cls == VC_INT ? DBX_I64 : DBX_U64);
+      default: return fa.arg_dtype;
+    }
+  }
+
+  // merge_result: compact the table into [aggs..., keys...] columns in HBM
+  int32_t finish() override {
+    if (!has_table) DBX_TRY(ensure_capacity(0));
+    int64_t ng, no;
+    DBX_TRY(read_groups(&ng, &no));
+    if (no) { err.set("internal: rows were dropped by the aggregate table (overflow)"); return DBX_ERR_CUDA; }
+    result_rows = ng;
+    auto ob = std::make_unique<OwnedBlock>();
+    ob->device = device;
+    const int64_t cap_rows = std::max<int64_t>(ng, 1);
+    auto dev_alloc = [&](size_t bytes, void** p) -> int32_t {
+      DBX_CUDA_TRY(err, cudaMalloc(p, bytes ? bytes : 1));
+      ob->dev_allocs.push_back(*p);
+      return DBX_OK;
+    };
+    FinalizeParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.n_aggs = plan.params.n_aggs;
+    std::vector<uint8_t*> valid_bytes;  // per output column (nullptr = not nullable)
+    for (int a = 0; a < fp.n_aggs; ++a) {
+      fp.aggs[a] = plan.fin[a];
+      int rdt = result_dtype(plan.fin[a]);
+      void* vals = nullptr;
+      DBX_TRY(dev_alloc((size_t)cap_rows * dtype_size(rdt), &vals));
+      fp.aggs[a].out = vals;
+      uint8_t* vb = nullptr;
+      if (plan.fin[a].kind != DBX_AGG_COUNT) DBX_TRY(dev_alloc((size_t)cap_rows, (void**)&vb));
+      fp.aggs[a].out_valid = vb;
+      valid_bytes.push_back(vb);
+      dbx_column c;
+      memset(&c, 0, sizeof(c));
+      c.dtype = rdt;
+      c.mem = DBX_MEM_DEVICE;
+      c.len = ng;
+      c.data = vals;
+      c.null_count = vb ? -1 : 0;
+      ob->cols.push_back(c);
+    }
+    fp.key_dtype = -1;
+    if (plan.grouped) {
+      fp.key_dtype = plan.key_dtype;
+      void* kv = nullptr;
+      DBX_TRY(dev_alloc((size_t)cap_rows * dtype_size(plan.key_dtype), &kv));
+      fp.out_key = kv;
+      uint8_t* vb = nullptr;
+      if (plan.key_nullable) DBX_TRY(dev_alloc((size_t)cap_rows, (void**)&vb));
+      fp.out_key_valid = vb;
+      valid_bytes.push_back(vb);
+      dbx_column c;
+      memset(&c, 0, sizeof(c));
+      c.dtype = plan.key_dtype;
+      c.mem = DBX_MEM_DEVICE;
+      c.len = ng;
+      c.data = kv;
+      c.null_count = vb ? -1 : 0;
+      ob->cols.push_back(c);
+    }
+    unsigned long long* out_count = nullptr;
+    DBX_TRY(dev_alloc(8, (void**)&out_count));
+    DBX_CUDA_TRY(err, cudaMemsetAsync(out_count, 0, 8, stream));
+    fp.out_count = out_count;
+    table_finalize_kernel<<<grid_for_entries(table.cap + 2), 256, 0, stream>>>(table.view(nullptr), fp);
+    count_launch();
+    DBX_CUDA_TRY(err, cudaGetLastError());
+    // validity bytes -> LSB-first bitmaps
+    for (size_t i = 0; i < valid_bytes.size(); ++i) {
+      if (!valid_bytes[i]) continue;
+      uint8_t* bits = nullptr;
+      DBX_TRY(dev_alloc((size_t)(cap_rows + 7) / 8 + 8, (void**)&bits));
+      pack_validity_kernel<<<grid_for_entries((ng + 7) / 8 + 1), 256, 0, stream>>>(valid_bytes[i], ng, bits);
+      count_launch();
+      DBX_CUDA_TRY(err, cudaGetLastError());
+      ob->cols[i].validity = bits;
+      ob->cols[i].validity_bit_offset = 0;
+    }
+    result_dev = std::move(ob);
+    return DBX_OK;
+  }
+
+  int32_t pull(int32_t out_mem, dbx_block* out, int32_t* has_block) override {
+    if (!finished) { err.set("pull before finish"); return DBX_ERR_STATE; }
+    if (pulled || !result_dev) { *has_block = 0; return DBX_OK; }
+    pulled = true;
+    *has_block = 1;
+    if (out_mem == DBX_MEM_DEVICE) {
+      DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
+      OwnedBlock* ob = result_dev.release();
+      return fill_owned_block(ob, out);
+    }
+    auto hb = std::make_unique<OwnedBlock>();
+    hb->device = device;
+    for (const dbx_column& dc : result_dev->cols) {
+      dbx_column c = dc;
+      c.mem = DBX_MEM_HOST;
+      size_t bytes = (size_t)dc.len * dtype_size(dc.dtype);
+      void* hp = nullptr;
+      DBX_CUDA_TRY(err, cudaMallocHost(&hp, bytes ? bytes : 1));
+      hb->host_allocs.push_back(hp);
+      if (bytes) DBX_CUDA_TRY(err, cudaMemcpyAsync(hp, dc.data, bytes, cudaMemcpyDeviceToHost, stream));
+      c.data = hp;
+      if (dc.validity) {
+        size_t vb = (size_t)(dc.len + 7) / 8;
+        void* hv = nullptr;
+        DBX_CUDA_TRY(err, cudaMallocHost(&hv, vb ? vb : 1));
+        hb->host_allocs.push_back(hv);
+        if (vb) DBX_CUDA_TRY(err, cudaMemcpyAsync(hv, dc.validity, vb, cudaMemcpyDeviceToHost, stream));
+        c.validity = (const uint8_t*)hv;
+      }
+      hb->cols.push_back(c);
+    }
+    DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
+    for (dbx_column& c : hb->cols) {
+      if (!c.validity) continue;
+      int64_t nulls = 0;
+      for (int64_t i = 0; i < c.len; ++i) nulls += !((c.validity[i >> 3] >> (i & 7)) & 1);
+      c.null_count = nulls;
+    }
+    result_dev.reset();
+    return fill_owned_block(hb.release(), out);
+  }
+};
+
+Op* make_agg_partial_op(const dbx_agg_params* p, const int32_t* types, int32_t n, int device, int32_t* st) {
+  auto* op = new AggPartialOp();
+  *st = op->init(p, types, n, device);
+  if (*st != DBX_OK) { g_create_error.set(op->err.msg); delete op; return nullptr; }
+  return op;
+}
+Op* make_agg_final_op(const dbx_agg_params* p, const int32_t* types, int32_t n, int device, int32_t* st) {
+  auto* op = new AggFinalOp();
+  *st = op->init(p, types, n, device);
+  if (*st != DBX_OK) { g_create_error.set(op->err.msg); delete op; return nullptr; }
+  return op;
+}
+
+}  // namespace dbx
+
+using namespace dbx;
+
+extern "C" {
+
+int32_t dbx_agg_final_merge_partial(dbx_op* final_op, dbx_op* partial_op) {
+  if (!final_op || !partial_op) return DBX_ERR_INVALID;
+  Op* f = reinterpret_cast<Op*>(final_op);
+  Op* p = reinterpret_cast<Op*>(partial_op);
+  if (f->kind != DBX_OP_AGG_FINAL || p->kind != DBX_OP_AGG_PARTIAL) { f->err.set("merge_partial: wrong operator kinds"); return DBX_ERR_INVALID; }
+  DBX_CUDA_TRY(f->err, cudaSetDevice(f->device));
+  return static_cast<AggFinalOp*>(f)->merge_partial(static_cast<AggPartialOp*>(p));
+}
+
+int32_t dbx_agg_partial_partition(dbx_op* partial_op, int32_t n_parts, void** dev_rows, int64_t* part_offsets,
+                                  int32_t* row_bytes) {
+  if (!partial_op || !dev_rows || !part_offsets || !row_bytes || n_parts < 1 || n_parts > 4096) return DBX_ERR_INVALID;
+  Op* o = reinterpret_cast<Op*>(partial_op);
+  if (o->kind != DBX_OP_AGG_PARTIAL) { o->err.set("partition: not a partial aggregate operator"); return DBX_ERR_INVALID; }
+  AggPartialOp* p = static_cast<AggPartialOp*>(o);
+  DBX_CUDA_TRY(p->err, cudaSetDevice(p->device));
+  DevBuf counts;
+  DBX_CUDA_TRY(p->err, counts.ensure((size_t)n_parts * 8));
+  DBX_CUDA_TRY(p->err, cudaMemsetAsync(counts.p, 0, (size_t)n_parts * 8, p->stream));
+  TableDev tv = p->table.view(nullptr);
+  int grid = grid_for_entries(tv.cap + 2);
+  table_partition_count_kernel<<<grid, 256, (size_t)n_parts * 4, p->stream>>>(tv, n_parts, (unsigned long long*)counts.p);
+  count_launch();
+  DBX_CUDA_TRY(p->err, cudaGetLastError());
+  std::vector<unsigned long long> h((size_t)n_parts);
+  DBX_CUDA_TRY(p->err, cudaMemcpyAsync(h.data(), counts.p, (size_t)n_parts * 8, cudaMemcpyDeviceToHost, p->stream));
+  DBX_CUDA_TRY(p->err, cudaStreamSynchronize(p->stream));
+  std::vector<unsigned long long> cursors((size_t)n_parts);
+  int64_t total = 0;
+  for (int i = 0; i < n_parts; ++i) { part_offsets[i] = total; cursors[i] = (unsigned long long)total; total += (int64_t)h[i]; }
+  part_offsets[n_parts] = total;
+  const int rb = 8 * (2 + p->plan.n_words);
+  *row_bytes = rb;
+  void* rows = nullptr;
+  DBX_CUDA_TRY(p->err, cudaMalloc(&rows, (size_t)std::max<int64_t>(total, 1) * rb));
+  DBX_CUDA_TRY(p->err, cudaMemcpyAsync(counts.p, cursors.data(), (size_t)n_parts * 8, cudaMemcpyHostToDevice, p->stream));
+  table_partition_scatter_kernel<<<grid, 256, 0, p->stream>>>(tv, n_parts, (unsigned long long*)counts.p, (uint64_t*)rows);
+  count_launch();
+  DBX_CUDA_TRY(p->err, cudaGetLastError());
+  DBX_CUDA_TRY(p->err, cudaStreamSynchronize(p->stream));
+  *dev_rows = rows;  // caller frees with dbx_device_free
+  return DBX_OK;
+}
+
+int32_t dbx_agg_final_merge_rows(dbx_op* final_op, const void* dev_rows, int64_t n_rows) {
+  if (!final_op || (n_rows > 0 && !dev_rows) || n_rows < 0) return DBX_ERR_INVALID;
+  Op* f = reinterpret_cast<Op*>(final_op);
+  if (f->kind != DBX_OP_AGG_FINAL) { f->err.set("merge_rows: not a final aggregate operator"); return DBX_ERR_INVALID; }
+  DBX_CUDA_TRY(f->err, cudaSetDevice(f->device));
+  return static_cast<AggFinalOp*>(f)->merge_rows(dev_rows, n_rows);
+}
+
+}  // extern "C"

@@ -1,0 +1,653 @@
+// agg_kernels.cuh — fused [filter ->] hash-aggregate kernels for sm_100a.
+//
+// Replaces, for one pushed DataBlock, the reference's per-block chain
+//   TransformFilter (FilterExecutor::select + take)           filter_executor.rs:82-160
+//   -> AggregateHashTable::add_groups                         aggregate_hashtable.rs:168-292
+//        group_hash_entries / HashIndex::probe_and_create     group_hash.rs:40, hash_index/index.rs:148-214
+//        accumulate_keys for sum / count / avg / min / max    aggregate_sum.rs:106-111, aggregate_count.rs:123-157,
+//                                                             aggregate_avg.rs:75-80
+// with ONE pass over HBM: each input column is read exactly once with 128-bit streaming
+// loads (evict-first), the predicate is evaluated in registers, and surviving rows update an
+// L2-resident open-addressing table with fire-and-forget `red.global` atomics.
+//
+// HBM-bound integer work: no tensor cores, no shared-memory staging of the stream (there is
+// no reuse); the levers are coalescing, bytes in flight, and keeping the table in L2.
+#pragma once
+#include "plan.h"
+
+namespace dbx {
+
+constexpr int kBlock = 256;       // threads per CTA
+constexpr int kRowsPerThread = 4; // one 256-bit load per 8-byte column per tile
+constexpr int kTileRows = kBlock * kRowsPerThread;
+
+struct RowVals {
+  uint64_t v[kRowsPerThread];
+};
+
+// ---------------------------------------------------------------- column tile loads
+template <typename T>
+__device__ __forceinline__ uint64_t widen(T x);
+template <> __device__ __forceinline__ uint64_t widen<int8_t>(int8_t x) { return (uint64_t)(int64_t)x; }
+template <> __device__ __forceinline__ uint64_t widen<int16_t>(int16_t x) { return (uint64_t)(int64_t)x; }
+template <> __device__ __forceinline__ uint64_t widen<int32_t>(int32_t x) { return (uint64_t)(int64_t)x; }
+template <> __device__ __forceinline__ uint64_t widen<uint8_t>(uint8_t x) { return x; }
+template <> __device__ __forceinline__ uint64_t widen<uint16_t>(uint16_t x) { return x; }
+template <> __device__ __forceinline__ uint64_t widen<uint32_t>(uint32_t x) { return x; }
+
+__device__ __forceinline__ uint64_t f32_bits_to_f64_bits(uint32_t b) {
+  return (uint64_t)__double_as_longlong((double)__uint_as_float(b));
+}
+
+// Row r of a tile belongs to thread (r / 4): each thread owns 4 consecutive rows, so an 8-byte
+// column is one 256-bit load per thread and tile, a 4-byte column one 128-bit load.
+template <bool INDIRECT>
+__device__ __forceinline__ void load_slot(const DevCol& c, int64_t tile_base, int64_t n_rows, const uint32_t* row_index,
+                                          uint64_t pol, RowVals& out, uint32_t& valid_mask) {
+  valid_mask = 0xF;
+  if (c.is_const) {
+#pragma unroll
+    for (int j = 0; j < kRowsPerThread; ++j) out.v[j] = c.const_bits;
+    if (c.is_const == 2) valid_mask = 0;
+    return;
+  }
+  const int64_t r0 = tile_base + (int64_t)kRowsPerThread * threadIdx.x;
+  int64_t rows[kRowsPerThread];
+#pragma unroll
+  for (int j = 0; j < kRowsPerThread; ++j) {
+    int64_t r = r0 + j;
+    if (INDIRECT) rows[j] = r < n_rows ? (int64_t)row_index[r] : -1;
+    else rows[j] = r < n_rows ? r : -1;
+  }
+  const bool full = !INDIRECT && (r0 + kRowsPerThread <= n_rows);
+  const char* base = (const char*)c.data;
+  switch (c.dtype) {
+    case DBX_I64: case DBX_U64: case DBX_F64: {
+      if (full && ((reinterpret_cast<uintptr_t>(base) & 31) == 0)) {
+        u64x4 q = ld_stream_256(base + r0 * 8);
+        out.v[0] = q.x; out.v[1] = q.y; out.v[2] = q.z; out.v[3] = q.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < kRowsPerThread; ++j) out.v[j] = rows[j] >= 0 ? ld_stream_u64(base + rows[j] * 8, pol) : 0;
+      }
+      break;
+    }
+    case DBX_I32: case DBX_U32: case DBX_F32: {
+      uint32_t w[kRowsPerThread];
+      if (full && ((reinterpret_cast<uintptr_t>(base) & 15) == 0)) {
+        uint4 q = ld_stream_128(base + r0 * 4, pol);
+        w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < kRowsPerThread; ++j) w[j] = rows[j] >= 0 ? ld_stream_u32(base + rows[j] * 4, pol) : 0;
+      }
+#pragma unroll
+      for (int j = 0; j < kRowsPerThread; ++j)
+        out.v[j] = c.dtype == DBX_I32 ? widen<int32_t>((int32_t)w[j]) : (c.dtype == DBX_U32 ? (uint64_t)w[j] : f32_bits_to_f64_bits(w[j]));
+      break;
+    }
+    case DBX_I16: case DBX_U16: {
+      uint16_t w[kRowsPerThread];
+      if (full && ((reinterpret_cast<uintptr_t>(base) & 7) == 0)) {
+        uint64_t q = ld_stream_u64(base + r0 * 2, pol);
+#pragma unroll
+        for (int j = 0; j < kRowsPerThread; ++j) w[j] = (uint16_t)(q >> (16 * j));
+      } else {
+#pragma unroll
+        for (int j = 0; j < kRowsPerThread; ++j) w[j] = rows[j] >= 0 ? ld_stream_u16(base + rows[j] * 2, pol) : 0;
+      }
+#pragma unroll
+      for (int j = 0; j < kRowsPerThread; ++j) out.v[j] = c.dtype == DBX_I16 ? widen<int16_t>((int16_t)w[j]) : (uint64_t)w[j];
+      break;
+    }
+    case DBX_I8: case DBX_U8: {
+      uint8_t w[kRowsPerThread];
+      if (full && ((reinterpret_cast<uintptr_t>(base) & 3) == 0)) {
+        uint32_t q = ld_stream_u32(base + r0, pol);
+#pragma unroll
+        for (int j = 0; j < kRowsPerThread; ++j) w[j] = (uint8_t)(q >> (8 * j));
+      } else {
+#pragma unroll
+        for (int j = 0; j < kRowsPerThread; ++j) w[j] = rows[j] >= 0 ? ld_stream_u8(base + rows[j], pol) : 0;
+      }
+#pragma unroll
+      for (int j = 0; j < kRowsPerThread; ++j) out.v[j] = c.dtype == DBX_I8 ? widen<int8_t>((int8_t)w[j]) : (uint64_t)w[j];
+      break;
+    }
+    case DBX_BOOL:
+#pragma unroll
+      for (int j = 0; j < kRowsPerThread; ++j)
+        out.v[j] = rows[j] >= 0 ? (uint64_t)bit_test((const uint8_t*)base, c.dbit_off + rows[j]) : 0;
+      break;
+    default:
+#pragma unroll
+      for (int j = 0; j < kRowsPerThread; ++j) out.v[j] = 0;
+      break;
+  }
+  if (c.validity) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < kRowsPerThread; ++j)
+      if (rows[j] >= 0 && bit_test(c.validity, c.vbit_off + rows[j])) m |= 1u << j;
+    valid_mask = m;
+  }
+}
+
+template <int NS>
+__device__ __forceinline__ uint64_t pick(const RowVals (&vals)[NS], int slot, int j) {
+  uint64_t r = vals[0].v[j];
+#pragma unroll
+  for (int s = 1; s < NS; ++s)
+    if (slot == s) r = vals[s].v[j];
+  return r;
+}
+template <int NS>
+__device__ __forceinline__ uint32_t pick_mask(const uint32_t (&m)[NS], int slot) {
+  uint32_t r = m[0];
+#pragma unroll
+  for (int s = 1; s < NS; ++s)
+    if (slot == s) r = m[s];
+  return r;
+}
+
+// OrderedFloat compare (src/common/base/src/base/ordered_float.rs:147-201)
+__device__ __forceinline__ int cmp_f64_ordered(double a, double b) {
+  bool an = a != a, bn = b != b;
+  if (an | bn) return an == bn ? 0 : (an ? 1 : -1);
+  return a < b ? -1 : (a > b ? 1 : 0);
+}
+__device__ __forceinline__ bool apply_cmp(int op, int c) {
+  switch (op) {
+    case DBX_EQ: return c == 0;
+    case DBX_NE: return c != 0;
+    case DBX_LT: return c < 0;
+    case DBX_LE: return c <= 0;
+    case DBX_GT: return c > 0;
+    default: return c >= 0;
+  }
+}
+
+// ---------------------------------------------------------------- predicate
+// Evaluates the flattened SelectExpr tree for the thread's kRowsPerThread rows; returns a
+// bitmask of selected rows.  NULL operands make a Compare false (select_column_scalar.rs).
+template <int NS>
+__device__ __forceinline__ uint32_t eval_predicate(const AggKernelParams& p, const RowVals (&vals)[NS],
+                                                   const uint32_t (&vmask)[NS], uint32_t in_range) {
+  if (p.n_nodes == 0) return in_range;
+  uint32_t stack[kRowsPerThread];
+#pragma unroll
+  for (int j = 0; j < kRowsPerThread; ++j) stack[j] = 0;
+  for (int n = 0; n < p.n_nodes; ++n) {
+    const PredNodeDev& nd = p.nodes[n];
+    if (nd.kind == DBX_PRED_CMP) {
+      uint32_t lm = pick_mask<NS>(vmask, nd.l_slot);
+      uint32_t rm = nd.r_slot >= 0 ? pick_mask<NS>(vmask, nd.r_slot) : 0xF;
+#pragma unroll
+      for (int j = 0; j < kRowsPerThread; ++j) {
+        uint64_t a = pick<NS>(vals, nd.l_slot, j);
+        uint64_t b = nd.r_slot >= 0 ? pick<NS>(vals, nd.r_slot, j) : nd.r_const;
+        int c;
+        if (nd.cls == VC_INT) {
+          int64_t x = (int64_t)a;
+          if (nd.l_mod) x = smod_magic(x, nd.mod);
+          int64_t y = (int64_t)b;
+          c = x < y ? -1 : (x > y ? 1 : 0);
+        } else if (nd.cls == VC_UINT) {
+          uint64_t x = a;
+          if (nd.l_mod) x = umod_magic(x, nd.mod);
+          c = x < b ? -1 : (x > b ? 1 : 0);
+        } else {
+          double x = __longlong_as_double((long long)a);
+          if (nd.l_mod) x = fmod(x, nd.mod_f);
+          c = cmp_f64_ordered(x, __longlong_as_double((long long)b));
+        }
+        bool r = apply_cmp(nd.cmp, c) && ((lm >> j) & 1) && ((rm >> j) & 1);
+        stack[j] = (stack[j] << 1) | (r ? 1u : 0u);
+      }
+    } else if (nd.kind == DBX_PRED_AND || nd.kind == DBX_PRED_OR) {
+      uint32_t k = (1u << nd.n_children) - 1;
+#pragma unroll
+      for (int j = 0; j < kRowsPerThread; ++j) {
+        uint32_t top = stack[j] & k;
+        uint32_t r = nd.kind == DBX_PRED_AND ? (top == k) : (top != 0);
+        stack[j] = ((stack[j] >> nd.n_children) << 1) | r;
+      }
+    } else if (nd.kind == DBX_PRED_BOOLCOL) {
+      uint32_t m = pick_mask<NS>(vmask, nd.value);
+#pragma unroll
+      for (int j = 0; j < kRowsPerThread; ++j) {
+        uint32_t r = (pick<NS>(vals, nd.value, j) != 0) && ((m >> j) & 1);
+        stack[j] = (stack[j] << 1) | r;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kRowsPerThread; ++j) stack[j] = (stack[j] << 1) | (nd.value ? 1u : 0u);
+    }
+  }
+  uint32_t sel = 0;
+#pragma unroll
+  for (int j = 0; j < kRowsPerThread; ++j) sel |= (stack[j] & 1u) << j;
+  return sel & in_range;
+}
+
+// ---------------------------------------------------------------- table
+__device__ __forceinline__ uint8_t* entry_ptr(const TableDev& t, int64_t slot) {
+  return t.base + ((uint64_t)slot << t.stride_shift);
+}
+
+// HashIndex::find_or_insert (hash_index/index.rs:92-111) for one 64-bit key word.
+// Returns the entry pointer, or nullptr if the probe limit was hit (row goes to overflow).
+__device__ __forceinline__ uint8_t* find_or_insert(const TableDev& t, uint64_t key, uint64_t first_probe_key,
+                                                   int64_t slot, uint32_t& new_groups) {
+  const int64_t mask = t.cap - 1;
+  uint64_t cur = first_probe_key;
+  for (int probes = 0; probes < t.probe_limit; ++probes) {
+    uint8_t* e = entry_ptr(t, slot);
+    if (cur == key) return e;
+    if (cur == kEmptyKey) {
+      unsigned long long old = atomicCAS((unsigned long long*)e, (unsigned long long)kEmptyKey, (unsigned long long)key);
+      if (old == kEmptyKey) { ++new_groups; return e; }
+      if (old == key) return e;
+    }
+    slot = (slot + 1) & mask;
+    cur = ld_table_u64(entry_ptr(t, slot));
+  }
+  return nullptr;
+}
+
+__device__ __forceinline__ void apply_update(const UpdateDev& u, uint8_t* e, uint64_t val, bool valid) {
+  void* w = e + 8 + 8 * u.word;
+  switch (u.op) {
+    case UPD_INC: red_add_u64(w, 1); break;
+    case UPD_INC_VALID: if (valid) red_add_u64(w, 1); break;
+    case UPD_ADD_INT: if (valid) red_add_u64(w, val); break;
+    case UPD_ADD_F64: if (valid) red_add_f64(w, __longlong_as_double((long long)val)); break;
+    case UPD_MIN_S64: if (valid) red_min_s64(w, (int64_t)val); break;
+    case UPD_MAX_S64: if (valid) red_max_s64(w, (int64_t)val); break;
+    case UPD_MIN_U64: if (valid) red_min_u64(w, val); break;
+    case UPD_MAX_U64: if (valid) red_max_u64(w, val); break;
+    case UPD_MIN_F64: if (valid) red_min_u64(w, f64_to_ordered(__longlong_as_double((long long)val))); break;
+    case UPD_MAX_F64: if (valid) red_max_u64(w, f64_to_ordered(__longlong_as_double((long long)val))); break;
+    default: break;
+  }
+}
+
+// ---------------------------------------------------------------- fused kernel (GROUP BY)
+template <int NS, bool INDIRECT>
+__global__ void __launch_bounds__(kBlock, 4) filter_group_agg_kernel(const __grid_constant__ AggKernelParams p) {
+  const int64_t n_tiles = (p.n_rows + kTileRows - 1) / kTileRows;
+  uint32_t new_groups = 0;
+  const TableDev& t = p.table;
+  const int64_t mask = t.cap - 1;
+  const uint64_t pol = make_policy_evict_first();
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t tile_base = tile * kTileRows;
+    RowVals vals[NS];
+    uint32_t vmask[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) load_slot<INDIRECT>(p.cols[s], tile_base, p.n_rows, p.row_index, pol, vals[s], vmask[s]);
+
+    const int64_t r0 = tile_base + (int64_t)kRowsPerThread * threadIdx.x;
+    uint32_t in_range = 0;
+#pragma unroll
+    for (int j = 0; j < kRowsPerThread; ++j)
+      if (r0 + j < p.n_rows) in_range |= 1u << j;
+    uint32_t sel = eval_predicate<NS>(p, vals, vmask, in_range);
+    if (sel == 0) continue;
+
+    // phase 1: slot + first probe for every selected row (independent L2 loads in flight)
+    uint64_t keys[kRowsPerThread];
+    int64_t slots[kRowsPerThread];
+    uint64_t first[kRowsPerThread];
+    const uint32_t kmask = pick_mask<NS>(vmask, p.key_slot);
+#pragma unroll
+    for (int j = 0; j < kRowsPerThread; ++j) {
+      keys[j] = pick<NS>(vals, p.key_slot, j);
+      slots[j] = (int64_t)(agg_hash_u64(keys[j]) & (uint64_t)mask);
+      first[j] = 0;
+      if ((sel >> j) & 1) {
+        bool special = keys[j] == kEmptyKey || !((kmask >> j) & 1);
+        if (!special) first[j] = ld_table_u64(entry_ptr(t, slots[j]));
+      }
+    }
+    // phase 2 + 3: resolve the entry, then fire-and-forget the state updates
+#pragma unroll
+    for (int j = 0; j < kRowsPerThread; ++j) {
+      if (!((sel >> j) & 1)) continue;
+      uint8_t* e;
+      if (!((kmask >> j) & 1)) {  // NULL group key -> dedicated entry (payload_row.rs NULL rules)
+        e = entry_ptr(t, t.cap + 1);
+        if (atomicExch((unsigned long long*)e, 1ULL) == kEmptyKey) ++new_groups;
+      } else if (keys[j] == kEmptyKey) {  // the key that equals the EMPTY sentinel
+        e = entry_ptr(t, t.cap);
+        if (atomicExch((unsigned long long*)e, 1ULL) == kEmptyKey) ++new_groups;
+      } else {
+        e = find_or_insert(t, keys[j], first[j], slots[j], new_groups);
+      }
+      if (e == nullptr) {
+        int64_t r = r0 + j;
+        unsigned long long idx = atomicAdd(t.n_overflow, 1ULL);
+        if (t.overflow_rows) t.overflow_rows[idx] = INDIRECT ? p.row_index[r] : (uint32_t)r;
+        continue;
+      }
+      for (int u = 0; u < p.n_updates; ++u) {
+        const UpdateDev& ud = p.upd[u];
+        uint64_t val = pick<NS>(vals, ud.slot, j);
+        bool valid = (pick_mask<NS>(vmask, ud.slot) >> j) & 1;
+        apply_update(ud, e, val, valid);
+      }
+    }
+  }
+  // one counter update per warp
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) new_groups += __shfl_xor_sync(0xffffffffu, new_groups, o);
+  if ((threadIdx.x & 31) == 0 && new_groups) atomicAdd(t.n_groups, (unsigned long long)new_groups);
+}
+
+// ---------------------------------------------------------------- fused kernel (no GROUP BY)
+// PartialSingleStateAggregator (transform_single_key.rs:93-141): a pure streaming reduce.
+// Per-thread accumulators -> warp shuffle -> one atomic per warp into the single state.
+__device__ __forceinline__ uint64_t upd_identity(int op) {
+  switch (op) {
+    case UPD_MIN_S64: return (uint64_t)INT64_MAX;
+    case UPD_MAX_S64: return (uint64_t)INT64_MIN;
+    case UPD_MIN_U64: case UPD_MIN_F64: return ~0ULL;
+    default: return 0;
+  }
+}
+__device__ __forceinline__ uint64_t upd_combine(int op, uint64_t a, uint64_t b) {
+  switch (op) {
+    case UPD_ADD_F64: return (uint64_t)__double_as_longlong(__longlong_as_double((long long)a) + __longlong_as_double((long long)b));
+    case UPD_MIN_S64: return (uint64_t)min((int64_t)a, (int64_t)b);
+    case UPD_MAX_S64: return (uint64_t)max((int64_t)a, (int64_t)b);
+    case UPD_MIN_U64: case UPD_MIN_F64: return a < b ? a : b;
+    case UPD_MAX_U64: case UPD_MAX_F64: return a > b ? a : b;
+    default: return a + b;
+  }
+}
+
+template <int NS>
+__global__ void __launch_bounds__(kBlock, 4) filter_single_agg_kernel(const __grid_constant__ AggKernelParams p) {
+  const int64_t n_tiles = (p.n_rows + kTileRows - 1) / kTileRows;
+  uint64_t acc[kMaxUpdates];
+#pragma unroll
+  for (int u = 0; u < kMaxUpdates; ++u) acc[u] = u < p.n_updates ? upd_identity(p.upd[u].op) : 0;
+  const uint64_t pol = make_policy_evict_first();
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t tile_base = tile * kTileRows;
+    RowVals vals[NS];
+    uint32_t vmask[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) load_slot<false>(p.cols[s], tile_base, p.n_rows, nullptr, pol, vals[s], vmask[s]);
+    const int64_t r0 = tile_base + (int64_t)kRowsPerThread * threadIdx.x;
+    uint32_t in_range = 0;
+#pragma unroll
+    for (int j = 0; j < kRowsPerThread; ++j)
+      if (r0 + j < p.n_rows) in_range |= 1u << j;
+    uint32_t sel = eval_predicate<NS>(p, vals, vmask, in_range);
+#pragma unroll
+    for (int u = 0; u < kMaxUpdates; ++u) {
+      if (u >= p.n_updates) break;
+      const UpdateDev& ud = p.upd[u];
+      uint32_t m = sel & (ud.op == UPD_INC ? 0xFu : pick_mask<NS>(vmask, ud.slot));
+#pragma unroll
+      for (int j = 0; j < kRowsPerThread; ++j) {
+        if (!((m >> j) & 1)) continue;
+        uint64_t val = pick<NS>(vals, ud.slot, j);
+        uint64_t x;
+        switch (ud.op) {
+          case UPD_INC: case UPD_INC_VALID: x = 1; break;
+          case UPD_MIN_F64: case UPD_MAX_F64: x = f64_to_ordered(__longlong_as_double((long long)val)); break;
+          default: x = val; break;
+        }
+        acc[u] = upd_combine(ud.op, acc[u], x);
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kMaxUpdates; ++u) {
+    if (u >= p.n_updates) break;
+    const int op = p.upd[u].op;
+    uint64_t a = acc[u];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a = upd_combine(op, a, __shfl_xor_sync(0xffffffffu, a, o));
+    if ((threadIdx.x & 31) == 0) {
+      void* w = p.single_state + p.upd[u].word;
+      switch (op) {
+        case UPD_ADD_F64: red_add_f64(w, __longlong_as_double((long long)a)); break;
+        case UPD_MIN_S64: red_min_s64(w, (int64_t)a); break;
+        case UPD_MAX_S64: red_max_s64(w, (int64_t)a); break;
+        case UPD_MIN_U64: case UPD_MIN_F64: red_min_u64(w, a); break;
+        case UPD_MAX_U64: case UPD_MAX_F64: red_max_u64(w, a); break;
+        default: red_add_u64(w, a); break;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- table maintenance
+struct WordInit {
+  uint64_t w[kMaxWords];
+};
+__global__ void table_init_kernel(uint8_t* base, int64_t n_entries, int stride_shift, int n_words,
+                                   const __grid_constant__ WordInit init) {
+  const int words_per_entry = 1 << (stride_shift - 3);
+  int64_t total = n_entries * words_per_entry;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int w = (int)(i & (words_per_entry - 1));
+    uint64_t v = w == 0 ? kEmptyKey : (w - 1 < n_words ? init.w[w - 1] : 0);
+    ((uint64_t*)base)[i] = v;
+  }
+}
+
+
+// Kinds of state words, for merging two states of the same group
+// (batch_merge_states: aggregate_sum.rs:126-129, aggregate_avg.rs:82-86, count: += , min/max).
+struct WordKinds {
+  int32_t op[kMaxWords];  // UPD_ADD_INT (also counts), UPD_ADD_F64, UPD_MIN_*, UPD_MAX_* (ordered image for F64)
+};
+
+__device__ __forceinline__ void merge_word(int op, void* w, uint64_t v) {
+  switch (op) {
+    case UPD_ADD_F64: red_add_f64(w, __longlong_as_double((long long)v)); break;
+    case UPD_MIN_S64: red_min_s64(w, (int64_t)v); break;
+    case UPD_MAX_S64: red_max_s64(w, (int64_t)v); break;
+    case UPD_MIN_U64: case UPD_MIN_F64: red_min_u64(w, v); break;
+    case UPD_MAX_U64: case UPD_MAX_F64: red_max_u64(w, v); break;
+    default: red_add_u64(w, v); break;
+  }
+}
+
+// Resolve the destination entry of a (key, key_kind) pair. key_kind: 0 normal, 1 key == EMPTY
+// sentinel, 2 NULL key.
+__device__ __forceinline__ uint8_t* resolve_entry(const TableDev& t, uint64_t key, int key_kind, uint32_t& new_groups) {
+  if (key_kind != 0) {
+    uint8_t* e = entry_ptr(t, t.cap + (key_kind == 2 ? 1 : 0));
+    if (atomicExch((unsigned long long*)e, 1ULL) == kEmptyKey) ++new_groups;
+    return e;
+  }
+  int64_t slot = (int64_t)(agg_hash_u64(key) & (uint64_t)(t.cap - 1));
+  uint64_t first = ld_table_u64(entry_ptr(t, slot));
+  return find_or_insert(t, key, first, slot, new_groups);
+}
+
+// AggregateHashTable::combine_payload (aggregate_hashtable.rs:349-380) / resize (:463-489):
+// every occupied entry of `src` is found-or-inserted in `dst` and its words merged.
+// One thread per source entry; entries that cannot be placed bump dst.n_overflow
+// (the host sizes dst so that this cannot happen, and checks).
+__global__ void table_merge_kernel(const __grid_constant__ TableDev src, const __grid_constant__ TableDev dst,
+                                   const __grid_constant__ WordKinds kinds) {
+  uint32_t new_groups = 0;
+  const int64_t n_entries = src.cap + 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_entries; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint8_t* se = src.base + ((uint64_t)i << src.stride_shift);
+    uint64_t key = *(const uint64_t*)se;
+    if (key == kEmptyKey) continue;
+    int key_kind = i >= src.cap ? (int)(i - src.cap) + 1 : 0;
+    uint8_t* de = resolve_entry(dst, key, key_kind, new_groups);
+    if (!de) { atomicAdd(dst.n_overflow, 1ULL); continue; }
+    for (int w = 0; w < src.n_words; ++w) merge_word(kinds.op[w], de + 8 + 8 * w, *(const uint64_t*)(se + 8 + 8 * w));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) new_groups += __shfl_xor_sync(0xffffffffu, new_groups, o);
+  if ((threadIdx.x & 31) == 0 && new_groups) atomicAdd(dst.n_groups, (unsigned long long)new_groups);
+}
+
+// Exchange rows for the partial -> final shuffle: [key:8][key_kind:8][words: 8*n_words].
+// Owner of a group = high 32 bits of agg_hash scaled to n_parts, i.e. radix partitioning on
+// the top hash bits like PartitionedPayload (partitioned_payload.rs:44-57) but for any n_parts.
+__device__ __forceinline__ int owner_of(uint64_t key, int key_kind, int n_parts) {
+  uint64_t h = key_kind == 2 ? kNullHashVal : agg_hash_u64(key);
+  return (int)(((h >> 32) * (uint64_t)n_parts) >> 32);
+}
+
+__global__ void table_partition_count_kernel(const __grid_constant__ TableDev src, int n_parts,
+                                             unsigned long long* counts) {
+  extern __shared__ unsigned int s_cnt[];
+  for (int i = threadIdx.x; i < n_parts; i += blockDim.x) s_cnt[i] = 0;
+  __syncthreads();
+  const int64_t n_entries = src.cap + 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_entries; i += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t key = *(const uint64_t*)(src.base + ((uint64_t)i << src.stride_shift));
+    if (key == kEmptyKey) continue;
+    int key_kind = i >= src.cap ? (int)(i - src.cap) + 1 : 0;
+    atomicAdd(&s_cnt[owner_of(key, key_kind, n_parts)], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_parts; i += blockDim.x)
+    if (s_cnt[i]) atomicAdd(&counts[i], (unsigned long long)s_cnt[i]);
+}
+
+__global__ void table_partition_scatter_kernel(const __grid_constant__ TableDev src, int n_parts,
+                                               unsigned long long* cursors /* pre-set to part offsets */,
+                                               uint64_t* rows_out) {
+  const int row_words = 2 + src.n_words;
+  const int64_t n_entries = src.cap + 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_entries; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint8_t* se = src.base + ((uint64_t)i << src.stride_shift);
+    uint64_t key = *(const uint64_t*)se;
+    if (key == kEmptyKey) continue;
+    int key_kind = i >= src.cap ? (int)(i - src.cap) + 1 : 0;
+    unsigned long long pos = atomicAdd(&cursors[owner_of(key, key_kind, n_parts)], 1ULL);
+    uint64_t* r = rows_out + pos * row_words;
+    r[0] = key_kind ? 0 : key;
+    r[1] = (uint64_t)key_kind;
+    for (int w = 0; w < src.n_words; ++w) r[2 + w] = *(const uint64_t*)(se + 8 + 8 * w);
+  }
+}
+
+// TransformFinalAggregate::handle_meta on received payload rows (transform_aggregate_final.rs:201-303)
+__global__ void rows_merge_kernel(const uint64_t* rows, int64_t n_rows, const __grid_constant__ TableDev dst,
+                                  const __grid_constant__ WordKinds kinds) {
+  uint32_t new_groups = 0;
+  const int row_words = 2 + dst.n_words;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t* r = rows + i * row_words;
+    uint8_t* de = resolve_entry(dst, r[0], (int)r[1], new_groups);
+    if (!de) { atomicAdd(dst.n_overflow, 1ULL); continue; }
+    for (int w = 0; w < dst.n_words; ++w) merge_word(kinds.op[w], de + 8 + 8 * w, r[2 + w]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) new_groups += __shfl_xor_sync(0xffffffffu, new_groups, o);
+  if ((threadIdx.x & 31) == 0 && new_groups) atomicAdd(dst.n_groups, (unsigned long long)new_groups);
+}
+
+// ---------------------------------------------------------------- finalize
+// AggregateHashTable::merge_result -> batch_merge_result (aggregate_hashtable.rs:382-408):
+// compacts the table into dense output columns [aggs..., keys...] (payload.rs:284-286).
+struct FinalAgg {
+  int32_t kind;       // dbx_agg_kind
+  int32_t acc_word;   // sum/avg/min/max accumulator word (-1: none)
+  int32_t cnt_word;   // word holding the number of non-NULL inputs
+  int32_t arg_dtype;  // dbx_dtype of the argument (decides result type / narrowing)
+  void* out;          // result values (8 B each except min/max of narrow types)
+  uint8_t* out_valid; // one byte per group (packed to a bitmap afterwards); nullptr for count
+};
+struct FinalizeParams {
+  FinalAgg aggs[DBX_MAX_AGGS];
+  int32_t n_aggs;
+  int32_t key_dtype;      // -1: no key output
+  void* out_key;
+  uint8_t* out_key_valid; // byte per group or nullptr
+  unsigned long long* out_count;
+};
+
+__device__ __forceinline__ void store_narrow(void* out, int64_t idx, int dtype, uint64_t bits) {
+  switch (dtype) {
+    case DBX_I8: case DBX_U8: ((uint8_t*)out)[idx] = (uint8_t)bits; break;
+    case DBX_I16: case DBX_U16: ((uint16_t*)out)[idx] = (uint16_t)bits; break;
+    case DBX_I32: case DBX_U32: ((uint32_t*)out)[idx] = (uint32_t)bits; break;
+    case DBX_F32: ((float*)out)[idx] = (float)__longlong_as_double((long long)bits); break;
+    default: ((uint64_t*)out)[idx] = bits; break;
+  }
+}
+
+__global__ void table_finalize_kernel(const __grid_constant__ TableDev src, const __grid_constant__ FinalizeParams fp) {
+  const int64_t n_entries = src.cap + 2;
+  const int64_t n_iter = (n_entries + (int64_t)gridDim.x * blockDim.x - 1) / ((int64_t)gridDim.x * blockDim.x);
+  for (int64_t it = 0; it < n_iter; ++it) {
+    int64_t i = it * (int64_t)gridDim.x * blockDim.x + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint8_t* se = nullptr;
+    uint64_t key = kEmptyKey;
+    if (i < n_entries) {
+      se = src.base + ((uint64_t)i << src.stride_shift);
+      key = *(const uint64_t*)se;
+    }
+    bool occ = key != kEmptyKey;
+    // warp-aggregated output slot allocation
+    unsigned ballot = __ballot_sync(0xffffffffu, occ);
+    if (!ballot) continue;
+    int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(fp.out_count, (unsigned long long)__popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (!occ) continue;
+    int64_t o = (int64_t)base + __popc(ballot & ((1u << lane) - 1));
+    int key_kind = i >= src.cap ? (int)(i - src.cap) + 1 : 0;
+    if (fp.key_dtype >= 0) {
+      uint64_t kb = key_kind == 1 ? kEmptyKey : (key_kind == 2 ? 0 : key);
+      store_narrow(fp.out_key, o, fp.key_dtype, kb);
+      if (fp.out_key_valid) fp.out_key_valid[o] = key_kind == 2 ? 0 : 1;
+    }
+    for (int a = 0; a < fp.n_aggs; ++a) {
+      const FinalAgg& fa = fp.aggs[a];
+      uint64_t cnt = *(const uint64_t*)(se + 8 + 8 * fa.cnt_word);
+      uint64_t acc = fa.acc_word >= 0 ? *(const uint64_t*)(se + 8 + 8 * fa.acc_word) : 0;
+      int cls = dtype_class(fa.arg_dtype);
+      switch (fa.kind) {
+        case DBX_AGG_COUNT: ((uint64_t*)fa.out)[o] = cnt; break;
+        case DBX_AGG_SUM: ((uint64_t*)fa.out)[o] = cnt ? acc : 0; break;
+        case DBX_AGG_AVG: {  // aggregate_avg.rs:88-96: value as f64 / count as f64
+          double num = cls == VC_FLT ? __longlong_as_double((long long)acc)
+                                     : (cls == VC_INT ? (double)(int64_t)acc : (double)acc);
+          ((double*)fa.out)[o] = cnt ? num / (double)cnt : 0.0;
+          break;
+        }
+        default: {  // min / max keep the argument type
+          uint64_t bits = acc;
+          if (cls == VC_FLT) bits = (uint64_t)__double_as_longlong(ordered_to_f64(acc));
+          store_narrow(fa.out, o, fa.arg_dtype, cnt ? bits : 0);
+          break;
+        }
+      }
+      if (fa.out_valid) fa.out_valid[o] = cnt ? 1 : 0;
+    }
+  }
+}
+
+// bytes (0/1) -> LSB-first bitmap (MutableBitmap layout), one output byte per thread
+__global__ void pack_validity_kernel(const uint8_t* bytes, int64_t n, uint8_t* bits) {
+  int64_t nb = (n + 7) / 8;
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t v = 0;
+    for (int k = 0; k < 8; ++k) {
+      int64_t i = b * 8 + k;
+      if (i < n && bytes[i]) v |= 1u << k;
+    }
+    bits[b] = (uint8_t)v;
+  }
+}
+
+}  // namespace dbx

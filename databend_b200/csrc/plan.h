@@ -1,0 +1,116 @@
+// plan.h — host-normalised, device-consumable description of a fused
+// [TransformFilter ->] TransformPartialAggregate step.  Built once per operator from
+// dbx_agg_params / dbx_predicate (include/dbx.h), passed BY VALUE to the kernels.
+#pragma once
+#include "common.cuh"
+
+namespace dbx {
+
+constexpr int kMaxSlots = 8;    // distinct input columns one kernel reads
+constexpr int kMaxUpdates = 16; // state-word updates per passing row
+constexpr int kMaxWords = 15;   // state words per group (entry = key + words)
+
+// x % d for a runtime-constant divisor without a hardware divide: Granlund–Montgomery
+// round-up method (N = 64):  m' = floor(2^64 (2^l - d) / d) + 1,
+//   t = mulhi(m', n);  q = (t + ((n - t) >> sh1)) >> sh2;  r = n - q d.
+// The reference strength-reduces the same way for unsigned divisors
+// (arithmetic_modulo.rs:119-147, crate strength_reduce); signed operands go through |x|, |d|
+// and take the sign of the dividend (Rust `%` truncates), MIN % -1 = 0 falls out (|d| = 1).
+struct ModMagic {
+  uint64_t d;   // |divisor|
+  uint64_t m;   // m'
+  int32_t sh1, sh2;
+};
+
+inline ModMagic make_mod_magic(uint64_t d) {
+  ModMagic mm;
+  mm.d = d;
+  int l = 0;
+  while (l < 64 && ((unsigned __int128)1 << l) < (unsigned __int128)d) ++l;  // l = ceil(log2 d)
+  unsigned __int128 num = (((unsigned __int128)1 << l) - d) << 64;
+  mm.m = (uint64_t)(num / d) + 1;
+  mm.sh1 = l < 1 ? l : 1;
+  mm.sh2 = l - 1 > 0 ? l - 1 : 0;
+  return mm;
+}
+
+__host__ __device__ __forceinline__ uint64_t mulhi_u64(uint64_t a, uint64_t b) {
+#ifdef __CUDA_ARCH__
+  return __umul64hi(a, b);
+#else
+  return (uint64_t)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+__host__ __device__ __forceinline__ uint64_t umod_magic(uint64_t n, const ModMagic& mm) {
+  uint64_t t = mulhi_u64(mm.m, n);
+  uint64_t q = (t + ((n - t) >> mm.sh1)) >> mm.sh2;
+  return n - q * mm.d;
+}
+__host__ __device__ __forceinline__ int64_t smod_magic(int64_t x, const ModMagic& mm) {
+  uint64_t ux = x < 0 ? (uint64_t)0 - (uint64_t)x : (uint64_t)x;
+  uint64_t r = umod_magic(ux, mm);
+  return x < 0 ? -(int64_t)r : (int64_t)r;
+}
+
+// One flattened SelectExpr node (postfix).  CMP: lhs = slot (optional modulo), rhs = const or slot.
+struct PredNodeDev {
+  int32_t kind;        // dbx_pred_kind
+  int32_t cmp;         // dbx_cmp_op
+  int32_t n_children;  // AND / OR
+  int32_t value;       // CONST value / BOOLCOL slot
+  int32_t cls;         // comparison class (ValClass) after widening
+  int32_t l_slot;
+  int32_t l_mod;       // 1: lhs = slot % mod
+  int32_t r_slot;      // -1: rhs is r_const
+  uint64_t r_const;    // bits in class `cls`
+  double mod_f;        // FLT modulo divisor
+  ModMagic mod;
+};
+
+enum UpdOp : int32_t {
+  UPD_INC = 0,        // word += 1                      (row count / count(*))
+  UPD_INC_VALID = 1,  // word += 1 if slot valid        (count(col), OrNull flag of a nullable arg)
+  UPD_ADD_INT = 2,    // word += value (two's complement wrapping == i64/u64 wrapping add)
+  UPD_ADD_F64 = 3,    // word(f64) += value
+  UPD_MIN_S64 = 4, UPD_MAX_S64 = 5, UPD_MIN_U64 = 6, UPD_MAX_U64 = 7,
+  UPD_MIN_F64 = 8, UPD_MAX_F64 = 9  // on the order-preserving u64 image of the double
+};
+struct UpdateDev {
+  int32_t op;
+  int32_t slot;  // input slot (unused for UPD_INC)
+  int32_t word;  // state word index
+  int32_t pad;
+};
+
+// Device hash table of group entries, AoS: [key:8][word0:8]...[word(nw-1):8] padded to `stride`
+// (a power of two >= 16) so that one group's key and states share 32 B sectors.
+// slots [0, cap) are open-addressed by agg_hash(key) & (cap-1); two extra entries hold the
+// key that collides with the EMPTY sentinel (index cap) and the NULL key (index cap + 1).
+constexpr uint64_t kEmptyKey = 0x8000000000000000ULL;
+struct TableDev {
+  uint8_t* base;
+  int64_t cap;            // power of two
+  int32_t stride_shift;   // log2(stride bytes)
+  int32_t n_words;
+  unsigned long long* n_groups;    // device counter: groups inserted so far
+  unsigned long long* n_overflow;  // device counter
+  uint32_t* overflow_rows;         // rows that could not be placed (nullptr: provably not needed)
+  int32_t probe_limit;
+  int32_t pad;
+};
+
+struct AggKernelParams {
+  DevCol cols[kMaxSlots];
+  PredNodeDev nodes[DBX_MAX_PRED_NODES];
+  UpdateDev upd[kMaxUpdates];
+  TableDev table;
+  int64_t n_rows;
+  const uint32_t* row_index;  // indirect mode: process rows row_index[0..n_rows)
+  unsigned long long* single_state;  // ungrouped: word array accumulated with one atomic per CTA
+  int32_t n_slots, n_nodes, n_updates;
+  int32_t key_slot;     // -1: no GROUP BY
+  int32_t key_nullable; // key column may carry a validity bitmap
+  int32_t pad;
+};
+
+}  // namespace dbx

@@ -1,0 +1,286 @@
+// runtime.cu — host runtime + the operator-independent part of the C-ABI.
+#include "runtime.h"
+
+#include <mutex>
+
+namespace dbx {
+
+thread_local ErrorSink g_create_error;
+std::atomic<int64_t> g_launches{0};
+
+// ---------------------------------------------------------------- Stager
+int32_t Stager::init(int device, cudaStream_t stream, ErrorSink* err) {
+  device_ = device;
+  stream_ = stream;
+  err_ = err;
+  for (auto& g : gens_) DBX_CUDA_TRY(*err_, cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
+  return DBX_OK;
+}
+Stager::~Stager() {
+  for (auto& g : gens_)
+    if (g.done) cudaEventDestroy(g.done);
+}
+int32_t Stager::begin() {
+  cur_ = (cur_ + 1) % kGenerations;
+  Gen& g = gens_[cur_];
+  if (g.pending) {
+    DBX_CUDA_TRY(*err_, cudaEventSynchronize(g.done));
+    g.pending = false;
+  }
+  return DBX_OK;
+}
+int32_t Stager::stage(const dbx_column& c, int slot, DevCol* out) {
+  Gen& g = gens_[cur_];
+  memset(out, 0, sizeof(*out));
+  out->dtype = c.dtype;
+  if (c.is_const) {
+    out->is_const = c.konst.is_null ? 2 : 1;
+    int cls = dtype_class(c.dtype);
+    out->const_bits = scalar_bits(c.konst, cls);
+    return DBX_OK;
+  }
+  const int64_t n = c.len;
+  const bool is_bool = c.dtype == DBX_BOOL;
+  if (!is_bool && dtype_size(c.dtype) == 0) {
+    err_->set("unsupported column dtype for this operator");
+    return DBX_ERR_UNSUPPORTED;
+  }
+  if (c.mem == DBX_MEM_DEVICE) {
+    out->data = c.data;
+    out->validity = c.validity;
+    out->vbit_off = c.validity_bit_offset;
+    out->dbit_off = c.data_bit_offset;
+    return DBX_OK;
+  }
+  if ((int)g.data.size() <= slot) { g.data.resize(slot + 1); g.validity.resize(slot + 1); }
+  if (is_bool) {
+    int64_t b0 = c.data_bit_offset >> 3, b1 = (c.data_bit_offset + n + 7) >> 3;
+    size_t bytes = (size_t)(b1 - b0);
+    DBX_CUDA_TRY(*err_, g.data[slot].ensure(bytes ? bytes : 1));
+    if (bytes) DBX_CUDA_TRY(*err_, cudaMemcpyAsync(g.data[slot].p, (const uint8_t*)c.data + b0, bytes, cudaMemcpyHostToDevice, stream_));
+    out->dbit_off = c.data_bit_offset & 7;
+    h2d_bytes += bytes;
+  } else {
+    size_t bytes = (size_t)n * dtype_size(c.dtype);
+    DBX_CUDA_TRY(*err_, g.data[slot].ensure(bytes ? bytes : 1));
+    if (bytes) DBX_CUDA_TRY(*err_, cudaMemcpyAsync(g.data[slot].p, c.data, bytes, cudaMemcpyHostToDevice, stream_));
+    h2d_bytes += bytes;
+  }
+  out->data = g.data[slot].p;
+  if (c.validity) {
+    int64_t b0 = c.validity_bit_offset >> 3, b1 = (c.validity_bit_offset + n + 7) >> 3;
+    size_t bytes = (size_t)(b1 - b0);
+    DBX_CUDA_TRY(*err_, g.validity[slot].ensure(bytes ? bytes : 1));
+    if (bytes) DBX_CUDA_TRY(*err_, cudaMemcpyAsync(g.validity[slot].p, c.validity + b0, bytes, cudaMemcpyHostToDevice, stream_));
+    out->validity = (const uint8_t*)g.validity[slot].p;
+    out->vbit_off = c.validity_bit_offset & 7;
+    h2d_bytes += bytes;
+  }
+  return DBX_OK;
+}
+int32_t Stager::end() {
+  Gen& g = gens_[cur_];
+  DBX_CUDA_TRY(*err_, cudaEventRecord(g.done, stream_));
+  g.pending = true;
+  return DBX_OK;
+}
+
+// ---------------------------------------------------------------- Op base
+int32_t Op::base_init(int dev) {
+  device = dev;
+  DBX_CUDA_TRY(err, cudaSetDevice(device));
+  DBX_CUDA_TRY(err, cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  DBX_CUDA_TRY(err, cudaEventCreate(&ev_k0));
+  DBX_CUDA_TRY(err, cudaEventCreate(&ev_k1));
+  return DBX_OK;
+}
+Op::~Op() {
+  if (ev_k0) cudaEventDestroy(ev_k0);
+  if (ev_k1) cudaEventDestroy(ev_k1);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+int32_t fill_owned_block(OwnedBlock* ob, dbx_block* out) {
+  out->num_cols = (int32_t)ob->cols.size();
+  out->cols = ob->cols.data();
+  out->num_rows = ob->cols.empty() ? 0 : ob->cols[0].len;
+  out->meta = nullptr;
+  out->owner = ob;
+  out->reserved = 0;
+  return DBX_OK;
+}
+
+// factories implemented next to each operator
+Op* make_agg_partial_op(const dbx_agg_params* p, const int32_t* types, int32_t n, int device, int32_t* st);
+Op* make_agg_final_op(const dbx_agg_params* p, const int32_t* types, int32_t n, int device, int32_t* st);
+Op* make_filter_op(const dbx_predicate* p, const int32_t* types, int32_t n, int device, int32_t* st);
+Op* make_topk_op(const dbx_topk_params* p, const int32_t* types, int32_t n, int device, int32_t* st);
+Op* make_join_op(const dbx_join_params* p, const int32_t* types, int32_t n, int device, int32_t* st);
+
+}  // namespace dbx
+
+using namespace dbx;
+
+// ================================================================ C-ABI (generic part)
+extern "C" {
+
+int32_t dbx_abi_version(void) { return DBX_ABI_VERSION; }
+
+int32_t dbx_device_count(int32_t* n) {
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess || c == 0) {
+    if (n) *n = 0;
+    g_create_error.set(std::string("no usable CUDA device: ") + cudaGetErrorString(e) + " (libdbx has no CPU fallback)");
+    return DBX_ERR_NO_DEVICE;
+  }
+  if (n) *n = c;
+  return DBX_OK;
+}
+
+const char* dbx_last_error(const dbx_op* op) {
+  if (!op) return g_create_error.msg.c_str();
+  return reinterpret_cast<const Op*>(op)->err.msg.c_str();
+}
+
+int32_t dbx_host_alloc(size_t bytes, void** out) {
+  DBX_CUDA_TRY(g_create_error, cudaMallocHost(out, bytes ? bytes : 1));
+  return DBX_OK;
+}
+int32_t dbx_host_free(void* p) {
+  DBX_CUDA_TRY(g_create_error, cudaFreeHost(p));
+  return DBX_OK;
+}
+int32_t dbx_host_register(void* p, size_t bytes) {
+  DBX_CUDA_TRY(g_create_error, cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+  return DBX_OK;
+}
+int32_t dbx_host_unregister(void* p) {
+  DBX_CUDA_TRY(g_create_error, cudaHostUnregister(p));
+  return DBX_OK;
+}
+int32_t dbx_device_alloc(int32_t device, size_t bytes, void** out) {
+  DBX_CUDA_TRY(g_create_error, cudaSetDevice(device));
+  DBX_CUDA_TRY(g_create_error, cudaMalloc(out, bytes ? bytes : 1));
+  return DBX_OK;
+}
+int32_t dbx_device_free(int32_t device, void* p) {
+  DBX_CUDA_TRY(g_create_error, cudaSetDevice(device));
+  DBX_CUDA_TRY(g_create_error, cudaFree(p));
+  return DBX_OK;
+}
+int32_t dbx_memcpy_h2d(int32_t device, void* dst, const void* src, size_t bytes) {
+  DBX_CUDA_TRY(g_create_error, cudaSetDevice(device));
+  DBX_CUDA_TRY(g_create_error, cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+  return DBX_OK;
+}
+int32_t dbx_memcpy_d2h(int32_t device, void* dst, const void* src, size_t bytes) {
+  DBX_CUDA_TRY(g_create_error, cudaSetDevice(device));
+  DBX_CUDA_TRY(g_create_error, cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+  return DBX_OK;
+}
+int32_t dbx_memcpy_d2d(int32_t device, void* dst, const void* src, size_t bytes) {
+  DBX_CUDA_TRY(g_create_error, cudaSetDevice(device));
+  DBX_CUDA_TRY(g_create_error, cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice));
+  return DBX_OK;
+}
+int32_t dbx_device_synchronize(int32_t device) {
+  DBX_CUDA_TRY(g_create_error, cudaSetDevice(device));
+  DBX_CUDA_TRY(g_create_error, cudaDeviceSynchronize());
+  return DBX_OK;
+}
+
+int32_t dbx_op_create(int32_t kind, const void* params, const int32_t* input_types, int32_t n_input_cols,
+                      int32_t device, dbx_op** out) {
+  if (!out || !params) { g_create_error.set("dbx_op_create: null argument"); return DBX_ERR_INVALID; }
+  *out = nullptr;
+  int32_t ndev = 0;
+  DBX_TRY(dbx_device_count(&ndev));
+  if (device < 0 || device >= ndev) { g_create_error.set("dbx_op_create: device index out of range"); return DBX_ERR_INVALID; }
+  int32_t st = DBX_OK;
+  Op* op = nullptr;
+  switch (kind) {
+    case DBX_OP_AGG_PARTIAL: op = make_agg_partial_op((const dbx_agg_params*)params, input_types, n_input_cols, device, &st); break;
+    case DBX_OP_AGG_FINAL: op = make_agg_final_op((const dbx_agg_params*)params, input_types, n_input_cols, device, &st); break;
+    case DBX_OP_FILTER: op = make_filter_op((const dbx_predicate*)params, input_types, n_input_cols, device, &st); break;
+    case DBX_OP_TOPK: op = make_topk_op((const dbx_topk_params*)params, input_types, n_input_cols, device, &st); break;
+    case DBX_OP_JOIN: op = make_join_op((const dbx_join_params*)params, input_types, n_input_cols, device, &st); break;
+    default: g_create_error.set("dbx_op_create: unknown operator kind"); return DBX_ERR_INVALID;
+  }
+  if (!op) return st == DBX_OK ? DBX_ERR_INVALID : st;
+  op->kind = kind;
+  *out = reinterpret_cast<dbx_op*>(op);
+  return DBX_OK;
+}
+
+int32_t dbx_op_destroy(dbx_op* op) {
+  if (!op) return DBX_OK;
+  Op* o = reinterpret_cast<Op*>(op);
+  cudaSetDevice(o->device);
+  if (o->stream) cudaStreamSynchronize(o->stream);
+  delete o;
+  return DBX_OK;
+}
+
+#define DBX_OP_ENTER(op)                                                       \
+  if (!(op)) return DBX_ERR_INVALID;                                           \
+  Op* o = reinterpret_cast<Op*>(op);                                           \
+  DBX_CUDA_TRY(o->err, cudaSetDevice(o->device));
+
+int32_t dbx_op_push(dbx_op* op, const dbx_block* block) {
+  DBX_OP_ENTER(op);
+  if (!block) { o->err.set("push: null block"); return DBX_ERR_INVALID; }
+  if (o->finished) { o->err.set("push after finish"); return DBX_ERR_STATE; }
+  return o->push(block);
+}
+int32_t dbx_op_finish(dbx_op* op) {
+  DBX_OP_ENTER(op);
+  if (o->finished) return DBX_OK;
+  int32_t st = o->finish();
+  if (st == DBX_OK) o->finished = true;
+  return st;
+}
+int32_t dbx_op_pull(dbx_op* op, int32_t out_mem, dbx_block* out, int32_t* has_block) {
+  DBX_OP_ENTER(op);
+  if (!out || !has_block) { o->err.set("pull: null argument"); return DBX_ERR_INVALID; }
+  *has_block = 0;
+  return o->pull(out_mem, out, has_block);
+}
+int32_t dbx_op_reset(dbx_op* op) {
+  DBX_OP_ENTER(op);
+  int32_t st = o->reset();
+  if (st == DBX_OK) o->finished = false;
+  return st;
+}
+int32_t dbx_block_release(dbx_block* block) {
+  if (!block || !block->owner) return DBX_OK;
+  OwnedBlock* ob = reinterpret_cast<OwnedBlock*>(block->owner);
+  cudaSetDevice(ob->device);
+  delete ob;
+  block->owner = nullptr;
+  block->cols = nullptr;
+  block->num_cols = 0;
+  return DBX_OK;
+}
+
+int64_t dbx_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int32_t dbx_op_last_kernel_ms(dbx_op* op, float* ms) {
+  DBX_OP_ENTER(op);
+  if (!o->timed) { o->err.set("no timed kernel on this handle yet"); return DBX_ERR_STATE; }
+  DBX_CUDA_TRY(o->err, cudaEventSynchronize(o->ev_k1));
+  DBX_CUDA_TRY(o->err, cudaEventElapsedTime(ms, o->ev_k0, o->ev_k1));
+  return DBX_OK;
+}
+int32_t dbx_op_stream(dbx_op* op, void** stream) {
+  DBX_OP_ENTER(op);
+  *stream = (void*)o->stream;
+  return DBX_OK;
+}
+int32_t dbx_op_synchronize(dbx_op* op) {
+  DBX_OP_ENTER(op);
+  DBX_CUDA_TRY(o->err, cudaStreamSynchronize(o->stream));
+  return DBX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,129 @@
+// runtime.h — host runtime of libdbx: operator base class, device buffers, host->HBM staging.
+#pragma once
+#include <memory>
+#include <vector>
+
+#include "common.cuh"
+
+namespace dbx {
+
+// RAII device allocation on a fixed device.
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int device = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept { *this = std::move(o); }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    release();
+    p = o.p; bytes = o.bytes; device = o.device;
+    o.p = nullptr; o.bytes = 0;
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) { cudaFree(p); p = nullptr; bytes = 0; }
+  }
+  // grow-only; contents are NOT preserved
+  cudaError_t ensure(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    release();
+    size_t cap = need + need / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, cap);
+    if (e == cudaSuccess) bytes = cap; else p = nullptr;
+    return e;
+  }
+};
+
+struct PinnedBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  ~PinnedBuf() { if (p) cudaFreeHost(p); }
+  cudaError_t ensure(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (p) { cudaFreeHost(p); p = nullptr; bytes = 0; }
+    cudaError_t e = cudaMallocHost(&p, need);
+    if (e == cudaSuccess) bytes = need;
+    return e;
+  }
+};
+
+// Library-owned output block: columns + the buffers that back them.
+struct OwnedBlock {
+  std::vector<dbx_column> cols;
+  std::vector<void*> host_allocs;  // cudaMallocHost
+  std::vector<void*> dev_allocs;   // cudaMalloc
+  int device = 0;
+  ~OwnedBlock() {
+    for (void* p : host_allocs) cudaFreeHost(p);
+    for (void* p : dev_allocs) cudaFree(p);
+  }
+};
+
+// Host -> HBM staging of the columns an operator reads from a pushed block.
+// A ring of generations lets push(i+1) copy while the kernel of push(i) still runs;
+// a generation is reused only after the event recorded behind its consumer has fired.
+class Stager {
+ public:
+  static constexpr int kGenerations = 4;
+  int32_t init(int device, cudaStream_t stream, ErrorSink* err);
+  ~Stager();
+  // Begin staging for one push: waits until the next generation is free.
+  int32_t begin();
+  // Make column `c` of the pushed block available on the device (copying if it lives on the
+  // host) and describe it as a DevCol.  `slot` indexes the per-generation buffers.
+  int32_t stage(const dbx_column& c, int slot, DevCol* out);
+  // Record that all kernels consuming this generation have been enqueued.
+  int32_t end();
+  int64_t h2d_bytes = 0;  // instrumentation
+
+ private:
+  struct Gen {
+    std::vector<DevBuf> data, validity;
+    cudaEvent_t done = nullptr;
+    bool pending = false;
+  };
+  Gen gens_[kGenerations];
+  int cur_ = -1;
+  int device_ = 0;
+  cudaStream_t stream_ = nullptr;
+  ErrorSink* err_ = nullptr;
+};
+
+// Operator handle behind `dbx_op*` (the Processor shell of the reference: event()/process()
+// are driven by the caller; push = transform/consume, finish = on_finish, pull = output port).
+class Op {
+ public:
+  virtual ~Op();
+  int32_t base_init(int device);
+  virtual int32_t push(const dbx_block* b) = 0;
+  virtual int32_t finish() = 0;
+  virtual int32_t pull(int32_t out_mem, dbx_block* out, int32_t* has_block) = 0;
+  virtual int32_t reset() { err.set("reset not supported by this operator"); return DBX_ERR_UNSUPPORTED; }
+
+  int kind = -1;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  ErrorSink err;
+  cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // bracket the dominant kernel(s) of the last push
+  bool timed = false;
+  bool finished = false;
+};
+
+// Converts a scalar to the 64-bit image the kernels use for its class (i64 / u64 / f64 bits).
+inline uint64_t scalar_bits(const dbx_scalar& s, int as_class) {
+  int cls = dtype_class(s.dtype);
+  if (as_class == VC_FLT) {
+    double d = cls == VC_FLT ? s.v.f64 : (cls == VC_INT ? (double)s.v.i64 : (double)s.v.u64);
+    uint64_t b;
+    memcpy(&b, &d, 8);
+    return b;
+  }
+  return s.v.u64;  // i64 and u64 share the two's complement image
+}
+
+int32_t fill_owned_block(OwnedBlock* ob, dbx_block* out);
+
+}  // namespace dbx

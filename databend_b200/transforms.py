@@ -1,0 +1,255 @@
+"""Host-side mirror of the reference's operator interface for the hot path.
+
+Each class corresponds to a reference Processor / Transform and forwards to one `dbx_op`
+handle of libdbx through the C-ABI (include/dbx.h).  Names, argument meaning and error
+behaviour follow the reference so the parity tests read like the reference's own tests:
+
+  TransformFilter             src/query/pipeline/transforms/src/processors/transforms/filters/filter_predicate.rs:35-104
+  AggregatorParams            src/query/service/src/pipelines/processors/transforms/aggregator/aggregator_params.rs:30-78
+  TransformPartialAggregate   .../aggregator/transform_aggregate_partial.rs:117-304  (AccumulatingTransform)
+  TransformFinalAggregate     .../aggregator/transform_aggregate_final.rs:67-330
+  (no GROUP BY)               .../aggregator/transform_single_key.rs:42-279
+
+In the reference a worker thread calls Processor::process(); here the caller drives
+transform()/on_finish() directly (the adaptor contract of transform_accumulating.rs:30-37).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import abi, expr as E
+from .block import Column, DataBlock, np_dtype
+from .lib import DbxError, check, load
+
+_AGG_NAMES = {"sum": abi.AGG_SUM, "count": abi.AGG_COUNT, "avg": abi.AGG_AVG, "min": abi.AGG_MIN, "max": abi.AGG_MAX}
+
+
+class DeviceBuffer:
+    """A cudaMalloc'ed buffer owned by Python (tests / bench)."""
+
+    def __init__(self, nbytes: int, device: int = 0):
+        self.device, self.nbytes = device, nbytes
+        p = C.c_void_p()
+        check(load().dbx_device_alloc(device, nbytes, C.byref(p)))
+        self.ptr = p.value
+
+    def free(self):
+        if self.ptr:
+            load().dbx_device_free(self.device, self.ptr)
+            self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def upload(self, arr: np.ndarray):
+        arr = np.ascontiguousarray(arr)
+        assert arr.nbytes <= self.nbytes
+        check(load().dbx_memcpy_h2d(self.device, self.ptr, arr.ctypes.data, arr.nbytes))
+
+    def download(self, dtype, count: int) -> np.ndarray:
+        out = np.empty(count, dtype=dtype)
+        check(load().dbx_memcpy_d2h(self.device, out.ctypes.data, self.ptr, out.nbytes))
+        return out
+
+
+def to_device(col: Column, device: int = 0) -> Column:
+    """Copy a host column into HBM (device-resident pipelines)."""
+    if col.is_const or col.data is None:
+        return col
+    buf = DeviceBuffer(max(1, col.data.nbytes), device)
+    buf.upload(col.data)
+    out = Column(col.dtype, col.length, dev_ptr=buf.ptr, vec_dim=col.vec_dim, data_bit_offset=col.data_bit_offset)
+    out._keep.append(buf)
+    if col.validity is not None:
+        vb = DeviceBuffer(max(1, col.validity.nbytes), device)
+        vb.upload(col.validity)
+        out.dev_validity = vb.ptr
+        out.validity_bit_offset = col.validity_bit_offset
+        out._keep.append(vb)
+    return out
+
+
+def _block_from_c(b: abi.Block, device: int) -> DataBlock:
+    """Copy a library-owned HOST output block into numpy-backed columns, then release it."""
+    cols = []
+    for i in range(b.num_cols):
+        c = b.cols[i]
+        n = c.len
+        assert c.mem == abi.MEM_HOST
+        nd = np_dtype(c.dtype)
+        arr = np.empty(n, dtype=nd)
+        if n:
+            C.memmove(arr.ctypes.data, c.data, arr.nbytes)
+        col = Column(c.dtype, n, data=arr)
+        if c.validity:
+            nb = (c.validity_bit_offset + n + 7) // 8
+            v = np.empty(max(nb, 1), dtype=np.uint8)
+            if nb:
+                C.memmove(v.ctypes.data, c.validity, nb)
+            col.validity = v
+            col.validity_bit_offset = c.validity_bit_offset
+        cols.append(col)
+    rows = b.num_rows
+    check(load().dbx_block_release(C.byref(b)))
+    return DataBlock(cols, rows)
+
+
+class _Op:
+    """Owns one dbx_op handle."""
+
+    def __init__(self, kind: int, params, input_types: Sequence[int], device: int):
+        self._h = C.c_void_p()
+        self.device = device
+        types = (C.c_int32 * max(1, len(input_types)))(*input_types)
+        self._params = params
+        check(load().dbx_op_create(kind, C.cast(C.byref(params), C.c_void_p), types, len(input_types), device,
+                                   C.byref(self._h)))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def push(self, block: DataBlock):
+        b, keep = block.as_c()
+        check(load().dbx_op_push(self._h, C.byref(b)), self._h)
+
+    def finish(self):
+        check(load().dbx_op_finish(self._h), self._h)
+
+    def pull_c(self, out_mem: int = abi.MEM_HOST) -> Optional[abi.Block]:
+        b = abi.Block()
+        has = C.c_int32(0)
+        check(load().dbx_op_pull(self._h, out_mem, C.byref(b), C.byref(has)), self._h)
+        return b if has.value else None
+
+    def reset(self):
+        check(load().dbx_op_reset(self._h), self._h)
+
+    def synchronize(self):
+        check(load().dbx_op_synchronize(self._h), self._h)
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float(0)
+        check(load().dbx_op_last_kernel_ms(self._h, C.byref(ms)), self._h)
+        return ms.value
+
+    def close(self):
+        if self._h:
+            load().dbx_op_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+@dataclass
+class AggregatorParams:
+    """AggregatorParams::try_create (aggregator_params.rs:44-78): group column offsets and the
+    aggregate functions with their argument offsets.  `aggregate_functions` entries are
+    (factory name, argument column offset or None for count())."""
+
+    group_columns: List[int]
+    aggregate_functions: List[Tuple[str, Optional[int]]]
+    expected_groups: int = 0
+
+    def to_c(self, filter_expr: Optional[E.Node] = None) -> abi.AggParams:
+        p = abi.AggParams()
+        p.n_group_cols = len(self.group_columns)
+        for i, g in enumerate(self.group_columns):
+            p.group_cols[i] = g
+        p.n_aggs = len(self.aggregate_functions)
+        for i, (name, arg) in enumerate(self.aggregate_functions):
+            if name not in _AGG_NAMES:
+                raise DbxError(abi.ERR_UNSUPPORTED, f"Unknown aggregate function {name}")  # factory.get error
+            p.aggs[i].kind = _AGG_NAMES[name]
+            p.aggs[i].arg_col = -1 if arg is None else arg
+        p.filter = E.build_predicate(filter_expr)
+        p.expected_groups = self.expected_groups
+        return p
+
+
+def schema_types(block_or_types, nullable: Optional[Sequence[bool]] = None) -> List[int]:
+    """DataSchema -> input_types[] with the DBX_NULLABLE flag for Nullable(T) columns."""
+    if isinstance(block_or_types, DataBlock):
+        out = []
+        for c in block_or_types.columns:
+            nul = c.validity is not None or c.dev_validity != 0 or (c.is_const and c.const_value is None)
+            out.append(c.dtype | (abi.NULLABLE if nul else 0))
+        return out
+    types = list(block_or_types)
+    if nullable:
+        types = [t | (abi.NULLABLE if n else 0) for t, n in zip(types, nullable)]
+    return types
+
+
+class TransformPartialAggregate(_Op):
+    """[TransformFilter ->] TransformPartialAggregate fused into one device pass.
+
+    transform(block) accumulates (AccumulatingTransform::transform returns no blocks while
+    the hash table has room); on_finish() yields the payload reference that
+    TransformFinalAggregate consumes (AggregateMeta::AggregatePayload)."""
+
+    def __init__(self, params: AggregatorParams, input_types: Sequence[int], filter_expr: Optional[E.Node] = None,
+                 device: int = 0):
+        self.params = params
+        super().__init__(abi.OP_AGG_PARTIAL, params.to_c(filter_expr), input_types, device)
+
+    def transform(self, block: DataBlock) -> List[DataBlock]:
+        self.push(block)
+        return []
+
+    def on_finish(self):
+        self.finish()
+        return self  # the payload stays in HBM; the handle is the AggregateMeta
+
+
+class TransformFinalAggregate(_Op):
+    def __init__(self, params: AggregatorParams, input_types: Sequence[int], device: int = 0):
+        self.params = params
+        super().__init__(abi.OP_AGG_FINAL, params.to_c(None), input_types, device)
+
+    def transform(self, partial: TransformPartialAggregate) -> List[DataBlock]:
+        """handle_meta -> combine_payload (transform_aggregate_final.rs:201-303)."""
+        check(load().dbx_agg_final_merge_partial(self._h, partial.handle), self._h)
+        return []
+
+    def merge_rows(self, dev_rows_ptr: int, n_rows: int):
+        check(load().dbx_agg_final_merge_rows(self._h, dev_rows_ptr, n_rows), self._h)
+
+    def on_finish(self, out_mem: int = abi.MEM_HOST):
+        """merge_result: returns the result blocks [aggs..., group keys...]."""
+        self.finish()
+        if out_mem == abi.MEM_HOST:
+            b = self.pull_c(abi.MEM_HOST)
+            return [] if b is None else [_block_from_c(b, self.device)]
+        b = self.pull_c(abi.MEM_DEVICE)
+        return [] if b is None else [b]
+
+
+def filter_group_aggregate(blocks: Sequence[DataBlock], params: AggregatorParams, filter_expr: Optional[E.Node] = None,
+                           input_types: Optional[Sequence[int]] = None, device: int = 0,
+                           n_partials: int = 1) -> DataBlock:
+    """Convenience pipeline: Filter -> Partial x n_partials -> Final, like
+    PipelineBuilder::build_aggregate_partial/final would wire it."""
+    types = list(input_types) if input_types is not None else schema_types(blocks[0])
+    partials = [TransformPartialAggregate(params, types, filter_expr, device) for _ in range(n_partials)]
+    for i, b in enumerate(blocks):
+        partials[i % n_partials].transform(b)
+    final = TransformFinalAggregate(params, types, device)
+    for p in partials:
+        final.transform(p.on_finish())
+    out = final.on_finish()
+    for p in partials:
+        p.close()
+    final.close()
+    return out[0]

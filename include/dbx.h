@@ -72,6 +72,10 @@ typedef enum dbx_dtype {
   DBX_VEC_F32 = 11 /* VectorColumn::Float32((Buffer<F32>, dim)), flat row-major (types/vector.rs:377-380) */
 } dbx_dtype;
 
+/* OR-ed into the entries of dbx_op_create's input_types[] when the column's DataType is
+ * Nullable(T) (nullability is part of the schema in the reference: types/nullable.rs). */
+#define DBX_NULLABLE 0x100
+
 typedef enum dbx_mem { DBX_MEM_HOST = 0, DBX_MEM_DEVICE = 1 } dbx_mem;
 
 /* A constant (BlockEntry::Const payload, or a literal in an expression). */
@@ -223,6 +227,7 @@ int32_t dbx_device_alloc(int32_t device, size_t bytes, void** out);
 int32_t dbx_device_free(int32_t device, void* p);
 int32_t dbx_memcpy_h2d(int32_t device, void* dst, const void* src, size_t bytes);
 int32_t dbx_memcpy_d2h(int32_t device, void* dst, const void* src, size_t bytes);
+int32_t dbx_memcpy_d2d(int32_t device, void* dst, const void* src, size_t bytes);
 int32_t dbx_device_synchronize(int32_t device);
 
 /* Operator lifecycle.  `params` is the struct matching `kind`
@@ -241,6 +246,11 @@ int32_t dbx_op_finish(dbx_op* op);
  * output columns live (host: pinned, zero-copy wrappable; device: stays in HBM). */
 int32_t dbx_op_pull(dbx_op* op, int32_t out_mem, dbx_block* out, int32_t* has_block);
 int32_t dbx_block_release(dbx_block* block);
+/* Re-arm a finished operator for the next query with the same parameters, keeping its
+ * device allocations (operator pooling; the table is re-initialised on the device). */
+int32_t dbx_op_reset(dbx_op* op);
+/* Block until everything enqueued on the handle's stream has completed. */
+int32_t dbx_op_synchronize(dbx_op* op);
 
 /* Join probe side: Join::probe_block(block) -> JoinStream::next()* ; output blocks are
  * pulled with dbx_op_pull until drained.  Join::final_probe is a no-op for inner joins. */

@@ -1,0 +1,288 @@
+"""Parity of the fused filter -> hash-aggregate CUDA path against the CPU oracle.
+
+Modelled on the reference's differential tests
+(src/query/service/tests/it/pipelines/filter/filter_executor.rs:18-70: random blocks + random
+predicates, operator == evaluator) and on functions/tests/it/aggregates/agg_hashtable.rs:52-199.
+Integer results are bit-exact; f64 sums are bit-exact on integer-valued data (< 2^53) and
+within rtol 1e-12 otherwise (atomic accumulation order differs from the CPU's).
+"""
+import numpy as np
+import pytest
+
+from databend_b200 import abi, expr as E
+from databend_b200.block import Column, DataBlock
+from databend_b200.lib import DbxError
+from databend_b200.transforms import (AggregatorParams, TransformFinalAggregate, TransformPartialAggregate,
+                                      filter_group_aggregate, schema_types, to_device)
+from helpers import assert_group_results_equal, sorted_group_result_from_block, sorted_group_result_from_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle():
+    from oracle import oracle as orc
+    return orc
+
+
+def run_both(block, params, filt, n_partials=1, split=None, device_resident=False, float_exact=True, rtol=0.0,
+             input_types=None):
+    orc = oracle()
+    types = input_types or schema_types(block)
+    blocks = [block] if not split else block.split_by_rows(split)
+    if device_resident:
+        blocks = [DataBlock([to_device(c) for c in b.columns], b.num_rows) for b in blocks]
+    out = filter_group_aggregate(blocks, params, filt, input_types=types, n_partials=n_partials)
+    ref = orc.filter_group_agg(block, params.to_c(filt), threads=4)
+    n_aggs, n_keys = len(params.aggregate_functions), len(params.group_columns)
+    g = sorted_group_result_from_block(out, n_aggs, n_keys)
+    o = sorted_group_result_from_oracle(ref, [block.columns[c].dtype for c in params.group_columns])
+    assert out.num_rows == (len(ref[2][0]) if ref[2] else len(ref[0][0]))
+    assert_group_results_equal(g, o, float_exact=float_exact, rtol=rtol)
+    return out
+
+
+def config2_block(n, seed=42, n_keys=1000):
+    orc = oracle()
+    k = orc.synth_fill(0, seed, n_keys, 0, n)
+    v = orc.synth_fill(1, seed + 1, 0, 0, n)
+    x = orc.synth_fill(2, seed + 2, 20, 0, n)
+    return DataBlock([Column.from_data(k), Column.from_data(v), Column.from_data(x)])
+
+
+CONFIG2 = AggregatorParams([0], [("sum", 1), ("count", 1), ("avg", 2)])
+V_MOD3 = E.eq(E.col(1) % E.lit(3), E.lit(0))
+
+
+def test_config1_sum_numbers_mod3(gpu):
+    """SELECT sum(number) FROM numbers(10000000) WHERE number % 3 = 0  ->  16666668333333"""
+    n = 10_000_000
+    blk = DataBlock([Column.from_data(np.arange(n, dtype=np.uint64))])
+    params = AggregatorParams([], [("sum", 0)])
+    out = run_both(blk, params, E.eq(E.col(0) % E.lit(3), E.lit(0)), split=65536 * 16)
+    assert out.num_rows == 1
+    assert int(out.columns[0].values()[0]) == 16666668333333
+    assert out.columns[0].dtype == abi.U64 and out.columns[0].valid_mask()[0]
+
+
+@pytest.mark.parametrize("n,n_keys", [(1, 1), (1000, 7), (65536, 1000), (300_001, 100_000), (2_000_000, 1_000_000)])
+def test_config2_shape_host_blocks(gpu, n, n_keys):
+    run_both(config2_block(n, n_keys=n_keys), CONFIG2, V_MOD3, split=65536)
+
+
+def test_config2_device_resident_single_push(gpu):
+    run_both(config2_block(3_000_000, n_keys=1_000_000), CONFIG2, V_MOD3, device_resident=True)
+
+
+def test_config2_multiple_partials_merge(gpu):
+    """max_threads copies of TransformPartialAggregate feeding one final (combine_payload)."""
+    run_both(config2_block(500_000, n_keys=50_000), CONFIG2, V_MOD3, n_partials=3, split=65536)
+
+
+def test_agg_hashtable_golden(gpu):
+    """functions/tests/it/aggregates/agg_hashtable.rs:52-199: keys x % 4, two tables combined:
+    min [0,1,2,3], max [0,1,2,3], sum [0, n/2, n, 3n/2], count n/2."""
+    for n in [100, 1000, 10_000, 100_000]:
+        vals = (np.arange(n) % 4).astype(np.int64)
+        blk = DataBlock([Column.from_data(vals)])
+        params = AggregatorParams([0], [("min", 0), ("max", 0), ("sum", 0), ("count", 0)])
+        types = schema_types(blk)
+        p1 = TransformPartialAggregate(params, types)
+        p2 = TransformPartialAggregate(params, types)
+        p1.transform(blk)
+        p2.transform(blk)
+        fin = TransformFinalAggregate(params, types)
+        fin.transform(p1.on_finish())
+        fin.transform(p2.on_finish())
+        out = fin.on_finish()[0]
+        g = sorted_group_result_from_block(out, 4, 1)
+        np.testing.assert_array_equal(g["keys"][0], [0, 1, 2, 3])
+        np.testing.assert_array_equal(g["aggs"][0], [0, 1, 2, 3])
+        np.testing.assert_array_equal(g["aggs"][1], [0, 1, 2, 3])
+        np.testing.assert_array_equal(g["aggs"][2], [0, n // 2, n, n // 2 * 3])
+        np.testing.assert_array_equal(g["aggs"][3], [n // 2] * 4)
+        assert g["aggs"][3].dtype == np.uint64 and g["aggs"][2].dtype == np.int64
+
+
+def test_empty_input(gpu):
+    blk = config2_block(1000)
+    types = schema_types(blk)
+    out = filter_group_aggregate([blk.slice(0, 0)], CONFIG2, V_MOD3, input_types=types)
+    assert out.num_rows == 0
+    # no GROUP BY over nothing: one row, sum NULL, count 0 (transform_single_key.rs)
+    params = AggregatorParams([], [("sum", 1), ("count", 1)])
+    out = filter_group_aggregate([blk.slice(0, 0)], params, None, input_types=types)
+    assert out.num_rows == 1
+    assert not out.columns[0].valid_mask()[0]
+    assert int(out.columns[1].values()[0]) == 0
+
+
+def test_all_rows_filtered_out(gpu):
+    blk = config2_block(10_000)
+    out = run_both(blk, CONFIG2, E.gt(E.col(1), E.lit(2**40)))
+    assert out.num_rows == 0
+
+
+def test_nullable_args_and_keys(gpu):
+    rng = np.random.default_rng(7)
+    n = 200_000
+    k = rng.integers(-50, 50, n).astype(np.int64)
+    kv = rng.random(n) > 0.1
+    v = rng.integers(-2**62, 2**62, n).astype(np.int64)
+    vv = rng.random(n) > 0.3
+    x = rng.integers(0, 2**20, n).astype(np.float64)
+    xv = rng.random(n) > 0.5
+    blk = DataBlock([Column.from_data(k, validity=kv), Column.from_data(v, validity=vv, validity_bit_offset=3),
+                     Column.from_data(x, validity=xv)])
+    params = AggregatorParams([0], [("sum", 1), ("count", 1), ("avg", 2), ("min", 1), ("max", 2), ("count", None)])
+    run_both(blk, params, None, split=50_000)
+    run_both(blk, params, E.and_(E.ne(E.col(1) % E.lit(7), E.lit(0)), E.lt(E.col(2), E.lit(600000.0))), split=77_777)
+
+
+def test_all_null_group_gives_null_sum(gpu):
+    """sum(all_null) -> NULL, count -> 0 (testdata/sum.txt, count.txt `all_null`)."""
+    blk = DataBlock([Column.from_data(np.array([0, 1, 0, 1], dtype=np.int64)),
+                     Column.from_data(np.array([1, 2, 3, 4], dtype=np.uint64), validity=[False] * 4)])
+    params = AggregatorParams([0], [("sum", 1), ("count", 1), ("avg", 1)])
+    out = run_both(blk, params, None)
+    assert not out.columns[0].valid_mask().any()
+    np.testing.assert_array_equal(out.columns[1].values(), [0, 0])
+
+
+def test_wrapping_integer_sum(gpu):
+    """Release builds wrap on i64/u64 overflow (Cargo.toml:577)."""
+    v = np.array([2**63 - 1, 2**63 - 1, 5, -(2**63)], dtype=np.int64)
+    u = np.array([2**64 - 1, 2**64 - 1, 7, 1], dtype=np.uint64)
+    blk = DataBlock([Column.from_data(np.zeros(4, dtype=np.int64)), Column.from_data(v), Column.from_data(u)])
+    params = AggregatorParams([0], [("sum", 1), ("sum", 2), ("avg", 1)])
+    run_both(blk, params, None)
+
+
+@pytest.mark.parametrize("dtype", [abi.I8, abi.I16, abi.I32, abi.U8, abi.U16, abi.U32, abi.U64, abi.F32, abi.F64])
+def test_argument_dtypes(gpu, dtype):
+    from databend_b200.block import np_dtype
+    rng = np.random.default_rng(dtype)
+    n = 100_003
+    nd = np_dtype(dtype)
+    if nd.kind == "f":
+        vals = rng.integers(-1000, 1000, n).astype(nd)  # integer-valued: sums exact in any order
+    else:
+        info = np.iinfo(nd)
+        vals = rng.integers(info.min, info.max, n, dtype=nd, endpoint=True)
+    k = rng.integers(0, 1000, n).astype(np.int32)
+    blk = DataBlock([Column.from_data(k), Column.from_data(vals)])
+    params = AggregatorParams([0], [("sum", 1), ("avg", 1), ("min", 1), ("max", 1), ("count", 1)])
+    run_both(blk, params, None, split=30_000)
+
+
+def test_key_dtypes_and_sentinel_key(gpu):
+    """i64::MIN is the table's EMPTY sentinel: it must still be a legal group key."""
+    k = np.array([-(2**63), 5, -(2**63), 2**63 - 1, 5, 0], dtype=np.int64)
+    v = np.arange(6, dtype=np.int64)
+    run_both(DataBlock([Column.from_data(k), Column.from_data(v)]), AggregatorParams([0], [("sum", 1), ("count", None)]), None)
+    ku = np.array([2**63, 5, 2**63, 2**64 - 1], dtype=np.uint64)
+    run_both(DataBlock([Column.from_data(ku), Column.from_data(v[:4])]), AggregatorParams([0], [("sum", 1)]), None)
+
+
+def test_const_columns(gpu):
+    """BlockEntry::Const arguments are not materialised (sum(const_int) -> 20, testdata/sum.txt)."""
+    blk = DataBlock([Column.from_data(np.array([4, 3, 2, 1], dtype=np.int64)), Column.new_const(abi.I32, 5, 4),
+                     Column.new_const(abi.I32, None, 4)])
+    types = [abi.I64, abi.I32, abi.I32 | abi.NULLABLE]
+    params = AggregatorParams([], [("sum", 1), ("sum", 2), ("count", 2), ("count", 1)])
+    out = run_both(blk, params, None, input_types=types)
+    assert int(out.columns[0].values()[0]) == 20
+    assert not out.columns[1].valid_mask()[0]
+    assert int(out.columns[2].values()[0]) == 0 and int(out.columns[3].values()[0]) == 4
+
+
+def test_predicate_shapes(gpu):
+    rng = np.random.default_rng(3)
+    n = 150_000
+    a = rng.integers(-1000, 1000, n).astype(np.int64)
+    b = rng.integers(-1000, 1000, n).astype(np.int64)
+    f = rng.normal(size=n)
+    f[rng.random(n) < 0.01] = np.nan
+    u = rng.integers(0, 2**64 - 1, n, dtype=np.uint64)
+    flag = rng.random(n) < 0.5
+    blk = DataBlock([Column.from_data(a), Column.from_data(b, validity=rng.random(n) > 0.2), Column.from_data(f),
+                     Column.from_data(u), Column.from_data(flag, abi.BOOL)])
+    params = AggregatorParams([0], [("sum", 1), ("count", None), ("max", 3)])
+    preds = [
+        E.eq(E.col(0) % E.lit(3), E.lit(0)),
+        E.eq(E.col(0) % E.lit(-7), E.lit(-2, abi.I64)),
+        E.lt(E.col(0), E.col(1)),
+        E.ge(E.col(2), E.lit(0.25)),
+        E.gt(E.col(2), E.lit(float("nan"))),  # NaN is the greatest value: nothing is greater
+        E.eq(E.col(2), E.lit(float("nan"))),  # all NaNs are equal
+        E.and_(E.ne(E.col(0), E.lit(5)), E.le(E.col(1), E.lit(100)), E.gt(E.col(3) % E.lit(10), E.lit(4))),
+        E.or_(E.lt(E.col(0), E.lit(-900, abi.I64)), E.and_(E.bool_column(4), E.gt(E.col(1), E.lit(990)))),
+        E.or_(E.bool_scalar(False), E.eq(E.lit(3), E.col(0))),
+        E.lt(E.col(0), E.lit(2**63 + 5)),
+        E.ge(E.col(3), E.lit(-1, abi.I64)),
+    ]
+    for p in preds:
+        run_both(blk, params, p, split=40_000)
+
+
+def test_division_by_zero_is_an_error(gpu):
+    """arithmetic_modulo.rs:137-140: literal divisor 0 -> 'Division by zero' (BadArguments)."""
+    blk = config2_block(100)
+    with pytest.raises(DbxError) as ei:
+        filter_group_aggregate([blk], CONFIG2, E.eq(E.col(1) % E.lit(0), E.lit(0)))
+    assert ei.value.status == abi.ERR_BAD_ARGUMENTS and "Division by zero" in ei.value.message
+
+
+def test_modulo_edge_values(gpu):
+    """MIN % -1 = 0; sign follows the dividend."""
+    a = np.array([-(2**63), -(2**63) + 1, -7, -1, 0, 1, 7, 2**63 - 1], dtype=np.int64)
+    blk = DataBlock([Column.from_data(a)])
+    params = AggregatorParams([0], [("count", None)])
+    for d in [1, -1, 2, -2, 3, 7, -7, 2**31, 2**62, -(2**63), 2**63 - 1, 10**18, 6700417]:
+        for rhs in [0, 1, -1, 2, -3]:
+            run_both(blk, params, E.eq(E.col(0) % E.lit(d, abi.I64), E.lit(rhs, abi.I64)))
+
+
+def test_table_growth_from_small_hint(gpu):
+    """expected_groups far too small: the table must grow (resize) without losing rows."""
+    blk = config2_block(400_000, n_keys=300_000)
+    params = AggregatorParams([0], [("sum", 1), ("count", 1), ("avg", 2)], expected_groups=16)
+    run_both(blk, params, V_MOD3, split=100_000)
+    run_both(blk, params, None, device_resident=True)
+
+
+def test_float_sum_tolerance(gpu):
+    rng = np.random.default_rng(11)
+    n = 200_000
+    blk = DataBlock([Column.from_data(rng.integers(0, 100, n).astype(np.int64)), Column.from_data(rng.random(n))])
+    params = AggregatorParams([0], [("sum", 1), ("avg", 1)])
+    run_both(blk, params, None, float_exact=False, rtol=1e-12)
+
+
+def test_operator_reset_reuse(gpu):
+    blk = config2_block(100_000, n_keys=5_000)
+    types = schema_types(blk)
+    part = TransformPartialAggregate(CONFIG2, types, V_MOD3)
+    fin = TransformFinalAggregate(CONFIG2, types)
+    ref = None
+    for _ in range(3):
+        part.reset()
+        fin.reset()
+        part.transform(blk)
+        fin.transform(part.on_finish())
+        out = fin.on_finish()[0]
+        g = sorted_group_result_from_block(out, 3, 1)
+        if ref is None:
+            ref = g
+        else:
+            assert_group_results_equal(g, ref)
+    o = sorted_group_result_from_oracle(oracle().filter_group_agg(blk, CONFIG2.to_c(V_MOD3), 2), [abi.I64])
+    assert_group_results_equal(ref, o)
+
+
+def test_schema_mismatch_is_rejected(gpu):
+    blk = config2_block(10)
+    part = TransformPartialAggregate(CONFIG2, schema_types(blk), V_MOD3)
+    with pytest.raises(DbxError):
+        part.transform(DataBlock([blk.columns[0]]))
+    with pytest.raises(DbxError):
+        TransformPartialAggregate(AggregatorParams([0], [("median", 1)]), schema_types(blk))
