@@ -9,6 +9,7 @@
 //   FinalSingleStateAggregator         .../aggregator/transform_single_key.rs:190-279
 //   AggregateHashTable                 src/query/expression/src/aggregate/aggregate_hashtable.rs:168-408
 #include <algorithm>
+#include <cstdlib>
 
 #include "agg_kernels.cuh"
 #include "runtime.h"
@@ -461,21 +462,62 @@ class AggPartialOp : public Op {
     return DBX_OK;
   }
 
-  template <bool INDIRECT>
-  int32_t launch_grouped(const AggKernelParams& kp) {
-    int grid = grid_for_rows(kp.n_rows);
-    switch (plan.n_slots) {
-      case 1: filter_group_agg_kernel<1, INDIRECT><<<grid, kBlock, 0, stream>>>(kp); break;
-      case 2: filter_group_agg_kernel<2, INDIRECT><<<grid, kBlock, 0, stream>>>(kp); break;
-      case 3: filter_group_agg_kernel<3, INDIRECT><<<grid, kBlock, 0, stream>>>(kp); break;
-      case 4: filter_group_agg_kernel<4, INDIRECT><<<grid, kBlock, 0, stream>>>(kp); break;
-      case 5: filter_group_agg_kernel<5, INDIRECT><<<grid, kBlock, 0, stream>>>(kp); break;
-      case 6: filter_group_agg_kernel<6, INDIRECT><<<grid, kBlock, 0, stream>>>(kp); break;
-      case 7: filter_group_agg_kernel<7, INDIRECT><<<grid, kBlock, 0, stream>>>(kp); break;
-      default: filter_group_agg_kernel<8, INDIRECT><<<grid, kBlock, 0, stream>>>(kp); break;
+  template <int NS, bool FAST, bool INDIRECT>
+  int32_t launch_one(const AggKernelParams& kp) {
+    static bool attr_set[16] = {};
+    const size_t smem = sizeof(StageSmem<NS>);
+    auto kern = filter_group_agg_kernel<NS, FAST, INDIRECT>;
+    if (!attr_set[device]) {
+      DBX_CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set[device] = true;
     }
+    int grid = grid_for_rows(kp.n_rows);
+    kern<<<grid, kBlock, smem, stream>>>(kp);
     count_launch();
     DBX_CUDA_TRY(err, cudaGetLastError());
+    return DBX_OK;
+  }
+  template <bool FAST, bool INDIRECT>
+  int32_t launch_ns(const AggKernelParams& kp) {
+    switch (plan.n_slots) {
+      case 1: return launch_one<1, FAST, INDIRECT>(kp);
+      case 2: return launch_one<2, FAST, INDIRECT>(kp);
+      case 3: return launch_one<3, FAST, INDIRECT>(kp);
+      case 4: return launch_one<4, FAST, INDIRECT>(kp);
+      case 5: return launch_one<5, FAST, INDIRECT>(kp);
+      case 6: return launch_one<6, FAST, INDIRECT>(kp);
+      case 7: return launch_one<7, FAST, INDIRECT>(kp);
+      default: return launch_one<8, FAST, INDIRECT>(kp);
+    }
+  }
+  // The straight-line variant applies to plain 8-byte device columns (no validity, 32 B aligned)
+  // with at most one Compare; it covers whole tiles, the generic kernel takes the remainder.
+  bool fast_eligible(const AggKernelParams& kp) const {
+    if (getenv("DBX_AGG_NO_FAST")) return false;
+    if (kp.n_nodes > 1) return false;
+    if (kp.n_nodes == 1 && (kp.nodes[0].kind != DBX_PRED_CMP || kp.nodes[0].r_slot >= 0)) return false;
+    for (int s = 0; s < kp.n_slots; ++s) {
+      const DevCol& c = kp.cols[s];
+      if (c.is_const || c.validity) return false;
+      if (c.dtype != DBX_I64 && c.dtype != DBX_U64 && c.dtype != DBX_F64) return false;
+      if (reinterpret_cast<uintptr_t>(c.data) & 31) return false;
+    }
+    return true;
+  }
+  int32_t launch_grouped(const AggKernelParams& kp, bool indirect) {
+    if (indirect) return launch_ns<false, true>(kp);
+    if (!fast_eligible(kp) || kp.n_rows < kTileRows) return launch_ns<false, false>(kp);
+    AggKernelParams a = kp;
+    const int64_t n_fast = kp.n_rows / kTileRows * kTileRows;
+    a.n_rows = n_fast;
+    DBX_TRY((launch_ns<true, false>(a)));
+    if (n_fast < kp.n_rows) {
+      AggKernelParams b = kp;
+      for (int s = 0; s < kp.n_slots; ++s) b.cols[s].data = (const char*)kp.cols[s].data + n_fast * 8;
+      b.n_rows = kp.n_rows - n_fast;
+      b.row_base = kp.row_base + (uint32_t)n_fast;
+      DBX_TRY((launch_ns<false, false>(b)));
+    }
     return DBX_OK;
   }
   int32_t launch_single(const AggKernelParams& kp) {
@@ -514,6 +556,8 @@ class AggPartialOp : public Op {
     kp->n_updates = plan.n_updates;
     kp->key_slot = plan.key_slot;
     kp->key_nullable = plan.key_nullable;
+    static const int dbg = getenv("DBX_AGG_DEBUG") ? atoi(getenv("DBX_AGG_DEBUG")) : 0;
+    kp->debug_flags = dbg;
   }
 
   int32_t push(const dbx_block* b) override {
@@ -551,13 +595,13 @@ class AggPartialOp : public Op {
       const bool safe = (groups_known + rows_since_read + m) * 2 <= table.cap;
       if (safe) {
         kp.table = table.view(nullptr);
-        DBX_TRY(launch_grouped<false>(kp));
+        DBX_TRY(launch_grouped(kp, false));
         rows_since_read += m;
         continue;
       }
       DBX_CUDA_TRY(err, ovf[0].ensure((size_t)m * 4));
       kp.table = table.view((uint32_t*)ovf[0].p);
-      DBX_TRY(launch_grouped<false>(kp));
+      DBX_TRY(launch_grouped(kp, false));
       unsigned long long ng = 0, no = 0;
       DBX_TRY(read_counters(&ng, &no));
       int cur = 0;
@@ -570,7 +614,7 @@ class AggPartialOp : public Op {
         fill_params(&kr, cols, row0, (int64_t)no);
         kr.row_index = (const uint32_t*)ovf[cur].p;
         kr.table = table.view((uint32_t*)ovf[cur ^ 1].p);
-        DBX_TRY(launch_grouped<true>(kr));
+        DBX_TRY(launch_grouped(kr, true));
         cur ^= 1;
         DBX_TRY(read_counters(&ng, &no));
       }

@@ -156,18 +156,38 @@ __device__ __forceinline__ int cmp_f64_ordered(double a, double b) {
   if (an | bn) return an == bn ? 0 : (an ? 1 : -1);
   return a < b ? -1 : (a > b ? 1 : 0);
 }
-__device__ __forceinline__ bool apply_cmp(int op, int c) {
-  switch (op) {
-    case DBX_EQ: return c == 0;
-    case DBX_NE: return c != 0;
-    case DBX_LT: return c < 0;
-    case DBX_LE: return c <= 0;
-    case DBX_GT: return c > 0;
-    default: return c >= 0;
-  }
-}
 
 // ---------------------------------------------------------------- predicate
+__device__ __forceinline__ bool apply_cmp(int op, int c) {
+  // if-chain (uniform branches) rather than a jump table: keeps the kernel small and off BRX
+  if (op == DBX_EQ) return c == 0;
+  if (op == DBX_NE) return c != 0;
+  if (op == DBX_LT) return c < 0;
+  if (op == DBX_LE) return c <= 0;
+  if (op == DBX_GT) return c > 0;
+  return c >= 0;
+}
+
+// One Compare node on one row.  a/b are the 64-bit images of the operands in class nd.cls.
+__device__ __forceinline__ bool eval_cmp(const PredNodeDev& nd, uint64_t a, uint64_t b) {
+  int c;
+  if (nd.cls == VC_INT) {
+    int64_t x = (int64_t)a;
+    if (nd.l_mod) x = smod_magic(x, nd.mod);
+    int64_t y = (int64_t)b;
+    c = x < y ? -1 : (x > y ? 1 : 0);
+  } else if (nd.cls == VC_UINT) {
+    uint64_t x = a;
+    if (nd.l_mod) x = umod_magic(x, nd.mod);
+    c = x < b ? -1 : (x > b ? 1 : 0);
+  } else {
+    double x = __longlong_as_double((long long)a);
+    if (nd.l_mod) x = fmod(x, nd.mod_f);
+    c = cmp_f64_ordered(x, __longlong_as_double((long long)b));
+  }
+  return apply_cmp(nd.cmp, c);
+}
+
 // Evaluates the flattened SelectExpr tree for the thread's kRowsPerThread rows; returns a
 // bitmask of selected rows.  NULL operands make a Compare false (select_column_scalar.rs).
 template <int NS>
@@ -186,22 +206,7 @@ __device__ __forceinline__ uint32_t eval_predicate(const AggKernelParams& p, con
       for (int j = 0; j < kRowsPerThread; ++j) {
         uint64_t a = pick<NS>(vals, nd.l_slot, j);
         uint64_t b = nd.r_slot >= 0 ? pick<NS>(vals, nd.r_slot, j) : nd.r_const;
-        int c;
-        if (nd.cls == VC_INT) {
-          int64_t x = (int64_t)a;
-          if (nd.l_mod) x = smod_magic(x, nd.mod);
-          int64_t y = (int64_t)b;
-          c = x < y ? -1 : (x > y ? 1 : 0);
-        } else if (nd.cls == VC_UINT) {
-          uint64_t x = a;
-          if (nd.l_mod) x = umod_magic(x, nd.mod);
-          c = x < b ? -1 : (x > b ? 1 : 0);
-        } else {
-          double x = __longlong_as_double((long long)a);
-          if (nd.l_mod) x = fmod(x, nd.mod_f);
-          c = cmp_f64_ordered(x, __longlong_as_double((long long)b));
-        }
-        bool r = apply_cmp(nd.cmp, c) && ((lm >> j) & 1) && ((rm >> j) & 1);
+        bool r = eval_cmp(nd, a, b) && ((lm >> j) & 1) && ((rm >> j) & 1);
         stack[j] = (stack[j] << 1) | (r ? 1u : 0u);
       }
     } else if (nd.kind == DBX_PRED_AND || nd.kind == DBX_PRED_OR) {
@@ -237,10 +242,9 @@ __device__ __forceinline__ uint8_t* entry_ptr(const TableDev& t, int64_t slot) {
 
 // HashIndex::find_or_insert (hash_index/index.rs:92-111) for one 64-bit key word.
 // Returns the entry pointer, or nullptr if the probe limit was hit (row goes to overflow).
-__device__ __forceinline__ uint8_t* find_or_insert(const TableDev& t, uint64_t key, uint64_t first_probe_key,
-                                                   int64_t slot, uint32_t& new_groups) {
+__device__ __noinline__ uint8_t* find_or_insert_slow(const TableDev& t, uint64_t key, uint64_t cur, int64_t slot,
+                                                     uint32_t& new_groups) {
   const int64_t mask = t.cap - 1;
-  uint64_t cur = first_probe_key;
   for (int probes = 0; probes < t.probe_limit; ++probes) {
     uint8_t* e = entry_ptr(t, slot);
     if (cur == key) return e;
@@ -254,95 +258,194 @@ __device__ __forceinline__ uint8_t* find_or_insert(const TableDev& t, uint64_t k
   }
   return nullptr;
 }
+__device__ __forceinline__ uint8_t* find_or_insert(const TableDev& t, uint64_t key, uint64_t first_probe_key,
+                                                   int64_t slot, uint32_t& new_groups) {
+  if (first_probe_key == key) return entry_ptr(t, slot);  // steady state: one probe, no call
+  return find_or_insert_slow(t, key, first_probe_key, slot, new_groups);
+}
 
-__device__ __forceinline__ void apply_update(const UpdateDev& u, uint8_t* e, uint64_t val, bool valid) {
-  void* w = e + 8 + 8 * u.word;
-  switch (u.op) {
-    case UPD_INC: red_add_u64(w, 1); break;
-    case UPD_INC_VALID: if (valid) red_add_u64(w, 1); break;
-    case UPD_ADD_INT: if (valid) red_add_u64(w, val); break;
-    case UPD_ADD_F64: if (valid) red_add_f64(w, __longlong_as_double((long long)val)); break;
-    case UPD_MIN_S64: if (valid) red_min_s64(w, (int64_t)val); break;
-    case UPD_MAX_S64: if (valid) red_max_s64(w, (int64_t)val); break;
-    case UPD_MIN_U64: if (valid) red_min_u64(w, val); break;
-    case UPD_MAX_U64: if (valid) red_max_u64(w, val); break;
-    case UPD_MIN_F64: if (valid) red_min_u64(w, f64_to_ordered(__longlong_as_double((long long)val))); break;
-    case UPD_MAX_F64: if (valid) red_max_u64(w, f64_to_ordered(__longlong_as_double((long long)val))); break;
-    default: break;
-  }
+__device__ __forceinline__ void apply_update(int op, void* w, uint64_t val, bool valid) {
+  if (op == UPD_INC) { red_add_u64(w, 1); return; }
+  if (!valid) return;
+  if (op == UPD_ADD_INT) { red_add_u64(w, val); return; }
+  if (op == UPD_ADD_F64) { red_add_f64(w, __longlong_as_double((long long)val)); return; }
+  if (op == UPD_INC_VALID) { red_add_u64(w, 1); return; }
+  if (op == UPD_MIN_S64) { red_min_s64(w, (int64_t)val); return; }
+  if (op == UPD_MAX_S64) { red_max_s64(w, (int64_t)val); return; }
+  if (op == UPD_MIN_U64) { red_min_u64(w, val); return; }
+  if (op == UPD_MAX_U64) { red_max_u64(w, val); return; }
+  if (op == UPD_MIN_F64) { red_min_u64(w, f64_to_ordered(__longlong_as_double((long long)val))); return; }
+  red_max_u64(w, f64_to_ordered(__longlong_as_double((long long)val)));
 }
 
 // ---------------------------------------------------------------- fused kernel (GROUP BY)
-template <int NS, bool INDIRECT>
-__global__ void __launch_bounds__(kBlock, 4) filter_group_agg_kernel(const __grid_constant__ AggKernelParams p) {
-  const int64_t n_tiles = (p.n_rows + kTileRows - 1) / kTileRows;
-  uint32_t new_groups = 0;
+// Per tile of 1024 rows (8 warps x 128 rows):
+//   1. every input column is read once with 256-bit streaming loads (4 consecutive rows / thread);
+//   2. the predicate is evaluated in registers;
+//   3. each warp compacts its surviving rows into a warp-private shared-memory staging area
+//      (values of every slot, validity bits, row id), so that
+//   4. the table phase runs with all 32 lanes busy on surviving rows only: hash -> one probe
+//      load -> fire-and-forget RED per state word.
+// FAST: all columns are plain 8-byte device columns without validity, 32 B aligned, rows a
+// multiple of the tile, predicate absent or one integer Compare: straight-line loads, and the
+// next tile is prefetched into registers before the table phase so the stream overlaps the
+// L2 atomics.
+constexpr int kWarpsPerBlock = kBlock / 32;
+constexpr int kWarpRows = 32 * kRowsPerThread;  // 128 rows per warp and tile
+
+template <int NS>
+struct StageSmem {
+  uint64_t val[kWarpsPerBlock][NS][kWarpRows];
+  uint32_t row[kWarpsPerBlock][kWarpRows];
+  uint8_t vmask[kWarpsPerBlock][kWarpRows];
+};
+
+template <int NS>
+__device__ __forceinline__ void table_phase(const AggKernelParams& p, StageSmem<NS>& sm, int warp, int lane, int total,
+                                            uint32_t& new_groups) {
   const TableDev& t = p.table;
   const int64_t mask = t.cap - 1;
-  const uint64_t pol = make_policy_evict_first();
-
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t tile_base = tile * kTileRows;
-    RowVals vals[NS];
-    uint32_t vmask[NS];
-#pragma unroll
-    for (int s = 0; s < NS; ++s) load_slot<INDIRECT>(p.cols[s], tile_base, p.n_rows, p.row_index, pol, vals[s], vmask[s]);
-
-    const int64_t r0 = tile_base + (int64_t)kRowsPerThread * threadIdx.x;
-    uint32_t in_range = 0;
-#pragma unroll
-    for (int j = 0; j < kRowsPerThread; ++j)
-      if (r0 + j < p.n_rows) in_range |= 1u << j;
-    uint32_t sel = eval_predicate<NS>(p, vals, vmask, in_range);
-    if (sel == 0) continue;
-
-    // phase 1: slot + first probe for every selected row (independent L2 loads in flight)
-    uint64_t keys[kRowsPerThread];
-    int64_t slots[kRowsPerThread];
-    uint64_t first[kRowsPerThread];
-    const uint32_t kmask = pick_mask<NS>(vmask, p.key_slot);
-#pragma unroll
-    for (int j = 0; j < kRowsPerThread; ++j) {
-      keys[j] = pick<NS>(vals, p.key_slot, j);
-      slots[j] = (int64_t)(agg_hash_u64(keys[j]) & (uint64_t)mask);
-      first[j] = 0;
-      if ((sel >> j) & 1) {
-        bool special = keys[j] == kEmptyKey || !((kmask >> j) & 1);
-        if (!special) first[j] = ld_table_u64(entry_ptr(t, slots[j]));
-      }
+  for (int i0 = 0; i0 < total; i0 += 32) {
+    const int i = i0 + lane;
+    const bool act = i < total;
+    uint64_t key = 0;
+    uint32_t vm = 0;
+    if (act) {
+      key = sm.val[warp][p.key_slot][i];
+      vm = sm.vmask[warp][i];
     }
-    // phase 2 + 3: resolve the entry, then fire-and-forget the state updates
-#pragma unroll
-    for (int j = 0; j < kRowsPerThread; ++j) {
-      if (!((sel >> j) & 1)) continue;
+    const bool key_null = !((vm >> p.key_slot) & 1);
+    const bool special = key_null || key == kEmptyKey;
+    const int64_t slot = (int64_t)(agg_hash_u64(key) & (uint64_t)mask);
+    uint64_t first = 0;
+    if (act && !special) first = ld_table_u64(entry_ptr(t, slot));
+    if (act) {
       uint8_t* e;
-      if (!((kmask >> j) & 1)) {  // NULL group key -> dedicated entry (payload_row.rs NULL rules)
-        e = entry_ptr(t, t.cap + 1);
-        if (atomicExch((unsigned long long*)e, 1ULL) == kEmptyKey) ++new_groups;
-      } else if (keys[j] == kEmptyKey) {  // the key that equals the EMPTY sentinel
-        e = entry_ptr(t, t.cap);
+      if (special) {  // NULL key / key equal to the EMPTY sentinel live in two dedicated entries
+        e = entry_ptr(t, t.cap + (key_null ? 1 : 0));
         if (atomicExch((unsigned long long*)e, 1ULL) == kEmptyKey) ++new_groups;
       } else {
-        e = find_or_insert(t, keys[j], first[j], slots[j], new_groups);
+        e = find_or_insert(t, key, first, slot, new_groups);
       }
       if (e == nullptr) {
-        int64_t r = r0 + j;
         unsigned long long idx = atomicAdd(t.n_overflow, 1ULL);
-        if (t.overflow_rows) t.overflow_rows[idx] = INDIRECT ? p.row_index[r] : (uint32_t)r;
-        continue;
-      }
-      for (int u = 0; u < p.n_updates; ++u) {
-        const UpdateDev& ud = p.upd[u];
-        uint64_t val = pick<NS>(vals, ud.slot, j);
-        bool valid = (pick_mask<NS>(vmask, ud.slot) >> j) & 1;
-        apply_update(ud, e, val, valid);
+        if (t.overflow_rows) t.overflow_rows[idx] = sm.row[warp][i];
+      } else if (!(p.debug_flags & 1)) {
+        for (int u = 0; u < p.n_updates; ++u) {
+          const UpdateDev ud = p.upd[u];
+          apply_update(ud.op, e + 8 + 8 * ud.word, sm.val[warp][ud.slot][i], (vm >> ud.slot) & 1);
+        }
       }
     }
+    __syncwarp();
   }
+}
+
+// warp-inclusive scan of a small count
+__device__ __forceinline__ int warp_inclusive_scan(int v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int n = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += n;
+  }
+  return v;
+}
+
+template <int NS, bool FAST, bool INDIRECT>
+__global__ void __launch_bounds__(kBlock, 4) filter_group_agg_kernel(const __grid_constant__ AggKernelParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  StageSmem<NS>& sm = *reinterpret_cast<StageSmem<NS>*>(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_tiles = FAST ? p.n_rows / kTileRows : (p.n_rows + kTileRows - 1) / kTileRows;
+  uint32_t new_groups = 0;
+  const uint64_t pol = make_policy_evict_first();
+
+  RowVals vals[NS];
+  uint32_t vmask[NS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) vmask[s] = 0xF;
+
+  int64_t tile = blockIdx.x;
+  if (FAST && tile < n_tiles) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      u64x4 q = ld_stream_256((const char*)p.cols[s].data + (tile * kTileRows + (int64_t)kRowsPerThread * threadIdx.x) * 8);
+      vals[s].v[0] = q.x; vals[s].v[1] = q.y; vals[s].v[2] = q.z; vals[s].v[3] = q.w;
+    }
+  }
+  for (; tile < n_tiles; tile += gridDim.x) {
+    __syncwarp();  // lanes must enter every tile together (divergent exits would serialise the warp)
+    const int64_t tile_base = tile * kTileRows;
+    const int64_t r0 = tile_base + (int64_t)kRowsPerThread * threadIdx.x;
+    uint32_t sel;
+    if (FAST) {
+      sel = 0xF;
+      if (p.n_nodes) {
+        const PredNodeDev& nd = p.nodes[0];
+#pragma unroll
+        for (int j = 0; j < kRowsPerThread; ++j)
+          if (!eval_cmp(nd, pick<NS>(vals, nd.l_slot, j), nd.r_const)) sel &= ~(1u << j);
+      }
+    } else {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) load_slot<INDIRECT>(p.cols[s], tile_base, p.n_rows, p.row_index, pol, vals[s], vmask[s]);
+      uint32_t in_range = 0;
+#pragma unroll
+      for (int j = 0; j < kRowsPerThread; ++j)
+        if (r0 + j < p.n_rows) in_range |= 1u << j;
+      sel = eval_predicate<NS>(p, vals, vmask, in_range);
+    }
+    // warp-level compaction of the surviving rows into shared memory
+    const int cnt = __popc(sel);
+    const int incl = warp_inclusive_scan(cnt, lane);
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0 || (p.debug_flags & 2)) {
+      if (p.debug_flags & 2) new_groups += cnt;
+      if (FAST) {
+        const int64_t nt = tile + gridDim.x;
+        if (nt < n_tiles) {
+#pragma unroll
+          for (int s = 0; s < NS; ++s) {
+            u64x4 q = ld_stream_256((const char*)p.cols[s].data + (nt * kTileRows + (int64_t)kRowsPerThread * threadIdx.x) * 8);
+            vals[s].v[0] = q.x; vals[s].v[1] = q.y; vals[s].v[2] = q.z; vals[s].v[3] = q.w;
+          }
+        }
+      }
+      continue;  // warp-uniform
+    }
+    int o = incl - cnt;
+#pragma unroll
+    for (int j = 0; j < kRowsPerThread; ++j) {
+      if ((sel >> j) & 1) {
+        uint32_t m = 0;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          sm.val[warp][s][o] = vals[s].v[j];
+          m |= ((vmask[s] >> j) & 1u) << s;
+        }
+        sm.vmask[warp][o] = (uint8_t)m;
+        sm.row[warp][o] = INDIRECT ? p.row_index[r0 + j] : (uint32_t)(r0 + j) + p.row_base;
+        ++o;
+      }
+    }
+    if (FAST) {  // prefetch the next tile: the loads fly while this warp works on the table
+      const int64_t nt = tile + gridDim.x;
+      if (nt < n_tiles) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          u64x4 q = ld_stream_256((const char*)p.cols[s].data + (nt * kTileRows + (int64_t)kRowsPerThread * threadIdx.x) * 8);
+          vals[s].v[0] = q.x; vals[s].v[1] = q.y; vals[s].v[2] = q.z; vals[s].v[3] = q.w;
+        }
+      }
+    }
+    __syncwarp();
+    table_phase<NS>(p, sm, warp, lane, total, new_groups);
+  }
+  __syncwarp();
   // one counter update per warp
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) new_groups += __shfl_xor_sync(0xffffffffu, new_groups, o);
-  if ((threadIdx.x & 31) == 0 && new_groups) atomicAdd(t.n_groups, (unsigned long long)new_groups);
+  if (lane == 0 && new_groups) atomicAdd(p.table.n_groups, (unsigned long long)new_groups);
 }
 
 // ---------------------------------------------------------------- fused kernel (no GROUP BY)
@@ -376,6 +479,7 @@ __global__ void __launch_bounds__(kBlock, 4) filter_single_agg_kernel(const __gr
   const uint64_t pol = make_policy_evict_first();
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    __syncwarp();
     const int64_t tile_base = tile * kTileRows;
     RowVals vals[NS];
     uint32_t vmask[NS];

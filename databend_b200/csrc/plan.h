@@ -110,7 +110,9 @@ struct AggKernelParams {
   int32_t n_slots, n_nodes, n_updates;
   int32_t key_slot;     // -1: no GROUP BY
   int32_t key_nullable; // key column may carry a validity bitmap
-  int32_t pad;
+  uint32_t row_base;    // added to in-launch row numbers when recording overflow rows
+  int32_t pad2;
+  int32_t debug_flags;  // perf bisecting only (env DBX_AGG_DEBUG): 1 = skip state updates, 2 = skip table probe
 };
 
 }  // namespace dbx

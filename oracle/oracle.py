@@ -117,7 +117,7 @@ def take(column: Column, sel: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
 def filter_block(block: DataBlock, pred: abi.Predicate) -> List[Tuple[np.ndarray, np.ndarray]]:
     """FilterExecutor::filter = select + take for every column."""
     sel = filter_select(block, pred)
-    return [take(c, sel) for c in block.columns]
+    return [take(c, sel) if c.dtype != abi.BOOL else None for c in block.columns]
 
 
 def _bits_to_array(bits: np.ndarray, dtype: int) -> np.ndarray:

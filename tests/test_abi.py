@@ -1,0 +1,63 @@
+"""The C-ABI library loads on a CPU-only box, exports every symbol include/dbx.h declares,
+and FAILS LOUDLY (no CPU fallback) when there is no GPU.  No compute calls are made here."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from databend_b200 import abi, build, lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    so = build.build()
+    assert os.path.exists(so)
+    L = lib.load()
+    with open(os.path.join(ROOT, "include", "dbx.h")) as f:
+        header = f.read()
+    declared = set(re.findall(r"^(?:int32_t|int64_t|const char\*)\s+(dbx_[a-z0-9_]+)\s*\(", header, flags=re.M))
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(L, name), f"libdbx.so does not export {name}"
+    assert set(abi.EXPORTS) == declared, set(abi.EXPORTS) ^ declared
+    assert L.dbx_abi_version() == abi.ABI_VERSION
+
+
+def test_struct_layouts_match_header_expectations():
+    # natural-alignment layouts of include/dbx.h (x86-64 / aarch64 LP64)
+    assert C.sizeof(abi.Scalar) == 16
+    assert C.sizeof(abi.Column) == 80
+    assert C.sizeof(abi.Block) == 40
+    assert C.sizeof(abi.Operand) == 32
+    assert C.sizeof(abi.PredNode) == 80
+    assert C.sizeof(abi.Predicate) == 8 + 16 * 80
+    assert C.sizeof(abi.AggDesc) == 8
+
+
+def test_no_gpu_means_loud_failure_not_cpu_fallback():
+    L = lib.load()
+    n = C.c_int32(-1)
+    st = L.dbx_device_count(C.byref(n))
+    if st == abi.OK:
+        pytest.skip("a GPU is present")
+    assert st == abi.ERR_NO_DEVICE
+    with pytest.raises(lib.DbxError) as ei:
+        lib.require_device()
+    assert "no CPU fallback" in str(ei.value)
+    # operator creation must fail too
+    from databend_b200.transforms import AggregatorParams, TransformPartialAggregate
+    with pytest.raises(lib.DbxError):
+        TransformPartialAggregate(AggregatorParams([0], [("sum", 1)]), [abi.I64, abi.I64])
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "databend_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cc")):
+                with open(os.path.join(dirpath, fn)) as f:
+                    src = f.read()
+                for pat in (r"^\s*(from|import)\s+oracle", r"libdbx_oracle", r"dbx_oracle\.h", r"\borc_[a-z_]+\s*\("):
+                    assert not re.search(pat, src, flags=re.M), f"{fn} uses the oracle ({pat})"
