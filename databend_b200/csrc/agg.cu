@@ -20,7 +20,7 @@ namespace {
 
 constexpr int64_t kChunkRows = 1LL << 28;        // rows per kernel launch (u32 overflow row ids)
 constexpr int64_t kDefaultTableBytes = 64 << 20; // default table = half of the 126 MB L2
-constexpr int kProbeLimit = 256;
+constexpr int kProbeLimit = 64;  // buckets (x4 slots)
 
 inline int grid_for_rows(int64_t n_rows) {
   int64_t tiles = (n_rows + kTileRows - 1) / kTileRows;
@@ -55,8 +55,6 @@ struct AggPlan {
   WordKinds kinds;
   int n_updates = 0;
   UpdateDev upd[kMaxUpdates];
-  int stride_shift = 4;
-
   FinalAgg fin[DBX_MAX_AGGS];  // out pointers filled at finalize time
 
   int slot_of(int col, ErrorSink* err) {
@@ -168,6 +166,12 @@ int32_t lower_cmp(AggPlan* pl, const dbx_pred_node& in, PredNodeDev* out, ErrorS
   }
   if (r.c.is_null) { out->kind = DBX_PRED_CONST; out->value = 0; return DBX_OK; }  // cmp with NULL is never true
   int rcls = dtype_class(r.c.dtype);
+  // `x % d = 0` / `x % d <> 0` on integers: exact divisibility test instead of a remainder
+  if (out->l_mod == 1 && lcls != VC_FLT && rcls != VC_FLT && r.c.v.u64 == 0 && (cmp == DBX_EQ || cmp == DBX_NE) &&
+      !pl->div_by_zero && !getenv("DBX_AGG_NO_DIVTEST")) {
+    out->mod = make_div_magic(out->mod.d);
+    out->l_mod = 2;
+  }
   if (lcls == VC_FLT) {
     out->cls = VC_FLT;
     out->r_const = scalar_bits(r.c, VC_FLT);
@@ -325,41 +329,38 @@ int32_t build_plan(const dbx_agg_params* p, const int32_t* types, int32_t n_cols
     if (n_cols == 0) { err->set("operator needs at least one input column"); return DBX_ERR_INVALID; }
     pl->slot_of(0, err);
   }
-  int bytes = 8 * (1 + pl->n_words);
-  pl->stride_shift = 4;
-  while ((1 << pl->stride_shift) < bytes) ++pl->stride_shift;
   return DBX_OK;
 }
 
 // ---------------------------------------------------------------- device table
 struct DeviceTable {
-  DevBuf buf;
+  DevBuf keys, states;
   DevBuf counters;  // [0] n_groups, [1] n_overflow
   int64_t cap = 0;
-  int stride_shift = 4;
   int n_words = 0;
 
   unsigned long long* n_groups() const { return (unsigned long long*)counters.p; }
   unsigned long long* n_overflow() const { return (unsigned long long*)counters.p + 1; }
+  size_t bytes() const { return (size_t)(cap + 2) * 8 * (1 + n_words); }
 
   int32_t create(int64_t capacity, const AggPlan& pl, cudaStream_t stream, ErrorSink* err) {
-    cap = capacity;
-    stride_shift = pl.stride_shift;
+    cap = capacity < 4 ? 4 : capacity;
     n_words = pl.n_words;
-    DBX_CUDA_TRY(*err, buf.ensure((size_t)(cap + 2) << stride_shift));
+    DBX_CUDA_TRY(*err, keys.ensure((size_t)(cap + 2) * 8 + 32));
+    DBX_CUDA_TRY(*err, states.ensure((size_t)(cap + 2) * 8 * n_words));
     DBX_CUDA_TRY(*err, counters.ensure(64));
     return clear(pl, stream, err);
   }
   int32_t clear(const AggPlan& pl, cudaStream_t stream, ErrorSink* err) {
     DBX_CUDA_TRY(*err, cudaMemsetAsync(counters.p, 0, 64, stream));
-    int64_t total_words = (cap + 2) << (stride_shift - 3);
-    int grid = (int)std::min<int64_t>((total_words + 255) / 256, (int64_t)kNumSMs * 16);
-    table_init_kernel<<<grid, 256, 0, stream>>>((uint8_t*)buf.p, cap + 2, stride_shift, n_words, pl.init);
+    int64_t total = (cap + 2) * (1 + n_words);
+    int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)kNumSMs * 16);
+    table_init_kernel<<<grid, 256, 0, stream>>>(view(nullptr), pl.init);
     count_launch();
     DBX_CUDA_TRY(*err, cudaGetLastError());
-    if (!pl.grouped) {  // the single state is entry 0 and always exists
+    if (!pl.grouped) {  // the single state is slot 0 (key 0) and always exists
       uint64_t zero = 0;
-      DBX_CUDA_TRY(*err, cudaMemcpyAsync(buf.p, &zero, 8, cudaMemcpyHostToDevice, stream));
+      DBX_CUDA_TRY(*err, cudaMemcpyAsync(keys.p, &zero, 8, cudaMemcpyHostToDevice, stream));
       unsigned long long one = 1;
       DBX_CUDA_TRY(*err, cudaMemcpyAsync(counters.p, &one, 8, cudaMemcpyHostToDevice, stream));
     }
@@ -367,16 +368,22 @@ struct DeviceTable {
   }
   TableDev view(uint32_t* overflow_rows) const {
     TableDev t;
-    t.base = (uint8_t*)buf.p;
+    t.keys = (uint64_t*)keys.p;
+    t.states = (uint64_t*)states.p;
     t.cap = cap;
-    t.stride_shift = stride_shift;
     t.n_words = n_words;
     t.n_groups = n_groups();
     t.n_overflow = n_overflow();
     t.overflow_rows = overflow_rows;
-    t.probe_limit = (int32_t)std::min<int64_t>(kProbeLimit, cap);
-    t.pad = 0;
+    t.probe_limit = (int32_t)std::min<int64_t>(kProbeLimit, cap >> 2);
     return t;
+  }
+  void swap(DeviceTable& o) {
+    std::swap(keys, o.keys);
+    std::swap(states, o.states);
+    std::swap(counters, o.counters);
+    std::swap(cap, o.cap);
+    std::swap(n_words, o.n_words);
   }
 };
 
@@ -409,9 +416,9 @@ class AggPartialOp : public Op {
     DBX_TRY(stager.init(dev, stream, &err));
     DBX_CUDA_TRY(err, host_counters.ensure(64));
     int64_t cap;
-    if (!plan.grouped) cap = 1;
+    if (!plan.grouped) cap = 4;
     else if (p->expected_groups > 0) cap = next_pow2(std::max<int64_t>(2 * p->expected_groups, 1024));
-    else cap = std::max<int64_t>(1024, kDefaultTableBytes >> plan.stride_shift);
+    else cap = std::max<int64_t>(1024, next_pow2(kDefaultTableBytes / (8 * (1 + plan.n_words)) + 1) / 2);
     initial_cap = cap;
     DBX_TRY(ensure_table());
     return DBX_OK;
@@ -420,7 +427,7 @@ class AggPartialOp : public Op {
   // (Re-)create or clear the table lazily: after a final operator adopted it, or after reset().
   int32_t ensure_table() {
     if (table_ready) return DBX_OK;
-    if (table.cap != initial_cap || !table.buf.p) DBX_TRY(table.create(initial_cap, plan, stream, &err));
+    if (table.cap != initial_cap || !table.keys.p) DBX_TRY(table.create(initial_cap, plan, stream, &err));
     else DBX_TRY(table.clear(plan, stream, &err));
     table_ready = true;
     groups_known = plan.grouped ? 0 : 1;
@@ -456,16 +463,14 @@ class AggPartialOp : public Op {
     count_launch();
     DBX_CUDA_TRY(err, cudaGetLastError());
     DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));  // old table is freed below
-    std::swap(table.buf, nt.buf);
-    std::swap(table.counters, nt.counters);
-    table.cap = new_cap;
+    table.swap(nt);
     return DBX_OK;
   }
 
   template <int NS, bool FAST, bool INDIRECT>
   int32_t launch_one(const AggKernelParams& kp) {
     static bool attr_set[16] = {};
-    const size_t smem = sizeof(StageSmem<NS>);
+    const size_t smem = sizeof(StageWarp<NS>) * kWarpsPerBlock;
     auto kern = filter_group_agg_kernel<NS, FAST, INDIRECT>;
     if (!attr_set[device]) {
       DBX_CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -586,7 +591,7 @@ class AggPartialOp : public Op {
       fill_params(&kp, cols, row0, m);
       if (!plan.grouped) {
         kp.table = table.view(nullptr);
-        kp.single_state = (unsigned long long*)((uint8_t*)table.buf.p + 8);
+        kp.single_state = (unsigned long long*)table.states.p;
         DBX_TRY(launch_single(kp));
         continue;
       }
@@ -685,7 +690,7 @@ class AggFinalOp : public Op {
 
   int32_t ensure_capacity(int64_t incoming) {
     if (!has_table) {
-      int64_t cap = plan.grouped ? next_pow2(std::max<int64_t>(1024, 2 * incoming)) : 1;
+      int64_t cap = plan.grouped ? next_pow2(std::max<int64_t>(1024, 2 * incoming)) : 4;
       DBX_TRY(table.create(cap, plan, stream, &err));
       has_table = true;
       return DBX_OK;
@@ -700,9 +705,7 @@ class AggFinalOp : public Op {
       count_launch();
       DBX_CUDA_TRY(err, cudaGetLastError());
       DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
-      std::swap(table.buf, nt.buf);
-      std::swap(table.counters, nt.counters);
-      table.cap = nt.cap;
+      table.swap(nt);
     }
     return DBX_OK;
   }
@@ -711,7 +714,7 @@ class AggFinalOp : public Op {
   int32_t merge_partial(AggPartialOp* part) {
     if (finished) { err.set("merge after finish"); return DBX_ERR_STATE; }
     if (part->device != device) { err.set("partial and final operators live on different devices"); return DBX_ERR_INVALID; }
-    if (part->plan.n_words != plan.n_words || part->plan.stride_shift != plan.stride_shift || part->plan.grouped != plan.grouped ||
+    if (part->plan.n_words != plan.n_words || part->plan.grouped != plan.grouped ||
         memcmp(&part->plan.kinds, &plan.kinds, sizeof(WordKinds)) != 0) {
       err.set("partial and final operators were created with different aggregate parameters");
       return DBX_ERR_INVALID;
@@ -726,11 +729,7 @@ class AggFinalOp : public Op {
       int32_t st = part->read_counters(&ng, &no);
       if (st != DBX_OK) { err.set(part->err.msg); return st; }
       if (no) { err.set("internal: rows were dropped by the partial table (overflow in safe mode)"); return DBX_ERR_CUDA; }
-      std::swap(table.buf, part->table.buf);
-      std::swap(table.counters, part->table.counters);
-      std::swap(table.cap, part->table.cap);
-      table.stride_shift = part->table.stride_shift;
-      table.n_words = part->table.n_words;
+      table.swap(part->table);
       has_table = true;
       part->table_ready = false;  // whatever buffer it now holds is re-created / cleared lazily
       return DBX_OK;

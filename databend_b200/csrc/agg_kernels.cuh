@@ -6,12 +6,16 @@
 //        group_hash_entries / HashIndex::probe_and_create     group_hash.rs:40, hash_index/index.rs:148-214
 //        accumulate_keys for sum / count / avg / min / max    aggregate_sum.rs:106-111, aggregate_count.rs:123-157,
 //                                                             aggregate_avg.rs:75-80
-// with ONE pass over HBM: each input column is read exactly once with 128-bit streaming
+// with ONE pass over HBM: each input column is read exactly once with 256-bit streaming
 // loads (evict-first), the predicate is evaluated in registers, and surviving rows update an
-// L2-resident open-addressing table with fire-and-forget `red.global` atomics.
+// L2-resident hash table with fire-and-forget `red.global` atomics.
 //
-// HBM-bound integer work: no tensor cores, no shared-memory staging of the stream (there is
-// no reuse); the levers are coalescing, bytes in flight, and keeping the table in L2.
+// HBM-bound integer work: no tensor cores; the levers are coalescing, bytes in flight,
+// keeping the table in L2, and keeping every lane busy in the table phase.
+//
+// Table layout (see TableDev in plan.h): like the reference's HashIndex (8 ctrl bytes per
+// group probed with one SIMD compare, hash_index/group.rs:24-55) the keys are probed a group
+// at a time — here a bucket of four 64-bit keys = one 32-byte sector = one 256-bit load.
 #pragma once
 #include "plan.h"
 
@@ -20,6 +24,8 @@ namespace dbx {
 constexpr int kBlock = 256;       // threads per CTA
 constexpr int kRowsPerThread = 4; // one 256-bit load per 8-byte column per tile
 constexpr int kTileRows = kBlock * kRowsPerThread;
+constexpr int kWarpsPerBlock = kBlock / 32;
+constexpr int kStageCap = 160;    // staged rows per warp: up to 31 carried over + 128 new
 
 struct RowVals {
   uint64_t v[kRowsPerThread];
@@ -61,68 +67,58 @@ __device__ __forceinline__ void load_slot(const DevCol& c, int64_t tile_base, in
   }
   const bool full = !INDIRECT && (r0 + kRowsPerThread <= n_rows);
   const char* base = (const char*)c.data;
-  switch (c.dtype) {
-    case DBX_I64: case DBX_U64: case DBX_F64: {
-      if (full && ((reinterpret_cast<uintptr_t>(base) & 31) == 0)) {
-        u64x4 q = ld_stream_256(base + r0 * 8);
-        out.v[0] = q.x; out.v[1] = q.y; out.v[2] = q.z; out.v[3] = q.w;
-      } else {
+  const int dt = c.dtype;
+  if (dt == DBX_I64 || dt == DBX_U64 || dt == DBX_F64) {
+    if (full && ((reinterpret_cast<uintptr_t>(base) & 31) == 0)) {
+      u64x4 q = ld_stream_256(base + r0 * 8);
+      out.v[0] = q.x; out.v[1] = q.y; out.v[2] = q.z; out.v[3] = q.w;
+    } else {
 #pragma unroll
-        for (int j = 0; j < kRowsPerThread; ++j) out.v[j] = rows[j] >= 0 ? ld_stream_u64(base + rows[j] * 8, pol) : 0;
-      }
-      break;
+      for (int j = 0; j < kRowsPerThread; ++j) out.v[j] = rows[j] >= 0 ? ld_stream_u64(base + rows[j] * 8, pol) : 0;
     }
-    case DBX_I32: case DBX_U32: case DBX_F32: {
-      uint32_t w[kRowsPerThread];
-      if (full && ((reinterpret_cast<uintptr_t>(base) & 15) == 0)) {
-        uint4 q = ld_stream_128(base + r0 * 4, pol);
-        w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
-      } else {
+  } else if (dt == DBX_I32 || dt == DBX_U32 || dt == DBX_F32) {
+    uint32_t w[kRowsPerThread];
+    if (full && ((reinterpret_cast<uintptr_t>(base) & 15) == 0)) {
+      uint4 q = ld_stream_128(base + r0 * 4, pol);
+      w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
+    } else {
 #pragma unroll
-        for (int j = 0; j < kRowsPerThread; ++j) w[j] = rows[j] >= 0 ? ld_stream_u32(base + rows[j] * 4, pol) : 0;
-      }
-#pragma unroll
-      for (int j = 0; j < kRowsPerThread; ++j)
-        out.v[j] = c.dtype == DBX_I32 ? widen<int32_t>((int32_t)w[j]) : (c.dtype == DBX_U32 ? (uint64_t)w[j] : f32_bits_to_f64_bits(w[j]));
-      break;
+      for (int j = 0; j < kRowsPerThread; ++j) w[j] = rows[j] >= 0 ? ld_stream_u32(base + rows[j] * 4, pol) : 0;
     }
-    case DBX_I16: case DBX_U16: {
-      uint16_t w[kRowsPerThread];
-      if (full && ((reinterpret_cast<uintptr_t>(base) & 7) == 0)) {
-        uint64_t q = ld_stream_u64(base + r0 * 2, pol);
 #pragma unroll
-        for (int j = 0; j < kRowsPerThread; ++j) w[j] = (uint16_t)(q >> (16 * j));
-      } else {
+    for (int j = 0; j < kRowsPerThread; ++j)
+      out.v[j] = dt == DBX_I32 ? widen<int32_t>((int32_t)w[j]) : (dt == DBX_U32 ? (uint64_t)w[j] : f32_bits_to_f64_bits(w[j]));
+  } else if (dt == DBX_I16 || dt == DBX_U16) {
+    uint16_t w[kRowsPerThread];
+    if (full && ((reinterpret_cast<uintptr_t>(base) & 7) == 0)) {
+      uint64_t q = ld_stream_u64(base + r0 * 2, pol);
 #pragma unroll
-        for (int j = 0; j < kRowsPerThread; ++j) w[j] = rows[j] >= 0 ? ld_stream_u16(base + rows[j] * 2, pol) : 0;
-      }
+      for (int j = 0; j < kRowsPerThread; ++j) w[j] = (uint16_t)(q >> (16 * j));
+    } else {
 #pragma unroll
-      for (int j = 0; j < kRowsPerThread; ++j) out.v[j] = c.dtype == DBX_I16 ? widen<int16_t>((int16_t)w[j]) : (uint64_t)w[j];
-      break;
+      for (int j = 0; j < kRowsPerThread; ++j) w[j] = rows[j] >= 0 ? ld_stream_u16(base + rows[j] * 2, pol) : 0;
     }
-    case DBX_I8: case DBX_U8: {
-      uint8_t w[kRowsPerThread];
-      if (full && ((reinterpret_cast<uintptr_t>(base) & 3) == 0)) {
-        uint32_t q = ld_stream_u32(base + r0, pol);
 #pragma unroll
-        for (int j = 0; j < kRowsPerThread; ++j) w[j] = (uint8_t)(q >> (8 * j));
-      } else {
+    for (int j = 0; j < kRowsPerThread; ++j) out.v[j] = dt == DBX_I16 ? widen<int16_t>((int16_t)w[j]) : (uint64_t)w[j];
+  } else if (dt == DBX_I8 || dt == DBX_U8) {
+    uint8_t w[kRowsPerThread];
+    if (full && ((reinterpret_cast<uintptr_t>(base) & 3) == 0)) {
+      uint32_t q = ld_stream_u32(base + r0, pol);
 #pragma unroll
-        for (int j = 0; j < kRowsPerThread; ++j) w[j] = rows[j] >= 0 ? ld_stream_u8(base + rows[j], pol) : 0;
-      }
+      for (int j = 0; j < kRowsPerThread; ++j) w[j] = (uint8_t)(q >> (8 * j));
+    } else {
 #pragma unroll
-      for (int j = 0; j < kRowsPerThread; ++j) out.v[j] = c.dtype == DBX_I8 ? widen<int8_t>((int8_t)w[j]) : (uint64_t)w[j];
-      break;
+      for (int j = 0; j < kRowsPerThread; ++j) w[j] = rows[j] >= 0 ? ld_stream_u8(base + rows[j], pol) : 0;
     }
-    case DBX_BOOL:
 #pragma unroll
-      for (int j = 0; j < kRowsPerThread; ++j)
-        out.v[j] = rows[j] >= 0 ? (uint64_t)bit_test((const uint8_t*)base, c.dbit_off + rows[j]) : 0;
-      break;
-    default:
+    for (int j = 0; j < kRowsPerThread; ++j) out.v[j] = dt == DBX_I8 ? widen<int8_t>((int8_t)w[j]) : (uint64_t)w[j];
+  } else if (dt == DBX_BOOL) {
 #pragma unroll
-      for (int j = 0; j < kRowsPerThread; ++j) out.v[j] = 0;
-      break;
+    for (int j = 0; j < kRowsPerThread; ++j)
+      out.v[j] = rows[j] >= 0 ? (uint64_t)bit_test((const uint8_t*)base, c.dbit_off + rows[j]) : 0;
+  } else {
+#pragma unroll
+    for (int j = 0; j < kRowsPerThread; ++j) out.v[j] = 0;
   }
   if (c.validity) {
     uint32_t m = 0;
@@ -170,6 +166,12 @@ __device__ __forceinline__ bool apply_cmp(int op, int c) {
 
 // One Compare node on one row.  a/b are the 64-bit images of the operands in class nd.cls.
 __device__ __forceinline__ bool eval_cmp(const PredNodeDev& nd, uint64_t a, uint64_t b) {
+  if (nd.l_mod == 2) {  // `x % d (= | <>) 0` on integers: exact divisibility test, no remainder needed
+    uint64_t ux = a;
+    if (nd.cls == VC_INT && (int64_t)a < 0) ux = (uint64_t)0 - a;
+    bool div = divisible_magic(ux, nd.mod);
+    return nd.cmp == DBX_EQ ? div : !div;
+  }
   int c;
   if (nd.cls == VC_INT) {
     int64_t x = (int64_t)a;
@@ -236,32 +238,45 @@ __device__ __forceinline__ uint32_t eval_predicate(const AggKernelParams& p, con
 }
 
 // ---------------------------------------------------------------- table
-__device__ __forceinline__ uint8_t* entry_ptr(const TableDev& t, int64_t slot) {
-  return t.base + ((uint64_t)slot << t.stride_shift);
+// 256-bit coherent load of one bucket (4 keys): goes to L2, the point of coherence of the CAS.
+__device__ __forceinline__ u64x4 ld_bucket(const uint64_t* p) {
+  u64x4 r;
+  asm volatile("ld.global.relaxed.gpu.L2::evict_last.v4.b64 {%0, %1, %2, %3}, [%4];"
+               : "=l"(r.x), "=l"(r.y), "=l"(r.z), "=l"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ int bucket_match(const u64x4& k, uint64_t key) {
+  return k.x == key ? 0 : (k.y == key ? 1 : (k.z == key ? 2 : (k.w == key ? 3 : -1)));
 }
 
-// HashIndex::find_or_insert (hash_index/index.rs:92-111) for one 64-bit key word.
-// Returns the entry pointer, or nullptr if the probe limit was hit (row goes to overflow).
-__device__ __noinline__ uint8_t* find_or_insert_slow(const TableDev& t, uint64_t key, uint64_t cur, int64_t slot,
-                                                     uint32_t& new_groups) {
-  const int64_t mask = t.cap - 1;
-  for (int probes = 0; probes < t.probe_limit; ++probes) {
-    uint8_t* e = entry_ptr(t, slot);
-    if (cur == key) return e;
-    if (cur == kEmptyKey) {
-      unsigned long long old = atomicCAS((unsigned long long*)e, (unsigned long long)kEmptyKey, (unsigned long long)key);
-      if (old == kEmptyKey) { ++new_groups; return e; }
-      if (old == key) return e;
+// HashIndex::find_or_insert (hash_index/index.rs:92-111) past the first probe: walks buckets
+// linearly; inserts into the first EMPTY position of the first non-full bucket with a CAS.
+// Returns the slot, or -1 if the probe limit was hit (the row then goes to the overflow list).
+__device__ __noinline__ int64_t find_or_insert_slow(const TableDev& t, uint64_t key, int64_t b, u64x4 kb,
+                                                    uint32_t& new_groups) {
+  const int64_t nb_mask = (t.cap >> 2) - 1;
+  int probes = 0, retries = 0;
+  while (probes < t.probe_limit) {
+    int m = bucket_match(kb, key);
+    if (m >= 0) return 4 * b + m;
+    int e = kb.x == kEmptyKey ? 0 : (kb.y == kEmptyKey ? 1 : (kb.z == kEmptyKey ? 2 : (kb.w == kEmptyKey ? 3 : -1)));
+    if (e >= 0 && retries < 64) {
+      unsigned long long old = atomicCAS((unsigned long long*)(t.keys + 4 * b + e), (unsigned long long)kEmptyKey,
+                                         (unsigned long long)key);
+      if (old == kEmptyKey) { ++new_groups; return 4 * b + e; }
+      if (old == key) return 4 * b + e;
+      ++retries;  // lost the race to another key: look at this bucket again
+      kb = ld_bucket(t.keys + 4 * b);
+      continue;
     }
-    slot = (slot + 1) & mask;
-    cur = ld_table_u64(entry_ptr(t, slot));
+    b = (b + 1) & nb_mask;
+    ++probes;
+    retries = 0;
+    kb = ld_bucket(t.keys + 4 * b);
   }
-  return nullptr;
-}
-__device__ __forceinline__ uint8_t* find_or_insert(const TableDev& t, uint64_t key, uint64_t first_probe_key,
-                                                   int64_t slot, uint32_t& new_groups) {
-  if (first_probe_key == key) return entry_ptr(t, slot);  // steady state: one probe, no call
-  return find_or_insert_slow(t, key, first_probe_key, slot, new_groups);
+  return -1;
 }
 
 __device__ __forceinline__ void apply_update(int op, void* w, uint64_t val, bool valid) {
@@ -278,87 +293,92 @@ __device__ __forceinline__ void apply_update(int op, void* w, uint64_t val, bool
   red_max_u64(w, f64_to_ordered(__longlong_as_double((long long)val)));
 }
 
+// Slot of a special key: the key equal to the EMPTY sentinel lives at slot cap, the NULL key
+// at slot cap + 1; keys[] there is a 0/1 "present" flag.
+__device__ __forceinline__ int64_t special_slot(const TableDev& t, bool key_null, uint32_t& new_groups) {
+  int64_t slot = t.cap + (key_null ? 1 : 0);
+  if (atomicExch((unsigned long long*)(t.keys + slot), 1ULL) == kEmptyKey) ++new_groups;
+  return slot;
+}
+
 // ---------------------------------------------------------------- fused kernel (GROUP BY)
 // Per tile of 1024 rows (8 warps x 128 rows):
 //   1. every input column is read once with 256-bit streaming loads (4 consecutive rows / thread);
 //   2. the predicate is evaluated in registers;
-//   3. each warp compacts its surviving rows into a warp-private shared-memory staging area
-//      (values of every slot, validity bits, row id), so that
-//   4. the table phase runs with all 32 lanes busy on surviving rows only: hash -> one probe
-//      load -> fire-and-forget RED per state word.
-// FAST: all columns are plain 8-byte device columns without validity, 32 B aligned, rows a
-// multiple of the tile, predicate absent or one integer Compare: straight-line loads, and the
-// next tile is prefetched into registers before the table phase so the stream overlaps the
-// L2 atomics.
-constexpr int kWarpsPerBlock = kBlock / 32;
-constexpr int kWarpRows = 32 * kRowsPerThread;  // 128 rows per warp and tile
-
+//   3. each warp appends its surviving rows to a warp-private shared-memory stage with ballot
+//      compaction (values of every slot, validity bits, row id);
+//   4. whenever >= 32 rows are staged the warp runs the table phase on exactly 32 of them, one
+//      per lane: hash -> one 256-bit bucket probe -> fire-and-forget RED per state word.
+//      Leftovers (< 32) are carried to the next tile, so no lane idles on filtered-out rows.
+// FAST: plain 8-byte device columns, no validity, 32 B aligned, whole tiles, at most one
+// Compare: straight-line loads, and the next tile is prefetched into registers before the
+// table phase so the HBM stream overlaps the L2 atomics.
 template <int NS>
-struct StageSmem {
-  uint64_t val[kWarpsPerBlock][NS][kWarpRows];
-  uint32_t row[kWarpsPerBlock][kWarpRows];
-  uint8_t vmask[kWarpsPerBlock][kWarpRows];
+struct StageWarp {
+  uint64_t val[NS][kStageCap];
+  uint32_t row[kStageCap];
+  uint8_t vm[kStageCap];
 };
 
-template <int NS>
-__device__ __forceinline__ void table_phase(const AggKernelParams& p, StageSmem<NS>& sm, int warp, int lane, int total,
-                                            uint32_t& new_groups) {
+template <int NS, bool FAST>
+__device__ __forceinline__ void table_phase32(const AggKernelParams& p, const StageWarp<NS>& sw, int first, int count,
+                                              int lane, uint32_t& new_groups) {
   const TableDev& t = p.table;
-  const int64_t mask = t.cap - 1;
-  for (int i0 = 0; i0 < total; i0 += 32) {
-    const int i = i0 + lane;
-    const bool act = i < total;
-    uint64_t key = 0;
-    uint32_t vm = 0;
-    if (act) {
-      key = sm.val[warp][p.key_slot][i];
-      vm = sm.vmask[warp][i];
-    }
-    const bool key_null = !((vm >> p.key_slot) & 1);
-    const bool special = key_null || key == kEmptyKey;
-    const int64_t slot = (int64_t)(agg_hash_u64(key) & (uint64_t)mask);
-    uint64_t first = 0;
-    if (act && !special) first = ld_table_u64(entry_ptr(t, slot));
-    if (act) {
-      uint8_t* e;
-      if (special) {  // NULL key / key equal to the EMPTY sentinel live in two dedicated entries
-        e = entry_ptr(t, t.cap + (key_null ? 1 : 0));
-        if (atomicExch((unsigned long long*)e, 1ULL) == kEmptyKey) ++new_groups;
-      } else {
-        e = find_or_insert(t, key, first, slot, new_groups);
-      }
-      if (e == nullptr) {
-        unsigned long long idx = atomicAdd(t.n_overflow, 1ULL);
-        if (t.overflow_rows) t.overflow_rows[idx] = sm.row[warp][i];
-      } else if (!(p.debug_flags & 1)) {
-        for (int u = 0; u < p.n_updates; ++u) {
-          const UpdateDev ud = p.upd[u];
-          apply_update(ud.op, e + 8 + 8 * ud.word, sm.val[warp][ud.slot][i], (vm >> ud.slot) & 1);
-        }
-      }
-    }
-    __syncwarp();
+  const int i = first + lane;
+  const bool act = lane < count;
+  uint64_t key = 0;
+  uint32_t vm = 0xFF;
+  if (act) {
+    key = sw.val[p.key_slot][i];
+    if (!FAST) vm = sw.vm[i];
   }
+  const bool key_null = !((vm >> p.key_slot) & 1);
+  const bool special = key_null || key == kEmptyKey;
+  const int64_t b = (int64_t)(agg_hash_u64(key) & (uint64_t)((t.cap >> 2) - 1));
+  u64x4 kb;
+  kb.x = kb.y = kb.z = kb.w = 0;
+  if (act && !special) kb = ld_bucket(t.keys + 4 * b);
+  if (act) {
+    int64_t slot;
+    if (special) {
+      slot = special_slot(t, key_null, new_groups);
+    } else {
+      int m = bucket_match(kb, key);
+      slot = m >= 0 ? 4 * b + m : find_or_insert_slow(t, key, b, kb, new_groups);
+    }
+    if (slot < 0) {
+      unsigned long long idx = atomicAdd(t.n_overflow, 1ULL);
+      if (t.overflow_rows) t.overflow_rows[idx] = sw.row[i];
+    } else if (!(p.debug_flags & 1)) {
+      uint64_t* w = t.states + slot * t.n_words;
+      for (int u = 0; u < p.n_updates; ++u) {
+        const UpdateDev ud = p.upd[u];
+        apply_update(ud.op, w + ud.word, sw.val[ud.slot][i], (vm >> ud.slot) & 1);
+      }
+    }
+  }
+  __syncwarp();
 }
 
-// warp-inclusive scan of a small count
-__device__ __forceinline__ int warp_inclusive_scan(int v, int lane) {
+template <int NS>
+__device__ __forceinline__ void prefetch_tile(const AggKernelParams& p, int64_t tile, RowVals (&vals)[NS]) {
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int n = __shfl_up_sync(0xffffffffu, v, o);
-    if (lane >= o) v += n;
+  for (int s = 0; s < NS; ++s) {
+    u64x4 q = ld_stream_256((const char*)p.cols[s].data + (tile * kTileRows + (int64_t)kRowsPerThread * threadIdx.x) * 8);
+    vals[s].v[0] = q.x; vals[s].v[1] = q.y; vals[s].v[2] = q.z; vals[s].v[3] = q.w;
   }
-  return v;
 }
 
 template <int NS, bool FAST, bool INDIRECT>
 __global__ void __launch_bounds__(kBlock, 4) filter_group_agg_kernel(const __grid_constant__ AggKernelParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  StageSmem<NS>& sm = *reinterpret_cast<StageSmem<NS>*>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  StageWarp<NS>& sw = reinterpret_cast<StageWarp<NS>*>(smem_raw)[warp];
   const int64_t n_tiles = FAST ? p.n_rows / kTileRows : (p.n_rows + kTileRows - 1) / kTileRows;
+  const uint32_t lt_mask = (1u << lane) - 1;
   uint32_t new_groups = 0;
   const uint64_t pol = make_policy_evict_first();
+  int n_staged = 0;  // warp-uniform
 
   RowVals vals[NS];
   uint32_t vmask[NS];
@@ -366,15 +386,9 @@ __global__ void __launch_bounds__(kBlock, 4) filter_group_agg_kernel(const __gri
   for (int s = 0; s < NS; ++s) vmask[s] = 0xF;
 
   int64_t tile = blockIdx.x;
-  if (FAST && tile < n_tiles) {
-#pragma unroll
-    for (int s = 0; s < NS; ++s) {
-      u64x4 q = ld_stream_256((const char*)p.cols[s].data + (tile * kTileRows + (int64_t)kRowsPerThread * threadIdx.x) * 8);
-      vals[s].v[0] = q.x; vals[s].v[1] = q.y; vals[s].v[2] = q.z; vals[s].v[3] = q.w;
-    }
-  }
+  if (FAST && tile < n_tiles) prefetch_tile<NS>(p, tile, vals);
   for (; tile < n_tiles; tile += gridDim.x) {
-    __syncwarp();  // lanes must enter every tile together (divergent exits would serialise the warp)
+    __syncwarp();  // lanes enter every tile together (diverged lanes would serialise the warp)
     const int64_t tile_base = tile * kTileRows;
     const int64_t r0 = tile_base + (int64_t)kRowsPerThread * threadIdx.x;
     uint32_t sel;
@@ -395,53 +409,37 @@ __global__ void __launch_bounds__(kBlock, 4) filter_group_agg_kernel(const __gri
         if (r0 + j < p.n_rows) in_range |= 1u << j;
       sel = eval_predicate<NS>(p, vals, vmask, in_range);
     }
-    // warp-level compaction of the surviving rows into shared memory
-    const int cnt = __popc(sel);
-    const int incl = warp_inclusive_scan(cnt, lane);
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    if (total == 0 || (p.debug_flags & 2)) {
-      if (p.debug_flags & 2) new_groups += cnt;
-      if (FAST) {
-        const int64_t nt = tile + gridDim.x;
-        if (nt < n_tiles) {
-#pragma unroll
-          for (int s = 0; s < NS; ++s) {
-            u64x4 q = ld_stream_256((const char*)p.cols[s].data + (nt * kTileRows + (int64_t)kRowsPerThread * threadIdx.x) * 8);
-            vals[s].v[0] = q.x; vals[s].v[1] = q.y; vals[s].v[2] = q.z; vals[s].v[3] = q.w;
-          }
-        }
-      }
-      continue;  // warp-uniform
-    }
-    int o = incl - cnt;
+    if (p.debug_flags & 2) sel = 0;
+    // ballot compaction: append the surviving rows behind the carried-over ones
 #pragma unroll
     for (int j = 0; j < kRowsPerThread; ++j) {
-      if ((sel >> j) & 1) {
+      const bool on = (sel >> j) & 1;
+      const uint32_t bal = __ballot_sync(0xffffffffu, on);
+      if (on) {
+        const int o = n_staged + __popc(bal & lt_mask);
         uint32_t m = 0;
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
-          sm.val[warp][s][o] = vals[s].v[j];
-          m |= ((vmask[s] >> j) & 1u) << s;
+          sw.val[s][o] = vals[s].v[j];
+          if (!FAST) m |= ((vmask[s] >> j) & 1u) << s;
         }
-        sm.vmask[warp][o] = (uint8_t)m;
-        sm.row[warp][o] = INDIRECT ? p.row_index[r0 + j] : (uint32_t)(r0 + j) + p.row_base;
-        ++o;
+        if (!FAST) sw.vm[o] = (uint8_t)m;
+        sw.row[o] = INDIRECT ? p.row_index[r0 + j] : (uint32_t)(r0 + j) + p.row_base;
       }
+      n_staged += __popc(bal);
     }
     if (FAST) {  // prefetch the next tile: the loads fly while this warp works on the table
       const int64_t nt = tile + gridDim.x;
-      if (nt < n_tiles) {
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-          u64x4 q = ld_stream_256((const char*)p.cols[s].data + (nt * kTileRows + (int64_t)kRowsPerThread * threadIdx.x) * 8);
-          vals[s].v[0] = q.x; vals[s].v[1] = q.y; vals[s].v[2] = q.z; vals[s].v[3] = q.w;
-        }
-      }
+      if (nt < n_tiles) prefetch_tile<NS>(p, nt, vals);
     }
     __syncwarp();
-    table_phase<NS>(p, sm, warp, lane, total, new_groups);
+    while (n_staged >= 32) {
+      n_staged -= 32;
+      table_phase32<NS, FAST>(p, sw, n_staged, 32, lane, new_groups);
+    }
   }
   __syncwarp();
+  if (n_staged > 0) table_phase32<NS, FAST>(p, sw, 0, n_staged, lane, new_groups);
   // one counter update per warp
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) new_groups += __shfl_xor_sync(0xffffffffu, new_groups, o);
@@ -452,31 +450,44 @@ __global__ void __launch_bounds__(kBlock, 4) filter_group_agg_kernel(const __gri
 // PartialSingleStateAggregator (transform_single_key.rs:93-141): a pure streaming reduce.
 // Per-thread accumulators -> warp shuffle -> one atomic per warp into the single state.
 __device__ __forceinline__ uint64_t upd_identity(int op) {
-  switch (op) {
-    case UPD_MIN_S64: return (uint64_t)INT64_MAX;
-    case UPD_MAX_S64: return (uint64_t)INT64_MIN;
-    case UPD_MIN_U64: case UPD_MIN_F64: return ~0ULL;
-    default: return 0;
-  }
+  if (op == UPD_MIN_S64) return (uint64_t)INT64_MAX;
+  if (op == UPD_MAX_S64) return (uint64_t)INT64_MIN;
+  if (op == UPD_MIN_U64 || op == UPD_MIN_F64) return ~0ULL;
+  return 0;
 }
 __device__ __forceinline__ uint64_t upd_combine(int op, uint64_t a, uint64_t b) {
-  switch (op) {
-    case UPD_ADD_F64: return (uint64_t)__double_as_longlong(__longlong_as_double((long long)a) + __longlong_as_double((long long)b));
-    case UPD_MIN_S64: return (uint64_t)min((int64_t)a, (int64_t)b);
-    case UPD_MAX_S64: return (uint64_t)max((int64_t)a, (int64_t)b);
-    case UPD_MIN_U64: case UPD_MIN_F64: return a < b ? a : b;
-    case UPD_MAX_U64: case UPD_MAX_F64: return a > b ? a : b;
-    default: return a + b;
-  }
+  if (op == UPD_ADD_F64) return (uint64_t)__double_as_longlong(__longlong_as_double((long long)a) + __longlong_as_double((long long)b));
+  if (op == UPD_MIN_S64) return (uint64_t)min((int64_t)a, (int64_t)b);
+  if (op == UPD_MAX_S64) return (uint64_t)max((int64_t)a, (int64_t)b);
+  if (op == UPD_MIN_U64 || op == UPD_MIN_F64) return a < b ? a : b;
+  if (op == UPD_MAX_U64 || op == UPD_MAX_F64) return a > b ? a : b;
+  return a + b;
+}
+__device__ __forceinline__ void merge_word(int op, void* w, uint64_t v) {
+  if (op == UPD_ADD_F64) { red_add_f64(w, __longlong_as_double((long long)v)); return; }
+  if (op == UPD_MIN_S64) { red_min_s64(w, (int64_t)v); return; }
+  if (op == UPD_MAX_S64) { red_max_s64(w, (int64_t)v); return; }
+  if (op == UPD_MIN_U64 || op == UPD_MIN_F64) { red_min_u64(w, v); return; }
+  if (op == UPD_MAX_U64 || op == UPD_MAX_F64) { red_max_u64(w, v); return; }
+  red_add_u64(w, v);
 }
 
 template <int NS>
 __global__ void __launch_bounds__(kBlock, 4) filter_single_agg_kernel(const __grid_constant__ AggKernelParams p) {
   const int64_t n_tiles = (p.n_rows + kTileRows - 1) / kTileRows;
-  uint64_t acc[kMaxUpdates];
-#pragma unroll
-  for (int u = 0; u < kMaxUpdates; ++u) acc[u] = u < p.n_updates ? upd_identity(p.upd[u].op) : 0;
+  __shared__ uint64_t s_acc[kWarpsPerBlock][kMaxUpdates];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint64_t pol = make_policy_evict_first();
+  // per-thread accumulators live in shared memory indexed by update (dynamic index without
+  // local-memory spills); one column of 32 lanes per warp would be too big, so each thread
+  // keeps its partials in registers for up to 4 updates and falls back to shared beyond that.
+  uint64_t acc0 = upd_identity(p.n_updates > 0 ? p.upd[0].op : 0);
+  uint64_t acc1 = upd_identity(p.n_updates > 1 ? p.upd[1].op : 0);
+  uint64_t acc2 = upd_identity(p.n_updates > 2 ? p.upd[2].op : 0);
+  uint64_t acc3 = upd_identity(p.n_updates > 3 ? p.upd[3].op : 0);
+  if (lane == 0)
+    for (int u = 0; u < kMaxUpdates; ++u) s_acc[warp][u] = upd_identity(u < p.n_updates ? p.upd[u].op : 0);
+  __syncwarp();
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     __syncwarp();
@@ -490,43 +501,41 @@ __global__ void __launch_bounds__(kBlock, 4) filter_single_agg_kernel(const __gr
 #pragma unroll
     for (int j = 0; j < kRowsPerThread; ++j)
       if (r0 + j < p.n_rows) in_range |= 1u << j;
-    uint32_t sel = eval_predicate<NS>(p, vals, vmask, in_range);
-#pragma unroll
-    for (int u = 0; u < kMaxUpdates; ++u) {
-      if (u >= p.n_updates) break;
-      const UpdateDev& ud = p.upd[u];
-      uint32_t m = sel & (ud.op == UPD_INC ? 0xFu : pick_mask<NS>(vmask, ud.slot));
+    const uint32_t sel = eval_predicate<NS>(p, vals, vmask, in_range);
+    for (int u = 0; u < p.n_updates; ++u) {
+      const UpdateDev ud = p.upd[u];
+      const uint32_t m = sel & (ud.op == UPD_INC ? 0xFu : pick_mask<NS>(vmask, ud.slot));
+      uint64_t part = upd_identity(ud.op);
 #pragma unroll
       for (int j = 0; j < kRowsPerThread; ++j) {
         if (!((m >> j) & 1)) continue;
         uint64_t val = pick<NS>(vals, ud.slot, j);
-        uint64_t x;
-        switch (ud.op) {
-          case UPD_INC: case UPD_INC_VALID: x = 1; break;
-          case UPD_MIN_F64: case UPD_MAX_F64: x = f64_to_ordered(__longlong_as_double((long long)val)); break;
-          default: x = val; break;
-        }
-        acc[u] = upd_combine(ud.op, acc[u], x);
+        uint64_t x = (ud.op == UPD_INC || ud.op == UPD_INC_VALID) ? 1
+                     : (ud.op == UPD_MIN_F64 || ud.op == UPD_MAX_F64) ? f64_to_ordered(__longlong_as_double((long long)val))
+                                                                       : val;
+        part = upd_combine(ud.op, part, x);
+      }
+      if (u == 0) acc0 = upd_combine(ud.op, acc0, part);
+      else if (u == 1) acc1 = upd_combine(ud.op, acc1, part);
+      else if (u == 2) acc2 = upd_combine(ud.op, acc2, part);
+      else if (u == 3) acc3 = upd_combine(ud.op, acc3, part);
+      else {  // rare: more than 4 state words — reduce across the warp right away
+        uint64_t a = part;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a = upd_combine(ud.op, a, __shfl_xor_sync(0xffffffffu, a, o));
+        if (lane == 0) s_acc[warp][u] = upd_combine(ud.op, s_acc[warp][u], a);
       }
     }
   }
-#pragma unroll
-  for (int u = 0; u < kMaxUpdates; ++u) {
-    if (u >= p.n_updates) break;
+  __syncwarp();
+  for (int u = 0; u < p.n_updates; ++u) {
     const int op = p.upd[u].op;
-    uint64_t a = acc[u];
+    uint64_t a = u == 0 ? acc0 : u == 1 ? acc1 : u == 2 ? acc2 : u == 3 ? acc3 : upd_identity(op);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) a = upd_combine(op, a, __shfl_xor_sync(0xffffffffu, a, o));
-    if ((threadIdx.x & 31) == 0) {
-      void* w = p.single_state + p.upd[u].word;
-      switch (op) {
-        case UPD_ADD_F64: red_add_f64(w, __longlong_as_double((long long)a)); break;
-        case UPD_MIN_S64: red_min_s64(w, (int64_t)a); break;
-        case UPD_MAX_S64: red_max_s64(w, (int64_t)a); break;
-        case UPD_MIN_U64: case UPD_MIN_F64: red_min_u64(w, a); break;
-        case UPD_MAX_U64: case UPD_MAX_F64: red_max_u64(w, a); break;
-        default: red_add_u64(w, a); break;
-      }
+    if (lane == 0) {
+      if (u >= 4) a = s_acc[warp][u];
+      merge_word(op, p.single_state + p.upd[u].word, a);
     }
   }
 }
@@ -535,17 +544,17 @@ __global__ void __launch_bounds__(kBlock, 4) filter_single_agg_kernel(const __gr
 struct WordInit {
   uint64_t w[kMaxWords];
 };
-__global__ void table_init_kernel(uint8_t* base, int64_t n_entries, int stride_shift, int n_words,
-                                   const __grid_constant__ WordInit init) {
-  const int words_per_entry = 1 << (stride_shift - 3);
-  int64_t total = n_entries * words_per_entry;
+__global__ void table_init_kernel(const __grid_constant__ TableDev t, const __grid_constant__ WordInit init) {
+  const int64_t n_slots = t.cap + 2;
+  const int64_t total = n_slots * (1 + t.n_words);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int w = (int)(i & (words_per_entry - 1));
-    uint64_t v = w == 0 ? kEmptyKey : (w - 1 < n_words ? init.w[w - 1] : 0);
-    ((uint64_t*)base)[i] = v;
+    if (i < n_slots) t.keys[i] = kEmptyKey;
+    else {
+      int64_t k = i - n_slots;
+      t.states[k] = init.w[k % t.n_words];
+    }
   }
 }
-
 
 // Kinds of state words, for merging two states of the same group
 // (batch_merge_states: aggregate_sum.rs:126-129, aggregate_avg.rs:82-86, count: += , min/max).
@@ -553,47 +562,31 @@ struct WordKinds {
   int32_t op[kMaxWords];  // UPD_ADD_INT (also counts), UPD_ADD_F64, UPD_MIN_*, UPD_MAX_* (ordered image for F64)
 };
 
-__device__ __forceinline__ void merge_word(int op, void* w, uint64_t v) {
-  switch (op) {
-    case UPD_ADD_F64: red_add_f64(w, __longlong_as_double((long long)v)); break;
-    case UPD_MIN_S64: red_min_s64(w, (int64_t)v); break;
-    case UPD_MAX_S64: red_max_s64(w, (int64_t)v); break;
-    case UPD_MIN_U64: case UPD_MIN_F64: red_min_u64(w, v); break;
-    case UPD_MAX_U64: case UPD_MAX_F64: red_max_u64(w, v); break;
-    default: red_add_u64(w, v); break;
-  }
-}
-
-// Resolve the destination entry of a (key, key_kind) pair. key_kind: 0 normal, 1 key == EMPTY
+// Resolve the destination slot of a (key, key_kind) pair. key_kind: 0 normal, 1 key == EMPTY
 // sentinel, 2 NULL key.
-__device__ __forceinline__ uint8_t* resolve_entry(const TableDev& t, uint64_t key, int key_kind, uint32_t& new_groups) {
-  if (key_kind != 0) {
-    uint8_t* e = entry_ptr(t, t.cap + (key_kind == 2 ? 1 : 0));
-    if (atomicExch((unsigned long long*)e, 1ULL) == kEmptyKey) ++new_groups;
-    return e;
-  }
-  int64_t slot = (int64_t)(agg_hash_u64(key) & (uint64_t)(t.cap - 1));
-  uint64_t first = ld_table_u64(entry_ptr(t, slot));
-  return find_or_insert(t, key, first, slot, new_groups);
+__device__ __forceinline__ int64_t resolve_slot(const TableDev& t, uint64_t key, int key_kind, uint32_t& new_groups) {
+  if (key_kind != 0) return special_slot(t, key_kind == 2, new_groups);
+  const int64_t b = (int64_t)(agg_hash_u64(key) & (uint64_t)((t.cap >> 2) - 1));
+  u64x4 kb = ld_bucket(t.keys + 4 * b);
+  int m = bucket_match(kb, key);
+  return m >= 0 ? 4 * b + m : find_or_insert_slow(t, key, b, kb, new_groups);
 }
 
 // AggregateHashTable::combine_payload (aggregate_hashtable.rs:349-380) / resize (:463-489):
-// every occupied entry of `src` is found-or-inserted in `dst` and its words merged.
-// One thread per source entry; entries that cannot be placed bump dst.n_overflow
-// (the host sizes dst so that this cannot happen, and checks).
+// every occupied slot of `src` is found-or-inserted in `dst` and its words merged.
 __global__ void table_merge_kernel(const __grid_constant__ TableDev src, const __grid_constant__ TableDev dst,
                                    const __grid_constant__ WordKinds kinds) {
   uint32_t new_groups = 0;
-  const int64_t n_entries = src.cap + 2;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_entries; i += (int64_t)gridDim.x * blockDim.x) {
-    const uint8_t* se = src.base + ((uint64_t)i << src.stride_shift);
-    uint64_t key = *(const uint64_t*)se;
+  const int64_t n_slots = src.cap + 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t key = src.keys[i];
     if (key == kEmptyKey) continue;
     int key_kind = i >= src.cap ? (int)(i - src.cap) + 1 : 0;
-    uint8_t* de = resolve_entry(dst, key, key_kind, new_groups);
-    if (!de) { atomicAdd(dst.n_overflow, 1ULL); continue; }
-    for (int w = 0; w < src.n_words; ++w) merge_word(kinds.op[w], de + 8 + 8 * w, *(const uint64_t*)(se + 8 + 8 * w));
+    int64_t d = resolve_slot(dst, key, key_kind, new_groups);
+    if (d < 0) { atomicAdd(dst.n_overflow, 1ULL); continue; }
+    for (int w = 0; w < src.n_words; ++w) merge_word(kinds.op[w], dst.states + d * dst.n_words + w, src.states[i * src.n_words + w]);
   }
+  __syncwarp();
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) new_groups += __shfl_xor_sync(0xffffffffu, new_groups, o);
   if ((threadIdx.x & 31) == 0 && new_groups) atomicAdd(dst.n_groups, (unsigned long long)new_groups);
@@ -603,7 +596,7 @@ __global__ void table_merge_kernel(const __grid_constant__ TableDev src, const _
 // Owner of a group = high 32 bits of agg_hash scaled to n_parts, i.e. radix partitioning on
 // the top hash bits like PartitionedPayload (partitioned_payload.rs:44-57) but for any n_parts.
 __device__ __forceinline__ int owner_of(uint64_t key, int key_kind, int n_parts) {
-  uint64_t h = key_kind == 2 ? kNullHashVal : agg_hash_u64(key);
+  uint64_t h = key_kind == 2 ? kNullHashVal : agg_hash_u64(key_kind == 1 ? kEmptyKey : key);
   return (int)(((h >> 32) * (uint64_t)n_parts) >> 32);
 }
 
@@ -612,9 +605,9 @@ __global__ void table_partition_count_kernel(const __grid_constant__ TableDev sr
   extern __shared__ unsigned int s_cnt[];
   for (int i = threadIdx.x; i < n_parts; i += blockDim.x) s_cnt[i] = 0;
   __syncthreads();
-  const int64_t n_entries = src.cap + 2;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_entries; i += (int64_t)gridDim.x * blockDim.x) {
-    uint64_t key = *(const uint64_t*)(src.base + ((uint64_t)i << src.stride_shift));
+  const int64_t n_slots = src.cap + 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t key = src.keys[i];
     if (key == kEmptyKey) continue;
     int key_kind = i >= src.cap ? (int)(i - src.cap) + 1 : 0;
     atomicAdd(&s_cnt[owner_of(key, key_kind, n_parts)], 1u);
@@ -628,17 +621,16 @@ __global__ void table_partition_scatter_kernel(const __grid_constant__ TableDev 
                                                unsigned long long* cursors /* pre-set to part offsets */,
                                                uint64_t* rows_out) {
   const int row_words = 2 + src.n_words;
-  const int64_t n_entries = src.cap + 2;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_entries; i += (int64_t)gridDim.x * blockDim.x) {
-    const uint8_t* se = src.base + ((uint64_t)i << src.stride_shift);
-    uint64_t key = *(const uint64_t*)se;
+  const int64_t n_slots = src.cap + 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t key = src.keys[i];
     if (key == kEmptyKey) continue;
     int key_kind = i >= src.cap ? (int)(i - src.cap) + 1 : 0;
     unsigned long long pos = atomicAdd(&cursors[owner_of(key, key_kind, n_parts)], 1ULL);
     uint64_t* r = rows_out + pos * row_words;
     r[0] = key_kind ? 0 : key;
     r[1] = (uint64_t)key_kind;
-    for (int w = 0; w < src.n_words; ++w) r[2 + w] = *(const uint64_t*)(se + 8 + 8 * w);
+    for (int w = 0; w < src.n_words; ++w) r[2 + w] = src.states[i * src.n_words + w];
   }
 }
 
@@ -649,10 +641,11 @@ __global__ void rows_merge_kernel(const uint64_t* rows, int64_t n_rows, const __
   const int row_words = 2 + dst.n_words;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += (int64_t)gridDim.x * blockDim.x) {
     const uint64_t* r = rows + i * row_words;
-    uint8_t* de = resolve_entry(dst, r[0], (int)r[1], new_groups);
-    if (!de) { atomicAdd(dst.n_overflow, 1ULL); continue; }
-    for (int w = 0; w < dst.n_words; ++w) merge_word(kinds.op[w], de + 8 + 8 * w, r[2 + w]);
+    int64_t d = resolve_slot(dst, r[0], (int)r[1], new_groups);
+    if (d < 0) { atomicAdd(dst.n_overflow, 1ULL); continue; }
+    for (int w = 0; w < dst.n_words; ++w) merge_word(kinds.op[w], dst.states + d * dst.n_words + w, r[2 + w]);
   }
+  __syncwarp();
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) new_groups += __shfl_xor_sync(0xffffffffu, new_groups, o);
   if ((threadIdx.x & 31) == 0 && new_groups) atomicAdd(dst.n_groups, (unsigned long long)new_groups);
@@ -679,26 +672,21 @@ struct FinalizeParams {
 };
 
 __device__ __forceinline__ void store_narrow(void* out, int64_t idx, int dtype, uint64_t bits) {
-  switch (dtype) {
-    case DBX_I8: case DBX_U8: ((uint8_t*)out)[idx] = (uint8_t)bits; break;
-    case DBX_I16: case DBX_U16: ((uint16_t*)out)[idx] = (uint16_t)bits; break;
-    case DBX_I32: case DBX_U32: ((uint32_t*)out)[idx] = (uint32_t)bits; break;
-    case DBX_F32: ((float*)out)[idx] = (float)__longlong_as_double((long long)bits); break;
-    default: ((uint64_t*)out)[idx] = bits; break;
-  }
+  if (dtype == DBX_I8 || dtype == DBX_U8) ((uint8_t*)out)[idx] = (uint8_t)bits;
+  else if (dtype == DBX_I16 || dtype == DBX_U16) ((uint16_t*)out)[idx] = (uint16_t)bits;
+  else if (dtype == DBX_I32 || dtype == DBX_U32) ((uint32_t*)out)[idx] = (uint32_t)bits;
+  else if (dtype == DBX_F32) ((float*)out)[idx] = (float)__longlong_as_double((long long)bits);
+  else ((uint64_t*)out)[idx] = bits;
 }
 
 __global__ void table_finalize_kernel(const __grid_constant__ TableDev src, const __grid_constant__ FinalizeParams fp) {
-  const int64_t n_entries = src.cap + 2;
-  const int64_t n_iter = (n_entries + (int64_t)gridDim.x * blockDim.x - 1) / ((int64_t)gridDim.x * blockDim.x);
+  const int64_t n_slots = src.cap + 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n_iter = (n_slots + stride - 1) / stride;
   for (int64_t it = 0; it < n_iter; ++it) {
-    int64_t i = it * (int64_t)gridDim.x * blockDim.x + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint8_t* se = nullptr;
+    int64_t i = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t key = kEmptyKey;
-    if (i < n_entries) {
-      se = src.base + ((uint64_t)i << src.stride_shift);
-      key = *(const uint64_t*)se;
-    }
+    if (i < n_slots) key = src.keys[i];
     bool occ = key != kEmptyKey;
     // warp-aggregated output slot allocation
     unsigned ballot = __ballot_sync(0xffffffffu, occ);
@@ -715,26 +703,22 @@ __global__ void table_finalize_kernel(const __grid_constant__ TableDev src, cons
       store_narrow(fp.out_key, o, fp.key_dtype, kb);
       if (fp.out_key_valid) fp.out_key_valid[o] = key_kind == 2 ? 0 : 1;
     }
+    const uint64_t* se = src.states + i * src.n_words;
     for (int a = 0; a < fp.n_aggs; ++a) {
       const FinalAgg& fa = fp.aggs[a];
-      uint64_t cnt = *(const uint64_t*)(se + 8 + 8 * fa.cnt_word);
-      uint64_t acc = fa.acc_word >= 0 ? *(const uint64_t*)(se + 8 + 8 * fa.acc_word) : 0;
+      uint64_t cnt = se[fa.cnt_word];
+      uint64_t acc = fa.acc_word >= 0 ? se[fa.acc_word] : 0;
       int cls = dtype_class(fa.arg_dtype);
-      switch (fa.kind) {
-        case DBX_AGG_COUNT: ((uint64_t*)fa.out)[o] = cnt; break;
-        case DBX_AGG_SUM: ((uint64_t*)fa.out)[o] = cnt ? acc : 0; break;
-        case DBX_AGG_AVG: {  // aggregate_avg.rs:88-96: value as f64 / count as f64
-          double num = cls == VC_FLT ? __longlong_as_double((long long)acc)
-                                     : (cls == VC_INT ? (double)(int64_t)acc : (double)acc);
-          ((double*)fa.out)[o] = cnt ? num / (double)cnt : 0.0;
-          break;
-        }
-        default: {  // min / max keep the argument type
-          uint64_t bits = acc;
-          if (cls == VC_FLT) bits = (uint64_t)__double_as_longlong(ordered_to_f64(acc));
-          store_narrow(fa.out, o, fa.arg_dtype, cnt ? bits : 0);
-          break;
-        }
+      if (fa.kind == DBX_AGG_COUNT) ((uint64_t*)fa.out)[o] = cnt;
+      else if (fa.kind == DBX_AGG_SUM) ((uint64_t*)fa.out)[o] = cnt ? acc : 0;
+      else if (fa.kind == DBX_AGG_AVG) {  // aggregate_avg.rs:88-96: value as f64 / count as f64
+        double num = cls == VC_FLT ? __longlong_as_double((long long)acc)
+                                   : (cls == VC_INT ? (double)(int64_t)acc : (double)acc);
+        ((double*)fa.out)[o] = cnt ? num / (double)cnt : 0.0;
+      } else {  // min / max keep the argument type
+        uint64_t bits = acc;
+        if (cls == VC_FLT) bits = (uint64_t)__double_as_longlong(ordered_to_f64(acc));
+        store_narrow(fa.out, o, fa.arg_dtype, cnt ? bits : 0);
       }
       if (fa.out_valid) fa.out_valid[o] = cnt ? 1 : 0;
     }

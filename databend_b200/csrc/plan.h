@@ -52,6 +52,29 @@ __host__ __device__ __forceinline__ int64_t smod_magic(int64_t x, const ModMagic
   return x < 0 ? -(int64_t)r : (int64_t)r;
 }
 
+// Exact divisibility test  d | n  without computing the remainder (Granlund–Montgomery /
+// Hacker's Delight 10-17): with d = d' 2^k, d' odd and inv = d'^-1 mod 2^64,
+//   d | n  <=>  rotr(n * inv, k) <= floor((2^64 - 1) / d).
+// Used for `x % d = 0` / `x % d <> 0`, the shape the configs filter on.
+inline ModMagic make_div_magic(uint64_t d) {
+  ModMagic mm;
+  int k = 0;
+  uint64_t dp = d;
+  while ((dp & 1) == 0) { dp >>= 1; ++k; }
+  uint64_t inv = dp;  // correct to 3 bits; each Newton step doubles the precision
+  for (int i = 0; i < 6; ++i) inv *= 2 - dp * inv;
+  mm.m = inv;
+  mm.sh1 = k;
+  mm.sh2 = 0;
+  mm.d = ~0ULL / d;
+  return mm;
+}
+__host__ __device__ __forceinline__ bool divisible_magic(uint64_t n, const ModMagic& mm) {
+  uint64_t q = n * mm.m;
+  q = (q >> mm.sh1) | (mm.sh1 ? (q << (64 - mm.sh1)) : 0);
+  return q <= mm.d;
+}
+
 // One flattened SelectExpr node (postfix).  CMP: lhs = slot (optional modulo), rhs = const or slot.
 struct PredNodeDev {
   int32_t kind;        // dbx_pred_kind
@@ -60,7 +83,7 @@ struct PredNodeDev {
   int32_t value;       // CONST value / BOOLCOL slot
   int32_t cls;         // comparison class (ValClass) after widening
   int32_t l_slot;
-  int32_t l_mod;       // 1: lhs = slot % mod
+  int32_t l_mod;       // 1: lhs = slot % mod; 2: divisibility test (slot % d  =/<>  0), mod = make_div_magic(d)
   int32_t r_slot;      // -1: rhs is r_const
   uint64_t r_const;    // bits in class `cls`
   double mod_f;        // FLT modulo divisor
@@ -82,21 +105,23 @@ struct UpdateDev {
   int32_t pad;
 };
 
-// Device hash table of group entries, AoS: [key:8][word0:8]...[word(nw-1):8] padded to `stride`
-// (a power of two >= 16) so that one group's key and states share 32 B sectors.
-// slots [0, cap) are open-addressed by agg_hash(key) & (cap-1); two extra entries hold the
-// key that collides with the EMPTY sentinel (index cap) and the NULL key (index cap + 1).
+// Device hash table of groups.
+//   keys[cap + 2]              cap = 4 * n_buckets (power of two); a bucket is 4 consecutive keys =
+//                              one 32-byte sector, probed with ONE 256-bit load; bucket of a key =
+//                              agg_hash(key) & (n_buckets - 1), linear probing over buckets;
+//                              keys[cap] / keys[cap + 1] are 0/1 "present" flags of the two special
+//                              groups: the key equal to the EMPTY sentinel, and the NULL key;
+//   states[(cap + 2) * n_words] state words of slot i at states[i * n_words ...].
 constexpr uint64_t kEmptyKey = 0x8000000000000000ULL;
 struct TableDev {
-  uint8_t* base;
-  int64_t cap;            // power of two
-  int32_t stride_shift;   // log2(stride bytes)
+  uint64_t* keys;
+  uint64_t* states;
+  int64_t cap;
   int32_t n_words;
+  int32_t probe_limit;             // buckets examined before a row is sent to the overflow list
   unsigned long long* n_groups;    // device counter: groups inserted so far
   unsigned long long* n_overflow;  // device counter
   uint32_t* overflow_rows;         // rows that could not be placed (nullptr: provably not needed)
-  int32_t probe_limit;
-  int32_t pad;
 };
 
 struct AggKernelParams {
