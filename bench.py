@@ -344,7 +344,7 @@ def run_dbx(args):
                    "parallelism": f"row-range x{world}" + ("" if world == 1 else " + NCCL all-to-all of partial groups")},
         "wall_ms_per_step": wall_ms, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "filter_group_agg_kernel<3,false>", "kernel_ms": k_ms,
+                     "traffic": None, "kernel": "filter_group_agg_kernel<3,FAST=1,INDIRECT=0>", "kernel_ms": k_ms,
                      "algorithmic_bytes_per_row": BYTES_PER_ROW, "peak_source": peak_src},
         "cpu_baseline": cpu, "e2e": e2e,
     }

@@ -123,7 +123,7 @@ class JoinParams(C.Structure):
         ("kind", C.c_int32),
         ("build_key_col", C.c_int32),
         ("probe_key_col", C.c_int32),
-        ("reserved", C.c_int32),
+        ("n_build_cols", C.c_int32),
         ("expected_build_rows", C.c_int64),
     ]
 

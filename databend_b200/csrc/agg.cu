@@ -789,7 +789,7 @@ class AggFinalOp : public Op {
     ob->device = device;
     const int64_t cap_rows = std::max<int64_t>(ng, 1);
     auto dev_alloc = [&](size_t bytes, void** p) -> int32_t {
-      DBX_CUDA_TRY(err, cudaMalloc(p, bytes ? bytes : 1));
+      DBX_CUDA_TRY(err, pool_alloc(device, stream, bytes, p));
       ob->dev_allocs.push_back(*p);
       return DBX_OK;
     };
@@ -874,14 +874,14 @@ class AggFinalOp : public Op {
       c.mem = DBX_MEM_HOST;
       size_t bytes = (size_t)dc.len * dtype_size(dc.dtype);
       void* hp = nullptr;
-      DBX_CUDA_TRY(err, cudaMallocHost(&hp, bytes ? bytes : 1));
+      DBX_CUDA_TRY(err, pinned_alloc(bytes, &hp));
       hb->host_allocs.push_back(hp);
       if (bytes) DBX_CUDA_TRY(err, cudaMemcpyAsync(hp, dc.data, bytes, cudaMemcpyDeviceToHost, stream));
       c.data = hp;
       if (dc.validity) {
         size_t vb = (size_t)(dc.len + 7) / 8;
         void* hv = nullptr;
-        DBX_CUDA_TRY(err, cudaMallocHost(&hv, vb ? vb : 1));
+        DBX_CUDA_TRY(err, pinned_alloc(vb, &hv));
         hb->host_allocs.push_back(hv);
         if (vb) DBX_CUDA_TRY(err, cudaMemcpyAsync(hv, dc.validity, vb, cudaMemcpyDeviceToHost, stream));
         c.validity = (const uint8_t*)hv;
@@ -953,13 +953,13 @@ int32_t dbx_agg_partial_partition(dbx_op* partial_op, int32_t n_parts, void** de
   const int rb = 8 * (2 + p->plan.n_words);
   *row_bytes = rb;
   void* rows = nullptr;
-  DBX_CUDA_TRY(p->err, cudaMalloc(&rows, (size_t)std::max<int64_t>(total, 1) * rb));
+  DBX_CUDA_TRY(p->err, pool_alloc(p->device, p->stream, (size_t)std::max<int64_t>(total, 1) * rb, &rows));
   DBX_CUDA_TRY(p->err, cudaMemcpyAsync(counts.p, cursors.data(), (size_t)n_parts * 8, cudaMemcpyHostToDevice, p->stream));
   table_partition_scatter_kernel<<<grid, 256, 0, p->stream>>>(tv, n_parts, (unsigned long long*)counts.p, (uint64_t*)rows);
   count_launch();
   DBX_CUDA_TRY(p->err, cudaGetLastError());
   DBX_CUDA_TRY(p->err, cudaStreamSynchronize(p->stream));
-  *dev_rows = rows;  // caller frees with dbx_device_free
+  *dev_rows = rows;  // caller frees with dbx_device_free (stream-ordered pool)
   return DBX_OK;
 }
 

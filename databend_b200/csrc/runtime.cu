@@ -2,11 +2,81 @@
 #include "runtime.h"
 
 #include <mutex>
+#include <unordered_map>
+#include <vector>
 
 namespace dbx {
 
 thread_local ErrorSink g_create_error;
 std::atomic<int64_t> g_launches{0};
+
+// ---------------------------------------------------------------- allocators
+namespace {
+std::mutex g_alloc_mu;
+cudaStream_t g_util_stream[64] = {};
+bool g_pool_ready[64] = {};
+std::unordered_map<void*, size_t> g_pinned_live;            // ptr -> size class
+std::unordered_map<size_t, std::vector<void*>> g_pinned_free;  // size class -> blocks
+
+cudaError_t ensure_pool(int device) {
+  if (g_pool_ready[device]) return cudaSuccess;
+  cudaMemPool_t pool;
+  cudaError_t e = cudaDeviceGetDefaultMemPool(&pool, device);
+  if (e != cudaSuccess) return e;
+  uint64_t thr = ~0ULL;
+  e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  if (e != cudaSuccess) return e;
+  e = cudaStreamCreateWithFlags(&g_util_stream[device], cudaStreamNonBlocking);
+  if (e != cudaSuccess) return e;
+  g_pool_ready[device] = true;
+  return cudaSuccess;
+}
+}  // namespace
+
+cudaError_t pool_alloc(int device, cudaStream_t stream, size_t bytes, void** out) {
+  {
+    std::lock_guard<std::mutex> lk(g_alloc_mu);
+    cudaError_t e = ensure_pool(device);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaMallocAsync(out, bytes ? bytes : 1, stream);
+}
+void pool_free(int device, void* p) {
+  if (!p) return;
+  cudaStream_t s;
+  {
+    std::lock_guard<std::mutex> lk(g_alloc_mu);
+    s = g_util_stream[device];
+  }
+  cudaFreeAsync(p, s);
+}
+cudaError_t pinned_alloc(size_t bytes, void** out) {
+  size_t cls = 4096;
+  while (cls < bytes) cls <<= 1;
+  {
+    std::lock_guard<std::mutex> lk(g_alloc_mu);
+    auto it = g_pinned_free.find(cls);
+    if (it != g_pinned_free.end() && !it->second.empty()) {
+      *out = it->second.back();
+      it->second.pop_back();
+      g_pinned_live[*out] = cls;
+      return cudaSuccess;
+    }
+  }
+  cudaError_t e = cudaMallocHost(out, cls);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(g_alloc_mu);
+  g_pinned_live[*out] = cls;
+  return cudaSuccess;
+}
+void pinned_free(void* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_alloc_mu);
+  auto it = g_pinned_live.find(p);
+  if (it == g_pinned_live.end()) { cudaFreeHost(p); return; }
+  g_pinned_free[it->second].push_back(p);
+  g_pinned_live.erase(it);
+}
 
 // ---------------------------------------------------------------- Stager
 int32_t Stager::init(int device, cudaStream_t stream, ErrorSink* err) {

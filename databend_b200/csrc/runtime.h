@@ -50,15 +50,25 @@ struct PinnedBuf {
   }
 };
 
+// Stream-ordered device allocations from the device's default memory pool (release threshold
+// raised so freed blocks are reused instead of returned to the driver): per-query result and
+// exchange buffers cost microseconds instead of a cudaMalloc/cudaFree round trip.
+cudaError_t pool_alloc(int device, cudaStream_t stream, size_t bytes, void** out);
+void pool_free(int device, void* p);
+// Cached pinned host allocations (cudaMallocHost is milliseconds per call): power-of-two size
+// classes, freed blocks are kept for reuse.
+cudaError_t pinned_alloc(size_t bytes, void** out);
+void pinned_free(void* p);
+
 // Library-owned output block: columns + the buffers that back them.
 struct OwnedBlock {
   std::vector<dbx_column> cols;
-  std::vector<void*> host_allocs;  // cudaMallocHost
-  std::vector<void*> dev_allocs;   // cudaMalloc
+  std::vector<void*> host_allocs;  // pinned_alloc
+  std::vector<void*> dev_allocs;   // pool_alloc
   int device = 0;
   ~OwnedBlock() {
-    for (void* p : host_allocs) cudaFreeHost(p);
-    for (void* p : dev_allocs) cudaFree(p);
+    for (void* p : host_allocs) pinned_free(p);
+    for (void* p : dev_allocs) pool_free(device, p);
   }
 };
 

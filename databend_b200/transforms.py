@@ -236,6 +236,58 @@ class TransformFinalAggregate(_Op):
         return [] if b is None else [b]
 
 
+class TransformTopN(_Op):
+    """ORDER BY key LIMIT k: TransformSortPartial + limit-aware merge / TransformPartialTopN+FinalTopN
+    (sorts/sort_partial.rs:24-60, top_n/transform_partial_top_n.rs:73-130) as one streaming device
+    top-k.  SortColumnDescription{offset, asc, nulls_first} + LimitType::LimitRows(k)
+    (kernels/sort.rs:41-63).  The result block is [key column, row_id Int64] in output order; ties
+    are broken by ascending row id."""
+
+    def __init__(self, offset: int, asc: bool, nulls_first: bool, limit: int, input_types: Sequence[int], device: int = 0):
+        p = abi.TopkParams()
+        p.key_col, p.asc, p.nulls_first, p.limit = offset, int(asc), int(nulls_first), limit
+        super().__init__(abi.OP_TOPK, p, input_types, device)
+
+    def transform(self, block: DataBlock) -> List[DataBlock]:
+        self.push(block)
+        return []
+
+    def on_finish(self) -> DataBlock:
+        self.finish()
+        b = self.pull_c(abi.MEM_HOST)
+        return _block_from_c(b, self.device)
+
+
+class HashJoin(_Op):
+    """Inner hash join behind the reference's `Join` trait (new_hash_join/join.rs:26-53):
+    add_block(build block) / final_build() / probe_block(block) -> joined blocks.
+    Output columns = probe columns then build columns (inner_join.rs:236-245); output row order is
+    unspecified (compare as multisets)."""
+
+    def __init__(self, build_types: Sequence[int], probe_types: Sequence[int], build_key: int, probe_key: int,
+                 device: int = 0):
+        p = abi.JoinParams()
+        p.kind, p.build_key_col, p.probe_key_col, p.n_build_cols = 0, build_key, probe_key, len(build_types)
+        super().__init__(abi.OP_JOIN, p, list(build_types) + list(probe_types), device)
+
+    def add_block(self, block: DataBlock):
+        self.push(block)
+
+    def final_build(self):
+        self.finish()
+
+    def probe_block(self, block: DataBlock, out_mem: int = abi.MEM_HOST) -> List[DataBlock]:
+        b, keep = block.as_c()
+        check(load().dbx_join_probe(self._h, C.byref(b)), self._h)
+        out = []
+        while True:
+            ob = self.pull_c(out_mem)
+            if ob is None:
+                break
+            out.append(_block_from_c(ob, self.device) if out_mem == abi.MEM_HOST else ob)
+        return out
+
+
 def filter_group_aggregate(blocks: Sequence[DataBlock], params: AggregatorParams, filter_expr: Optional[E.Node] = None,
                            input_types: Optional[Sequence[int]] = None, device: int = 0,
                            n_partials: int = 1) -> DataBlock:

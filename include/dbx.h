@@ -193,7 +193,7 @@ typedef struct dbx_join_params {
   int32_t kind;          /* dbx_join_kind */
   int32_t build_key_col; /* key column index in build blocks */
   int32_t probe_key_col; /* key column index in probe blocks */
-  int32_t reserved;
+  int32_t n_build_cols;  /* dbx_op_create's input_types = build schema (n_build_cols) then probe schema */
   int64_t expected_build_rows; /* hint; 0 = unknown */
 } dbx_join_params;
 

@@ -1,0 +1,121 @@
+"""Parity of the streaming device top-k against the CPU oracle (ORDER BY key LIMIT k).
+
+Mirrors src/query/expression/tests/it/sort.rs:29-100 (golden) and the OrderedFloat total order
+(ordered_float.rs:147-201).  Bit-exact: the returned row ids must equal the oracle's, with ties
+broken by ascending row id on both sides."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from databend_b200 import abi
+from databend_b200.block import Column, DataBlock
+from databend_b200.transforms import TransformTopN, schema_types, to_device
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def oracle():
+    from oracle import oracle as orc
+    return orc
+
+
+def run_topk(col, asc, nulls_first, k, split=None, device_resident=False):
+    blk = DataBlock([col])
+    op = TransformTopN(0, asc, nulls_first, k, schema_types(blk))
+    blocks = blk.split_by_rows(split) if split else [blk]
+    for b in blocks:
+        if device_resident:
+            b = DataBlock([to_device(c) for c in b.columns], b.num_rows)
+        op.transform(b)
+    out = op.on_finish()
+    op.close()
+    ref = oracle().topk(col, asc, nulls_first, k)
+    got_rows = out.columns[1].values()
+    np.testing.assert_array_equal(got_rows, ref)
+    # the key column carries the original values of those rows
+    valid = col.valid_mask()[ref]
+    np.testing.assert_array_equal(out.columns[0].valid_mask() if col.validity is not None else np.ones(len(ref), bool), valid)
+    src = col.values()[ref]
+    got = out.columns[0].values()
+    if src.dtype.kind == "f":
+        np.testing.assert_array_equal(got[valid].view(np.uint64 if src.itemsize == 8 else np.uint32),
+                                      src[valid].view(np.uint64 if src.itemsize == 8 else np.uint32))
+    else:
+        np.testing.assert_array_equal(got[valid], src[valid])
+    return out
+
+
+def test_sort_goldens(gpu):
+    DT = {"I64": abi.I64}
+    with open(os.path.join(GOLD, "sort.json")) as f:
+        for c in json.load(f)["cases"]:
+            col = Column.from_data(c["values"], DT[c["dtype"]])
+            k = c["limit"] if c["limit"] is not None else len(c["values"])
+            out = run_topk(col, c["asc"], c["nulls_first"], k)
+            assert list(out.columns[1].values()) == c["rows"], c["src"]
+            assert list(out.columns[0].values()) == c["sorted"], c["src"]
+
+
+@pytest.mark.parametrize("n,k", [(1, 1), (10, 100), (1000, 10), (65536, 1000), (3_000_000, 1000)])
+@pytest.mark.parametrize("asc", [True, False])
+def test_config4_uniform_f64(gpu, n, k, asc):
+    x = oracle().synth_fill(3, 4242, 0, 0, n)
+    run_topk(Column.from_data(x), asc, False, k, split=65536 * 4)
+
+
+def test_device_resident_single_push(gpu):
+    x = oracle().synth_fill(3, 7, 0, 0, 5_000_000)
+    run_topk(Column.from_data(x), True, False, 1000, device_resident=True)
+
+
+def test_adversarial_floats(gpu):
+    """1% NaN, +-0, +-inf, heavy duplicates: key-sequence parity with row-id tiebreak."""
+    rng = np.random.default_rng(5)
+    n = 400_000
+    x = rng.integers(-50, 50, n).astype(np.float64) / 4.0
+    x[rng.random(n) < 0.01] = np.nan
+    x[rng.random(n) < 0.01] = -0.0
+    x[rng.random(n) < 0.001] = np.inf
+    x[rng.random(n) < 0.001] = -np.inf
+    for asc in (True, False):
+        run_topk(Column.from_data(x), asc, False, 1000, split=50_000)
+
+
+def test_sorted_inputs_worst_case(gpu):
+    """Descending input with ASC order: every row beats the boundary (worst case for the filter)."""
+    n = 600_000
+    x = np.arange(n, 0, -1).astype(np.float64)
+    run_topk(Column.from_data(x), True, False, 500, split=200_000)
+    run_topk(Column.from_data(x[::-1].copy()), True, False, 500)
+
+
+def test_nulls_first_and_last(gpu):
+    rng = np.random.default_rng(9)
+    n = 100_000
+    x = rng.normal(size=n)
+    valid = rng.random(n) > 0.001
+    for nulls_first in (True, False):
+        for asc in (True, False):
+            run_topk(Column.from_data(x, validity=valid), asc, nulls_first, 300, split=30_000)
+    # fewer non-null rows than k: NULLs fill the tail (nulls last) / the head (nulls first)
+    few = Column.from_data(x[:50], validity=[i % 5 != 0 for i in range(50)])
+    run_topk(few, True, False, 45)
+    run_topk(few, True, True, 45)
+
+
+@pytest.mark.parametrize("dtype", [abi.I8, abi.I16, abi.I32, abi.I64, abi.U8, abi.U32, abi.U64, abi.F32])
+def test_key_dtypes(gpu, dtype):
+    from databend_b200.block import np_dtype
+    rng = np.random.default_rng(dtype)
+    nd = np_dtype(dtype)
+    n = 200_000
+    if nd.kind == "f":
+        vals = rng.normal(size=n).astype(nd)
+    else:
+        info = np.iinfo(nd)
+        vals = rng.integers(info.min, info.max, n, dtype=nd, endpoint=True)
+    for asc in (True, False):
+        run_topk(Column.from_data(vals), asc, False, 777, split=64_000)
