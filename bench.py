@@ -144,6 +144,7 @@ def run_dbx(args):
     import torch.distributed as dist
     from databend_b200 import abi, build, lib
     from databend_b200.block import Column, DataBlock
+    from databend_b200.exchange import all_to_all_rows
     from databend_b200.transforms import (DeviceBuffer, TransformFinalAggregate, TransformPartialAggregate)
 
     build.build()
@@ -194,18 +195,12 @@ def run_dbx(args):
             lib.check(L.dbx_agg_partial_partition(part.handle, world, C.byref(rows_ptr), offs, C.byref(rb)), part.handle)
             row_bytes = rb.value
             send_counts = [offs[i + 1] - offs[i] for i in range(world)]
-            sc = torch.tensor(send_counts, dtype=torch.int64, device=f"cuda:{dev}")
-            rc = torch.empty_like(sc)
-            dist.all_to_all_single(rc, sc)
-            recv_counts = rc.tolist()
             total_send = offs[world]
             send = torch.empty(max(total_send, 1) * row_bytes, dtype=torch.uint8, device=f"cuda:{dev}")
             if total_send:
                 lib.check(L.dbx_memcpy_d2d(dev, send.data_ptr(), rows_ptr.value, total_send * row_bytes))
             lib.check(L.dbx_device_free(dev, rows_ptr))
-            recv = torch.empty(max(sum(recv_counts), 1) * row_bytes, dtype=torch.uint8, device=f"cuda:{dev}")
-            dist.all_to_all_single(recv[: sum(recv_counts) * row_bytes], send[: total_send * row_bytes],
-                                   [c * row_bytes for c in recv_counts], [c * row_bytes for c in send_counts])
+            recv, recv_counts = all_to_all_rows(send, send_counts, row_bytes)
             torch.cuda.current_stream().synchronize()
             fin.merge_rows(recv.data_ptr(), sum(recv_counts))
         return fin.on_finish(out_mem)

@@ -1,0 +1,62 @@
+"""Partial -> final exchange across GPUs: ONE variable-size all-to-all of partial group rows.
+
+Replaces the reference's cluster shuffle of aggregate partials
+(src/query/service/src/pipelines/processors/transforms/aggregator/build_partition_bucket.rs:41-131
+within a node, Arrow-Flight exchange between nodes: servers/flight/v1/exchange/*) with
+torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU tests): a count exchange followed by
+the payload exchange.  Only plumbing lives here; partitioning and merging are CUDA kernels behind
+dbx_agg_partial_partition / dbx_agg_final_merge_rows.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+_M64 = (1 << 64) - 1
+_NULL_HASH = 0xd1cefa08eb382d69
+_EMPTY_KEY = 0x8000000000000000
+
+
+def agg_hash_np(x: np.ndarray) -> np.ndarray:
+    """group_hash.rs:555-570 on a uint64 array (host restatement used by host-side tests)."""
+    x = x.astype(np.uint64).copy()
+    c = np.uint64(0xd6e8feb86659fd93)
+    s = np.uint64(32)
+    with np.errstate(over="ignore"):
+        x ^= x >> s
+        x *= c
+        x ^= x >> s
+        x *= c
+        x ^= x >> s
+    return x
+
+
+def owner_of(keys: np.ndarray, key_kind: np.ndarray, n_parts: int) -> np.ndarray:
+    """Owner rank of a group: top 32 hash bits scaled to n_parts (same rule as the device kernel
+    `owner_of` in csrc/agg_kernels.cuh; radix partitioning on hash bits like
+    partitioned_payload.rs:44-57 generalised to any partition count)."""
+    k = np.where(key_kind == 1, np.uint64(_EMPTY_KEY), keys.astype(np.uint64))
+    h = agg_hash_np(k)
+    h = np.where(key_kind == 2, np.uint64(_NULL_HASH), h)
+    return (((h >> np.uint64(32)) * np.uint64(n_parts)) >> np.uint64(32)).astype(np.int64)
+
+
+def all_to_all_rows(send: torch.Tensor, send_counts: Sequence[int], row_bytes: int, group=None) -> Tuple[torch.Tensor, List[int]]:
+    """Exchange fixed-width rows.  `send` is a uint8 tensor holding sum(send_counts) rows laid out
+    partition after partition; returns (recv uint8 tensor, recv_counts)."""
+    world = dist.get_world_size(group)
+    assert len(send_counts) == world
+    dev = send.device
+    sc = torch.tensor(list(send_counts), dtype=torch.int64, device=dev)
+    rc = torch.empty_like(sc)
+    dist.all_to_all_single(rc, sc, group=group)
+    recv_counts = [int(v) for v in rc.tolist()]
+    total_recv = sum(recv_counts)
+    recv = torch.empty(max(total_recv, 1) * row_bytes, dtype=torch.uint8, device=dev)
+    total_send = sum(send_counts)
+    dist.all_to_all_single(recv[: total_recv * row_bytes], send[: total_send * row_bytes],
+                           [c * row_bytes for c in recv_counts], [c * row_bytes for c in send_counts], group=group)
+    return recv, recv_counts

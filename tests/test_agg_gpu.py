@@ -286,3 +286,51 @@ def test_schema_mismatch_is_rejected(gpu):
         part.transform(DataBlock([blk.columns[0]]))
     with pytest.raises(DbxError):
         TransformPartialAggregate(AggregatorParams([0], [("median", 1)]), schema_types(blk))
+
+
+def test_partition_exchange_merge_simulated_ranks(gpu):
+    """The N>1 path on ONE GPU: N row-range partials -> hash-partition each into N owner runs ->
+    final r merges run r of every partial (what the NCCL all-to-all delivers) -> the union of the
+    finals equals the oracle.  Also checks the device owner rule against the host restatement."""
+    import ctypes as C
+    from databend_b200.exchange import owner_of
+    from databend_b200.lib import check, load
+    from databend_b200.transforms import DeviceBuffer
+    L = load()
+    world = 4
+    blk = config2_block(600_000, n_keys=40_000)
+    blk.columns[0].data[:7] = -(2**63)  # the sentinel-valued key travels through the exchange too
+    types = schema_types(blk)
+    parts, runs = [], []
+    for r in range(world):
+        lo, hi = blk.num_rows * r // world, blk.num_rows * (r + 1) // world
+        p = TransformPartialAggregate(CONFIG2, types, V_MOD3)
+        p.transform(blk.slice(lo, hi))
+        p.on_finish()
+        rows_ptr, offs, rb = C.c_void_p(), (C.c_int64 * (world + 1))(), C.c_int32(0)
+        check(L.dbx_agg_partial_partition(p.handle, world, C.byref(rows_ptr), offs, C.byref(rb)), p.handle)
+        total = offs[world]
+        host = np.empty(total * rb.value // 8, dtype=np.uint64)
+        check(L.dbx_memcpy_d2h(0, host.ctypes.data, rows_ptr, total * rb.value))
+        host = host.reshape(total, rb.value // 8)
+        for q in range(world):
+            seg = host[offs[q]:offs[q + 1]]
+            assert (owner_of(seg[:, 0], seg[:, 1], world) == q).all()
+        parts.append(p)
+        runs.append((rows_ptr, list(offs), rb.value))
+    outs = []
+    for q in range(world):
+        fin = TransformFinalAggregate(CONFIG2, types)
+        for (rows_ptr, offs, rb) in runs:
+            n = offs[q + 1] - offs[q]
+            fin.merge_rows(rows_ptr.value + offs[q] * rb, n)
+        outs.append(fin.on_finish()[0])
+        fin.close()
+    for (rows_ptr, _, _) in runs:
+        check(L.dbx_device_free(0, rows_ptr))
+    merged = DataBlock([Column.from_data(np.concatenate([o.columns[i].values() for o in outs]), outs[0].columns[i].dtype,
+                                         validity=np.concatenate([o.columns[i].valid_mask() for o in outs]))
+                        for i in range(4)])
+    g = sorted_group_result_from_block(merged, 3, 1)
+    o = sorted_group_result_from_oracle(oracle().filter_group_agg(blk, CONFIG2.to_c(V_MOD3), 4), [abi.I64])
+    assert_group_results_equal(g, o)
