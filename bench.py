@@ -37,6 +37,7 @@ METRIC = "rows/sec filter->hash-agg (sum,count,avg GROUP BY 1e6 int64 keys) over
 SEEDS = (42, 43, 44)
 N_KEYS = 1_000_000
 BYTES_PER_ROW = 24.0  # three 8-byte columns, each read exactly once
+NCU_TRAFFIC_PER_LAUNCH = 7.070684e9 + 0.526446e9  # bytes; one 2^28-row launch of the fused kernel (r01 capture)
 
 
 def peaks():
@@ -110,7 +111,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = orc.num_threads()
+    threads = len(os.sched_getaffinity(0))  # torchrun pins OMP_NUM_THREADS=1: ask for every host core explicitly
     n = args.cpu_rows
     params, filt = make_query()
     k = orc.synth_fill(0, SEEDS[0], N_KEYS, 0, n)
@@ -310,7 +311,7 @@ def run_dbx(args):
     cpu = None
     if world == 1 and not args.no_cpu:
         from oracle import oracle as orc
-        threads = orc.num_threads()
+        threads = len(os.sched_getaffinity(0))
         cn = args.cpu_rows
         k = orc.synth_fill(0, SEEDS[0], N_KEYS, 0, cn)
         v = orc.synth_fill(1, SEEDS[1], 0, 0, cn)
@@ -339,7 +340,8 @@ def run_dbx(args):
                    "parallelism": f"row-range x{world}" + ("" if world == 1 else " + NCCL all-to-all of partial groups")},
         "wall_ms_per_step": wall_ms, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "filter_group_agg_kernel<3,FAST=1,INDIRECT=0>", "kernel_ms": k_ms,
+                     "traffic": NCU_TRAFFIC_PER_LAUNCH, "traffic_note": "dram read+write per 2^28-row launch from profiles/r01_filter_group_agg_ncu_full.csv (ncu --set full)",
+                     "achieved_per_launch_bytes": BYTES_PER_ROW * min(n, 1 << 28), "kernel": "filter_group_agg_kernel<3,FAST=1,INDIRECT=0>", "kernel_ms": k_ms,
                      "algorithmic_bytes_per_row": BYTES_PER_ROW, "peak_source": peak_src},
         "cpu_baseline": cpu, "e2e": e2e,
     }
