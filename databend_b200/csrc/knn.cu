@@ -1,0 +1,605 @@
+// knn.cu — dbx_eval_distance (row-wise cosine_distance / l2_distance) and dbx_knn_* (brute-force
+// `ORDER BY distance(c, q) LIMIT k` for a batch of queries).
+//
+// Reference replaced (paths relative to /root/reference):
+//   cosine_distance / l2_distance            src/common/vector/src/distance.rs:19-35,65-80
+//   calculate_distance (row-wise driver)     src/query/functions/src/scalars/vector.rs:497-556
+//   EvalScalar -> TopN pipeline blocks/block_operator.rs:90-98 + top_n/*.rs
+//
+// kNN plan (one call = one batch of queries):
+//   1. corpus: bf16 copy + per-row scale, made once at dbx_knn_create and kept in HBM next to
+//      the f32 corpus;
+//   2. similarity GEMM on tensor cores in passes of geometrically growing corpus ranges; the
+//      epilogue keeps only entries that beat the per-query boundary (k'-th best so far, k' = 8k
+//      rounded up to 64), exactly like the top-k operator's boundary filter;
+//   3. between passes the candidate list is cut back to k' per query (radix sort by
+//      (query, similarity)), which tightens the boundaries;
+//   4. the surviving k' candidates per query are re-evaluated EXACTLY in f32 with the reference's
+//      evaluation order and sorted by (distance, row id): returned distances are bit-identical to
+//      the row-wise function, the bf16 GEMM only decides which rows get that far.
+#include <cuda.h>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <limits>
+
+#include "knn_kernels.cuh"
+#include "runtime.h"
+
+namespace dbx {
+
+namespace {
+
+inline int grid_1d(int64_t n, int block = 256) {
+  return (int)std::max<int64_t>(1, std::min<int64_t>((n + block - 1) / block, (int64_t)kNumSMs * 16));
+}
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// per query: [start, end) of its run in the sorted candidate keys
+__global__ void seg_bounds_kernel(const uint64_t* keys, int64_t n, int nq, int64_t* seg) {
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q <= nq; q += gridDim.x * blockDim.x) {
+    const uint64_t target = (uint64_t)q << 32;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+      int64_t mid = (lo + hi) >> 1;
+      if (keys[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    seg[q] = lo;
+  }
+}
+// keep the best k' of every query: compact them to the front (query after query) and publish the
+// new boundary (similarity of the k'-th, or -inf while a query has fewer than k' candidates)
+__global__ void retain_kernel(const uint64_t* keys, const uint32_t* rows, const int64_t* seg, int nq, int kprime,
+                              uint64_t* out_keys, uint32_t* out_rows, float* bound, unsigned long long* out_count) {
+  __shared__ int64_t s_off;
+  // single block: exclusive scan of min(len, k') by thread 0 is fine for nq <= 65536 queries
+  if (threadIdx.x == 0) s_off = 0;
+  __syncthreads();
+  for (int q0 = 0; q0 < nq; q0 += blockDim.x) {
+    const int q = q0 + threadIdx.x;
+    int64_t len = 0;
+    if (q < nq) len = min((int64_t)kprime, seg[q + 1] - seg[q]);
+    // block-wide exclusive scan via shared memory (blockDim <= 1024)
+    __shared__ int64_t s_len[1024];
+    s_len[threadIdx.x] = len;
+    __syncthreads();
+    int64_t off = s_off;
+    for (int i = 0; i < threadIdx.x; ++i) off += s_len[i];
+    if (q < nq) {
+      const int64_t src = seg[q];
+      for (int64_t j = 0; j < len; ++j) { out_keys[off + j] = keys[src + j]; out_rows[off + j] = rows[src + j]; }
+      float b = -INFINITY;
+      if (len == kprime) {
+        uint32_t o = ~(uint32_t)(keys[src + len - 1] & 0xFFFFFFFFu);
+        uint32_t bits = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+        b = __uint_as_float(bits);
+      }
+      bound[q] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int64_t tot = 0;
+      for (int i = 0; i < blockDim.x; ++i) tot += s_len[i];
+      s_off += tot;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out_count = (unsigned long long)s_off;
+}
+// exact f32 distance of every retained (query, row) pair
+__device__ __forceinline__ uint32_t dist_to_ordered32(float d) {  // OrderedFloat: NaN last, -0 == +0
+  if (d != d) return 0xFFFFFFFFu;
+  if (d == 0.0f) return 0x80000000u;
+  const uint32_t b = __float_as_uint(d);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__global__ void rerank_kernel(int kind, const float* queries, const float* corpus, int dim, const uint64_t* keys,
+                              const uint32_t* rows, int64_t n, uint64_t* out_keys, float* out_dist) {
+  if (kind == DBX_DIST_COSINE) {
+    const int lane = threadIdx.x & 31, g = lane >> 3;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t base = warp * 4; base < n; base += n_warps * 4) {
+      const int64_t i = base + g < n ? base + g : n - 1;
+      const uint32_t q = (uint32_t)(keys[i] >> 32);
+      const float d = exact_cosine_g8(corpus + (int64_t)rows[i] * dim, queries + (int64_t)q * dim, dim, lane);
+      if (base + g < n && (lane & 7) == 0) {
+        out_dist[i] = d;
+        out_keys[i] = ((uint64_t)q << 32) | dist_to_ordered32(d);
+      }
+    }
+    return;
+  }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t q = (uint32_t)(keys[i] >> 32);
+    const float d = exact_l2(corpus + (int64_t)rows[i] * dim, queries + (int64_t)q * dim, dim);
+    out_dist[i] = d;
+    out_keys[i] = ((uint64_t)q << 32) | dist_to_ordered32(d);  // ascending distance, NaN last (OrderedFloat)
+  }
+}
+// Certificate of exactness.  Every corpus row that is NOT among a query's candidates has an
+// approximate similarity <= bound[q]; the bf16 rounding of both operands changes a dot product
+// by at most 2^-7 * |q||c| (two relative errors of 2^-8, Cauchy-Schwarz), so such a row's exact
+// similarity is <= bound + E.  If the k-th returned row is better than that, the candidate set
+// provably contained the exact top k; otherwise the query is re-done on the exact path.
+__global__ void certify_kernel(int kind, int nq, int k, int kk, const int64_t* seg, const float* bound, const float* q_scale,
+                               const unsigned int* max_norm_bits, const float* out_dist, uint8_t* flags) {
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+    const int64_t m = seg[q + 1] - seg[q];
+    bool ok;
+    if (m < kk) ok = false;
+    else if (kk == 0) ok = true;
+    else if (bound[q] == -INFINITY) ok = true;  // every row with a finite similarity is a candidate
+    else {
+      const float dk = out_dist[(int64_t)q * k + kk - 1];
+      if (kind == DBX_DIST_COSINE) {
+        ok = (1.0f - dk) >= bound[q] + 0.0079f;
+      } else {
+        const float qq = q_scale[q], cmax = __uint_as_float(*max_norm_bits);
+        const float e = 0.015640f * sqrtf(qq) * cmax + 2e-5f * (qq + cmax * cmax);
+        ok = dk * dk * 1.00001f <= -bound[q] - e;
+      }
+    }
+    flags[q] = ok ? 0 : 1;
+  }
+}
+// exact path: keys of one query's distances to every corpus row
+__global__ void exact_keys_kernel(const float* dist, int64_t n, uint32_t* keys, uint32_t* rows) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    keys[i] = dist_to_ordered32(dist[i]);
+    rows[i] = (uint32_t)i;
+  }
+}
+__global__ void exact_emit_kernel(const uint32_t* sorted_rows, const float* dist, int kk, int k, int64_t* out_idx, float* out_dist) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < kk) { out_idx[j] = (int64_t)sorted_rows[j]; out_dist[j] = dist[sorted_rows[j]]; }
+  else if (j < k) { out_idx[j] = -1; out_dist[j] = nanf(""); }
+}
+__global__ void iota32_kernel(uint32_t* p, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = (uint32_t)i;
+}
+__global__ void gather_key_kernel(const uint64_t* src, const uint32_t* idx, uint64_t* dst, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[idx[i]];
+}
+__global__ void emit_topk_kernel(const uint64_t* sorted_keys, const uint32_t* perm, const uint32_t* rows, const float* dist,
+                                 const int64_t* seg, int nq, int k, int64_t* out_idx, float* out_dist) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nq * k; i += gridDim.x * blockDim.x) {
+    const int q = i / k, j = i % k;
+    const int64_t s = seg[q] + j;
+    if (s < seg[q + 1]) {
+      const uint32_t src = perm[s];
+      out_idx[i] = (int64_t)rows[src];
+      out_dist[i] = dist[src];
+    } else {
+      out_idx[i] = -1;
+      out_dist[i] = nanf("");
+    }
+  }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+// bf16 matrix [rows, dim_pad] row-major, box = [64 (K), box_rows], 128-byte swizzle
+bool make_tmap(CUtensorMap* m, const void* base, int64_t rows, int dim_pad, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)dim_pad, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)dim_pad * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kGemmBK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+}  // namespace dbx
+
+using namespace dbx;
+
+struct dbx_knn {
+  ErrorSink err;
+  int device = 0;
+  int kind = 0;
+  int dim = 0, dim_pad = 0;
+  int64_t n = 0;
+  cudaStream_t stream = nullptr;
+  const float* corpus = nullptr;  // f32 [n, dim] in HBM (borrowed if the caller passed device memory)
+  DevBuf corpus_own, corpus_bf16, c_scale;
+  // per-search scratch (grow-only)
+  DevBuf q_f32, q_bf16, q_scale, bound, seg, cand_key[2], cand_row[2], counters, perm[2], key_tmp, dist, cub_tmp;
+  DevBuf out_idx_dev, out_dist_dev, max_norm, flags, ex_dist, ex_key[2], ex_row[2], ex_tmp;
+  PinnedBuf host, host_flags;
+  int64_t stat_certified = 0, stat_exact = 0, stat_candidates = 0, stat_passes = 0;
+  int64_t cand_cap = 0;
+  int64_t last_gemm_launches = 0;
+  float last_gemm_ms = 0.f;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+// Exact answer for one query: distance to every corpus row (row-wise kernel, reference evaluation
+// order), stable radix sort by the OrderedFloat key (ties keep ascending row id), first k.
+static int32_t knn_exact_query(dbx_knn* h, int q, int k, int kk) {
+  ErrorSink& err = h->err;
+  cudaStream_t st = h->stream;
+  const int64_t n = h->n;
+  int64_t* oi = (int64_t*)h->out_idx_dev.p + (int64_t)q * k;
+  float* od = (float*)h->out_dist_dev.p + (int64_t)q * k;
+  if (n > 0) {
+    DBX_CUDA_TRY(err, h->ex_dist.ensure((size_t)n * 4));
+    for (int i = 0; i < 2; ++i) {
+      DBX_CUDA_TRY(err, h->ex_key[i].ensure((size_t)n * 4));
+      DBX_CUDA_TRY(err, h->ex_row[i].ensure((size_t)n * 4));
+    }
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                    (int)n, 0, 32, st);
+    DBX_CUDA_TRY(err, h->ex_tmp.ensure(tmp + 256));
+    distance_rows_kernel<<<grid_1d(h->kind == DBX_DIST_COSINE ? n * 8 : n, 128), 128, 0, st>>>(
+        h->kind, h->corpus, 0, (const float*)h->q_f32.p + (int64_t)q * h->dim, 1, n, h->dim, nullptr, 0, nullptr, 0, (float*)h->ex_dist.p, nullptr);
+    exact_keys_kernel<<<grid_1d(n), 256, 0, st>>>((const float*)h->ex_dist.p, n, (uint32_t*)h->ex_key[0].p, (uint32_t*)h->ex_row[0].p);
+    tmp = h->ex_tmp.bytes;
+    DBX_CUDA_TRY(err, cub::DeviceRadixSort::SortPairs(h->ex_tmp.p, tmp, (const uint32_t*)h->ex_key[0].p, (uint32_t*)h->ex_key[1].p,
+                                                      (const uint32_t*)h->ex_row[0].p, (uint32_t*)h->ex_row[1].p, (int)n, 0, 32, st));
+    count_launch(3);
+  }
+  exact_emit_kernel<<<(k + 255) / 256, 256, 0, st>>>((const uint32_t*)h->ex_row[1].p, (const float*)h->ex_dist.p, kk, k, oi, od);
+  count_launch();
+  DBX_CUDA_TRY(err, cudaGetLastError());
+  return DBX_OK;
+}
+
+extern "C" {
+
+const char* dbx_knn_last_error(const dbx_knn* h) { return h ? h->err.msg.c_str() : g_create_error.msg.c_str(); }
+
+int32_t dbx_knn_create(int32_t kind, int32_t device, const dbx_column* corpus, dbx_knn** out) {
+  if (!corpus || !out) { g_create_error.set("dbx_knn_create: null argument"); return DBX_ERR_INVALID; }
+  *out = nullptr;
+  if (kind != DBX_DIST_COSINE && kind != DBX_DIST_L2) { g_create_error.set("dbx_knn_create: unknown distance kind"); return DBX_ERR_INVALID; }
+  if (corpus->dtype != DBX_VEC_F32 || corpus->vec_dim <= 0) { g_create_error.set("dbx_knn_create: corpus must be a VECTOR(Float32) column"); return DBX_ERR_INVALID; }
+  if (corpus->validity) { g_create_error.set("dbx_knn_create: NULL vectors in the corpus are not supported yet"); return DBX_ERR_UNSUPPORTED; }
+  if (corpus->len >= (1LL << 31)) { g_create_error.set("dbx_knn_create: corpus too large for 32-bit row ids"); return DBX_ERR_UNSUPPORTED; }
+  int32_t ndev = 0;
+  DBX_TRY(dbx_device_count(&ndev));
+  std::unique_ptr<dbx_knn> h(new dbx_knn());
+  ErrorSink& err = g_create_error;
+  h->device = device; h->kind = kind; h->dim = corpus->vec_dim; h->dim_pad = round_up(corpus->vec_dim, kGemmBK); h->n = corpus->len;
+  DBX_CUDA_TRY(err, cudaSetDevice(device));
+  DBX_CUDA_TRY(err, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  DBX_CUDA_TRY(err, cudaEventCreate(&h->ev0));
+  DBX_CUDA_TRY(err, cudaEventCreate(&h->ev1));
+  const size_t bytes = (size_t)h->n * h->dim * 4;
+  if (corpus->mem == DBX_MEM_DEVICE) {
+    h->corpus = (const float*)corpus->data;
+  } else {
+    DBX_CUDA_TRY(err, h->corpus_own.ensure(bytes ? bytes : 4));
+    DBX_CUDA_TRY(err, cudaMemcpyAsync(h->corpus_own.p, corpus->data, bytes, cudaMemcpyHostToDevice, h->stream));
+    h->corpus = (const float*)h->corpus_own.p;
+  }
+  // the bf16 copy is padded by one GEMM tile of rows so that every TMA box stays inside the tensor
+  const int64_t n_alloc = h->n + kGemmBN;
+  DBX_CUDA_TRY(err, h->corpus_bf16.ensure((size_t)n_alloc * h->dim_pad * 2));
+  DBX_CUDA_TRY(err, cudaMemsetAsync(h->corpus_bf16.p, 0, (size_t)n_alloc * h->dim_pad * 2, h->stream));
+  DBX_CUDA_TRY(err, h->c_scale.ensure((size_t)n_alloc * 4));
+  DBX_CUDA_TRY(err, cudaMemsetAsync(h->c_scale.p, 0, (size_t)n_alloc * 4, h->stream));
+  DBX_CUDA_TRY(err, h->max_norm.ensure(4));
+  DBX_CUDA_TRY(err, cudaMemsetAsync(h->max_norm.p, 0, 4, h->stream));
+  if (h->n) {
+    prep_rows_kernel<<<grid_1d(h->n * 32), 256, 0, h->stream>>>(h->corpus, h->n, h->dim, h->dim_pad, (__nv_bfloat16*)h->corpus_bf16.p,
+                                                              (float*)h->c_scale.p, kind, (unsigned int*)h->max_norm.p);
+    count_launch();
+    DBX_CUDA_TRY(err, cudaGetLastError());
+  }
+  DBX_CUDA_TRY(err, h->counters.ensure(64));
+  DBX_CUDA_TRY(err, h->host.ensure(64));
+  DBX_CUDA_TRY(err, cudaStreamSynchronize(h->stream));
+  *out = h.release();
+  return DBX_OK;
+}
+
+int32_t dbx_knn_destroy(dbx_knn* h) {
+  if (!h) return DBX_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  delete h;
+  return DBX_OK;
+}
+
+int32_t dbx_knn_last_gemm_ms(dbx_knn* h, float* ms, int64_t* launches) {
+  if (!h) return DBX_ERR_INVALID;
+  if (ms) *ms = h->last_gemm_ms;
+  if (launches) *launches = h->last_gemm_launches;
+  return DBX_OK;
+}
+
+int32_t dbx_knn_search(dbx_knn* h, const dbx_column* queries, int32_t k, int32_t out_mem, int64_t* out_idx, float* out_dist) {
+  if (!h) return DBX_ERR_INVALID;
+  ErrorSink& err = h->err;
+  if (!queries || !out_idx || !out_dist || k <= 0) { err.set("dbx_knn_search: bad argument"); return DBX_ERR_INVALID; }
+  if (queries->dtype != DBX_VEC_F32 || queries->vec_dim != h->dim) { err.set("Vector length not equal: query dimension differs from the corpus"); return DBX_ERR_INVALID; }
+  if (queries->validity) { err.set("dbx_knn_search: NULL query vectors are not supported yet"); return DBX_ERR_UNSUPPORTED; }
+  if (k > 1024) { err.set("dbx_knn_search: k > 1024 is not supported"); return DBX_ERR_UNSUPPORTED; }
+  DBX_CUDA_TRY(err, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const int nq = (int)queries->len;
+  if (nq == 0) return DBX_OK;
+  if (nq > 65536) { err.set("dbx_knn_search: more than 65536 queries per batch"); return DBX_ERR_UNSUPPORTED; }
+  const int nq_pad = round_up(nq, kGemmBM);
+  const int dim = h->dim, dim_pad = h->dim_pad;
+  const int kprime = round_up(std::max(8 * k, 64), 64);
+
+  // ---- queries: f32 (exact re-rank) + bf16 + scale
+  DBX_CUDA_TRY(err, h->q_f32.ensure((size_t)nq_pad * dim * 4));
+  DBX_CUDA_TRY(err, h->q_bf16.ensure((size_t)nq_pad * dim_pad * 2));
+  DBX_CUDA_TRY(err, h->q_scale.ensure((size_t)nq_pad * 4));
+  DBX_CUDA_TRY(err, h->bound.ensure((size_t)nq_pad * 4));
+  DBX_CUDA_TRY(err, h->seg.ensure((size_t)(nq + 2) * 8));
+  DBX_CUDA_TRY(err, cudaMemsetAsync(h->q_f32.p, 0, (size_t)nq_pad * dim * 4, st));
+  DBX_CUDA_TRY(err, cudaMemcpyAsync(h->q_f32.p, queries->data, (size_t)nq * dim * 4,
+                                    queries->mem == DBX_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  prep_rows_kernel<<<grid_1d((int64_t)nq_pad * 32), 256, 0, st>>>((const float*)h->q_f32.p, nq_pad, dim, dim_pad, (__nv_bfloat16*)h->q_bf16.p,
+                                                                (float*)h->q_scale.p, h->kind, nullptr);
+  count_launch();
+  {
+    std::vector<float> ninf((size_t)nq_pad, -std::numeric_limits<float>::infinity());
+    DBX_CUDA_TRY(err, cudaMemcpyAsync(h->bound.p, ninf.data(), (size_t)nq_pad * 4, cudaMemcpyHostToDevice, st));
+    DBX_CUDA_TRY(err, cudaStreamSynchronize(st));
+  }
+
+  // ---- candidate storage
+  const int64_t want_cap = std::max<int64_t>(1 << 22, 4LL * nq * kprime);
+  if (want_cap > h->cand_cap) {
+    for (int i = 0; i < 2; ++i) {
+      DBX_CUDA_TRY(err, h->cand_key[i].ensure((size_t)want_cap * 8));
+      DBX_CUDA_TRY(err, h->cand_row[i].ensure((size_t)want_cap * 4));
+      DBX_CUDA_TRY(err, h->perm[i].ensure((size_t)want_cap * 4));
+    }
+    DBX_CUDA_TRY(err, h->key_tmp.ensure((size_t)want_cap * 8));
+    DBX_CUDA_TRY(err, h->dist.ensure((size_t)want_cap * 4));
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, (int)want_cap, 0, 64, st);
+    DBX_CUDA_TRY(err, h->cub_tmp.ensure(tmp + 256));
+    h->cand_cap = want_cap;
+  }
+  const int64_t cap = h->cand_cap;
+  unsigned long long* d_count = (unsigned long long*)h->counters.p;
+  DBX_CUDA_TRY(err, cudaMemsetAsync(d_count, 0, 8, st));
+  int cur = 0;           // candidates live in cand_*[cur][0..n_cand)
+  int64_t n_cand = 0;
+
+  auto select = [&]() -> int32_t {  // cut every query back to its best k', tighten boundaries
+    if (n_cand == 0) return DBX_OK;
+    size_t tmp = h->cub_tmp.bytes;
+    DBX_CUDA_TRY(err, cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tmp, (const uint64_t*)h->cand_key[cur].p, (uint64_t*)h->cand_key[cur ^ 1].p,
+                                                      (const uint32_t*)h->cand_row[cur].p, (uint32_t*)h->cand_row[cur ^ 1].p, (int)n_cand, 0, 64, st));
+    seg_bounds_kernel<<<grid_1d(nq + 1), 256, 0, st>>>((const uint64_t*)h->cand_key[cur ^ 1].p, n_cand, nq, (int64_t*)h->seg.p);
+    retain_kernel<<<1, 1024, 0, st>>>((const uint64_t*)h->cand_key[cur ^ 1].p, (const uint32_t*)h->cand_row[cur ^ 1].p, (const int64_t*)h->seg.p, nq,
+                                      kprime, (uint64_t*)h->cand_key[cur].p, (uint32_t*)h->cand_row[cur].p, (float*)h->bound.p, d_count);
+    count_launch(3);
+    DBX_CUDA_TRY(err, cudaGetLastError());
+    DBX_CUDA_TRY(err, cudaMemcpyAsync(h->host.p, d_count, 8, cudaMemcpyDeviceToHost, st));
+    DBX_CUDA_TRY(err, cudaStreamSynchronize(st));
+    n_cand = (int64_t)*(unsigned long long*)h->host.p;
+    return DBX_OK;
+  };
+
+  // ---- similarity passes over geometrically growing corpus ranges
+  CUtensorMap tmap_q, tmap_c;
+  const bool use_ref = getenv("DBX_KNN_REF_GEMM") != nullptr;
+  if (!use_ref) {
+    if (!make_tmap(&tmap_q, h->q_bf16.p, nq_pad, dim_pad, kGemmBM) || !make_tmap(&tmap_c, h->corpus_bf16.p, h->n + kGemmBN, dim_pad, kGemmBN)) {
+      err.set("cuTensorMapEncodeTiled failed (TMA descriptors for the similarity GEMM)");
+      return DBX_ERR_CUDA;
+    }
+    static bool attr = false;
+    if (!attr) {
+      DBX_CUDA_TRY(err, cudaFuncSetAttribute(knn_gemm_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(GemmSmem) + 1024)));
+      attr = true;
+    }
+  }
+  h->last_gemm_ms = 0.f;
+  h->last_gemm_launches = 0;
+  int64_t done = 0;
+  // first pass: small enough that even "everything passes" fits the candidate list
+  int64_t chunk = std::max<int64_t>(kGemmBN, std::min<int64_t>((cap / 2) / std::max(nq, 1) / kGemmBN * kGemmBN, 1 << 16));
+  while (done < h->n) {
+    const int64_t m = std::min<int64_t>(chunk, h->n - done);
+    KnnGemmParams gp;
+    memset(&gp, 0, sizeof(gp));
+    gp.kind = h->kind; gp.nq = nq; gp.nq_pad = nq_pad; gp.dim_pad = dim_pad; gp.n0 = done; gp.n_rows = m;
+    gp.q_scale = (const float*)h->q_scale.p; gp.c_scale = (const float*)h->c_scale.p; gp.bound = (const float*)h->bound.p;
+    gp.cand_key = (uint64_t*)h->cand_key[cur].p; gp.cand_row = (uint32_t*)h->cand_row[cur].p; gp.cand_count = d_count; gp.cand_cap = cap;
+    DBX_CUDA_TRY(err, cudaEventRecord(h->ev0, st));
+    if (use_ref) {
+      knn_ref_filter_kernel<<<grid_1d((int64_t)nq * m), 256, 0, st>>>((const __nv_bfloat16*)h->q_bf16.p, (const __nv_bfloat16*)h->corpus_bf16.p, gp);
+    } else {
+      const int64_t tiles = ((m + kGemmBN - 1) / kGemmBN) * (nq_pad / kGemmBM);
+      const int grid = (int)std::min<int64_t>(tiles, kNumSMs);
+      knn_gemm_filter_kernel<<<grid, kGemmThreads, sizeof(GemmSmem) + 1024, st>>>(tmap_q, tmap_c, gp);
+    }
+    count_launch();
+    DBX_CUDA_TRY(err, cudaGetLastError());
+    DBX_CUDA_TRY(err, cudaEventRecord(h->ev1, st));
+    DBX_CUDA_TRY(err, cudaMemcpyAsync(h->host.p, d_count, 8, cudaMemcpyDeviceToHost, st));
+    DBX_CUDA_TRY(err, cudaStreamSynchronize(st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    const int64_t cnt = (int64_t)*(unsigned long long*)h->host.p;
+    if (cnt > cap) {  // more survivors than the list holds: drop this pass, tighten, retry smaller
+      unsigned long long back = (unsigned long long)n_cand;
+      DBX_CUDA_TRY(err, cudaMemcpyAsync(d_count, &back, 8, cudaMemcpyHostToDevice, st));
+      DBX_TRY(select());
+      if (m <= kGemmBN) { err.set("kNN candidate list too small for one GEMM tile"); return DBX_ERR_CUDA; }
+      chunk = std::max<int64_t>(kGemmBN, (m / 4) / kGemmBN * kGemmBN);
+      continue;
+    }
+    h->last_gemm_ms += ms;
+    h->last_gemm_launches += 1;
+    h->stat_passes = h->last_gemm_launches;
+    n_cand = cnt;
+    done += m;
+    DBX_TRY(select());
+    chunk = std::min<int64_t>(chunk * 8, 1LL << 24);
+  }
+
+  // ---- exact re-rank of the k' survivors per query, ordered by (distance, row id)
+  DBX_CUDA_TRY(err, h->out_idx_dev.ensure((size_t)nq * k * 8));
+  DBX_CUDA_TRY(err, h->out_dist_dev.ensure((size_t)nq * k * 4));
+  if (n_cand > 0) {
+    size_t tmp = h->cub_tmp.bytes;
+    // stable pass 1: by row id; stable pass 2: by (query, exact distance)
+    rerank_kernel<<<grid_1d(n_cand), 256, 0, st>>>(h->kind, (const float*)h->q_f32.p, h->corpus, dim, (const uint64_t*)h->cand_key[cur].p,
+                                                   (const uint32_t*)h->cand_row[cur].p, n_cand, (uint64_t*)h->key_tmp.p, (float*)h->dist.p);
+    iota32_kernel<<<grid_1d(n_cand), 256, 0, st>>>((uint32_t*)h->perm[0].p, n_cand);
+    DBX_CUDA_TRY(err, cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tmp, (const uint32_t*)h->cand_row[cur].p, (uint32_t*)h->cand_row[cur ^ 1].p,
+                                                      (const uint32_t*)h->perm[0].p, (uint32_t*)h->perm[1].p, (int)n_cand, 0, 32, st));
+    gather_key_kernel<<<grid_1d(n_cand), 256, 0, st>>>((const uint64_t*)h->key_tmp.p, (const uint32_t*)h->perm[1].p, (uint64_t*)h->cand_key[cur ^ 1].p, n_cand);
+    tmp = h->cub_tmp.bytes;
+    DBX_CUDA_TRY(err, cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tmp, (const uint64_t*)h->cand_key[cur ^ 1].p, (uint64_t*)h->key_tmp.p,
+                                                      (const uint32_t*)h->perm[1].p, (uint32_t*)h->perm[0].p, (int)n_cand, 0, 64, st));
+    seg_bounds_kernel<<<grid_1d(nq + 1), 256, 0, st>>>((const uint64_t*)h->key_tmp.p, n_cand, nq, (int64_t*)h->seg.p);
+    count_launch(6);
+  } else {
+    DBX_CUDA_TRY(err, cudaMemsetAsync(h->seg.p, 0, (size_t)(nq + 2) * 8, st));
+  }
+  emit_topk_kernel<<<grid_1d((int64_t)nq * k), 256, 0, st>>>((const uint64_t*)h->key_tmp.p, (const uint32_t*)h->perm[0].p, (const uint32_t*)h->cand_row[cur].p,
+                                                            (const float*)h->dist.p, (const int64_t*)h->seg.p, nq, k, (int64_t*)h->out_idx_dev.p,
+                                                            (float*)h->out_dist_dev.p);
+  count_launch();
+  DBX_CUDA_TRY(err, cudaGetLastError());
+
+  // ---- certificate; queries that fail it are answered by the exact path
+  const int kk = (int)std::min<int64_t>(k, h->n);
+  DBX_CUDA_TRY(err, h->flags.ensure((size_t)nq));
+  DBX_CUDA_TRY(err, h->host_flags.ensure((size_t)nq));
+  certify_kernel<<<grid_1d(nq), 256, 0, st>>>(h->kind, nq, k, kk, (const int64_t*)h->seg.p, (const float*)h->bound.p, (const float*)h->q_scale.p,
+                                             (const unsigned int*)h->max_norm.p, (const float*)h->out_dist_dev.p, (uint8_t*)h->flags.p);
+  count_launch();
+  DBX_CUDA_TRY(err, cudaGetLastError());
+  DBX_CUDA_TRY(err, cudaMemcpyAsync(h->host_flags.p, h->flags.p, (size_t)nq, cudaMemcpyDeviceToHost, st));
+  DBX_CUDA_TRY(err, cudaStreamSynchronize(st));
+  h->stat_candidates = n_cand;
+  h->stat_exact = 0;
+  const uint8_t* hf = (const uint8_t*)h->host_flags.p;
+  const bool force_exact = getenv("DBX_KNN_FORCE_EXACT") != nullptr;
+  for (int q = 0; q < nq; ++q) {
+    if (!hf[q] && !force_exact) continue;
+    DBX_TRY(knn_exact_query(h, q, k, kk));
+    h->stat_exact += 1;
+  }
+  h->stat_certified = nq - h->stat_exact;
+
+  const cudaMemcpyKind ck = out_mem == DBX_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  DBX_CUDA_TRY(err, cudaMemcpyAsync(out_idx, h->out_idx_dev.p, (size_t)nq * k * 8, ck, st));
+  DBX_CUDA_TRY(err, cudaMemcpyAsync(out_dist, h->out_dist_dev.p, (size_t)nq * k * 4, ck, st));
+  DBX_CUDA_TRY(err, cudaStreamSynchronize(st));
+  return DBX_OK;
+}
+
+int32_t dbx_knn_last_stats(dbx_knn* h, int64_t* out8) {
+  if (!h || !out8) return DBX_ERR_INVALID;
+  memset(out8, 0, 8 * sizeof(int64_t));
+  out8[0] = h->stat_certified; out8[1] = h->stat_exact; out8[2] = h->stat_candidates; out8[3] = h->stat_passes;
+  return DBX_OK;
+}
+
+// ScalarFunction::eval for cosine_distance / l2_distance (scalars/vector.rs:263-281,497-556)
+int32_t dbx_eval_distance(int32_t kind, int32_t device, const dbx_column* lhs, const dbx_column* rhs, dbx_column* out) {
+  ErrorSink& err = g_create_error;
+  if (!lhs || !rhs || !out) { err.set("dbx_eval_distance: null argument"); return DBX_ERR_INVALID; }
+  if (kind != DBX_DIST_COSINE && kind != DBX_DIST_L2) { err.set("dbx_eval_distance: unknown distance kind"); return DBX_ERR_INVALID; }
+  if (lhs->dtype != DBX_VEC_F32 || rhs->dtype != DBX_VEC_F32) { err.set("dbx_eval_distance: arguments must be VECTOR(Float32)"); return DBX_ERR_INVALID; }
+  if (lhs->vec_dim != rhs->vec_dim) {  // distance.rs:20-26
+    err.set("Vector length not equal: " + std::to_string(lhs->vec_dim) + " != " + std::to_string(rhs->vec_dim));
+    return DBX_ERR_INVALID;
+  }
+  const int64_t rows = out->len;
+  if ((!lhs->is_const && lhs->len != rows) || (!rhs->is_const && rhs->len != rows)) { err.set("dbx_eval_distance: column lengths differ"); return DBX_ERR_INVALID; }
+  if (out->dtype != DBX_F32 || !out->data) { err.set("dbx_eval_distance: out must be a caller-provided Float32 column"); return DBX_ERR_INVALID; }
+  int32_t ndev = 0;
+  DBX_TRY(dbx_device_count(&ndev));
+  DBX_CUDA_TRY(err, cudaSetDevice(device));
+  if (rows == 0) return DBX_OK;
+  const int dim = lhs->vec_dim;
+  // const sides carry their single vector in `data` (len 1)
+  DevBuf la, ra, lvb, rvb, ob, ovb, obits;
+  auto to_dev = [&](const dbx_column* c, DevBuf& buf, const float** p) -> int32_t {
+    const size_t bytes = (size_t)(c->is_const ? 1 : c->len) * dim * 4;
+    if (c->is_const && (c->konst.is_null || !c->data)) {  // NULL constant: every output row is NULL
+      DBX_CUDA_TRY(err, buf.ensure(bytes));
+      DBX_CUDA_TRY(err, cudaMemset(buf.p, 0, bytes));
+      *p = (const float*)buf.p;
+      return DBX_OK;
+    }
+    if (c->mem == DBX_MEM_DEVICE) { *p = (const float*)c->data; return DBX_OK; }
+    DBX_CUDA_TRY(err, buf.ensure(bytes));
+    DBX_CUDA_TRY(err, cudaMemcpy(buf.p, c->data, bytes, cudaMemcpyHostToDevice));
+    *p = (const float*)buf.p;
+    return DBX_OK;
+  };
+  auto valid_to_dev = [&](const dbx_column* c, DevBuf& buf, const uint8_t** p, int64_t* off) -> int32_t {
+    *p = nullptr; *off = 0;
+    if (!c->validity || c->is_const) return DBX_OK;
+    if (c->mem == DBX_MEM_DEVICE) { *p = c->validity; *off = c->validity_bit_offset; return DBX_OK; }
+    const int64_t b0 = c->validity_bit_offset >> 3, b1 = (c->validity_bit_offset + c->len + 7) >> 3;
+    DBX_CUDA_TRY(err, buf.ensure((size_t)(b1 - b0) + 1));
+    DBX_CUDA_TRY(err, cudaMemcpy(buf.p, c->validity + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice));
+    *p = (const uint8_t*)buf.p; *off = c->validity_bit_offset & 7;
+    return DBX_OK;
+  };
+  const float *lp, *rp;
+  const uint8_t *lv, *rv;
+  int64_t lvo, rvo;
+  DBX_TRY(to_dev(lhs, la, &lp));
+  DBX_TRY(to_dev(rhs, ra, &rp));
+  DBX_TRY(valid_to_dev(lhs, lvb, &lv, &lvo));
+  DBX_TRY(valid_to_dev(rhs, rvb, &rv, &rvo));
+  const bool const_null = (lhs->is_const && (lhs->konst.is_null || !lhs->data)) || (rhs->is_const && (rhs->konst.is_null || !rhs->data));
+  float* op = (float*)out->data;
+  if (out->mem != DBX_MEM_DEVICE) { DBX_CUDA_TRY(err, ob.ensure((size_t)rows * 4)); op = (float*)ob.p; }
+  uint8_t* ovalid = nullptr;
+  const bool want_valid = out->validity != nullptr;
+  if (want_valid) { DBX_CUDA_TRY(err, ovb.ensure((size_t)rows)); ovalid = (uint8_t*)ovb.p; }
+  if ((lv || rv || const_null) && !want_valid) { err.set("dbx_eval_distance: nullable inputs need out->validity"); return DBX_ERR_INVALID; }
+  distance_rows_kernel<<<grid_1d(kind == DBX_DIST_COSINE ? rows * 8 : rows, 128), 128>>>(kind, lp, lhs->is_const, rp, rhs->is_const, rows, dim, lv, lvo, rv, rvo, op, ovalid);
+  count_launch();
+  DBX_CUDA_TRY(err, cudaGetLastError());
+  if (out->mem != DBX_MEM_DEVICE) DBX_CUDA_TRY(err, cudaMemcpy((void*)out->data, op, (size_t)rows * 4, cudaMemcpyDeviceToHost));
+  if (want_valid) {
+    std::vector<uint8_t> hb((size_t)rows);
+    DBX_CUDA_TRY(err, cudaMemcpy(hb.data(), ovalid, (size_t)rows, cudaMemcpyDeviceToHost));
+    std::vector<uint8_t> bits((size_t)(rows + 7) / 8, 0);
+    int64_t nulls = 0;
+    for (int64_t i = 0; i < rows; ++i) {
+      bool ok = hb[i] && !const_null;
+      if (ok) bits[i >> 3] |= (uint8_t)(1u << (i & 7)); else ++nulls;
+    }
+    if (out->mem == DBX_MEM_DEVICE) DBX_CUDA_TRY(err, cudaMemcpy((void*)out->validity, bits.data(), bits.size(), cudaMemcpyHostToDevice));
+    else memcpy((void*)out->validity, bits.data(), bits.size());
+    out->null_count = nulls;
+    out->validity_bit_offset = 0;
+  }
+  DBX_CUDA_TRY(err, cudaDeviceSynchronize());
+  return DBX_OK;
+}
+
+}  // extern "C"

@@ -68,6 +68,8 @@ def load():
         "dbx_knn_search": (i32, [vp, P(abi.Column), i32, i32, vp, vp]),
         "dbx_knn_destroy": (i32, [vp]),
         "dbx_knn_last_error": (C.c_char_p, [vp]),
+        "dbx_knn_last_gemm_ms": (i32, [vp, P(C.c_float), P(i64)]),
+        "dbx_knn_last_stats": (i32, [vp, P(i64)]),
         "dbx_synth_fill": (i32, [i32, i32, u64, i64, i64, i64, vp]),
         "dbx_kernel_launch_count": (i64, []),
         "dbx_op_last_kernel_ms": (i32, [vp, P(C.c_float)]),

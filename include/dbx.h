@@ -284,6 +284,12 @@ int32_t dbx_knn_create(int32_t kind, int32_t device, const dbx_column* corpus, d
 int32_t dbx_knn_search(dbx_knn* h, const dbx_column* queries, int32_t k, int32_t out_mem, int64_t* out_idx,
                        float* out_dist);
 int32_t dbx_knn_destroy(dbx_knn* h);
+/* Device time (ms, CUDA events) and launch count of the tensor-core similarity passes of the last search. */
+int32_t dbx_knn_last_gemm_ms(dbx_knn* h, float* ms, int64_t* launches);
+/* Instrumentation of the last search: out8[0] queries whose result the certificate proved exact,
+ * out8[1] queries answered by the exact (CUDA-core, row-wise) path, out8[2] candidates re-ranked,
+ * out8[3] similarity passes. */
+int32_t dbx_knn_last_stats(dbx_knn* h, int64_t* out8);
 const char* dbx_knn_last_error(const dbx_knn* h);
 
 /* Deterministic synthetic column generator (counter-based: splitmix64(seed + row)),
