@@ -22,6 +22,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <limits>
@@ -51,43 +52,62 @@ __global__ void seg_bounds_kernel(const uint64_t* keys, int64_t n, int nq, int64
   }
 }
 // keep the best k' of every query: compact them to the front (query after query) and publish the
-// new boundary (similarity of the k'-th, or -inf while a query has fewer than k' candidates)
-__global__ void retain_kernel(const uint64_t* keys, const uint32_t* rows, const int64_t* seg, int nq, int kprime,
-                              uint64_t* out_keys, uint32_t* out_rows, float* bound, unsigned long long* out_count) {
-  __shared__ int64_t s_off;
-  // single block: exclusive scan of min(len, k') by thread 0 is fine for nq <= 65536 queries
-  if (threadIdx.x == 0) s_off = 0;
+// new boundary (similarity of the k'-th, or -inf while a query has fewer than k' candidates).
+// Step 1 (one block): exclusive scan of min(len, k') over the queries -> off[q], total.
+__global__ void retain_scan_kernel(const int64_t* seg, int nq, int kprime, int64_t* off, unsigned long long* out_count) {
+  __shared__ int64_t s_warp[32];
+  __shared__ int64_t s_carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0;
   __syncthreads();
   for (int q0 = 0; q0 < nq; q0 += blockDim.x) {
     const int q = q0 + threadIdx.x;
-    int64_t len = 0;
-    if (q < nq) len = min((int64_t)kprime, seg[q + 1] - seg[q]);
-    // block-wide exclusive scan via shared memory (blockDim <= 1024)
-    __shared__ int64_t s_len[1024];
-    s_len[threadIdx.x] = len;
+    const int64_t len = q < nq ? min((int64_t)kprime, seg[q + 1] - seg[q]) : 0;
+    int64_t incl = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int64_t up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    int64_t off = s_off;
-    for (int i = 0; i < threadIdx.x; ++i) off += s_len[i];
-    if (q < nq) {
-      const int64_t src = seg[q];
-      for (int64_t j = 0; j < len; ++j) { out_keys[off + j] = keys[src + j]; out_rows[off + j] = rows[src + j]; }
+    if (warp == 0) {
+      int64_t w = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int64_t up = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += up;
+      }
+      s_warp[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const int64_t base = s_carry + (warp ? s_warp[warp - 1] : 0);
+    if (q < nq) off[q] = base + incl - len;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) s_carry = base + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { off[nq] = s_carry; *out_count = (unsigned long long)s_carry; }
+}
+// Step 2: one warp per query copies its survivors and writes the boundary.
+__global__ void retain_copy_kernel(const uint64_t* keys, const uint32_t* rows, const int64_t* seg, const int64_t* off, int nq, int kprime,
+                                   uint64_t* out_keys, uint32_t* out_rows, float* bound) {
+  const int lane = threadIdx.x & 31;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nq; q += n_warps) {
+    const int64_t src = seg[q], dst = off[q];
+    const int len = (int)(off[q + 1] - dst);
+    for (int j = lane; j < len; j += 32) { out_keys[dst + j] = keys[src + j]; out_rows[dst + j] = rows[src + j]; }
+    if (lane == 0) {
       float b = -INFINITY;
       if (len == kprime) {
-        uint32_t o = ~(uint32_t)(keys[src + len - 1] & 0xFFFFFFFFu);
-        uint32_t bits = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+        const uint32_t o = ~(uint32_t)(keys[src + len - 1] & 0xFFFFFFFFu);
+        const uint32_t bits = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
         b = __uint_as_float(bits);
       }
       bound[q] = b;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int64_t tot = 0;
-      for (int i = 0; i < blockDim.x; ++i) tot += s_len[i];
-      s_off += tot;
-    }
-    __syncthreads();
   }
-  if (threadIdx.x == 0) *out_count = (unsigned long long)s_off;
 }
 // exact f32 distance of every retained (query, row) pair
 __device__ __forceinline__ uint32_t dist_to_ordered32(float d) {  // OrderedFloat: NaN last, -0 == +0
@@ -158,6 +178,9 @@ __global__ void exact_emit_kernel(const uint32_t* sorted_rows, const float* dist
   if (j < kk) { out_idx[j] = (int64_t)sorted_rows[j]; out_dist[j] = dist[sorted_rows[j]]; }
   else if (j < k) { out_idx[j] = -1; out_dist[j] = nanf(""); }
 }
+__global__ void fill_f32_kernel(float* p, int64_t n, float v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
 __global__ void iota32_kernel(uint32_t* p, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = (uint32_t)i;
 }
@@ -222,15 +245,76 @@ struct dbx_knn {
   const float* corpus = nullptr;  // f32 [n, dim] in HBM (borrowed if the caller passed device memory)
   DevBuf corpus_own, corpus_bf16, c_scale;
   // per-search scratch (grow-only)
-  DevBuf q_f32, q_bf16, q_scale, bound, seg, cand_key[2], cand_row[2], counters, perm[2], key_tmp, dist, cub_tmp;
+  DevBuf q_f32, q_bf16, q_scale, bound, seg, seg_off, cand_key[2], cand_row[2], counters, perm[2], key_tmp, dist, cub_tmp;
   DevBuf out_idx_dev, out_dist_dev, max_norm, flags, ex_dist, ex_key[2], ex_row[2], ex_tmp;
   PinnedBuf host, host_flags;
-  int64_t stat_certified = 0, stat_exact = 0, stat_candidates = 0, stat_passes = 0;
+  int64_t stat_certified = 0, stat_exact = 0, stat_candidates = 0, stat_passes = 0, stat_cluster = 0, stat_grid = 0, stat_us_passes = 0, stat_us_rerank = 0;
   int64_t cand_cap = 0;
   int64_t last_gemm_launches = 0;
   float last_gemm_ms = 0.f;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
+
+// Launch plumbing of the similarity GEMM for a cluster size C in {1,2,4,8}.
+template <int C>
+static int32_t gemm_prepare_t(ErrorSink& err, int* max_clusters) {
+  static int cached = -1;
+  if (cached < 0) {
+    const int smem = (int)(sizeof(GemmSmem) + 1024);
+    DBX_CUDA_TRY(err, cudaFuncSetAttribute(knn_gemm_filter_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int n = kNumSMs / C;
+    if (C > 1) {
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(C * (kNumSMs / C));
+      cfg.blockDim = dim3(kGemmThreads);
+      cfg.dynamicSmemBytes = smem;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int q = 0;
+      DBX_CUDA_TRY(err, cudaOccupancyMaxActiveClusters(&q, knn_gemm_filter_kernel<C>, &cfg));
+      if (q < 1) { err.set("similarity GEMM: no co-resident cluster fits on this device"); return DBX_ERR_CUDA; }
+      n = std::min(n, q);
+    }
+    cached = n;
+  }
+  *max_clusters = cached;
+  return DBX_OK;
+}
+template <int C>
+static int32_t gemm_launch_t(ErrorSink& err, int n_clusters, cudaStream_t st, const CUtensorMap& tq, const CUtensorMap& tc, const KnnGemmParams& gp) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(n_clusters * C);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = sizeof(GemmSmem) + 1024;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  DBX_CUDA_TRY(err, cudaLaunchKernelEx(&cfg, knn_gemm_filter_kernel<C>, tq, tc, gp));
+  return DBX_OK;
+}
+static int32_t knn_gemm_prepare(ErrorSink& err, int cluster, int* max_clusters) {
+  switch (cluster) {
+    case 1: return gemm_prepare_t<1>(err, max_clusters);
+    case 2: return gemm_prepare_t<2>(err, max_clusters);
+    case 4: return gemm_prepare_t<4>(err, max_clusters);
+    default: return gemm_prepare_t<8>(err, max_clusters);
+  }
+}
+static int32_t knn_gemm_launch(ErrorSink& err, int cluster, int n_clusters, cudaStream_t st, const CUtensorMap& tq, const CUtensorMap& tc,
+                               const KnnGemmParams& gp) {
+  switch (cluster) {
+    case 1: return gemm_launch_t<1>(err, n_clusters, st, tq, tc, gp);
+    case 2: return gemm_launch_t<2>(err, n_clusters, st, tq, tc, gp);
+    case 4: return gemm_launch_t<4>(err, n_clusters, st, tq, tc, gp);
+    default: return gemm_launch_t<8>(err, n_clusters, st, tq, tc, gp);
+  }
+}
 
 // Exact answer for one query: distance to every corpus row (row-wise kernel, reference evaluation
 // order), stable radix sort by the OrderedFloat key (ties keep ascending row id), first k.
@@ -342,7 +426,18 @@ int32_t dbx_knn_search(dbx_knn* h, const dbx_column* queries, int32_t k, int32_t
   const int nq = (int)queries->len;
   if (nq == 0) return DBX_OK;
   if (nq > 65536) { err.set("dbx_knn_search: more than 65536 queries per batch"); return DBX_ERR_UNSUPPORTED; }
-  const int nq_pad = round_up(nq, kGemmBM);
+  // cluster size of the similarity GEMM (corpus tile multicast to `cluster` query blocks); must
+  // divide the number of 128-query blocks so that no padded query block is computed
+  int cluster = 1;
+  {
+    const int n_mblk = round_up(nq, kGemmBM) / kGemmBM;
+    if (n_mblk % 2 == 0) cluster = 2;  // measured on B200: 2 > 1 > 4 > 8 (larger clusters leave SMs idle)
+    if (const char* e = getenv("DBX_KNN_CLUSTER")) {
+      const int c = atoi(e);
+      if (c == 1 || c == 2 || c == 4 || c == 8) cluster = c;
+    }
+  }
+  const int nq_pad = round_up(nq, kGemmBM * cluster);
   const int dim = h->dim, dim_pad = h->dim_pad;
   const int kprime = round_up(std::max(8 * k, 64), 64);
 
@@ -352,17 +447,15 @@ int32_t dbx_knn_search(dbx_knn* h, const dbx_column* queries, int32_t k, int32_t
   DBX_CUDA_TRY(err, h->q_scale.ensure((size_t)nq_pad * 4));
   DBX_CUDA_TRY(err, h->bound.ensure((size_t)nq_pad * 4));
   DBX_CUDA_TRY(err, h->seg.ensure((size_t)(nq + 2) * 8));
+  DBX_CUDA_TRY(err, h->seg_off.ensure((size_t)(nq + 2) * 8));
   DBX_CUDA_TRY(err, cudaMemsetAsync(h->q_f32.p, 0, (size_t)nq_pad * dim * 4, st));
   DBX_CUDA_TRY(err, cudaMemcpyAsync(h->q_f32.p, queries->data, (size_t)nq * dim * 4,
                                     queries->mem == DBX_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
   prep_rows_kernel<<<grid_1d((int64_t)nq_pad * 32), 256, 0, st>>>((const float*)h->q_f32.p, nq_pad, dim, dim_pad, (__nv_bfloat16*)h->q_bf16.p,
                                                                 (float*)h->q_scale.p, h->kind, nullptr);
   count_launch();
-  {
-    std::vector<float> ninf((size_t)nq_pad, -std::numeric_limits<float>::infinity());
-    DBX_CUDA_TRY(err, cudaMemcpyAsync(h->bound.p, ninf.data(), (size_t)nq_pad * 4, cudaMemcpyHostToDevice, st));
-    DBX_CUDA_TRY(err, cudaStreamSynchronize(st));
-  }
+  fill_f32_kernel<<<grid_1d(nq_pad), 256, 0, st>>>((float*)h->bound.p, nq_pad, -std::numeric_limits<float>::infinity());
+  count_launch();
 
   // ---- candidate storage
   const int64_t want_cap = std::max<int64_t>(1 << 22, 4LL * nq * kprime);
@@ -386,15 +479,23 @@ int32_t dbx_knn_search(dbx_knn* h, const dbx_column* queries, int32_t k, int32_t
   int cur = 0;           // candidates live in cand_*[cur][0..n_cand)
   int64_t n_cand = 0;
 
+  int q_bits = 1;
+  while ((1 << q_bits) < nq) ++q_bits;
+  const int key_bits = 32 + q_bits;  // (query << 32) | score: the sorts skip the unused high bits
+  int row_bits = 1;
+  while (row_bits < 32 && (1LL << row_bits) < h->n) ++row_bits;
+  auto t_start = std::chrono::steady_clock::now();
   auto select = [&]() -> int32_t {  // cut every query back to its best k', tighten boundaries
     if (n_cand == 0) return DBX_OK;
     size_t tmp = h->cub_tmp.bytes;
     DBX_CUDA_TRY(err, cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tmp, (const uint64_t*)h->cand_key[cur].p, (uint64_t*)h->cand_key[cur ^ 1].p,
-                                                      (const uint32_t*)h->cand_row[cur].p, (uint32_t*)h->cand_row[cur ^ 1].p, (int)n_cand, 0, 64, st));
+                                                      (const uint32_t*)h->cand_row[cur].p, (uint32_t*)h->cand_row[cur ^ 1].p, (int)n_cand, 0, key_bits, st));
     seg_bounds_kernel<<<grid_1d(nq + 1), 256, 0, st>>>((const uint64_t*)h->cand_key[cur ^ 1].p, n_cand, nq, (int64_t*)h->seg.p);
-    retain_kernel<<<1, 1024, 0, st>>>((const uint64_t*)h->cand_key[cur ^ 1].p, (const uint32_t*)h->cand_row[cur ^ 1].p, (const int64_t*)h->seg.p, nq,
-                                      kprime, (uint64_t*)h->cand_key[cur].p, (uint32_t*)h->cand_row[cur].p, (float*)h->bound.p, d_count);
-    count_launch(3);
+    retain_scan_kernel<<<1, 1024, 0, st>>>((const int64_t*)h->seg.p, nq, kprime, (int64_t*)h->seg_off.p, d_count);
+    retain_copy_kernel<<<grid_1d((int64_t)nq * 32), 256, 0, st>>>((const uint64_t*)h->cand_key[cur ^ 1].p, (const uint32_t*)h->cand_row[cur ^ 1].p,
+                                                                 (const int64_t*)h->seg.p, (const int64_t*)h->seg_off.p, nq, kprime,
+                                                                 (uint64_t*)h->cand_key[cur].p, (uint32_t*)h->cand_row[cur].p, (float*)h->bound.p);
+    count_launch(4);
     DBX_CUDA_TRY(err, cudaGetLastError());
     DBX_CUDA_TRY(err, cudaMemcpyAsync(h->host.p, d_count, 8, cudaMemcpyDeviceToHost, st));
     DBX_CUDA_TRY(err, cudaStreamSynchronize(st));
@@ -405,16 +506,15 @@ int32_t dbx_knn_search(dbx_knn* h, const dbx_column* queries, int32_t k, int32_t
   // ---- similarity passes over geometrically growing corpus ranges
   CUtensorMap tmap_q, tmap_c;
   const bool use_ref = getenv("DBX_KNN_REF_GEMM") != nullptr;
+  int max_clusters = kNumSMs / cluster;
   if (!use_ref) {
-    if (!make_tmap(&tmap_q, h->q_bf16.p, nq_pad, dim_pad, kGemmBM) || !make_tmap(&tmap_c, h->corpus_bf16.p, h->n + kGemmBN, dim_pad, kGemmBN)) {
+    if (!make_tmap(&tmap_q, h->q_bf16.p, nq_pad, dim_pad, kGemmBM) ||
+        !make_tmap(&tmap_c, h->corpus_bf16.p, h->n + kGemmBN, dim_pad, kGemmBN / cluster)) {
       err.set("cuTensorMapEncodeTiled failed (TMA descriptors for the similarity GEMM)");
       return DBX_ERR_CUDA;
     }
-    static bool attr = false;
-    if (!attr) {
-      DBX_CUDA_TRY(err, cudaFuncSetAttribute(knn_gemm_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(GemmSmem) + 1024)));
-      attr = true;
-    }
+    DBX_TRY(knn_gemm_prepare(err, cluster, &max_clusters));
+    h->stat_cluster = cluster; h->stat_grid = (int64_t)max_clusters * cluster;
   }
   h->last_gemm_ms = 0.f;
   h->last_gemm_launches = 0;
@@ -432,9 +532,9 @@ int32_t dbx_knn_search(dbx_knn* h, const dbx_column* queries, int32_t k, int32_t
     if (use_ref) {
       knn_ref_filter_kernel<<<grid_1d((int64_t)nq * m), 256, 0, st>>>((const __nv_bfloat16*)h->q_bf16.p, (const __nv_bfloat16*)h->corpus_bf16.p, gp);
     } else {
-      const int64_t tiles = ((m + kGemmBN - 1) / kGemmBN) * (nq_pad / kGemmBM);
-      const int grid = (int)std::min<int64_t>(tiles, kNumSMs);
-      knn_gemm_filter_kernel<<<grid, kGemmThreads, sizeof(GemmSmem) + 1024, st>>>(tmap_q, tmap_c, gp);
+      const int64_t tiles = ((m + kGemmBN - 1) / kGemmBN) * (nq_pad / (kGemmBM * cluster));
+      const int n_clusters = (int)std::min<int64_t>(tiles, max_clusters);
+      DBX_TRY(knn_gemm_launch(err, cluster, n_clusters, st, tmap_q, tmap_c, gp));
     }
     count_launch();
     DBX_CUDA_TRY(err, cudaGetLastError());
@@ -461,6 +561,7 @@ int32_t dbx_knn_search(dbx_knn* h, const dbx_column* queries, int32_t k, int32_t
     chunk = std::min<int64_t>(chunk * 8, 1LL << 24);
   }
 
+  auto t_passes = std::chrono::steady_clock::now();
   // ---- exact re-rank of the k' survivors per query, ordered by (distance, row id)
   DBX_CUDA_TRY(err, h->out_idx_dev.ensure((size_t)nq * k * 8));
   DBX_CUDA_TRY(err, h->out_dist_dev.ensure((size_t)nq * k * 4));
@@ -471,11 +572,11 @@ int32_t dbx_knn_search(dbx_knn* h, const dbx_column* queries, int32_t k, int32_t
                                                    (const uint32_t*)h->cand_row[cur].p, n_cand, (uint64_t*)h->key_tmp.p, (float*)h->dist.p);
     iota32_kernel<<<grid_1d(n_cand), 256, 0, st>>>((uint32_t*)h->perm[0].p, n_cand);
     DBX_CUDA_TRY(err, cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tmp, (const uint32_t*)h->cand_row[cur].p, (uint32_t*)h->cand_row[cur ^ 1].p,
-                                                      (const uint32_t*)h->perm[0].p, (uint32_t*)h->perm[1].p, (int)n_cand, 0, 32, st));
+                                                      (const uint32_t*)h->perm[0].p, (uint32_t*)h->perm[1].p, (int)n_cand, 0, row_bits, st));
     gather_key_kernel<<<grid_1d(n_cand), 256, 0, st>>>((const uint64_t*)h->key_tmp.p, (const uint32_t*)h->perm[1].p, (uint64_t*)h->cand_key[cur ^ 1].p, n_cand);
     tmp = h->cub_tmp.bytes;
     DBX_CUDA_TRY(err, cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tmp, (const uint64_t*)h->cand_key[cur ^ 1].p, (uint64_t*)h->key_tmp.p,
-                                                      (const uint32_t*)h->perm[1].p, (uint32_t*)h->perm[0].p, (int)n_cand, 0, 64, st));
+                                                      (const uint32_t*)h->perm[1].p, (uint32_t*)h->perm[0].p, (int)n_cand, 0, key_bits, st));
     seg_bounds_kernel<<<grid_1d(nq + 1), 256, 0, st>>>((const uint64_t*)h->key_tmp.p, n_cand, nq, (int64_t*)h->seg.p);
     count_launch(6);
   } else {
@@ -497,6 +598,9 @@ int32_t dbx_knn_search(dbx_knn* h, const dbx_column* queries, int32_t k, int32_t
   DBX_CUDA_TRY(err, cudaGetLastError());
   DBX_CUDA_TRY(err, cudaMemcpyAsync(h->host_flags.p, h->flags.p, (size_t)nq, cudaMemcpyDeviceToHost, st));
   DBX_CUDA_TRY(err, cudaStreamSynchronize(st));
+  auto t_rerank = std::chrono::steady_clock::now();
+  h->stat_us_passes = std::chrono::duration_cast<std::chrono::microseconds>(t_passes - t_start).count();
+  h->stat_us_rerank = std::chrono::duration_cast<std::chrono::microseconds>(t_rerank - t_passes).count();
   h->stat_candidates = n_cand;
   h->stat_exact = 0;
   const uint8_t* hf = (const uint8_t*)h->host_flags.p;
@@ -518,7 +622,7 @@ int32_t dbx_knn_search(dbx_knn* h, const dbx_column* queries, int32_t k, int32_t
 int32_t dbx_knn_last_stats(dbx_knn* h, int64_t* out8) {
   if (!h || !out8) return DBX_ERR_INVALID;
   memset(out8, 0, 8 * sizeof(int64_t));
-  out8[0] = h->stat_certified; out8[1] = h->stat_exact; out8[2] = h->stat_candidates; out8[3] = h->stat_passes;
+  out8[0] = h->stat_certified; out8[1] = h->stat_exact; out8[2] = h->stat_candidates; out8[3] = h->stat_passes; out8[4] = h->stat_cluster; out8[5] = h->stat_grid; out8[6] = h->stat_us_passes; out8[7] = h->stat_us_rerank;
   return DBX_OK;
 }
 

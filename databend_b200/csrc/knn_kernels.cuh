@@ -155,9 +155,12 @@ __global__ void distance_rows_kernel(int kind, const float* lhs, int lhs_const, 
 }
 
 // ---------------------------------------------------------------- corpus / query preparation
-// f32 rows -> bf16 copy (round to nearest even) + per-row scale for the GEMM epilogue:
-//   cosine: inv_norm = 1 / sqrt(sum a^2)      L2: sq_norm = sum a^2
+// f32 rows -> bf16 operand of the similarity GEMM (round to nearest even):
+//   cosine: the row is normalised first (x / |x|), so the GEMM yields cosine similarities directly
+//           and the epilogue is a bare compare; scale[r] = 1/|x| (kept for inspection);
+//   L2:     the row is copied as is; scale[r] = |x|^2, combined in the epilogue.
 // The sums here only steer candidate selection (returned distances are recomputed exactly).
+// A zero vector becomes a NaN operand row: its similarities are NaN and never pass the filter.
 // max_norm_bits (optional): bit pattern of the largest row norm (non-negative floats order like
 // their bit patterns), the corpus-side constant of the L2 certificate.
 __global__ void prep_rows_kernel(const float* src, int64_t rows, int dim, int dim_pad, __nv_bfloat16* dst, float* scale,
@@ -170,14 +173,15 @@ __global__ void prep_rows_kernel(const float* src, int64_t rows, int dim, int di
     const float* a = src + r * dim;
     __nv_bfloat16* d = dst + r * dim_pad;
     float s = 0.0f;
-    for (int i = lane; i < dim_pad; i += 32) {
-      float x = i < dim ? a[i] : 0.0f;
-      d[i] = __float2bfloat16_rn(x);
-      s += x * x;
-    }
+    for (int i = lane; i < dim; i += 32) { const float x = a[i]; s += x * x; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) scale[r] = kind == DBX_DIST_COSINE ? rsqrtf(s) : s;
+    const float mul = kind == DBX_DIST_COSINE ? rsqrtf(s) : 1.0f;
+    for (int i = lane * 2; i < dim_pad; i += 64) {  // dim_pad is a multiple of 64
+      const float x0 = i < dim ? a[i] * mul : 0.0f, x1 = i + 1 < dim ? a[i + 1] * mul : 0.0f;
+      *reinterpret_cast<__nv_bfloat162*>(d + i) = __floats2bfloat162_rn(x0, x1);
+    }
+    if (lane == 0) scale[r] = kind == DBX_DIST_COSINE ? mul : s;
     if (s == s) wmax = fmaxf(wmax, sqrtf(s));
   }
   if (max_norm_bits && lane == 0 && wmax > 0.0f) atomicMax(max_norm_bits, __float_as_uint(wmax));
@@ -193,6 +197,7 @@ constexpr int kUmmaK = 16;
 constexpr uint32_t kTmemCols = 512;  // two 256-column accumulators
 constexpr uint32_t kStageBytesA = kGemmBM * kGemmBK * 2;
 constexpr uint32_t kStageBytesB = kGemmBN * kGemmBK * 2;
+constexpr int kCandStage = 512;   // staged survivors per epilogue warp
 
 struct GemmSmem {
   alignas(1024) uint8_t a[kGemmStages][kStageBytesA];
@@ -202,17 +207,21 @@ struct GemmSmem {
   uint64_t tmem_full_bar[2];
   uint64_t tmem_empty_bar[2];
   uint32_t tmem_base;
+  // per epilogue warp: survivors are staged here and written out in coalesced bursts, one
+  // reservation (atomic on the global candidate counter) per burst instead of one per survivor
+  alignas(16) uint64_t stage_key[4][kCandStage];
+  uint32_t stage_row[4][kCandStage];
 };
 
 struct KnnGemmParams {
   int32_t kind;
   int32_t nq;            // valid queries
-  int32_t nq_pad;        // multiple of kGemmBM
+  int32_t nq_pad;        // multiple of kGemmBM * cluster size
   int32_t dim_pad;       // multiple of kGemmBK
   int64_t n0;            // first corpus row of this pass
   int64_t n_rows;        // corpus rows in this pass
-  const float* q_scale;  // cosine: 1/|q|    L2: |q|^2
-  const float* c_scale;  // cosine: 1/|c|    L2: |c|^2   (indexed by global corpus row)
+  const float* q_scale;  // L2: |q|^2                (cosine: unused, operands are pre-normalised)
+  const float* c_scale;  // L2: |c|^2 by global row  (cosine: unused)
   const float* bound;    // per query: only score >= bound can still reach the top k'
   uint64_t* cand_key;    // (query << 32) | ~ordered(score): ascending sort = best first
   uint32_t* cand_row;    // corpus row
@@ -251,6 +260,24 @@ __device__ __forceinline__ void tma_load_2d(const void* tmap, uint64_t* bar, voi
       "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// Same box delivered to the same shared-memory offset of every CTA in `mask`; each destination
+// CTA's mbarrier (same offset) receives the complete_tx for the bytes that landed in ITS smem.
+__device__ __forceinline__ void tma_load_2d_multicast(const void* tmap, uint64_t* bar, void* dst, int32_t c0, int32_t c1,
+                                                      uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%4, %5}], [%2], %3;" ::"r"(smem_u32(dst)),
+      "l"(tmap), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp layout):
 // start>>4 | LBO(=1, ignored for swizzled K-major)<<16 | SBO(1024 B between 8-row groups)>>4 <<32 |
 // version 1 <<46 | layout SWIZZLE_128B(2) <<61
@@ -286,27 +313,58 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// arrive (once the MMAs issued so far retire) on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
 __device__ __forceinline__ uint32_t f32_to_ordered32(float f) {
   if (f != f) return 0u;  // NaN: worst similarity
   uint32_t b = __float_as_uint(f);
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-// Persistent kernel: tile t -> (n_blk = t / n_mblk, m_blk = t % n_mblk); consecutive tiles share
-// the corpus tile, so the 8 query blocks reuse it out of L2 while HBM sees the corpus once.
+// One reservation + coalesced copy of a warp's staged survivors into the global candidate list.
+__device__ __forceinline__ void flush_stage(const uint64_t* skey, const uint32_t* srow, int cnt, int lane, const KnnGemmParams& p) {
+  if (cnt == 0) return;
+  __syncwarp();
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(p.cand_count, (unsigned long long)cnt);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if ((int64_t)(base + cnt) <= p.cand_cap) {
+    for (int i = lane; i < cnt; i += 32) {
+      p.cand_key[base + i] = skey[i];
+      p.cand_row[base + i] = srow[i];
+    }
+  }
+  __syncwarp();
+}
+
+// Persistent, warp-specialised kernel.  A cluster of C CTAs works on C consecutive query blocks
+// against the SAME 256-row corpus tile: every CTA streams its own query tile (A) and 1/C of the
+// corpus tile (B), which TMA multicasts into the shared memory of all C CTAs — so per CTA the
+// L2 -> SM traffic per k-block drops from 16+32 KB to 16+32/C KB (the 1-CTA kernel is bound by
+// exactly that traffic: 96 B/clk/SM at full tensor rate).  Consecutive cluster tiles walk the
+// query blocks first, so a corpus tile is fetched from HBM once and re-read from L2.
+template <int C>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 knn_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
                        const __grid_constant__ KnnGemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   GemmSmem& sm = *reinterpret_cast<GemmSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_mblk = p.nq_pad / kGemmBM;
+  const uint32_t cta_rank = C > 1 ? cluster_ctarank() : 0u;
+  const int64_t cluster_id = blockIdx.x / C, n_clusters = gridDim.x / C;
+  const int n_mgrp = p.nq_pad / (kGemmBM * C);  // groups of C query blocks
   const int64_t n_nblk = (p.n_rows + kGemmBN - 1) / kGemmBN;
-  const int64_t n_tiles = n_nblk * n_mblk;
+  const int64_t n_tiles = n_nblk * n_mgrp;      // cluster-level tiles
   const int n_kblk = p.dim_pad / kGemmBK;
+  constexpr uint16_t kMask = (uint16_t)((1u << C) - 1u);
+  constexpr int kSliceRows = kGemmBN / C;       // corpus rows this CTA fetches for the whole cluster
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kGemmStages; ++s) { mbar_init(&sm.full_bar[s], 1); mbar_init(&sm.empty_bar[s], 1); }
+    for (int s = 0; s < kGemmStages; ++s) { mbar_init(&sm.full_bar[s], 1); mbar_init(&sm.empty_bar[s], C); }
     for (int a = 0; a < 2; ++a) { mbar_init(&sm.tmem_full_bar[a], 1); mbar_init(&sm.tmem_empty_bar[a], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
@@ -317,7 +375,7 @@ knn_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (C > 1) cluster_sync_all(); else __syncthreads();  // peers' barriers are initialised before anyone signals them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = sm.tmem_base;
 
@@ -326,14 +384,24 @@ knn_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int m_blk = (int)(t % n_mblk);
-        const int64_t n_blk = t / n_mblk;
+      for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
+        const int m_blk = (int)(t % n_mgrp) * C + (int)cta_rank;
+        const int64_t n_blk = t / n_mgrp;
+        const int32_t row_b = (int32_t)(p.n0 + n_blk * kGemmBN) + (int32_t)cta_rank * kSliceRows;
         for (int kb = 0; kb < n_kblk; ++kb) {
-          mbar_wait(&sm.empty_bar[stage], phase ^ 1);
+          mbar_wait(&sm.empty_bar[stage], phase ^ 1);  // all C CTAs have consumed this slot
           mbar_expect_tx(&sm.full_bar[stage], kStageBytesA + kStageBytesB);
           tma_load_2d(&tmap_q, &sm.full_bar[stage], sm.a[stage], kb * kGemmBK, m_blk * kGemmBM);
-          tma_load_2d(&tmap_c, &sm.full_bar[stage], sm.b[stage], kb * kGemmBK, (int32_t)(p.n0 + n_blk * kGemmBN));
+          if (C > 1)
+            tma_load_2d_multicast(&tmap_c, &sm.full_bar[stage], sm.b[stage] + cta_rank * (kSliceRows * kGemmBK * 2), kb * kGemmBK, row_b, kMask);
+          else
+            tma_load_2d(&tmap_c, &sm.full_bar[stage], sm.b[stage], kb * kGemmBK, row_b);
+          if (++stage == kGemmStages) { stage = 0; phase ^= 1; }
+        }
+      }
+      if (C > 1) {  // tail: do not leave while peers may still signal this CTA's barriers
+        for (int i = 0; i < kGemmStages; ++i) {
+          mbar_wait(&sm.empty_bar[stage], phase ^ 1);
           if (++stage == kGemmStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -346,7 +414,7 @@ knn_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
         mbar_wait(&sm.tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * kGemmBN;
@@ -360,7 +428,9 @@ knn_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             const uint64_t bdesc = make_smem_desc(b_addr + k * kUmmaK * 2);
             umma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&sm.empty_bar[stage]);  // frees the smem stage once these MMAs retire
+          // frees the smem stage once these MMAs retire — in every CTA of the cluster, because
+          // each of them writes a slice of the next fill into this CTA's slot
+          if (C > 1) umma_commit_multicast(&sm.empty_bar[stage], kMask); else umma_commit(&sm.empty_bar[stage]);
           if (++stage == kGemmStages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&sm.tmem_full_bar[acc]);  // accumulator complete -> epilogue
@@ -369,17 +439,19 @@ knn_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
       }
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> similarity -> boundary filter -> candidate list =====
+    // ===== epilogue: TMEM -> registers -> score -> boundary filter -> candidate list =====
     const int quarter = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-      const int m_blk = (int)(t % n_mblk);
-      const int64_t n_blk = t / n_mblk;
+    const bool is_l2 = p.kind != DBX_DIST_COSINE;
+    int stage_cnt = 0;  // warp-uniform
+    for (int64_t t = cluster_id; t < n_tiles; t += n_clusters) {
+      const int m_blk = (int)(t % n_mgrp) * C + (int)cta_rank;
+      const int64_t n_blk = t / n_mgrp;
       const int q = m_blk * kGemmBM + quarter * 32 + lane;
       const bool q_ok = q < p.nq;
-      const float qs = q_ok ? p.q_scale[q] : 0.0f;
-      const float bound = q_ok ? p.bound[q] : __int_as_float(0x7f800000);
+      const float qq = (q_ok && is_l2) ? p.q_scale[q] : 0.0f;
+      const float bound = q_ok ? p.bound[q] : __int_as_float(0x7f800000);  // +inf: nothing passes
       mbar_wait(&sm.tmem_full_bar[acc], acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int64_t row0 = p.n0 + n_blk * kGemmBN;
@@ -398,32 +470,70 @@ knn_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
               "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
             : "r"(taddr)
             : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         const int64_t rbase = row0 + c * 32;
+        const int64_t left = row_end - rbase;  // rows of this chunk that exist
+        const uint32_t col_mask = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << (int)left) - 1u));
+        float cc_lane = 0.0f;
+        if (is_l2) cc_lane = (lane < left) ? __ldg(p.c_scale + rbase + lane) : 0.0f;
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         uint32_t pass = 0;
-        float sc[32];
+        if (!is_l2) {
+          // cosine: operands are pre-normalised, the accumulator IS the similarity
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int64_t r = rbase + j;
-          const float cs = r < row_end ? __ldg(p.c_scale + r) : 0.0f;
-          const float dot = __uint_as_float(v[j]);
-          // cosine: similarity = dot / (|q||c|);  L2: -(|q|^2 + |c|^2 - 2 dot)  (larger = closer)
-          const float s = p.kind == DBX_DIST_COSINE ? dot * qs * cs : -(qs + cs - 2.0f * dot);
-          sc[j] = s;
-          if (q_ok && r < row_end && s >= bound) pass |= 1u << j;
+          for (int j = 0; j < 32; ++j) pass |= (__uint_as_float(v[j]) >= bound) ? (1u << j) : 0u;
+        } else {
+          // L2: score = -(|q|^2 + |c|^2 - 2 q.c)   (larger = closer)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float cc = __shfl_sync(0xffffffffu, cc_lane, j);
+            const float sc = 2.0f * __uint_as_float(v[j]) - qq - cc;
+            v[j] = __float_as_uint(sc);
+            pass |= (sc >= bound) ? (1u << j) : 0u;
+          }
         }
-        if (pass) {
+        pass &= col_mask;
+        if (__any_sync(0xffffffffu, pass != 0)) {
           const int n = __popc(pass);
-          unsigned long long pos = atomicAdd(p.cand_count, (unsigned long long)n);
-          if ((int64_t)(pos + n) <= p.cand_cap) {
+          int incl = n;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+          }
+          const int total = __shfl_sync(0xffffffffu, incl, 31);
+          const int excl = incl - n;
+          if (total > kCandStage / 2) {
+            // dense chunk (loose boundary in the first passes): reserve once per warp, write direct
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(p.cand_count, (unsigned long long)total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if ((int64_t)(base + total) <= p.cand_cap) {
+              unsigned long long pos = base + excl;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if ((pass >> j) & 1) {
+                  p.cand_key[pos] = ((uint64_t)(uint32_t)q << 32) | (uint64_t)(~f32_to_ordered32(__uint_as_float(v[j])));
+                  p.cand_row[pos] = (uint32_t)(rbase + j);
+                  ++pos;
+                }
+              }
+            }
+          } else {
+            if (stage_cnt + total > kCandStage) {
+              flush_stage(sm.stage_key[quarter], sm.stage_row[quarter], stage_cnt, lane, p);
+              stage_cnt = 0;
+            }
+            int pos = stage_cnt + excl;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               if ((pass >> j) & 1) {
-                p.cand_key[pos] = ((uint64_t)(uint32_t)q << 32) | (uint64_t)(~f32_to_ordered32(sc[j]));
-                p.cand_row[pos] = (uint32_t)(rbase + j);
+                sm.stage_key[quarter][pos] = ((uint64_t)(uint32_t)q << 32) | (uint64_t)(~f32_to_ordered32(__uint_as_float(v[j])));
+                sm.stage_row[quarter][pos] = (uint32_t)(rbase + j);
                 ++pos;
               }
             }
+            stage_cnt += total;
+            __syncwarp();
           }
         }
       }
@@ -432,9 +542,11 @@ knn_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    flush_stage(sm.stage_key[quarter], sm.stage_row[quarter], stage_cnt, lane, p);
   }
+  __syncwarp();
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (C > 1) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
@@ -452,8 +564,7 @@ __global__ void knn_ref_filter_kernel(const __nv_bfloat16* q, const __nv_bfloat1
     const __nv_bfloat16* b = c + r * p.dim_pad;
     float dot = 0.0f;
     for (int k = 0; k < p.dim_pad; ++k) dot += __bfloat162float(a[k]) * __bfloat162float(b[k]);
-    const float qs = p.q_scale[qi], cs = p.c_scale[r];
-    const float s = p.kind == DBX_DIST_COSINE ? dot * qs * cs : -(qs + cs - 2.0f * dot);
+    const float s = p.kind == DBX_DIST_COSINE ? dot : 2.0f * dot - p.q_scale[qi] - p.c_scale[r];
     if (s >= p.bound[qi]) {
       unsigned long long pos = atomicAdd(p.cand_count, 1ULL);
       if ((int64_t)pos < p.cand_cap) {

@@ -111,7 +111,7 @@ class VectorTopN:
     def stats(self) -> dict:
         s = (C.c_int64 * 8)()
         load().dbx_knn_last_stats(self._h, s)
-        return {"certified": s[0], "exact_fallback": s[1], "candidates": s[2], "passes": s[3]}
+        return {"certified": s[0], "exact_fallback": s[1], "candidates": s[2], "passes": s[3], "cluster": s[4], "grid": s[5], "us_passes": s[6], "us_rerank": s[7]}
 
     def close(self):
         if self._h:

@@ -288,7 +288,8 @@ int32_t dbx_knn_destroy(dbx_knn* h);
 int32_t dbx_knn_last_gemm_ms(dbx_knn* h, float* ms, int64_t* launches);
 /* Instrumentation of the last search: out8[0] queries whose result the certificate proved exact,
  * out8[1] queries answered by the exact (CUDA-core, row-wise) path, out8[2] candidates re-ranked,
- * out8[3] similarity passes. */
+ * out8[3] similarity passes, out8[4] cluster size of the GEMM, out8[5] its grid (CTAs),
+ * out8[6] / out8[7] host wall microseconds of the similarity passes / of re-rank + certificate. */
 int32_t dbx_knn_last_stats(dbx_knn* h, int64_t* out8);
 const char* dbx_knn_last_error(const dbx_knn* h);
 
