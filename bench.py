@@ -138,6 +138,113 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+
+# ---------------------------------------------------------------------------------- kNN leg
+def run_knn(args, L, dev, rank, world, barrier):
+    """configs[4]: cosine_distance brute-force kNN, corpus sharded by rows across ranks, queries
+    replicated; per-rank top-k all-gathered and merged.  Returns the "knn" object of the JSON line."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from databend_b200 import abi, lib
+    from databend_b200.block import Column
+    from databend_b200.transforms import DeviceBuffer
+    from databend_b200.vector import VectorTopN
+
+    n_total, dim, nq, k = args.knn_rows, args.knn_dim, args.knn_queries, args.knn_k
+    r0, r1 = n_total * rank // world, n_total * (rank + 1) // world
+    n = r1 - r0
+    cbuf = DeviceBuffer(n * dim * 4, dev)
+    lib.check(L.dbx_synth_fill(dev, 4, 42, 0, r0 * dim, n * dim, cbuf.ptr))
+    qbuf = DeviceBuffer(nq * dim * 4, dev)
+    lib.check(L.dbx_synth_fill(dev, 4, 43, 0, 0, nq * dim, qbuf.ptr))
+    t0 = time.perf_counter()
+    op = VectorTopN("cosine_distance", Column.device(abi.VEC_F32, n, cbuf.ptr, vec_dim=dim), dev)
+    create_s = time.perf_counter() - t0
+    q_dev = Column.device(abi.VEC_F32, nq, qbuf.ptr, vec_dim=dim)
+    q_host = Column.vector(qbuf.download(np.float32, nq * dim).reshape(nq, dim))
+
+    def search(q):
+        idx, d = op.search(q, k)
+        if world == 1:
+            return idx, d
+        ti = torch.from_numpy(idx + r0).to(f"cuda:{dev}")
+        td = torch.from_numpy(d).to(f"cuda:{dev}")
+        gi = [torch.empty_like(ti) for _ in range(world)]
+        gd = [torch.empty_like(td) for _ in range(world)]
+        dist.all_gather(gi, ti)
+        dist.all_gather(gd, td)
+        ai, ad = torch.cat(gi, 1), torch.cat(gd, 1)
+        # merge: ascending (distance, row id); NaN last like OrderedFloat
+        key = torch.where(torch.isnan(ad), torch.full_like(ad, float("inf")), ad)
+        o1 = torch.argsort(ai, dim=1, stable=True)
+        key1, ai1, ad1 = key.gather(1, o1), ai.gather(1, o1), ad.gather(1, o1)
+        o2 = torch.argsort(key1, dim=1, stable=True)[:, :k]
+        return ai1.gather(1, o2).cpu().numpy(), ad1.gather(1, o2).cpu().numpy()
+
+    def timed(q, steps, warmup):
+        for _ in range(warmup):
+            search(q)
+        barrier()
+        gemm = []
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            res = search(q)
+            gemm.append(op.last_gemm_ms()[0])
+        barrier()
+        ms = (time.perf_counter() - t0) * 1e3 / steps
+        t = torch.tensor([ms, sum(gemm) / len(gemm)], dtype=torch.float64, device=f"cuda:{dev}")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist(), res
+
+    launches0 = L.dbx_kernel_launch_count()
+    (ms_dev, gemm_ms), res = timed(q_dev, args.steps, args.warmup)
+    launches = L.dbx_kernel_launch_count() - launches0
+    (ms_host, _), _ = timed(q_host, max(1, min(args.steps, 3)), 1)
+    stats = op.stats()
+    op.close()
+    if rank != 0:
+        return None
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak, src = 1400.0, "fallback (B200_PROFILING.md sustained)"
+    if os.path.exists(p):
+        with open(p) as f:
+            peak, src = json.load(f).get("bf16_tflops_sustained", 1400.0), "measured sustained cuBLAS bf16 (MEASURED_PEAKS.json)"
+    flop = 2.0 * nq * n * dim  # per rank and batch: the similarity GEMM (SURVEY 8d row 5)
+    achieved = flop / (gemm_ms * 1e-3) / 1e12
+    out = {
+        "metric": "kNN QPS @768d (cosine_distance, brute force, exact top-k)", "value": nq / (ms_dev * 1e-3), "unit": "queries/s",
+        "ms_per_batch": ms_dev, "n_gpus": world, "scaling": "strong", "dtype": "bf16 candidate GEMM (f32 accumulate) + exact f32 re-rank",
+        "config": {"workload": "configs[4]", "corpus_rows": n_total, "rows_per_gpu": n, "dim": dim, "queries": nq, "k": k,
+                   "data": "synthetic N(0,1), device-generated", "create_s": create_s,
+                   "parallelism": f"corpus rows x{world}" + ("" if world == 1 else " + all-gather of per-GPU top-k")},
+        "gpu_launches_per_batch": int(launches // max(1, args.steps)),
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": f"knn_gemm_filter_kernel<{stats['cluster']}>", "kernel_ms": gemm_ms,
+                     "flop_per_launch_set": flop, "peak_source": src},
+        "certified_queries": stats["certified"], "exact_fallback_queries": stats["exact_fallback"],
+        "e2e": {"value": nq / (ms_host * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4,
+                "d2h_bytes_per_step": nq * k * 12, "ms_per_batch": ms_host,
+                "timing": "host wall clock around VectorTopN.search() with HOST query vectors, max over ranks"},
+    }
+    if world == 1 and not args.no_cpu:
+        from oracle import oracle as orc
+        threads = len(os.sched_getaffinity(0))
+        sn, sq = min(n_total, 1_000_000), 8
+        rng = np.random.default_rng(0)
+        c = rng.standard_normal((sn, dim)).astype(np.float32)
+        qs = rng.standard_normal((sq, dim)).astype(np.float32)
+        orc.distance_rows(abi.DIST_COSINE, c, qs[0], threads=threads)
+        t0 = time.perf_counter()
+        for i in range(sq):
+            d = orc.distance_rows(abi.DIST_COSINE, c, qs[i], threads=threads)
+            np.argpartition(d, k)[:k]
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": sq / dt * sn / n_total, "unit": "queries/s", "cores": threads, "kind": "port",
+                               "sample": f"{sq} queries x {sn} rows, row-wise cosine_distance (oracle, OpenMP) + top-k, scaled by {sn}/{n_total} rows"}
+    return out
+
 # ---------------------------------------------------------------------------------- GPU arm
 def run_dbx(args):
     import numpy as np
@@ -168,7 +275,7 @@ def run_dbx(args):
     types = [abi.I64, abi.I64, abi.F64]
 
     bufs = [DeviceBuffer(n * 8, dev) for _ in range(3)]
-    lib.check(L.dbx_synth_fill(dev, 0, SEEDS[0], N_KEYS, r_begin, n, bufs[0].ptr))
+    lib.check(L.dbx_synth_fill(dev, 0, SEEDS[0], args.keys, r_begin, n, bufs[0].ptr))
     lib.check(L.dbx_synth_fill(dev, 1, SEEDS[1], 0, r_begin, n, bufs[1].ptr))
     lib.check(L.dbx_synth_fill(dev, 2, SEEDS[2], 20, r_begin, n, bufs[2].ptr))
     dblock = DataBlock([Column.device(abi.I64, n, bufs[0].ptr), Column.device(abi.I64, n, bufs[1].ptr),
@@ -184,11 +291,23 @@ def run_dbx(args):
 
     kernel_ms = []
 
+    use_peer = world > 1 and os.environ.get("DBX_EXCHANGE", "peer") == "peer"
+    xchg = None
+    if use_peer:
+        from databend_b200.exchange import PeerExchange
+        xchg = PeerExchange(part, rank, world)
+        xchg.connect()
+
     def exchange_and_finish(out_mem):
-        """partial -> (N>1: hash-partition + one all-to-all) -> final -> result block"""
+        """partial -> (N>1: hash-partition + exchange) -> final -> result block"""
         part.on_finish()
         if world == 1:
             fin.transform(part)
+        elif use_peer:
+            # rows go straight into the owners' HBM over NVLink; the merge kernel waits on the
+            # sources' flags on the device: no NCCL call, staging copy or host sync in between
+            xchg.scatter(part)
+            xchg.merge(fin)
         else:
             rows_ptr = C.c_void_p()
             offs = (C.c_int64 * (world + 1))()
@@ -302,6 +421,17 @@ def run_dbx(args):
         for p in hp:
             L.dbx_host_free(p)
 
+    knn = None
+    if xchg is not None:
+        barrier()
+        xchg.close()
+    if not args.no_knn:
+        part.close()
+        fin.close()
+        for b_ in bufs:
+            b_.free()
+        knn = run_knn(args, L, dev, rank, world, barrier)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -337,13 +467,13 @@ def run_dbx(args):
                    "rows": total_rows, "rows_per_gpu": n, "groups_out": int(groups) * (1 if world == 1 else world),
                    "columns": "k:int64 v:int64 x:float64", "l2": "inputs (24 B/row x rows) far larger than the 126 MB L2",
                    "timing": "CUDA events on the operators' stream, max over ranks; wall_ms_per_step alongside",
-                   "parallelism": f"row-range x{world}" + ("" if world == 1 else " + NCCL all-to-all of partial groups")},
+                   "parallelism": f"row-range x{world}" + ("" if world == 1 else (" + peer-memory (NVLink) scatter of partial groups" if use_peer else " + NCCL all-to-all of partial groups"))},
         "wall_ms_per_step": wall_ms, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_TRAFFIC_PER_LAUNCH, "traffic_note": "dram read+write per 2^28-row launch from profiles/r01_filter_group_agg_ncu_full.csv (ncu --set full)",
                      "achieved_per_launch_bytes": BYTES_PER_ROW * min(n, 1 << 28), "kernel": "filter_group_agg_kernel<3,FAST=1,INDIRECT=0>", "kernel_ms": k_ms,
                      "algorithmic_bytes_per_row": BYTES_PER_ROW, "peak_source": peak_src},
-        "cpu_baseline": cpu, "e2e": e2e,
+        "cpu_baseline": cpu, "e2e": e2e, "knn": knn,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -360,8 +490,14 @@ def main():
     ap.add_argument("--e2e-rows", type=int, default=0, help="0 = same as --rows")
     ap.add_argument("--block-rows", type=int, default=1 << 22, help="rows per pushed host block in the e2e leg (max_block_size)")
     ap.add_argument("--cpu-rows", type=int, default=50_000_000)
+    ap.add_argument("--keys", type=int, default=N_KEYS, help="distinct group keys (the named config uses 1e6)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-knn", action="store_true", help="skip the kNN leg (second half of BASELINE.json's metric)")
+    ap.add_argument("--knn-rows", type=int, default=10_000_000)
+    ap.add_argument("--knn-dim", type=int, default=768)
+    ap.add_argument("--knn-queries", type=int, default=1024)
+    ap.add_argument("--knn-k", type=int, default=10)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -135,6 +135,8 @@ EXPORTS = [
     "dbx_device_alloc", "dbx_device_free", "dbx_memcpy_h2d", "dbx_memcpy_d2h", "dbx_memcpy_d2d", "dbx_device_synchronize",
     "dbx_op_create", "dbx_op_destroy", "dbx_op_push", "dbx_op_finish", "dbx_op_pull", "dbx_block_release", "dbx_op_reset", "dbx_op_synchronize",
     "dbx_join_probe", "dbx_agg_final_merge_partial", "dbx_agg_partial_partition", "dbx_agg_final_merge_rows",
+    "dbx_agg_exchange_create", "dbx_agg_exchange_local_buffer", "dbx_agg_exchange_connect", "dbx_agg_exchange_scatter",
+    "dbx_agg_exchange_merge", "dbx_agg_exchange_destroy", "dbx_agg_exchange_last_error",
     "dbx_eval_distance", "dbx_knn_create", "dbx_knn_search", "dbx_knn_destroy", "dbx_knn_last_error", "dbx_knn_last_gemm_ms", "dbx_knn_last_stats",
     "dbx_synth_fill", "dbx_kernel_launch_count", "dbx_op_last_kernel_ms", "dbx_op_stream",
 ]

@@ -56,6 +56,12 @@ struct AggPlan {
   int n_updates = 0;
   UpdateDev upd[kMaxUpdates];
   FinalAgg fin[DBX_MAX_AGGS];  // out pointers filled at finalize time
+  // state layout: words that are updated in pairs by one TMA bulk reduction sit in arrays of
+  // 16-byte pairs; w_pair[w] = pair index or -1, w_pos[w] = 0/1 position inside the pair
+  int n_pairs = 0;
+  PairDev pairs[kMaxPairs];
+  int w_pair[kMaxWords];
+  int w_pos[kMaxWords];
 
   int slot_of(int col, ErrorSink* err) {
     for (int s = 0; s < n_slots; ++s)
@@ -269,7 +275,7 @@ int32_t build_plan(const dbx_agg_params* p, const int32_t* types, int32_t n_cols
   memset(&pl->init, 0, sizeof(pl->init));
   memset(&pl->kinds, 0, sizeof(pl->kinds));
   pl->add_word(0, UPD_ADD_INT);
-  pl->upd[pl->n_updates++] = UpdateDev{UPD_INC, 0, 0, 0};
+  pl->upd[pl->n_updates++] = UpdateDev{UPD_INC, 0, 0, 0, 0, 0};
   int cnt_word_of_col[64], acc_word_of_col[64];
   for (int i = 0; i < 64; ++i) cnt_word_of_col[i] = acc_word_of_col[i] = -1;
 
@@ -297,7 +303,7 @@ int32_t build_plan(const dbx_agg_params* p, const int32_t* types, int32_t n_cols
     } else {
       if (cnt_word_of_col[ad.arg_col] < 0) {
         cnt_word_of_col[ad.arg_col] = pl->add_word(0, UPD_ADD_INT);
-        pl->upd[pl->n_updates++] = UpdateDev{UPD_INC_VALID, slot, cnt_word_of_col[ad.arg_col], 0};
+        pl->upd[pl->n_updates++] = UpdateDev{UPD_INC_VALID, slot, cnt_word_of_col[ad.arg_col], 0, 0, 0};
       }
       fa.cnt_word = cnt_word_of_col[ad.arg_col];
     }
@@ -309,7 +315,7 @@ int32_t build_plan(const dbx_agg_params* p, const int32_t* types, int32_t n_cols
         if (acc_word_of_col[ad.arg_col] < 0) {
           int op = cls == VC_FLT ? UPD_ADD_F64 : UPD_ADD_INT;
           acc_word_of_col[ad.arg_col] = pl->add_word(0, op);
-          pl->upd[pl->n_updates++] = UpdateDev{op, slot, acc_word_of_col[ad.arg_col], 0};
+          pl->upd[pl->n_updates++] = UpdateDev{op, slot, acc_word_of_col[ad.arg_col], 0, 0, 0};
         }
         fa.acc_word = acc_word_of_col[ad.arg_col];
         break;
@@ -319,7 +325,7 @@ int32_t build_plan(const dbx_agg_params* p, const int32_t* types, int32_t n_cols
         int op = cls == VC_FLT ? (mn ? UPD_MIN_F64 : UPD_MAX_F64) : cls == VC_UINT ? (mn ? UPD_MIN_U64 : UPD_MAX_U64) : (mn ? UPD_MIN_S64 : UPD_MAX_S64);
         uint64_t iv = op == UPD_MIN_S64 ? (uint64_t)INT64_MAX : op == UPD_MAX_S64 ? (uint64_t)INT64_MIN : (op == UPD_MIN_U64 || op == UPD_MIN_F64) ? ~0ULL : 0ULL;
         fa.acc_word = pl->add_word(iv, op);
-        pl->upd[pl->n_updates++] = UpdateDev{op, slot, fa.acc_word, 0};
+        pl->upd[pl->n_updates++] = UpdateDev{op, slot, fa.acc_word, 0, 0, 0};
         break;
       }
       default: err->set("unknown aggregate kind"); return DBX_ERR_INVALID;
@@ -328,6 +334,31 @@ int32_t build_plan(const dbx_agg_params* p, const int32_t* types, int32_t n_cols
   if (pl->n_slots == 0) {  // e.g. count(*) without filter: still need a row source
     if (n_cols == 0) { err->set("operator needs at least one input column"); return DBX_ERR_INVALID; }
     pl->slot_of(0, err);
+  }
+  // Pair up additive words of the same class (integer adds incl. counters, or f64 adds), in
+  // plan order: each pair costs one L2 reduction per row instead of two (the table phase is
+  // bound by L2 atomic operations per row, not by bytes).
+  for (int w = 0; w < kMaxWords; ++w) { pl->w_pair[w] = -1; pl->w_pos[w] = 0; }
+  pl->n_pairs = 0;
+  if (pl->grouped && getenv("DBX_AGG_BULK")) {  // opt-in: measured slower than REDs in the full kernel
+    for (int cls = 0; cls < 2 && pl->n_pairs < kMaxPairs; ++cls) {
+      int pending = -1;
+      for (int u = 0; u < pl->n_updates && pl->n_pairs < kMaxPairs; ++u) {
+        const int op = pl->upd[u].op;
+        const bool is_int = op == UPD_INC || op == UPD_INC_VALID || op == UPD_ADD_INT;
+        const bool is_f64 = op == UPD_ADD_F64;
+        if (!(cls == 0 ? is_int : is_f64)) continue;
+        if (pending < 0) { pending = u; continue; }
+        PairDev& pd = pl->pairs[pl->n_pairs];
+        pd.upd0 = pending; pd.upd1 = u; pd.is_f64 = cls; pd.pad = 0;
+        pl->w_pair[pl->upd[pending].word] = pl->n_pairs; pl->w_pos[pl->upd[pending].word] = 0;
+        pl->w_pair[pl->upd[u].word] = pl->n_pairs; pl->w_pos[pl->upd[u].word] = 1;
+        pl->upd[pending].paired = 1;
+        pl->upd[u].paired = 1;
+        pl->n_pairs += 1;
+        pending = -1;
+      }
+    }
   }
   return DBX_OK;
 }
@@ -338,6 +369,9 @@ struct DeviceTable {
   DevBuf counters;  // [0] n_groups, [1] n_overflow
   int64_t cap = 0;
   int n_words = 0;
+  int n_pairs = 0;
+  int w_pair[kMaxWords];
+  int w_pos[kMaxWords];
 
   unsigned long long* n_groups() const { return (unsigned long long*)counters.p; }
   unsigned long long* n_overflow() const { return (unsigned long long*)counters.p + 1; }
@@ -346,6 +380,9 @@ struct DeviceTable {
   int32_t create(int64_t capacity, const AggPlan& pl, cudaStream_t stream, ErrorSink* err) {
     cap = capacity < 4 ? 4 : capacity;
     n_words = pl.n_words;
+    n_pairs = pl.n_pairs;
+    memcpy(w_pair, pl.w_pair, sizeof(w_pair));
+    memcpy(w_pos, pl.w_pos, sizeof(w_pos));
     DBX_CUDA_TRY(*err, keys.ensure((size_t)(cap + 2) * 8 + 32));
     DBX_CUDA_TRY(*err, states.ensure((size_t)(cap + 2) * 8 * n_words));
     DBX_CUDA_TRY(*err, counters.ensure(64));
@@ -372,6 +409,22 @@ struct DeviceTable {
     t.states = (uint64_t*)states.p;
     t.cap = cap;
     t.n_words = n_words;
+    // pair arrays first (16-byte aligned: every region has an even number of words), then the
+    // unpaired words row-major (one entry per slot, so a row's REDs fall into 1-2 sectors)
+    {
+      const int64_t n_slots = cap + 2;
+      const int64_t row_base = 2 * n_slots * n_pairs;
+      int n_single = 0;
+      for (int w = 0; w < n_words; ++w) n_single += w_pair[w] < 0;
+      for (int w = 0; w < kMaxWords; ++w) { t.w_off[w] = 0; t.w_stride[w] = 1; }
+      t.row_base = row_base;
+      t.n_single = n_single;
+      int idx = 0;
+      for (int w = 0; w < n_words; ++w) {
+        if (w_pair[w] >= 0) { t.w_off[w] = 2 * n_slots * w_pair[w] + w_pos[w]; t.w_stride[w] = 2; }
+        else { t.w_off[w] = row_base + idx++; t.w_stride[w] = n_single; }
+      }
+    }
     t.n_groups = n_groups();
     t.n_overflow = n_overflow();
     t.overflow_rows = overflow_rows;
@@ -384,6 +437,9 @@ struct DeviceTable {
     std::swap(counters, o.counters);
     std::swap(cap, o.cap);
     std::swap(n_words, o.n_words);
+    std::swap(n_pairs, o.n_pairs);
+    std::swap(w_pair, o.w_pair);
+    std::swap(w_pos, o.w_pos);
   }
 };
 
@@ -470,10 +526,12 @@ class AggPartialOp : public Op {
   template <int NS, bool FAST, bool INDIRECT>
   int32_t launch_one(const AggKernelParams& kp) {
     static bool attr_set[16] = {};
-    const size_t smem = sizeof(StageWarp<NS>) * kWarpsPerBlock;
+    const size_t smem_rows = (sizeof(StageWarp<NS>) * kWarpsPerBlock + 15) & ~(size_t)15;
+    const size_t smem_bulk = (size_t)kWarpsPerBlock * kBulkGen * kMaxPairs * 32 * 16;
+    const size_t smem = smem_rows + (kp.n_pairs ? smem_bulk : 0);
     auto kern = filter_group_agg_kernel<NS, FAST, INDIRECT>;
     if (!attr_set[device]) {
-      DBX_CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      DBX_CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_rows + smem_bulk)));
       attr_set[device] = true;
     }
     int grid = grid_for_rows(kp.n_rows);
@@ -555,12 +613,21 @@ class AggPartialOp : public Op {
     }
     memcpy(kp->nodes, plan.nodes, sizeof(PredNodeDev) * plan.n_nodes);
     memcpy(kp->upd, plan.upd, sizeof(UpdateDev) * plan.n_updates);
+    for (int u = 0; u < plan.n_updates; ++u) {  // position of an unpaired word inside the row-major entry
+      int idx = 0;
+      for (int w = 0; w < plan.upd[u].word; ++w) idx += plan.w_pair[w] < 0;
+      kp->upd[u].ridx = idx;
+    }
     kp->n_rows = n;
     kp->n_slots = plan.n_slots;
     kp->n_nodes = plan.n_nodes;
     kp->n_updates = plan.n_updates;
     kp->key_slot = plan.key_slot;
     kp->key_nullable = plan.key_nullable;
+    kp->n_pairs = plan.n_pairs;
+    memcpy(kp->pairs, plan.pairs, sizeof(PairDev) * kMaxPairs);
+    static const uint32_t bulk_lanes = getenv("DBX_AGG_BULK_LANES") ? (uint32_t)strtoul(getenv("DBX_AGG_BULK_LANES"), nullptr, 16) : 0xFFFFFFFFu;
+    kp->bulk_lanes = bulk_lanes;
     static const int dbg = getenv("DBX_AGG_DEBUG") ? atoi(getenv("DBX_AGG_DEBUG")) : 0;
     kp->debug_flags = dbg;
   }
@@ -665,6 +732,7 @@ class AggFinalOp : public Op {
   std::unique_ptr<OwnedBlock> result_dev;  // finalized columns in HBM
   int64_t result_rows = 0;
   bool pulled = false;
+  unsigned long long* exchange_status = nullptr;  // device: set by a peer-memory exchange merge
 
   int32_t init(const dbx_agg_params* p, const int32_t* types, int32_t n, int dev) {
     DBX_TRY(base_init(dev));
@@ -674,6 +742,7 @@ class AggFinalOp : public Op {
   }
   int32_t reset() override {
     has_table = false;
+    exchange_status = nullptr;
     result_dev.reset();
     result_rows = 0;
     pulled = false;
@@ -682,9 +751,15 @@ class AggFinalOp : public Op {
 
   int32_t read_groups(int64_t* ng, int64_t* no) {
     DBX_CUDA_TRY(err, cudaMemcpyAsync(host_counters.p, table.counters.p, 16, cudaMemcpyDeviceToHost, stream));
+    if (exchange_status) DBX_CUDA_TRY(err, cudaMemcpyAsync((char*)host_counters.p + 16, exchange_status, 16, cudaMemcpyDeviceToHost, stream));
     DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
     *ng = (int64_t)((unsigned long long*)host_counters.p)[0];
     *no = (int64_t)((unsigned long long*)host_counters.p)[1];
+    if (exchange_status) {
+      const unsigned long long* st = (const unsigned long long*)host_counters.p + 2;
+      if (st[0]) { err.set("exchange: timed out waiting for a peer rank's partition"); return DBX_ERR_STATE; }
+      if (st[1]) { err.set("exchange: a peer had more groups for this rank than the receive region holds"); return DBX_ERR_OOM; }
+    }
     return DBX_OK;
   }
 
@@ -969,6 +1044,162 @@ int32_t dbx_agg_final_merge_rows(dbx_op* final_op, const void* dev_rows, int64_t
   if (f->kind != DBX_OP_AGG_FINAL) { f->err.set("merge_rows: not a final aggregate operator"); return DBX_ERR_INVALID; }
   DBX_CUDA_TRY(f->err, cudaSetDevice(f->device));
   return static_cast<AggFinalOp*>(f)->merge_rows(dev_rows, n_rows);
+}
+
+}  // extern "C"
+
+// ================================================================ peer-memory exchange
+struct dbx_agg_exchange {
+  dbx::ErrorSink err;
+  int device = 0, rank = 0, n_ranks = 1, row_words = 0;
+  int64_t region_rows = 0, table_cap = 0;
+  dbx::DevBuf recv, scratch, status;  // scratch: [n_ranks] cursors + done counter
+  dbx::PinnedBuf host_status;
+  void* peer_base[dbx::kMaxRanks] = {};
+  bool peer_is_ipc[dbx::kMaxRanks] = {};
+  bool connected = false;
+  unsigned long long epoch = 0;
+  cudaEvent_t ev_scatter = nullptr, ev_merge = nullptr;
+  size_t recv_bytes() const {
+    return sizeof(dbx::ExchangeHeader) + (size_t)2 * n_ranks * region_rows * row_words * 8;
+  }
+};
+
+extern "C" {
+
+const char* dbx_agg_exchange_last_error(const dbx_agg_exchange* x) { return x ? x->err.msg.c_str() : g_create_error.msg.c_str(); }
+
+int32_t dbx_agg_exchange_create(dbx_op* partial_op, int32_t rank, int32_t n_ranks, int64_t region_rows, dbx_agg_exchange** out,
+                                void* ipc_handle_out) {
+  if (!partial_op || !out || n_ranks < 1 || n_ranks > kMaxRanks || rank < 0 || rank >= n_ranks) { g_create_error.set("dbx_agg_exchange_create: bad argument"); return DBX_ERR_INVALID; }
+  Op* o = reinterpret_cast<Op*>(partial_op);
+  if (o->kind != DBX_OP_AGG_PARTIAL) { g_create_error.set("dbx_agg_exchange_create: not a partial aggregate operator"); return DBX_ERR_INVALID; }
+  AggPartialOp* p = static_cast<AggPartialOp*>(o);
+  if (!p->plan.grouped) { g_create_error.set("dbx_agg_exchange_create: aggregation without GROUP BY needs no exchange (all-reduce the single state)"); return DBX_ERR_UNSUPPORTED; }
+  ErrorSink& err = g_create_error;
+  std::unique_ptr<dbx_agg_exchange> x(new dbx_agg_exchange());
+  x->device = p->device; x->rank = rank; x->n_ranks = n_ranks; x->row_words = 2 + p->plan.n_words;
+  // a source can send at most all of its groups to one owner; a partial table holds at most cap/2
+  x->region_rows = region_rows > 0 ? region_rows : std::max<int64_t>(p->initial_cap / 2 + 2, 1024);
+  x->table_cap = std::max<int64_t>(p->initial_cap, next_pow2(2 * x->region_rows - 4));
+  DBX_CUDA_TRY(err, cudaSetDevice(x->device));
+  DBX_CUDA_TRY(err, x->recv.ensure(x->recv_bytes()));
+  DBX_CUDA_TRY(err, cudaMemset(x->recv.p, 0, sizeof(ExchangeHeader)));
+  DBX_CUDA_TRY(err, x->scratch.ensure(8 * (kMaxRanks + 2)));
+  DBX_CUDA_TRY(err, x->status.ensure(64));
+  DBX_CUDA_TRY(err, cudaMemset(x->status.p, 0, 64));
+  DBX_CUDA_TRY(err, x->host_status.ensure(64));
+  DBX_CUDA_TRY(err, cudaEventCreateWithFlags(&x->ev_scatter, cudaEventDisableTiming));
+  DBX_CUDA_TRY(err, cudaEventCreateWithFlags(&x->ev_merge, cudaEventDisableTiming));
+  if (ipc_handle_out) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t hd;
+    DBX_CUDA_TRY(err, cudaIpcGetMemHandle(&hd, x->recv.p));
+    memcpy(ipc_handle_out, &hd, 64);
+  }
+  *out = x.release();
+  return DBX_OK;
+}
+
+int32_t dbx_agg_exchange_local_buffer(dbx_agg_exchange* x, void** base, int64_t* region_rows, int32_t* row_bytes) {
+  if (!x) return DBX_ERR_INVALID;
+  if (base) *base = x->recv.p;
+  if (region_rows) *region_rows = x->region_rows;
+  if (row_bytes) *row_bytes = x->row_words * 8;
+  return DBX_OK;
+}
+
+/* all_handles: n_ranks x 64 bytes (cudaIpcMemHandle_t of every rank, own entry ignored), or
+ * NULL when `same_process_ptrs` gives the receive buffers directly (ranks simulated in one process). */
+int32_t dbx_agg_exchange_connect(dbx_agg_exchange* x, const void* all_handles, void* const* same_process_ptrs) {
+  if (!x || (!all_handles && !same_process_ptrs)) return DBX_ERR_INVALID;
+  DBX_CUDA_TRY(x->err, cudaSetDevice(x->device));
+  for (int r = 0; r < x->n_ranks; ++r) {
+    if (r == x->rank) { x->peer_base[r] = x->recv.p; continue; }
+    if (same_process_ptrs) { x->peer_base[r] = same_process_ptrs[r]; continue; }
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, (const char*)all_handles + (size_t)r * 64, 64);
+    void* p = nullptr;
+    DBX_CUDA_TRY(x->err, cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+    x->peer_base[r] = p;
+    x->peer_is_ipc[r] = true;
+  }
+  x->connected = true;
+  return DBX_OK;
+}
+
+/* Hash-partition the finished partial's groups by owner and store every row straight into the
+ * owner's receive region (peer memory).  Enqueued on the partial's stream; no host sync. */
+int32_t dbx_agg_exchange_scatter(dbx_agg_exchange* x, dbx_op* partial_op) {
+  if (!x || !partial_op) return DBX_ERR_INVALID;
+  if (!x->connected) { x->err.set("exchange: scatter before connect"); return DBX_ERR_STATE; }
+  AggPartialOp* p = static_cast<AggPartialOp*>(reinterpret_cast<Op*>(partial_op));
+  DBX_CUDA_TRY(x->err, cudaSetDevice(x->device));
+  { int32_t st = p->ensure_table(); if (st != DBX_OK) { x->err.set(p->err.msg); return st; } }
+  if (2 + p->plan.n_words != x->row_words) { x->err.set("exchange: operator state layout differs from the exchange's"); return DBX_ERR_INVALID; }
+  x->epoch += 1;
+  // region reuse: this rank's merge of the previous epoch must precede the scatter that lets peers move on
+  DBX_CUDA_TRY(x->err, cudaStreamWaitEvent(p->stream, x->ev_merge, 0));
+  DBX_CUDA_TRY(x->err, cudaMemsetAsync(x->scratch.p, 0, 8 * (kMaxRanks + 2), p->stream));
+  ExchangeScatterParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.src = p->table.view(nullptr);
+  for (int r = 0; r < x->n_ranks; ++r) sp.peer_base[r] = x->peer_base[r];
+  sp.cursors = (unsigned long long*)x->scratch.p;
+  sp.done = (unsigned int*)((unsigned long long*)x->scratch.p + kMaxRanks);
+  sp.region_rows = x->region_rows;
+  sp.epoch = x->epoch;
+  sp.n_ranks = x->n_ranks; sp.rank = x->rank; sp.row_words = x->row_words; sp.parity = (int)(x->epoch & 1);
+  exchange_scatter_kernel<<<grid_for_entries(sp.src.cap + 2), 256, 0, p->stream>>>(sp);
+  count_launch();
+  DBX_CUDA_TRY(x->err, cudaGetLastError());
+  DBX_CUDA_TRY(x->err, cudaEventRecord(x->ev_scatter, p->stream));
+  return DBX_OK;
+}
+
+/* Merge every source's region of the current epoch into the final operator's table; the kernel
+ * waits on the sources' release flags (device side).  Enqueued on the final's stream. */
+int32_t dbx_agg_exchange_merge(dbx_agg_exchange* x, dbx_op* final_op) {
+  if (!x || !final_op) return DBX_ERR_INVALID;
+  Op* o = reinterpret_cast<Op*>(final_op);
+  if (o->kind != DBX_OP_AGG_FINAL) { x->err.set("exchange: merge target is not a final aggregate operator"); return DBX_ERR_INVALID; }
+  AggFinalOp* f = static_cast<AggFinalOp*>(o);
+  DBX_CUDA_TRY(x->err, cudaSetDevice(x->device));
+  if (f->finished) { x->err.set("merge after finish"); return DBX_ERR_STATE; }
+  if (!f->has_table) {  // owned groups <= all groups: same capacity rule as one source's partial
+    int32_t st = f->table.create(x->table_cap, f->plan, f->stream, &f->err);
+    if (st != DBX_OK) { x->err.set(f->err.msg); return st; }
+    f->has_table = true;
+  }
+  DBX_CUDA_TRY(x->err, cudaStreamWaitEvent(f->stream, x->ev_scatter, 0));
+  ExchangeMergeParams mp;
+  memset(&mp, 0, sizeof(mp));
+  mp.dst = f->table.view(nullptr);
+  mp.kinds = f->plan.kinds;
+  mp.base = x->recv.p;
+  mp.status = (unsigned long long*)x->status.p;
+  mp.region_rows = x->region_rows;
+  mp.epoch = x->epoch;
+  mp.spin_limit_cycles = 20LL * 1000 * 1000 * 1000;  // ~10 s: a peer that never arrives must not hang the GPU
+  mp.n_ranks = x->n_ranks; mp.row_words = x->row_words; mp.parity = (int)(x->epoch & 1);
+  exchange_merge_kernel<<<grid_for_entries(x->region_rows), 256, 0, f->stream>>>(mp);
+  count_launch();
+  DBX_CUDA_TRY(x->err, cudaGetLastError());
+  DBX_CUDA_TRY(x->err, cudaEventRecord(x->ev_merge, f->stream));
+  f->exchange_status = (unsigned long long*)x->status.p;
+  return DBX_OK;
+}
+
+int32_t dbx_agg_exchange_destroy(dbx_agg_exchange* x) {
+  if (!x) return DBX_OK;
+  cudaSetDevice(x->device);
+  cudaDeviceSynchronize();
+  for (int r = 0; r < x->n_ranks; ++r)
+    if (x->peer_is_ipc[r] && x->peer_base[r]) cudaIpcCloseMemHandle(x->peer_base[r]);
+  if (x->ev_scatter) cudaEventDestroy(x->ev_scatter);
+  if (x->ev_merge) cudaEventDestroy(x->ev_merge);
+  delete x;
+  return DBX_OK;
 }
 
 }  // extern "C"

@@ -320,12 +320,23 @@ struct StageWarp {
   uint8_t vm[kStageCap];
 };
 
+constexpr int kBulkGen = 2;  // generations of bulk-reduction staging slots per lane
+
+// value a row adds to an additive state word (0 when its argument is NULL)
+__device__ __forceinline__ uint64_t update_contribution(const UpdateDev& ud, uint64_t val, bool valid) {
+  if (ud.op == UPD_INC) return 1;
+  if (ud.op == UPD_INC_VALID) return valid ? 1 : 0;
+  return valid ? val : 0;  // UPD_ADD_INT: two's complement image; UPD_ADD_F64: +0.0 has all-zero bits
+}
+
 template <int NS, bool FAST>
 __device__ __forceinline__ void table_phase32(const AggKernelParams& p, const StageWarp<NS>& sw, int first, int count,
-                                              int lane, uint32_t& new_groups) {
+                                              int lane, uint32_t& new_groups, uint64_t* bulk_stage, int& bulk_gen) {
   const TableDev& t = p.table;
   const int i = first + lane;
   const bool act = lane < count;
+  const bool use_bulk = p.n_pairs && ((p.bulk_lanes >> lane) & 1);
+  int64_t good_slot = -1;
   uint64_t key = 0;
   uint32_t vm = 0xFF;
   if (act) {
@@ -350,12 +361,42 @@ __device__ __forceinline__ void table_phase32(const AggKernelParams& p, const St
       unsigned long long idx = atomicAdd(t.n_overflow, 1ULL);
       if (t.overflow_rows) t.overflow_rows[idx] = sw.row[i];
     } else if (!(p.debug_flags & 1)) {
-      uint64_t* w = t.states + slot * t.n_words;
+      good_slot = slot;
+      uint64_t* row = t.states + t.row_base + slot * t.n_single;
       for (int u = 0; u < p.n_updates; ++u) {
         const UpdateDev ud = p.upd[u];
-        apply_update(ud.op, w + ud.word, sw.val[ud.slot][i], (vm >> ud.slot) & 1);
+        if (ud.paired) {
+          if (!use_bulk) apply_update(ud.op, word_ptr(t, slot, ud.word), sw.val[ud.slot][i], (vm >> ud.slot) & 1);
+          continue;
+        }
+        apply_update(ud.op, row + ud.ridx, sw.val[ud.slot][i], (vm >> ud.slot) & 1);
       }
     }
+  }
+  if (p.n_pairs) {
+    // Paired words: stage the row's two contributions (16 B) in shared memory and hand them to
+    // the TMA unit as one bulk reduction into the table.  The staging slots are reused every
+    // kBulkGen calls, after the bulk group that read them has drained (wait_group.read).
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kBulkGen - 1) : "memory");
+    if (good_slot >= 0 && use_bulk) {
+      for (int pr = 0; pr < p.n_pairs; ++pr) {
+        const PairDev pd = p.pairs[pr];
+        uint64_t* s = bulk_stage + ((size_t)(bulk_gen * kMaxPairs + pr) * 32 + lane) * 2;
+        s[0] = update_contribution(p.upd[pd.upd0], sw.val[p.upd[pd.upd0].slot][i], (vm >> p.upd[pd.upd0].slot) & 1);
+        s[1] = update_contribution(p.upd[pd.upd1], sw.val[p.upd[pd.upd1].slot][i], (vm >> p.upd[pd.upd1].slot) & 1);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      for (int pr = 0; pr < p.n_pairs; ++pr) {
+        const PairDev pd = p.pairs[pr];
+        const uint64_t* s = bulk_stage + ((size_t)(bulk_gen * kMaxPairs + pr) * 32 + lane) * 2;
+        uint64_t* dst = word_ptr(t, good_slot, p.upd[pd.upd0].word);
+        const uint32_t sa = (uint32_t)__cvta_generic_to_shared(s);
+        if (pd.is_f64) asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], 16;" ::"l"(dst), "r"(sa) : "memory");
+        else asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.u64 [%0], [%1], 16;" ::"l"(dst), "r"(sa) : "memory");
+      }
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    bulk_gen = (bulk_gen + 1) % kBulkGen;
   }
   __syncwarp();
 }
@@ -374,6 +415,10 @@ __global__ void __launch_bounds__(kBlock, 4) filter_group_agg_kernel(const __gri
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   StageWarp<NS>& sw = reinterpret_cast<StageWarp<NS>*>(smem_raw)[warp];
+  // bulk-reduction staging: [warp][generation][pair][lane] x 16 bytes, behind the row stages
+  uint64_t* bulk_stage = reinterpret_cast<uint64_t*>(smem_raw + ((sizeof(StageWarp<NS>) * kWarpsPerBlock + 15) & ~(size_t)15)) +
+                         (size_t)warp * kBulkGen * kMaxPairs * 32 * 2;
+  int bulk_gen = 0;
   const int64_t n_tiles = FAST ? p.n_rows / kTileRows : (p.n_rows + kTileRows - 1) / kTileRows;
   const uint32_t lt_mask = (1u << lane) - 1;
   uint32_t new_groups = 0;
@@ -435,11 +480,12 @@ __global__ void __launch_bounds__(kBlock, 4) filter_group_agg_kernel(const __gri
     __syncwarp();
     while (n_staged >= 32) {
       n_staged -= 32;
-      table_phase32<NS, FAST>(p, sw, n_staged, 32, lane, new_groups);
+      table_phase32<NS, FAST>(p, sw, n_staged, 32, lane, new_groups, bulk_stage, bulk_gen);
     }
   }
   __syncwarp();
-  if (n_staged > 0) table_phase32<NS, FAST>(p, sw, 0, n_staged, lane, new_groups);
+  if (n_staged > 0) table_phase32<NS, FAST>(p, sw, 0, n_staged, lane, new_groups, bulk_stage, bulk_gen);
+  if (p.n_pairs) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   // one counter update per warp
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) new_groups += __shfl_xor_sync(0xffffffffu, new_groups, o);
@@ -535,7 +581,7 @@ __global__ void __launch_bounds__(kBlock, 4) filter_single_agg_kernel(const __gr
     for (int o = 16; o > 0; o >>= 1) a = upd_combine(op, a, __shfl_xor_sync(0xffffffffu, a, o));
     if (lane == 0) {
       if (u >= 4) a = s_acc[warp][u];
-      merge_word(op, p.single_state + p.upd[u].word, a);
+      merge_word(op, word_ptr(p.table, 0, p.upd[u].word), a);
     }
   }
 }
@@ -550,8 +596,9 @@ __global__ void table_init_kernel(const __grid_constant__ TableDev t, const __gr
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     if (i < n_slots) t.keys[i] = kEmptyKey;
     else {
-      int64_t k = i - n_slots;
-      t.states[k] = init.w[k % t.n_words];
+      const int64_t k = i - n_slots;
+      const int w = (int)(k / n_slots);
+      *word_ptr(t, k - w * n_slots, w) = init.w[w];
     }
   }
 }
@@ -584,7 +631,7 @@ __global__ void table_merge_kernel(const __grid_constant__ TableDev src, const _
     int key_kind = i >= src.cap ? (int)(i - src.cap) + 1 : 0;
     int64_t d = resolve_slot(dst, key, key_kind, new_groups);
     if (d < 0) { atomicAdd(dst.n_overflow, 1ULL); continue; }
-    for (int w = 0; w < src.n_words; ++w) merge_word(kinds.op[w], dst.states + d * dst.n_words + w, src.states[i * src.n_words + w]);
+    for (int w = 0; w < src.n_words; ++w) merge_word(kinds.op[w], word_ptr(dst, d, w), *word_ptr(src, i, w));
   }
   __syncwarp();
 #pragma unroll
@@ -630,7 +677,7 @@ __global__ void table_partition_scatter_kernel(const __grid_constant__ TableDev 
     uint64_t* r = rows_out + pos * row_words;
     r[0] = key_kind ? 0 : key;
     r[1] = (uint64_t)key_kind;
-    for (int w = 0; w < src.n_words; ++w) r[2 + w] = src.states[i * src.n_words + w];
+    for (int w = 0; w < src.n_words; ++w) r[2 + w] = *word_ptr(src, i, w);
   }
 }
 
@@ -643,12 +690,142 @@ __global__ void rows_merge_kernel(const uint64_t* rows, int64_t n_rows, const __
     const uint64_t* r = rows + i * row_words;
     int64_t d = resolve_slot(dst, r[0], (int)r[1], new_groups);
     if (d < 0) { atomicAdd(dst.n_overflow, 1ULL); continue; }
-    for (int w = 0; w < dst.n_words; ++w) merge_word(kinds.op[w], dst.states + d * dst.n_words + w, r[2 + w]);
+    for (int w = 0; w < dst.n_words; ++w) merge_word(kinds.op[w], word_ptr(dst, d, w), r[2 + w]);
   }
   __syncwarp();
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) new_groups += __shfl_xor_sync(0xffffffffu, new_groups, o);
   if ((threadIdx.x & 31) == 0 && new_groups) atomicAdd(dst.n_groups, (unsigned long long)new_groups);
+}
+
+// ---------------------------------------------------------------- partial -> final exchange over peer memory
+// One process per GPU; every rank owns a receive buffer in its HBM that all peers map (CUDA IPC
+// over NVLink / NVSwitch).  The partial's groups are hash-partitioned by owner and each row is
+// stored DIRECTLY into the owner's receive region by the scatter kernel (no staging copy, no
+// count exchange, no NCCL on the data path); a release-flag per (source, owner) tells the owner's
+// merge kernel that the region is complete.  Mirrors build_partition_bucket.rs:41-131 + the
+// Flight exchange of AggregateMeta partitions, as one fused partition+send kernel.
+constexpr int kMaxRanks = 16;
+struct ExchangeHeader {
+  unsigned long long count[2][kMaxRanks];  // [parity][source rank]: rows that source wrote
+  unsigned long long flag[kMaxRanks];      // [source rank]: last epoch the source completed
+  unsigned long long overflow[kMaxRanks];  // [source rank]: epoch in which the region was too small
+  unsigned long long pad[16];
+};
+struct ExchangeScatterParams {
+  TableDev src;
+  void* peer_base[kMaxRanks];  // receive buffer (header first) of every rank, as mapped here
+  unsigned long long* cursors; // [n_ranks] rows reserved per owner (zeroed before the launch)
+  unsigned int* done;          // CTAs finished (zeroed before the launch)
+  int64_t region_rows;
+  unsigned long long epoch;
+  int32_t n_ranks, rank, row_words, parity;
+};
+__device__ __forceinline__ uint64_t* exchange_region(void* base, int n_ranks, int parity, int src, int64_t region_rows, int row_words) {
+  return reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(base) + sizeof(ExchangeHeader)) +
+         ((int64_t)(parity * n_ranks + src) * region_rows) * row_words;
+}
+
+__global__ void __launch_bounds__(256) exchange_scatter_kernel(const __grid_constant__ ExchangeScatterParams x) {
+  __shared__ unsigned int s_cnt[kMaxRanks];
+  __shared__ unsigned long long s_base[kMaxRanks];
+  __shared__ int s_last;
+  const TableDev& src = x.src;
+  const int64_t n_slots = src.cap + 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n_iter = (n_slots + stride - 1) / stride;
+  for (int64_t it = 0; it < n_iter; ++it) {
+    if (threadIdx.x < kMaxRanks) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t i = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t key = kEmptyKey;
+    if (i < n_slots) key = src.keys[i];
+    const bool occ = key != kEmptyKey;
+    const int key_kind = (occ && i >= src.cap) ? (int)(i - src.cap) + 1 : 0;
+    int owner = 0;
+    unsigned int local = 0;
+    if (occ) {
+      owner = owner_of(key, key_kind, x.n_ranks);
+      local = atomicAdd(&s_cnt[owner], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < x.n_ranks && s_cnt[threadIdx.x])
+      s_base[threadIdx.x] = atomicAdd(&x.cursors[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+    __syncthreads();
+    if (occ) {
+      const unsigned long long pos = s_base[owner] + local;
+      if ((int64_t)pos < x.region_rows) {
+        uint64_t* r = exchange_region(x.peer_base[owner], x.n_ranks, x.parity, x.rank, x.region_rows, x.row_words) + pos * x.row_words;
+        r[0] = key_kind ? 0 : key;
+        r[1] = (uint64_t)key_kind;
+        for (int w = 0; w < src.n_words; ++w) r[2 + w] = *word_ptr(src, i, w);
+      }
+    }
+    __syncthreads();
+  }
+  // publish: the last CTA to finish writes the row counts and then the completion flags
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(x.done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (s_last && threadIdx.x < x.n_ranks) {
+    __threadfence_system();
+    const unsigned long long cnt = atomicAdd(&x.cursors[threadIdx.x], 0ULL);
+    ExchangeHeader* h = reinterpret_cast<ExchangeHeader*>(x.peer_base[threadIdx.x]);
+    const bool over = (int64_t)cnt > x.region_rows;
+    h->count[x.parity][x.rank] = over ? (unsigned long long)x.region_rows : cnt;
+    if (over) h->overflow[x.rank] = x.epoch;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&h->flag[x.rank]), "l"(x.epoch) : "memory");
+  }
+}
+
+struct ExchangeMergeParams {
+  TableDev dst;
+  WordKinds kinds;
+  void* base;  // this rank's receive buffer
+  unsigned long long* status;  // [0] != 0: timed out waiting for a peer; [1] != 0: a region overflowed
+  int64_t region_rows;
+  unsigned long long epoch;
+  long long spin_limit_cycles;
+  int32_t n_ranks, row_words, parity, pad;
+};
+__global__ void __launch_bounds__(256) exchange_merge_kernel(const __grid_constant__ ExchangeMergeParams x) {
+  ExchangeHeader* h = reinterpret_cast<ExchangeHeader*>(x.base);
+  __shared__ int s_fail;
+  if (threadIdx.x == 0) s_fail = 0;
+  __syncthreads();
+  if (threadIdx.x < x.n_ranks) {  // wait until every source has released its region for this epoch
+    const long long t0 = clock64();
+    while (true) {
+      unsigned long long f;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(&h->flag[threadIdx.x]) : "memory");
+      if (f >= x.epoch) break;
+      if (clock64() - t0 > x.spin_limit_cycles) { s_fail = 1; break; }
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+  if (s_fail) {
+    if (threadIdx.x == 0) atomicExch(&x.status[0], 1ULL);
+    return;
+  }
+  uint32_t new_groups = 0;
+  for (int s = 0; s < x.n_ranks; ++s) {
+    const int64_t cnt = (int64_t)h->count[x.parity][s];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && h->overflow[s] == x.epoch) atomicExch(&x.status[1], 1ULL);
+    const uint64_t* rows = exchange_region(x.base, x.n_ranks, x.parity, s, x.region_rows, x.row_words);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (int64_t)gridDim.x * blockDim.x) {
+      const uint64_t* r = rows + i * x.row_words;
+      int64_t d = resolve_slot(x.dst, r[0], (int)r[1], new_groups);
+      if (d < 0) { atomicAdd(x.dst.n_overflow, 1ULL); continue; }
+      for (int w = 0; w < x.dst.n_words; ++w) merge_word(x.kinds.op[w], word_ptr(x.dst, d, w), r[2 + w]);
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) new_groups += __shfl_xor_sync(0xffffffffu, new_groups, o);
+  if ((threadIdx.x & 31) == 0 && new_groups) atomicAdd(x.dst.n_groups, (unsigned long long)new_groups);
 }
 
 // ---------------------------------------------------------------- finalize
@@ -703,11 +880,10 @@ __global__ void table_finalize_kernel(const __grid_constant__ TableDev src, cons
       store_narrow(fp.out_key, o, fp.key_dtype, kb);
       if (fp.out_key_valid) fp.out_key_valid[o] = key_kind == 2 ? 0 : 1;
     }
-    const uint64_t* se = src.states + i * src.n_words;
     for (int a = 0; a < fp.n_aggs; ++a) {
       const FinalAgg& fa = fp.aggs[a];
-      uint64_t cnt = se[fa.cnt_word];
-      uint64_t acc = fa.acc_word >= 0 ? se[fa.acc_word] : 0;
+      uint64_t cnt = *word_ptr(src, i, fa.cnt_word);
+      uint64_t acc = fa.acc_word >= 0 ? *word_ptr(src, i, fa.acc_word) : 0;
       int cls = dtype_class(fa.arg_dtype);
       if (fa.kind == DBX_AGG_COUNT) ((uint64_t*)fa.out)[o] = cnt;
       else if (fa.kind == DBX_AGG_SUM) ((uint64_t*)fa.out)[o] = cnt ? acc : 0;

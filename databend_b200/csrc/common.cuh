@@ -139,6 +139,14 @@ __device__ __forceinline__ void red_add_u64(void* p, uint64_t v) {
 __device__ __forceinline__ void red_add_f64(void* p, double v) {
   asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
+// same, with an L2 eviction-priority hint (evict_last keeps the hash table resident while the
+// column stream, loaded evict_first, passes through)
+__device__ __forceinline__ void red_add_u64_hint(void* p, uint64_t v, uint64_t pol) {
+  asm volatile("red.global.add.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void red_add_f64_hint(void* p, double v, uint64_t pol) {
+  asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void red_min_s64(void* p, int64_t v) {
   asm volatile("red.global.min.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }

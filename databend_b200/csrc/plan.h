@@ -9,6 +9,7 @@ namespace dbx {
 constexpr int kMaxSlots = 8;    // distinct input columns one kernel reads
 constexpr int kMaxUpdates = 16; // state-word updates per passing row
 constexpr int kMaxWords = 15;   // state words per group (entry = key + words)
+constexpr int kMaxPairs = 2;    // 16-byte pairs of additive state words updated by ONE TMA bulk reduction
 
 // x % d for a runtime-constant divisor without a hardware divide: Granlund–Montgomery
 // round-up method (N = 64):  m' = floor(2^64 (2^l - d) / d) + 1,
@@ -102,6 +103,16 @@ struct UpdateDev {
   int32_t op;
   int32_t slot;  // input slot (unused for UPD_INC)
   int32_t word;  // state word index
+  int32_t paired; // 1: this update is carried by a pair's bulk reduction (PairDev), not by its own RED
+  int32_t ridx;   // unpaired words: index inside the slot's row-major entry (TableDev::row_base / n_single)
+  int32_t pad;
+};
+// Two additive state words of the same class (both integer adds, or both f64 adds) stored next
+// to each other (16 bytes, 16-byte aligned) and updated per row by one
+// cp.reduce.async.bulk (.add.u64 / .add.f64) of 16 bytes instead of two REDs.
+struct PairDev {
+  int32_t upd0, upd1;  // indices into upd[]: words (word0, word0 + 1 in the pair array)
+  int32_t is_f64;
   int32_t pad;
 };
 
@@ -111,12 +122,18 @@ struct UpdateDev {
 //                              agg_hash(key) & (n_buckets - 1), linear probing over buckets;
 //                              keys[cap] / keys[cap + 1] are 0/1 "present" flags of the two special
 //                              groups: the key equal to the EMPTY sentinel, and the NULL key;
-//   states[(cap + 2) * n_words] state words of slot i at states[i * n_words ...].
+//   states[(cap + 2) * n_words] state word w of slot i at states[w_off[w] + i * w_stride[w]]:
+//                              paired words live in arrays of 16-byte pairs (stride 2), the others
+//                              in one array per word (stride 1) — see WordLayout in agg.cu.
 constexpr uint64_t kEmptyKey = 0x8000000000000000ULL;
 struct TableDev {
   uint64_t* keys;
   uint64_t* states;
   int64_t cap;
+  int64_t w_off[kMaxWords];
+  int64_t row_base;                // unpaired words: entry of slot i at states[row_base + i * n_single ...]
+  int32_t w_stride[kMaxWords];
+  int32_t n_single;
   int32_t n_words;
   int32_t probe_limit;             // buckets examined before a row is sent to the overflow list
   unsigned long long* n_groups;    // device counter: groups inserted so far
@@ -124,10 +141,15 @@ struct TableDev {
   uint32_t* overflow_rows;         // rows that could not be placed (nullptr: provably not needed)
 };
 
+__host__ __device__ __forceinline__ uint64_t* word_ptr(const TableDev& t, int64_t slot, int w) {
+  return t.states + t.w_off[w] + slot * t.w_stride[w];
+}
+
 struct AggKernelParams {
   DevCol cols[kMaxSlots];
   PredNodeDev nodes[DBX_MAX_PRED_NODES];
   UpdateDev upd[kMaxUpdates];
+  PairDev pairs[kMaxPairs];
   TableDev table;
   int64_t n_rows;
   const uint32_t* row_index;  // indirect mode: process rows row_index[0..n_rows)
@@ -136,7 +158,8 @@ struct AggKernelParams {
   int32_t key_slot;     // -1: no GROUP BY
   int32_t key_nullable; // key column may carry a validity bitmap
   uint32_t row_base;    // added to in-launch row numbers when recording overflow rows
-  int32_t pad2;
+  int32_t n_pairs;      // > 0: paired words go through TMA bulk reductions
+  uint32_t bulk_lanes;  // lanes (bit mask) that use the bulk path; the others use REDs for the paired words too
   int32_t debug_flags;  // perf bisecting only (env DBX_AGG_DEBUG): 1 = skip state updates, 2 = skip table probe
 };
 

@@ -9,11 +9,15 @@ dbx_agg_partial_partition / dbx_agg_final_merge_rows.
 """
 from __future__ import annotations
 
-from typing import List, Sequence, Tuple
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
 import torch.distributed as dist
+
+from . import abi
+from .lib import DbxError, load
 
 _M64 = (1 << 64) - 1
 _NULL_HASH = 0xd1cefa08eb382d69
@@ -60,3 +64,61 @@ def all_to_all_rows(send: torch.Tensor, send_counts: Sequence[int], row_bytes: i
     dist.all_to_all_single(recv[: total_recv * row_bytes], send[: total_send * row_bytes],
                            [c * row_bytes for c in recv_counts], [c * row_bytes for c in send_counts], group=group)
     return recv, recv_counts
+
+
+class PeerExchange:
+    """Partial -> final shuffle through peer memory (NVLink), the B200-native replacement of the
+    all-to-all above: `scatter(partial)` partitions the partial's groups and stores every row
+    straight into its owner's receive buffer, `merge(final)` waits on the device for all sources
+    and merges.  Only the one-time exchange of the 64-byte IPC handles goes through
+    torch.distributed.  One instance per rank; `connect()` is collective."""
+
+    def __init__(self, partial, rank: int, world: int, region_rows: int = 0):
+        self.rank, self.world = rank, world
+        self._h = C.c_void_p()
+        self._handle = (C.c_ubyte * 64)()
+        st = load().dbx_agg_exchange_create(partial.handle, rank, world, region_rows, C.byref(self._h), self._handle)
+        self._check(st, created=False)
+
+    def _check(self, st, created=True):
+        if st != abi.OK:
+            msg = load().dbx_agg_exchange_last_error(self._h if created else None)
+            raise DbxError(st, (msg or b"").decode("utf-8", "replace"))
+
+    def ipc_handle(self) -> bytes:
+        return bytes(self._handle)
+
+    def local_buffer(self) -> Tuple[int, int, int]:
+        base, rows, rb = C.c_void_p(), C.c_int64(0), C.c_int32(0)
+        self._check(load().dbx_agg_exchange_local_buffer(self._h, C.byref(base), C.byref(rows), C.byref(rb)))
+        return base.value, rows.value, rb.value
+
+    def connect(self, group=None):
+        """Collective: all-gather the IPC handles and map every peer's receive buffer."""
+        handles: List[Optional[bytes]] = [None] * self.world
+        dist.all_gather_object(handles, self.ipc_handle(), group=group)
+        blob = b"".join(handles)
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._check(load().dbx_agg_exchange_connect(self._h, buf, None))
+
+    def connect_local(self, peers: Sequence["PeerExchange"]):
+        """Ranks simulated inside one process (tests): wire the receive buffers directly."""
+        ptrs = (C.c_void_p * self.world)(*[p.local_buffer()[0] for p in peers])
+        self._check(load().dbx_agg_exchange_connect(self._h, None, ptrs))
+
+    def scatter(self, partial):
+        self._check(load().dbx_agg_exchange_scatter(self._h, partial.handle))
+
+    def merge(self, final):
+        self._check(load().dbx_agg_exchange_merge(self._h, final.handle))
+
+    def close(self):
+        if self._h:
+            load().dbx_agg_exchange_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

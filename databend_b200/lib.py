@@ -63,6 +63,13 @@ def load():
         "dbx_agg_final_merge_partial": (i32, [vp, vp]),
         "dbx_agg_partial_partition": (i32, [vp, i32, P(vp), P(i64), P(i32)]),
         "dbx_agg_final_merge_rows": (i32, [vp, vp, i64]),
+        "dbx_agg_exchange_create": (i32, [vp, i32, i32, i64, P(vp), vp]),
+        "dbx_agg_exchange_local_buffer": (i32, [vp, P(vp), P(i64), P(i32)]),
+        "dbx_agg_exchange_connect": (i32, [vp, vp, P(vp)]),
+        "dbx_agg_exchange_scatter": (i32, [vp, vp]),
+        "dbx_agg_exchange_merge": (i32, [vp, vp]),
+        "dbx_agg_exchange_destroy": (i32, [vp]),
+        "dbx_agg_exchange_last_error": (C.c_char_p, [vp]),
         "dbx_eval_distance": (i32, [i32, i32, P(abi.Column), P(abi.Column), P(abi.Column)]),
         "dbx_knn_create": (i32, [i32, i32, P(abi.Column), P(vp)]),
         "dbx_knn_search": (i32, [vp, P(abi.Column), i32, i32, vp, vp]),

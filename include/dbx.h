@@ -269,6 +269,27 @@ int32_t dbx_agg_partial_partition(dbx_op* partial_op, int32_t n_parts, void** de
 /* AGG_FINAL: merge `n_rows` such rows (device memory, e.g. the all-to-all receive buffer). */
 int32_t dbx_agg_final_merge_rows(dbx_op* final_op, const void* dev_rows, int64_t n_rows);
 
+/* Peer-memory exchange of aggregate partials between the GPUs of one box (one process per GPU):
+ * the multi-GPU form of the partial -> final shuffle (build_partition_bucket.rs:41-131; between
+ * nodes the reference ships AggregateMeta partitions over Arrow Flight,
+ * servers/flight/v1/exchange/*).  Every rank creates an exchange (a receive buffer in its HBM),
+ * the 64-byte CUDA-IPC handles are all-gathered by the host (torch.distributed / any transport)
+ * and passed to connect; then per query
+ *     scatter(partial)  partition + store rows straight into the owners' buffers over NVLink
+ *     merge(final)      wait (on the device) for every source's release flag, merge the regions
+ * with no NCCL call, staging copy or host synchronisation on the data path.
+ * region_rows = 0 sizes a region for the worst case (all groups of one source to one owner). */
+typedef struct dbx_agg_exchange dbx_agg_exchange;
+int32_t dbx_agg_exchange_create(dbx_op* partial_op, int32_t rank, int32_t n_ranks, int64_t region_rows,
+                                dbx_agg_exchange** out, void* ipc_handle_out /* 64 bytes, may be NULL */);
+int32_t dbx_agg_exchange_local_buffer(dbx_agg_exchange* x, void** base, int64_t* region_rows, int32_t* row_bytes);
+int32_t dbx_agg_exchange_connect(dbx_agg_exchange* x, const void* all_handles /* n_ranks x 64 B */,
+                                 void* const* same_process_ptrs /* or the buffers themselves */);
+int32_t dbx_agg_exchange_scatter(dbx_agg_exchange* x, dbx_op* partial_op);
+int32_t dbx_agg_exchange_merge(dbx_agg_exchange* x, dbx_op* final_op);
+int32_t dbx_agg_exchange_destroy(dbx_agg_exchange* x);
+const char* dbx_agg_exchange_last_error(const dbx_agg_exchange* x);
+
 /* ScalarFunction::eval replacement for the vector distances (scalars/vector.rs:497-556):
  * out[i] = distance(lhs[i], rhs[i]) row-wise, either side may be const.  f32 result. */
 int32_t dbx_eval_distance(int32_t kind, int32_t device, const dbx_column* lhs, const dbx_column* rhs,

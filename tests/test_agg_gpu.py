@@ -334,3 +334,73 @@ def test_partition_exchange_merge_simulated_ranks(gpu):
     g = sorted_group_result_from_block(merged, 3, 1)
     o = sorted_group_result_from_oracle(oracle().filter_group_agg(blk, CONFIG2.to_c(V_MOD3), 4), [abi.I64])
     assert_group_results_equal(g, o)
+
+
+def test_peer_memory_exchange_simulated_ranks(gpu):
+    """The peer-memory exchange (scatter straight into the owners' receive regions + flag-gated
+    merge) with N ranks simulated on ONE GPU: three consecutive queries (epochs alternate the
+    region parity), each checked against the oracle; every group lands on exactly its owner."""
+    from databend_b200.exchange import PeerExchange, owner_of
+    world = 4
+    types = None
+    parts, fins, xs = [], [], []
+    blk0 = config2_block(10, n_keys=5)
+    types = schema_types(blk0)
+    for r in range(world):
+        parts.append(TransformPartialAggregate(CONFIG2, types, V_MOD3))
+        fins.append(TransformFinalAggregate(CONFIG2, types))
+    for r in range(world):
+        xs.append(PeerExchange(parts[r], r, world))
+    for r in range(world):
+        xs[r].connect_local(xs)
+    for epoch, (rows, keys) in enumerate([(400_000, 30_000), (250_000, 90_000), (123_457, 1_000)]):
+        blk = config2_block(rows, n_keys=keys, seed=100 + epoch)
+        blk.columns[0].data[:3] = -(2**63)  # sentinel-valued key
+        for r in range(world):
+            parts[r].reset()
+            fins[r].reset()
+            lo, hi = rows * r // world, rows * (r + 1) // world
+            parts[r].transform(blk.slice(lo, hi))
+            parts[r].on_finish()
+        for r in range(world):
+            xs[r].scatter(parts[r])
+        for r in range(world):
+            parts[r].synchronize()  # one GPU: all scatters must have run before a merge may spin
+        for r in range(world):
+            xs[r].merge(fins[r])
+        outs = [fins[r].on_finish()[0] for r in range(world)]
+        for r, o in enumerate(outs):
+            k = o.columns[3].values()
+            kind = np.where(k == -(2**63), 1, 0)
+            assert (owner_of(k.view(np.uint64), kind, world) == r).all()
+        merged = DataBlock([Column.from_data(np.concatenate([o.columns[i].values() for o in outs]), outs[0].columns[i].dtype,
+                                             validity=np.concatenate([o.columns[i].valid_mask() for o in outs]))
+                            for i in range(4)])
+        g = sorted_group_result_from_block(merged, 3, 1)
+        o = sorted_group_result_from_oracle(oracle().filter_group_agg(blk, CONFIG2.to_c(V_MOD3), 4), [abi.I64])
+        assert_group_results_equal(g, o)
+    for x in xs:
+        x.close()
+    for p in parts + fins:
+        p.close()
+
+
+def test_peer_memory_exchange_region_overflow_is_loud(gpu):
+    """A receive region that is too small must fail the query, never drop groups silently."""
+    from databend_b200.exchange import PeerExchange
+    from databend_b200.lib import DbxError
+    blk = config2_block(100_000, n_keys=20_000)
+    types = schema_types(blk)
+    p = TransformPartialAggregate(CONFIG2, types, V_MOD3)
+    f = TransformFinalAggregate(CONFIG2, types)
+    x = PeerExchange(p, 0, 1, region_rows=64)
+    x.connect_local([x])
+    p.transform(blk)
+    p.on_finish()
+    x.scatter(p)
+    x.merge(f)
+    with pytest.raises(DbxError, match="receive region"):
+        f.on_finish()
+    x.close()
+    p.close()
+    f.close()
