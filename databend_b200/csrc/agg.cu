@@ -525,13 +525,20 @@ class AggPartialOp : public Op {
 
   template <int NS, bool FAST, bool INDIRECT>
   int32_t launch_one(const AggKernelParams& kp) {
+    // the TMA bulk-reduction variant exists for the straight-line kernel only; everywhere else
+    // paired words are updated with plain REDs
+    if (FAST && !INDIRECT && kp.n_pairs > 0) return launch_kernel<NS, FAST, INDIRECT, true>(kp);
+    return launch_kernel<NS, FAST, INDIRECT, false>(kp);
+  }
+  template <int NS, bool FAST, bool INDIRECT, bool BULK>
+  int32_t launch_kernel(const AggKernelParams& kp) {
     static bool attr_set[16] = {};
     const size_t smem_rows = (sizeof(StageWarp<NS>) * kWarpsPerBlock + 15) & ~(size_t)15;
     const size_t smem_bulk = (size_t)kWarpsPerBlock * kBulkGen * kMaxPairs * 32 * 16;
-    const size_t smem = smem_rows + (kp.n_pairs ? smem_bulk : 0);
-    auto kern = filter_group_agg_kernel<NS, FAST, INDIRECT>;
+    const size_t smem = smem_rows + (BULK ? smem_bulk : 0);
+    auto kern = filter_group_agg_kernel<NS, FAST, INDIRECT, BULK>;
     if (!attr_set[device]) {
-      DBX_CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_rows + smem_bulk)));
+      DBX_CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_set[device] = true;
     }
     int grid = grid_for_rows(kp.n_rows);
@@ -854,15 +861,32 @@ class AggFinalOp : public Op {
   }
 
   // merge_result: compact the table into [aggs..., keys...] columns in HBM
+  // The output columns are sized for the most groups a healthy table holds (half its slots) and
+  // the finalize kernel is enqueued right away; the group count is read back afterwards, so the
+  // whole operator costs ONE host synchronisation.  (A fuller table — only possible after merges
+  // the host did not size — repeats the pass with the exact count.)
   int32_t finish() override {
     if (!has_table) DBX_TRY(ensure_capacity(0));
-    int64_t ng, no;
-    DBX_TRY(read_groups(&ng, &no));
+    int64_t ng = 0, no = 0;
+    int32_t st = finalize_pass(plan.grouped ? table.cap / 2 + 2 : 1, &ng, &no);
+    if (st != DBX_OK) return st;
     if (no) { err.set("internal: rows were dropped by the aggregate table (overflow)"); return DBX_ERR_CUDA; }
+    if (ng > result_capacity) {
+      result_dev.reset();
+      DBX_TRY(finalize_pass(ng, &ng, &no));
+    }
     result_rows = ng;
+    for (dbx_column& c : result_dev->cols) c.len = ng;
+    return DBX_OK;
+  }
+
+  int64_t result_capacity = 0;
+  int32_t finalize_pass(int64_t capacity, int64_t* ng_out, int64_t* no_out) {
     auto ob = std::make_unique<OwnedBlock>();
     ob->device = device;
-    const int64_t cap_rows = std::max<int64_t>(ng, 1);
+    const int64_t cap_rows = std::max<int64_t>(capacity, 1);
+    const int64_t ng = cap_rows;  // column lengths are patched by finish() once the count is known
+    result_capacity = cap_rows;
     auto dev_alloc = [&](size_t bytes, void** p) -> int32_t {
       DBX_CUDA_TRY(err, pool_alloc(device, stream, bytes, p));
       ob->dev_allocs.push_back(*p);
@@ -914,6 +938,7 @@ class AggFinalOp : public Op {
     DBX_TRY(dev_alloc(8, (void**)&out_count));
     DBX_CUDA_TRY(err, cudaMemsetAsync(out_count, 0, 8, stream));
     fp.out_count = out_count;
+    fp.out_capacity = cap_rows;
     table_finalize_kernel<<<grid_for_entries(table.cap + 2), 256, 0, stream>>>(table.view(nullptr), fp);
     count_launch();
     DBX_CUDA_TRY(err, cudaGetLastError());
@@ -922,14 +947,14 @@ class AggFinalOp : public Op {
       if (!valid_bytes[i]) continue;
       uint8_t* bits = nullptr;
       DBX_TRY(dev_alloc((size_t)(cap_rows + 7) / 8 + 8, (void**)&bits));
-      pack_validity_kernel<<<grid_for_entries((ng + 7) / 8 + 1), 256, 0, stream>>>(valid_bytes[i], ng, bits);
+      pack_validity_kernel<<<grid_for_entries((ng + 7) / 8 + 1), 256, 0, stream>>>(valid_bytes[i], out_count, cap_rows, bits);
       count_launch();
       DBX_CUDA_TRY(err, cudaGetLastError());
       ob->cols[i].validity = bits;
       ob->cols[i].validity_bit_offset = 0;
     }
     result_dev = std::move(ob);
-    return DBX_OK;
+    return read_groups(ng_out, no_out);  // the one synchronisation: also completes the kernels above
   }
 
   int32_t pull(int32_t out_mem, dbx_block* out, int32_t* has_block) override {
@@ -1150,7 +1175,7 @@ int32_t dbx_agg_exchange_scatter(dbx_agg_exchange* x, dbx_op* partial_op) {
   sp.region_rows = x->region_rows;
   sp.epoch = x->epoch;
   sp.n_ranks = x->n_ranks; sp.rank = x->rank; sp.row_words = x->row_words; sp.parity = (int)(x->epoch & 1);
-  exchange_scatter_kernel<<<grid_for_entries(sp.src.cap + 2), 256, 0, p->stream>>>(sp);
+  exchange_scatter_kernel<<<grid_for_entries(sp.src.cap + 2), 256, (size_t)256 * x->row_words * 8, p->stream>>>(sp);
   count_launch();
   DBX_CUDA_TRY(x->err, cudaGetLastError());
   DBX_CUDA_TRY(x->err, cudaEventRecord(x->ev_scatter, p->stream));

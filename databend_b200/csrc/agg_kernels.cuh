@@ -329,13 +329,13 @@ __device__ __forceinline__ uint64_t update_contribution(const UpdateDev& ud, uin
   return valid ? val : 0;  // UPD_ADD_INT: two's complement image; UPD_ADD_F64: +0.0 has all-zero bits
 }
 
-template <int NS, bool FAST>
+template <int NS, bool FAST, bool BULK>
 __device__ __forceinline__ void table_phase32(const AggKernelParams& p, const StageWarp<NS>& sw, int first, int count,
                                               int lane, uint32_t& new_groups, uint64_t* bulk_stage, int& bulk_gen) {
   const TableDev& t = p.table;
   const int i = first + lane;
   const bool act = lane < count;
-  const bool use_bulk = p.n_pairs && ((p.bulk_lanes >> lane) & 1);
+  const bool use_bulk = BULK && ((p.bulk_lanes >> lane) & 1);
   int64_t good_slot = -1;
   uint64_t key = 0;
   uint32_t vm = 0xFF;
@@ -373,7 +373,7 @@ __device__ __forceinline__ void table_phase32(const AggKernelParams& p, const St
       }
     }
   }
-  if (p.n_pairs) {
+  if (BULK) {
     // Paired words: stage the row's two contributions (16 B) in shared memory and hand them to
     // the TMA unit as one bulk reduction into the table.  The staging slots are reused every
     // kBulkGen calls, after the bulk group that read them has drained (wait_group.read).
@@ -410,7 +410,7 @@ __device__ __forceinline__ void prefetch_tile(const AggKernelParams& p, int64_t 
   }
 }
 
-template <int NS, bool FAST, bool INDIRECT>
+template <int NS, bool FAST, bool INDIRECT, bool BULK = false>
 __global__ void __launch_bounds__(kBlock, 4) filter_group_agg_kernel(const __grid_constant__ AggKernelParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -480,12 +480,12 @@ __global__ void __launch_bounds__(kBlock, 4) filter_group_agg_kernel(const __gri
     __syncwarp();
     while (n_staged >= 32) {
       n_staged -= 32;
-      table_phase32<NS, FAST>(p, sw, n_staged, 32, lane, new_groups, bulk_stage, bulk_gen);
+      table_phase32<NS, FAST, BULK>(p, sw, n_staged, 32, lane, new_groups, bulk_stage, bulk_gen);
     }
   }
   __syncwarp();
-  if (n_staged > 0) table_phase32<NS, FAST>(p, sw, 0, n_staged, lane, new_groups, bulk_stage, bulk_gen);
-  if (p.n_pairs) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (n_staged > 0) table_phase32<NS, FAST, BULK>(p, sw, 0, n_staged, lane, new_groups, bulk_stage, bulk_gen);
+  if (BULK) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   // one counter update per warp
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) new_groups += __shfl_xor_sync(0xffffffffu, new_groups, o);
@@ -726,11 +726,19 @@ __device__ __forceinline__ uint64_t* exchange_region(void* base, int n_ranks, in
          ((int64_t)(parity * n_ranks + src) * region_rows) * row_words;
 }
 
+constexpr int kExchMaxRowWords = 2 + kMaxWords;
 __global__ void __launch_bounds__(256) exchange_scatter_kernel(const __grid_constant__ ExchangeScatterParams x) {
+  // Per 256-slot step: count the step's groups per owner, reserve a run in every owner's region
+  // with ONE atomic per owner, lay the rows out owner after owner in shared memory, then copy
+  // each owner's run with consecutive 8-byte stores — NVLink sees full 128-byte lines instead of
+  // scattered 8-byte writes.
+  extern __shared__ __align__(16) uint64_t s_rows[];  // [256][row_words]
   __shared__ unsigned int s_cnt[kMaxRanks];
+  __shared__ unsigned int s_off[kMaxRanks + 1];
   __shared__ unsigned long long s_base[kMaxRanks];
   __shared__ int s_last;
   const TableDev& src = x.src;
+  const int rw = x.row_words;
   const int64_t n_slots = src.cap + 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t n_iter = (n_slots + stride - 1) / stride;
@@ -749,17 +757,31 @@ __global__ void __launch_bounds__(256) exchange_scatter_kernel(const __grid_cons
       local = atomicAdd(&s_cnt[owner], 1u);
     }
     __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int o = 0;
+      for (int r = 0; r < x.n_ranks; ++r) { s_off[r] = o; o += s_cnt[r]; }
+      s_off[x.n_ranks] = o;
+    }
     if (threadIdx.x < x.n_ranks && s_cnt[threadIdx.x])
       s_base[threadIdx.x] = atomicAdd(&x.cursors[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
     __syncthreads();
     if (occ) {
-      const unsigned long long pos = s_base[owner] + local;
-      if ((int64_t)pos < x.region_rows) {
-        uint64_t* r = exchange_region(x.peer_base[owner], x.n_ranks, x.parity, x.rank, x.region_rows, x.row_words) + pos * x.row_words;
-        r[0] = key_kind ? 0 : key;
-        r[1] = (uint64_t)key_kind;
-        for (int w = 0; w < src.n_words; ++w) r[2 + w] = *word_ptr(src, i, w);
-      }
+      uint64_t* r = s_rows + (size_t)(s_off[owner] + local) * rw;
+      r[0] = key_kind ? 0 : key;
+      r[1] = (uint64_t)key_kind;
+      for (int w = 0; w < src.n_words; ++w) r[2 + w] = *word_ptr(src, i, w);
+    }
+    __syncthreads();
+    for (int o = 0; o < x.n_ranks; ++o) {
+      const unsigned int cnt = s_cnt[o];
+      if (!cnt) continue;
+      const unsigned long long base = s_base[o];
+      // rows beyond the region are dropped here and reported through the overflow flag
+      const int64_t room = x.region_rows - (int64_t)base;
+      const int64_t n_ok = room <= 0 ? 0 : (room < (int64_t)cnt ? room : (int64_t)cnt);
+      uint64_t* dst = exchange_region(x.peer_base[o], x.n_ranks, x.parity, x.rank, x.region_rows, rw) + base * rw;
+      const uint64_t* from = s_rows + (size_t)s_off[o] * rw;
+      for (int64_t j = threadIdx.x; j < n_ok * rw; j += blockDim.x) dst[j] = from[j];
     }
     __syncthreads();
   }
@@ -846,6 +868,7 @@ struct FinalizeParams {
   void* out_key;
   uint8_t* out_key_valid; // byte per group or nullptr
   unsigned long long* out_count;
+  int64_t out_capacity;   // rows the output columns can hold
 };
 
 __device__ __forceinline__ void store_narrow(void* out, int64_t idx, int dtype, uint64_t bits) {
@@ -856,24 +879,33 @@ __device__ __forceinline__ void store_narrow(void* out, int64_t idx, int dtype, 
   else ((uint64_t*)out)[idx] = bits;
 }
 
-__global__ void table_finalize_kernel(const __grid_constant__ TableDev src, const __grid_constant__ FinalizeParams fp) {
+__global__ void __launch_bounds__(256) table_finalize_kernel(const __grid_constant__ TableDev src, const __grid_constant__ FinalizeParams fp) {
+  __shared__ unsigned int s_warp_cnt[8];
+  __shared__ unsigned long long s_block_base;
   const int64_t n_slots = src.cap + 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t n_iter = (n_slots + stride - 1) / stride;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int64_t it = 0; it < n_iter; ++it) {
     int64_t i = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t key = kEmptyKey;
     if (i < n_slots) key = src.keys[i];
     bool occ = key != kEmptyKey;
-    // warp-aggregated output slot allocation
-    unsigned ballot = __ballot_sync(0xffffffffu, occ);
-    if (!ballot) continue;
-    int lane = threadIdx.x & 31;
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(fp.out_count, (unsigned long long)__popc(ballot));
-    base = __shfl_sync(0xffffffffu, base, 0);
+    // output slot allocation: one atomic per CTA and step (warp ballots + an 8-entry scan)
+    const unsigned ballot = __ballot_sync(0xffffffffu, occ);
+    if (lane == 0) s_warp_cnt[warp] = __popc(ballot);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int tot = 0;
+      for (int w = 0; w < 8; ++w) { const unsigned int c = s_warp_cnt[w]; s_warp_cnt[w] = tot; tot += c; }
+      s_block_base = tot ? atomicAdd(fp.out_count, (unsigned long long)tot) : 0ULL;
+    }
+    __syncthreads();
+    const unsigned long long base = s_block_base + s_warp_cnt[warp];
+    __syncthreads();
     if (!occ) continue;
     int64_t o = (int64_t)base + __popc(ballot & ((1u << lane) - 1));
+    if (o >= fp.out_capacity) continue;  // the host re-runs with a larger output (never silently)
     int key_kind = i >= src.cap ? (int)(i - src.cap) + 1 : 0;
     if (fp.key_dtype >= 0) {
       uint64_t kb = key_kind == 1 ? kEmptyKey : (key_kind == 2 ? 0 : key);
@@ -902,7 +934,8 @@ __global__ void table_finalize_kernel(const __grid_constant__ TableDev src, cons
 }
 
 // bytes (0/1) -> LSB-first bitmap (MutableBitmap layout), one output byte per thread
-__global__ void pack_validity_kernel(const uint8_t* bytes, int64_t n, uint8_t* bits) {
+__global__ void pack_validity_kernel(const uint8_t* bytes, const unsigned long long* n_dev, int64_t n_max, uint8_t* bits) {
+  const int64_t n = min((int64_t)*n_dev, n_max);
   int64_t nb = (n + 7) / 8;
   for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (int64_t)gridDim.x * blockDim.x) {
     uint32_t v = 0;
