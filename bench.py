@@ -307,6 +307,7 @@ def run_dbx(args):
             # rows go straight into the owners' HBM over NVLink; the merge kernel waits on the
             # sources' flags on the device: no NCCL call, staging copy or host sync in between
             xchg.scatter(part)
+            part.reset()  # re-arm the partial now: its table is cleared while the owners merge
             xchg.merge(fin)
         else:
             rows_ptr = C.c_void_p()
@@ -326,7 +327,8 @@ def run_dbx(args):
         return fin.on_finish(out_mem)
 
     def step_device():
-        part.reset()
+        if not use_peer:
+            part.reset()
         fin.reset()
         part.transform(dblock)
         kernel_ms.append(part.last_kernel_ms())
@@ -391,7 +393,8 @@ def run_dbx(args):
         hblocks = hblock.split_by_rows(args.block_rows)
 
         def step_host():
-            part.reset()
+            if not use_peer:
+                part.reset()
             fin.reset()
             for b in hblocks:
                 part.transform(b)

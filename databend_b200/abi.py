@@ -137,6 +137,7 @@ EXPORTS = [
     "dbx_join_probe", "dbx_agg_final_merge_partial", "dbx_agg_partial_partition", "dbx_agg_final_merge_rows",
     "dbx_agg_exchange_create", "dbx_agg_exchange_local_buffer", "dbx_agg_exchange_connect", "dbx_agg_exchange_scatter",
     "dbx_agg_exchange_merge", "dbx_agg_exchange_destroy", "dbx_agg_exchange_last_error",
+    "dbx_hash_partition",
     "dbx_eval_distance", "dbx_knn_create", "dbx_knn_search", "dbx_knn_destroy", "dbx_knn_last_error", "dbx_knn_last_gemm_ms", "dbx_knn_last_stats",
     "dbx_synth_fill", "dbx_kernel_launch_count", "dbx_op_last_kernel_ms", "dbx_op_stream",
 ]

@@ -8,6 +8,8 @@
 //   TransformFinalAggregate            .../aggregator/transform_aggregate_final.rs:67-330
 //   FinalSingleStateAggregator         .../aggregator/transform_single_key.rs:190-279
 //   AggregateHashTable                 src/query/expression/src/aggregate/aggregate_hashtable.rs:168-408
+#include <cub/device/device_scan.cuh>
+
 #include <algorithm>
 #include <cstdlib>
 
@@ -449,6 +451,49 @@ inline int64_t next_pow2(int64_t x) {
   return p;
 }
 
+// Hand a finished device-resident result to the caller: as is (device), or copied into pinned
+// host memory (zero-copy wrappable by the caller, released through dbx_block_release).
+// BOOL columns hold packed bits (like validity).
+int32_t pull_owned_block(std::unique_ptr<OwnedBlock>& result_dev, int device, cudaStream_t stream, ErrorSink& err, int32_t out_mem,
+                         dbx_block* out) {
+  if (out_mem == DBX_MEM_DEVICE) {
+    DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
+    OwnedBlock* ob = result_dev.release();
+    return fill_owned_block(ob, out);
+  }
+  auto hb = std::make_unique<OwnedBlock>();
+  hb->device = device;
+  for (const dbx_column& dc : result_dev->cols) {
+    dbx_column c = dc;
+    c.mem = DBX_MEM_HOST;
+    if (dc.is_const) { hb->cols.push_back(c); continue; }
+    size_t bytes = dc.dtype == DBX_BOOL ? (size_t)(dc.len + 7) / 8 : (size_t)dc.len * dtype_size(dc.dtype);
+    void* hp = nullptr;
+    DBX_CUDA_TRY(err, pinned_alloc(bytes, &hp));
+    hb->host_allocs.push_back(hp);
+    if (bytes) DBX_CUDA_TRY(err, cudaMemcpyAsync(hp, dc.data, bytes, cudaMemcpyDeviceToHost, stream));
+    c.data = hp;
+    if (dc.validity) {
+      size_t vb = (size_t)(dc.len + 7) / 8;
+      void* hv = nullptr;
+      DBX_CUDA_TRY(err, pinned_alloc(vb, &hv));
+      hb->host_allocs.push_back(hv);
+      if (vb) DBX_CUDA_TRY(err, cudaMemcpyAsync(hv, dc.validity, vb, cudaMemcpyDeviceToHost, stream));
+      c.validity = (const uint8_t*)hv;
+    }
+    hb->cols.push_back(c);
+  }
+  DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
+  for (dbx_column& c : hb->cols) {
+    if (!c.validity) continue;
+    int64_t nulls = 0;
+    for (int64_t i = 0; i < c.len; ++i) nulls += !((c.validity[i >> 3] >> (i & 7)) & 1);
+    c.null_count = nulls;
+  }
+  result_dev.reset();
+  return fill_owned_block(hb.release(), out);
+}
+
 }  // namespace
 
 // ================================================================ partial
@@ -730,6 +775,9 @@ class AggPartialOp : public Op {
 };
 
 // ================================================================ final
+class AggFinalOp;
+int32_t exchange_launch_merge(dbx_agg_exchange* x, AggFinalOp* f, int64_t cap);
+
 class AggFinalOp : public Op {
  public:
   AggPlan plan;
@@ -740,6 +788,8 @@ class AggFinalOp : public Op {
   int64_t result_rows = 0;
   bool pulled = false;
   unsigned long long* exchange_status = nullptr;  // device: set by a peer-memory exchange merge
+  dbx_agg_exchange* exchange_src = nullptr;       // the exchange whose regions this table was merged from
+  int64_t last_groups = 0;                        // result size of the previous query (sizing hint, survives reset)
 
   int32_t init(const dbx_agg_params* p, const int32_t* types, int32_t n, int dev) {
     DBX_TRY(base_init(dev));
@@ -750,6 +800,7 @@ class AggFinalOp : public Op {
   int32_t reset() override {
     has_table = false;
     exchange_status = nullptr;
+    exchange_src = nullptr;
     result_dev.reset();
     result_rows = 0;
     pulled = false;
@@ -870,7 +921,15 @@ class AggFinalOp : public Op {
     int64_t ng = 0, no = 0;
     int32_t st = finalize_pass(plan.grouped ? table.cap / 2 + 2 : 1, &ng, &no);
     if (st != DBX_OK) return st;
+    if (no && exchange_src) {
+      // the table was sized from the previous query's result and this one has more groups: the
+      // received regions are still intact, so merge them again into a worst-case table
+      result_dev.reset();
+      DBX_TRY(exchange_launch_merge(exchange_src, this, 0));
+      DBX_TRY(finalize_pass(table.cap / 2 + 2, &ng, &no));
+    }
     if (no) { err.set("internal: rows were dropped by the aggregate table (overflow)"); return DBX_ERR_CUDA; }
+    last_groups = ng;
     if (ng > result_capacity) {
       result_dev.reset();
       DBX_TRY(finalize_pass(ng, &ng, &no));
@@ -962,43 +1021,192 @@ class AggFinalOp : public Op {
     if (pulled || !result_dev) { *has_block = 0; return DBX_OK; }
     pulled = true;
     *has_block = 1;
-    if (out_mem == DBX_MEM_DEVICE) {
-      DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
-      OwnedBlock* ob = result_dev.release();
-      return fill_owned_block(ob, out);
-    }
-    auto hb = std::make_unique<OwnedBlock>();
-    hb->device = device;
-    for (const dbx_column& dc : result_dev->cols) {
-      dbx_column c = dc;
-      c.mem = DBX_MEM_HOST;
-      size_t bytes = (size_t)dc.len * dtype_size(dc.dtype);
-      void* hp = nullptr;
-      DBX_CUDA_TRY(err, pinned_alloc(bytes, &hp));
-      hb->host_allocs.push_back(hp);
-      if (bytes) DBX_CUDA_TRY(err, cudaMemcpyAsync(hp, dc.data, bytes, cudaMemcpyDeviceToHost, stream));
-      c.data = hp;
-      if (dc.validity) {
-        size_t vb = (size_t)(dc.len + 7) / 8;
-        void* hv = nullptr;
-        DBX_CUDA_TRY(err, pinned_alloc(vb, &hv));
-        hb->host_allocs.push_back(hv);
-        if (vb) DBX_CUDA_TRY(err, cudaMemcpyAsync(hv, dc.validity, vb, cudaMemcpyDeviceToHost, stream));
-        c.validity = (const uint8_t*)hv;
-      }
-      hb->cols.push_back(c);
-    }
-    DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
-    for (dbx_column& c : hb->cols) {
-      if (!c.validity) continue;
-      int64_t nulls = 0;
-      for (int64_t i = 0; i < c.len; ++i) nulls += !((c.validity[i >> 3] >> (i & 7)) & 1);
-      c.null_count = nulls;
-    }
-    result_dev.reset();
-    return fill_owned_block(hb.release(), out);
+    return pull_owned_block(result_dev, device, stream, err, out_mem, out);
   }
 };
+
+// ================================================================ standalone filter
+// TransformFilter (filter_predicate.rs:35-104): Transform::transform(DataBlock) -> DataBlock, one
+// output block per pushed block, rows in input order.  BlockEntry::Const columns stay const.
+class FilterOp : public Op {
+ public:
+  AggPlan plan;
+  Stager stager;
+  DevBuf nibbles, tile_counts, tile_offsets, cub_tmp, dev_total;
+  PinnedBuf host;
+  std::vector<std::unique_ptr<OwnedBlock>> out_q;
+  size_t out_head = 0;
+  int64_t rows_in = 0, rows_out = 0;
+
+  int32_t init(const dbx_predicate* pred, const int32_t* types, int32_t n, int dev) {
+    DBX_TRY(base_init(dev));
+    dbx_agg_params ap;
+    memset(&ap, 0, sizeof(ap));
+    ap.filter = *pred;
+    DBX_TRY(build_plan(&ap, types, n, &plan, &err));
+    for (int i = 0; i < n; ++i)
+      if (plan.col_dtype[i] != DBX_BOOL && dtype_size(plan.col_dtype[i]) == 0) { err.set("filter: unsupported column type (numeric and boolean columns only)"); return DBX_ERR_UNSUPPORTED; }
+    DBX_TRY(stager.init(dev, stream, &err));
+    DBX_CUDA_TRY(err, host.ensure(64));
+    DBX_CUDA_TRY(err, dev_total.ensure(64));
+    return DBX_OK;
+  }
+  int32_t reset() override { out_q.clear(); out_head = 0; rows_in = rows_out = 0; return DBX_OK; }
+
+  template <int NS>
+  void launch_select(const AggKernelParams& kp, int grid) {
+    filter_select_kernel<NS><<<grid, kBlock, 0, stream>>>(kp, (uint8_t*)nibbles.p, (uint32_t*)tile_counts.p);
+  }
+
+  int32_t push(const dbx_block* b) override {
+    if (b->num_cols != plan.n_cols) { err.set("push: block column count differs from the operator's input schema"); return DBX_ERR_INVALID; }
+    for (int i = 0; i < plan.n_cols; ++i) {
+      if (b->cols[i].dtype != plan.col_dtype[i]) { err.set("push: block column dtype differs from the operator's input schema"); return DBX_ERR_INVALID; }
+      if (b->cols[i].len != b->num_rows) { err.set("push: column length differs from num_rows"); return DBX_ERR_INVALID; }
+    }
+    const int64_t n = b->num_rows;
+    if (n >= (1LL << 31)) { err.set("filter: blocks of 2^31 rows or more are not supported"); return DBX_ERR_UNSUPPORTED; }
+    if (plan.div_by_zero && n > 0) {  // rem_scalar: divisor literal 0 fails the whole block (arithmetic_modulo.rs:137-140)
+      err.set("Division by zero, during run expr: modulo (first failing row 0)");
+      return DBX_ERR_BAD_ARGUMENTS;
+    }
+    rows_in += n;
+    auto ob = std::make_unique<OwnedBlock>();
+    ob->device = device;
+    const int64_t n_tiles = (n + kTileRows - 1) / kTileRows;
+    int64_t total = 0;
+    DevCol pcols[kMaxSlots];
+    DevCol ccols[64];
+    if (n > 0) {
+      DBX_TRY(stager.begin());
+      int col_slot[64];
+      for (int c = 0; c < plan.n_cols; ++c) col_slot[c] = -1;
+      for (int s = 0; s < plan.n_slots; ++s) { DBX_TRY(stager.stage(b->cols[plan.slot_col[s]], s, &pcols[s])); col_slot[plan.slot_col[s]] = s; }
+      for (int c = 0; c < plan.n_cols; ++c) {
+        if (col_slot[c] >= 0) ccols[c] = pcols[col_slot[c]];
+        else DBX_TRY(stager.stage(b->cols[c], plan.n_slots + c, &ccols[c]));
+      }
+      DBX_CUDA_TRY(err, nibbles.ensure((size_t)n_tiles * kBlock));
+      DBX_CUDA_TRY(err, tile_counts.ensure((size_t)(n_tiles + 1) * 4));
+      DBX_CUDA_TRY(err, tile_offsets.ensure((size_t)(n_tiles + 1) * 4));
+      size_t tmp = 0;
+      cub::DeviceScan::ExclusiveSum(nullptr, tmp, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n_tiles, stream);
+      DBX_CUDA_TRY(err, cub_tmp.ensure(tmp + 256));
+      AggKernelParams kp;
+      memset(&kp, 0, sizeof(kp));
+      for (int s = 0; s < plan.n_slots; ++s) kp.cols[s] = pcols[s];
+      memcpy(kp.nodes, plan.nodes, sizeof(PredNodeDev) * plan.n_nodes);
+      kp.n_rows = n; kp.n_slots = plan.n_slots; kp.n_nodes = plan.n_nodes; kp.key_slot = -1;
+      const int grid = grid_for_rows(n);
+      DBX_CUDA_TRY(err, cudaEventRecord(ev_k0, stream));
+      switch (plan.n_slots) {
+        case 1: launch_select<1>(kp, grid); break;
+        case 2: launch_select<2>(kp, grid); break;
+        case 3: launch_select<3>(kp, grid); break;
+        case 4: launch_select<4>(kp, grid); break;
+        case 5: launch_select<5>(kp, grid); break;
+        case 6: launch_select<6>(kp, grid); break;
+        case 7: launch_select<7>(kp, grid); break;
+        default: launch_select<8>(kp, grid); break;
+      }
+      count_launch();
+      DBX_CUDA_TRY(err, cudaGetLastError());
+      tmp = cub_tmp.bytes;
+      DBX_CUDA_TRY(err, cub::DeviceScan::ExclusiveSum(cub_tmp.p, tmp, (const uint32_t*)tile_counts.p, (uint32_t*)tile_offsets.p, (int)n_tiles, stream));
+      count_launch(2);
+      uint32_t* h = (uint32_t*)host.p;
+      DBX_CUDA_TRY(err, cudaMemcpyAsync(h, (uint32_t*)tile_offsets.p + (n_tiles - 1), 4, cudaMemcpyDeviceToHost, stream));
+      DBX_CUDA_TRY(err, cudaMemcpyAsync(h + 1, (uint32_t*)tile_counts.p + (n_tiles - 1), 4, cudaMemcpyDeviceToHost, stream));
+      DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
+      total = (int64_t)h[0] + (int64_t)h[1];
+      unsigned long long t64 = (unsigned long long)total;
+      DBX_CUDA_TRY(err, cudaMemcpyAsync(dev_total.p, &t64, 8, cudaMemcpyHostToDevice, stream));
+    }
+    rows_out += total;
+    auto dev_alloc = [&](size_t bytes, void** p) -> int32_t {
+      DBX_CUDA_TRY(err, pool_alloc(device, stream, bytes ? bytes : 1, p));
+      ob->dev_allocs.push_back(*p);
+      return DBX_OK;
+    };
+    TakeParams tp;
+    memset(&tp, 0, sizeof(tp));
+    struct Pack { uint8_t* bytes; int col; bool is_data; };
+    std::vector<Pack> packs;
+    int n_take = 0;
+    for (int c = 0; c < plan.n_cols; ++c) {
+      const dbx_column& ic = b->cols[c];
+      dbx_column oc;
+      memset(&oc, 0, sizeof(oc));
+      oc.dtype = ic.dtype; oc.mem = DBX_MEM_DEVICE; oc.len = total; oc.vec_dim = 0; oc.null_count = 0;
+      if (ic.is_const) {  // BlockEntry::Const survives a filter as a shorter const entry
+        oc.is_const = 1; oc.konst = ic.konst; oc.mem = DBX_MEM_HOST;
+        ob->cols.push_back(oc);
+        continue;
+      }
+      if (total > 0) {
+        TakeCol& tc = tp.cols[n_take++];
+        tc.src = ccols[c].data; tc.src_valid = ccols[c].validity; tc.src_vbit_off = ccols[c].vbit_off; tc.src_dbit_off = ccols[c].dbit_off;
+        tc.dtype = ic.dtype; tc.is_const = 0;
+        void* vals = nullptr;
+        DBX_TRY(dev_alloc(ic.dtype == DBX_BOOL ? (size_t)total : (size_t)total * dtype_size(ic.dtype), &vals));
+        tc.dst = vals;
+        oc.data = vals;
+        if (ic.dtype == DBX_BOOL) packs.push_back(Pack{(uint8_t*)vals, (int)ob->cols.size(), true});
+        if (ic.validity) {
+          uint8_t* vb = nullptr;
+          DBX_TRY(dev_alloc((size_t)total, (void**)&vb));
+          tc.dst_valid = vb;
+          packs.push_back(Pack{vb, (int)ob->cols.size(), false});
+          oc.null_count = -1;
+        }
+      }
+      ob->cols.push_back(oc);
+    }
+    if (total > 0) {
+      tp.n_cols = n_take; tp.n_rows = n; tp.sel_nibbles = (const uint8_t*)nibbles.p; tp.tile_offsets = (const uint32_t*)tile_offsets.p;
+      filter_take_kernel<<<grid_for_rows(n), kBlock, 0, stream>>>(tp);
+      count_launch();
+      DBX_CUDA_TRY(err, cudaGetLastError());
+      for (const Pack& pk : packs) {
+        uint8_t* bits = nullptr;
+        DBX_TRY(dev_alloc((size_t)(total + 7) / 8 + 8, (void**)&bits));
+        pack_validity_kernel<<<grid_for_entries((total + 7) / 8 + 1), 256, 0, stream>>>(pk.bytes, (const unsigned long long*)dev_total.p, total, bits);
+        count_launch();
+        DBX_CUDA_TRY(err, cudaGetLastError());
+        if (pk.is_data) { ob->cols[pk.col].data = bits; ob->cols[pk.col].data_bit_offset = 0; }
+        else { ob->cols[pk.col].validity = bits; ob->cols[pk.col].validity_bit_offset = 0; }
+      }
+    }
+    if (n > 0) {
+      DBX_CUDA_TRY(err, cudaEventRecord(ev_k1, stream));
+      timed = true;
+      DBX_TRY(stager.end());
+    }
+    out_q.push_back(std::move(ob));
+    return DBX_OK;
+  }
+
+  int32_t finish() override { return DBX_OK; }
+
+  // Transform is 1:1: output blocks can be pulled as soon as they were pushed
+  int32_t pull(int32_t out_mem, dbx_block* out, int32_t* has_block) override {
+    if (out_head >= out_q.size()) { *has_block = 0; return DBX_OK; }
+    std::unique_ptr<OwnedBlock> ob = std::move(out_q[out_head++]);
+    if (out_head == out_q.size()) { out_q.clear(); out_head = 0; }
+    *has_block = 1;
+    const int64_t rows = ob->cols.empty() ? 0 : ob->cols[0].len;
+    int32_t st = pull_owned_block(ob, device, stream, err, out_mem, out);
+    if (st == DBX_OK) out->num_rows = rows;
+    return st;
+  }
+};
+
+Op* make_filter_op(const dbx_predicate* p, const int32_t* types, int32_t n, int device, int32_t* st) {
+  auto* op = new FilterOp();
+  *st = op->init(p, types, n, device);
+  if (*st != DBX_OK) { g_create_error.set(op->err.msg); delete op; return nullptr; }
+  return op;
+}
 
 Op* make_agg_partial_op(const dbx_agg_params* p, const int32_t* types, int32_t n, int device, int32_t* st) {
   auto* op = new AggPartialOp();
@@ -1191,8 +1399,24 @@ int32_t dbx_agg_exchange_merge(dbx_agg_exchange* x, dbx_op* final_op) {
   AggFinalOp* f = static_cast<AggFinalOp*>(o);
   DBX_CUDA_TRY(x->err, cudaSetDevice(x->device));
   if (f->finished) { x->err.set("merge after finish"); return DBX_ERR_STATE; }
-  if (!f->has_table) {  // owned groups <= all groups: same capacity rule as one source's partial
-    int32_t st = f->table.create(x->table_cap, f->plan, f->stream, &f->err);
+  // table size: from the previous query's result when there is one (an owner holds ~1/n_ranks of
+  // the groups, so this is far smaller than the worst case and cheaper to clear and scan); finish()
+  // falls back to the worst-case size if it turns out too small
+  int64_t cap = 0;
+  if (f->last_groups > 0) cap = std::min<int64_t>(x->table_cap, next_pow2(std::max<int64_t>(4 * f->last_groups, 1024)));
+  DBX_TRY(exchange_launch_merge(x, f, cap));
+  f->exchange_status = (unsigned long long*)x->status.p;
+  return DBX_OK;
+}
+
+}  // extern "C"
+
+namespace dbx {
+// (re-)create the final's table with `cap` slots (0 = worst case) and merge the current epoch's regions
+int32_t exchange_launch_merge(dbx_agg_exchange* x, AggFinalOp* f, int64_t cap) {
+  if (cap <= 0) cap = x->table_cap;
+  {
+    int32_t st = f->table.create(cap, f->plan, f->stream, &f->err);
     if (st != DBX_OK) { x->err.set(f->err.msg); return st; }
     f->has_table = true;
   }
@@ -1212,8 +1436,12 @@ int32_t dbx_agg_exchange_merge(dbx_agg_exchange* x, dbx_op* final_op) {
   DBX_CUDA_TRY(x->err, cudaGetLastError());
   DBX_CUDA_TRY(x->err, cudaEventRecord(x->ev_merge, f->stream));
   f->exchange_status = (unsigned long long*)x->status.p;
+  f->exchange_src = x;
   return DBX_OK;
 }
+}  // namespace dbx
+
+extern "C" {
 
 int32_t dbx_agg_exchange_destroy(dbx_agg_exchange* x) {
   if (!x) return DBX_OK;

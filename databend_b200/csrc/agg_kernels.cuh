@@ -586,6 +586,112 @@ __global__ void __launch_bounds__(kBlock, 4) filter_single_agg_kernel(const __gr
   }
 }
 
+// ---------------------------------------------------------------- standalone filter (TransformFilter)
+// FilterExecutor::filter = select + take (filter_executor.rs:82-160, kernels/filter.rs:36-70,
+// kernels/take.rs:43-60): rows for which the predicate is true, in input order, for every column.
+//   pass 1  filter_select_kernel: predicate in registers -> 4-bit selection per thread + per-tile count
+//   (scan of the tile counts)
+//   pass 2  filter_take_kernel: every thread knows its output position (tile offset + block scan of
+//           the popcounts) and copies its selected rows of every column — order preserved, no atomics.
+template <int NS>
+__global__ void __launch_bounds__(kBlock) filter_select_kernel(const __grid_constant__ AggKernelParams p, uint8_t* sel_nibbles,
+                                                               uint32_t* tile_counts) {
+  __shared__ uint32_t s_cnt[kWarpsPerBlock];
+  const int64_t n_tiles = (p.n_rows + kTileRows - 1) / kTileRows;
+  const uint64_t pol = make_policy_evict_first();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t tile_base = tile * kTileRows;
+    RowVals vals[NS];
+    uint32_t vmask[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) load_slot<false>(p.cols[s], tile_base, p.n_rows, nullptr, pol, vals[s], vmask[s]);
+    const int64_t r0 = tile_base + (int64_t)kRowsPerThread * threadIdx.x;
+    uint32_t in_range = 0;
+#pragma unroll
+    for (int j = 0; j < kRowsPerThread; ++j)
+      if (r0 + j < p.n_rows) in_range |= 1u << j;
+    const uint32_t sel = eval_predicate<NS>(p, vals, vmask, in_range);
+    sel_nibbles[tile * kBlock + threadIdx.x] = (uint8_t)sel;
+    uint32_t c = __popc(sel);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) s_cnt[warp] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t t = 0;
+      for (int w = 0; w < kWarpsPerBlock; ++w) t += s_cnt[w];
+      tile_counts[tile] = t;
+    }
+    __syncthreads();
+  }
+}
+
+struct TakeCol {
+  const void* src;
+  const uint8_t* src_valid;  // bitmap or nullptr
+  int64_t src_vbit_off, src_dbit_off;
+  void* dst;                 // values (BOOL: one byte per row, packed afterwards)
+  uint8_t* dst_valid;        // one byte per row or nullptr
+  int32_t dtype, is_const;
+  uint64_t const_bits;
+};
+struct TakeParams {
+  TakeCol cols[64];
+  int32_t n_cols;
+  int64_t n_rows;
+  const uint8_t* sel_nibbles;
+  const uint32_t* tile_offsets;  // exclusive scan of the tile counts
+};
+__global__ void __launch_bounds__(kBlock) filter_take_kernel(const __grid_constant__ TakeParams p) {
+  __shared__ uint32_t s_warp[kWarpsPerBlock];
+  const int64_t n_tiles = (p.n_rows + kTileRows - 1) / kTileRows;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t sel = p.sel_nibbles[tile * kBlock + threadIdx.x];
+    const uint32_t n = __popc(sel);
+    uint32_t incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (int w = 0; w < warp; ++w) wbase += s_warp[w];
+    __syncthreads();
+    if (!sel) continue;
+    const int64_t out0 = (int64_t)p.tile_offsets[tile] + wbase + incl - n;
+    const int64_t r0 = tile * kTileRows + (int64_t)kRowsPerThread * threadIdx.x;
+    for (int c = 0; c < p.n_cols; ++c) {
+      const TakeCol& tc = p.cols[c];
+      const int esz = dtype_size(tc.dtype);
+      int64_t o = out0;
+#pragma unroll
+      for (int j = 0; j < kRowsPerThread; ++j) {
+        if (!((sel >> j) & 1)) continue;
+        const int64_t r = r0 + j;
+        if (tc.dtype == DBX_BOOL) {
+          ((uint8_t*)tc.dst)[o] = tc.is_const ? (uint8_t)(tc.const_bits != 0) : (uint8_t)bit_test((const uint8_t*)tc.src, tc.src_dbit_off + r);
+        } else if (tc.is_const) {
+          if (esz == 8) ((uint64_t*)tc.dst)[o] = tc.const_bits;
+          else if (esz == 4) ((uint32_t*)tc.dst)[o] = tc.dtype == DBX_F32 ? __float_as_uint((float)__longlong_as_double((long long)tc.const_bits)) : (uint32_t)tc.const_bits;
+          else if (esz == 2) ((uint16_t*)tc.dst)[o] = (uint16_t)tc.const_bits;
+          else ((uint8_t*)tc.dst)[o] = (uint8_t)tc.const_bits;
+        } else {
+          if (esz == 8) ((uint64_t*)tc.dst)[o] = ((const uint64_t*)tc.src)[r];
+          else if (esz == 4) ((uint32_t*)tc.dst)[o] = ((const uint32_t*)tc.src)[r];
+          else if (esz == 2) ((uint16_t*)tc.dst)[o] = ((const uint16_t*)tc.src)[r];
+          else ((uint8_t*)tc.dst)[o] = ((const uint8_t*)tc.src)[r];
+        }
+        if (tc.dst_valid) tc.dst_valid[o] = tc.is_const == 2 ? 0 : (tc.src_valid ? (uint8_t)bit_test(tc.src_valid, tc.src_vbit_off + r) : 1);
+        ++o;
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- table maintenance
 struct WordInit {
   uint64_t w[kMaxWords];
@@ -644,7 +750,7 @@ __global__ void table_merge_kernel(const __grid_constant__ TableDev src, const _
 // the top hash bits like PartitionedPayload (partitioned_payload.rs:44-57) but for any n_parts.
 __device__ __forceinline__ int owner_of(uint64_t key, int key_kind, int n_parts) {
   uint64_t h = key_kind == 2 ? kNullHashVal : agg_hash_u64(key_kind == 1 ? kEmptyKey : key);
-  return (int)(((h >> 32) * (uint64_t)n_parts) >> 32);
+  return hash_to_part(h, n_parts);
 }
 
 __global__ void table_partition_count_kernel(const __grid_constant__ TableDev src, int n_parts,

@@ -172,6 +172,20 @@ __host__ __device__ __forceinline__ uint64_t agg_hash_u64(uint64_t x) {
 }
 constexpr uint64_t kNullHashVal = 0xd1cefa08eb382d69ULL;  // group_hash.rs:38
 
+// Owner / partition of a hash among n parts: the top 32 hash bits scaled to [0, n), i.e.
+// mulhi32(hash >> 32, n) — radix partitioning on the top bits (partitioned_payload.rs:44-57)
+// generalised to any n.  Written with __umulhi on the device: the equivalent 64-bit
+// multiply-and-shift form was miscompiled by ptxas 12.9 inside a shared-memory histogram loop
+// (misaligned ATOMS address, found with compute-sanitizer).
+__host__ __device__ __forceinline__ int hash_to_part(uint64_t h, int n) {
+  const uint32_t hi = (uint32_t)(h >> 32);
+#ifdef __CUDA_ARCH__
+  return (int)__umulhi(hi, (uint32_t)n);
+#else
+  return (int)(((uint64_t)hi * (uint32_t)n) >> 32);
+#endif
+}
+
 // Order-preserving map double -> u64 under OrderedFloat (NaN greatest, all NaN equal).
 __device__ __forceinline__ uint64_t f64_to_ordered(double d) {
   if (d != d) return 0xFFFFFFFFFFFFFFFFULL;

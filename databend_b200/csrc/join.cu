@@ -8,9 +8,12 @@
 //   InnerHashJoin::probe_block / InnerHashJoinStream::next                          new_hash_join/memory/inner_join.rs:122-262
 //
 // B200 design.  Build rows stay in HBM as columns.  The table is an open-addressed multimap of
-// 16-byte entries {key, build_row + 1}; a bucket is two entries = one 32-byte sector, so one
-// 256-bit load yields key AND row id of two candidates (the reference reads an 8-byte header,
-// then chases the entry chain).  The probe kernel streams the probe key column once, walks
+// 32-byte entries {key, build_row + 1 | validity flags, payload0, payload1} = one sector = one
+// 256-bit load: the probe of a row with up to two 8-byte build columns next to the key touches
+// ONE random sector (the reference reads an 8-byte header, then chases the entry chain, then
+// gathers the build row).  A 1e9-row probe into a 1e7-row build side is bound by HBM's
+// random-sector rate, not by bytes: every avoided gather is worth as much as the probe itself.
+// Build columns that do not fit the entry are gathered by build row as before.  The probe kernel streams the probe key column once, walks
 // buckets until it sees an empty entry, and writes each joined row directly into the output
 // columns at a position claimed with a warp-aggregated atomic: no (probe,build) index pairs are
 // materialised and no second gather pass runs (the reference does DataBlock::take +
@@ -18,6 +21,8 @@
 // several threads build the chains — and results are compared as multisets.
 // NULL keys never match (fixed_keys.rs: rows with a NULL key are skipped on both sides).
 #include <algorithm>
+#include <cstdlib>
+#include <vector>
 
 #include "runtime.h"
 
@@ -30,12 +35,36 @@ constexpr int kMaxJoinCols = 16;
 
 struct JoinEntry {
   uint64_t key;
-  uint64_t row1;  // build row + 1; 0 = empty
+  uint64_t row1;  // (build row + 1) | validity of p0 << 62 | validity of p1 << 63; 0 = empty
+  uint64_t p0, p1;  // raw bytes of up to two build columns (zero-extended to 8 bytes)
 };
+constexpr uint64_t kRowMask = (1ULL << 62) - 1;
 
+// Radix layout: the table is cut into n_part regions of `region` entries (both powers of two);
+// a key lives in region part_owner(key, n_part) (top hash bits) at slot hash & (region - 1)
+// (low hash bits), probing wraps inside the region.  A probe block that was hash-partitioned the
+// same way walks ONE region at a time, which then sits in L2 (and in the TLB) instead of
+// scattering single-sector reads over a table many times larger than either.
 struct JoinTableDev {
-  JoinEntry* entries;  // cap entries, cap = 2 * n_buckets (power of two)
+  JoinEntry* entries;  // cap entries (power of two), one per 32-byte sector
   int64_t cap;
+  int64_t region;
+  int32_t n_part;
+  int32_t pad;
+};
+__device__ __forceinline__ int64_t join_home(const JoinTableDev& t, uint64_t k, int64_t* region_base) {
+  const uint64_t h = agg_hash_u64(k);
+  const int64_t part = t.n_part > 1 ? (int64_t)hash_to_part(h, t.n_part) : 0;
+  *region_base = part * t.region;
+  return (int64_t)(h & (uint64_t)(t.region - 1));
+}
+
+// build column carried inside the table entry
+struct InlineColDev {
+  const void* src;
+  const uint8_t* valid_bytes;  // one byte per build row, or null
+  int32_t size;
+  int32_t on;
 };
 
 // One column copied into the output for every match.
@@ -46,7 +75,7 @@ struct JoinColDev {
   int64_t src_vbit_off;
   uint8_t* dst_valid;           // one byte per output row, or null
   int32_t size;                 // bytes per value
-  int32_t pad;
+  int32_t from;                 // build side: 0 gather by build row, 1 the entry's key, 2 entry.p0, 3 entry.p1
 };
 
 struct JoinProbeParams {
@@ -55,6 +84,7 @@ struct JoinProbeParams {
   JoinColDev probe_cols[kMaxJoinCols];
   JoinColDev build_cols[kMaxJoinCols];
   int32_t n_probe_cols, n_build_cols;
+  int64_t row_begin;  // rows [row_begin, row_begin + n_rows) of the (partitioned) probe columns
   int64_t n_rows;
   int64_t out_cap;
   unsigned long long* cursor;  // number of matches (may exceed out_cap: then the host retries)
@@ -76,19 +106,44 @@ __device__ __forceinline__ uint64_t load_key(const DevCol& c, int64_t row) {
 // HashJoinHashTable::insert (hashjoin_hashtable.rs:110-141): every build row with a valid key
 // claims the first free entry along its probe sequence (CAS on the row field; the key is written
 // afterwards — build and probe are separated by a kernel boundary).
+__device__ __forceinline__ uint64_t load_raw(const void* base, int size, int64_t row) {
+  switch (size) {
+    case 8: return ((const uint64_t*)base)[row];
+    case 4: return ((const uint32_t*)base)[row];
+    case 2: return ((const uint16_t*)base)[row];
+    default: return ((const uint8_t*)base)[row];
+  }
+}
 __global__ void join_build_kernel(const __grid_constant__ DevCol key, int64_t n_rows, int64_t row_base,
-                                  const __grid_constant__ JoinTableDev t) {
-  const int64_t mask = t.cap - 1;
+                                  const __grid_constant__ JoinTableDev t, const __grid_constant__ InlineColDev i0,
+                                  const __grid_constant__ InlineColDev i1) {
+  const int64_t mask = t.region - 1;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x) {
     if (key.validity && !bit_test(key.validity, key.vbit_off + r)) continue;
     const uint64_t k = load_key(key, r);
-    int64_t s = (int64_t)((agg_hash_u64(k) << 1) & (uint64_t)mask);  // first entry of the home bucket
+    uint64_t tag = (uint64_t)(row_base + r + 1);
+    uint64_t p0 = 0, p1 = 0;
+    if (i0.on) { p0 = load_raw(i0.src, i0.size, r); if (!i0.valid_bytes || i0.valid_bytes[r]) tag |= 1ULL << 62; }
+    if (i1.on) { p1 = load_raw(i1.src, i1.size, r); if (!i1.valid_bytes || i1.valid_bytes[r]) tag |= 1ULL << 63; }
+    int64_t rb;
+    int64_t s = join_home(t, k, &rb);
     for (;;) {
-      unsigned long long old = atomicCAS((unsigned long long*)&t.entries[s].row1, 0ULL, (unsigned long long)(row_base + r + 1));
-      if (old == 0ULL) { t.entries[s].key = k; break; }
+      JoinEntry* e = t.entries + rb + s;
+      unsigned long long old = atomicCAS((unsigned long long*)&e->row1, 0ULL, (unsigned long long)tag);
+      if (old == 0ULL) { e->key = k; e->p0 = p0; e->p1 = p1; break; }
       s = (s + 1) & mask;
     }
   }
+}
+
+__device__ __forceinline__ void store_value(const JoinColDev& c, uint64_t bits, bool valid, int64_t dst_row) {
+  switch (c.size) {
+    case 8: ((uint64_t*)c.dst)[dst_row] = bits; break;
+    case 4: ((uint32_t*)c.dst)[dst_row] = (uint32_t)bits; break;
+    case 2: ((uint16_t*)c.dst)[dst_row] = (uint16_t)bits; break;
+    default: ((uint8_t*)c.dst)[dst_row] = (uint8_t)bits; break;
+  }
+  if (c.dst_valid) c.dst_valid[dst_row] = valid ? 1 : 0;
 }
 
 __device__ __forceinline__ void copy_value(const JoinColDev& c, int64_t src_row, int64_t dst_row) {
@@ -102,49 +157,91 @@ __device__ __forceinline__ void copy_value(const JoinColDev& c, int64_t src_row,
 }
 
 // probe_block + InnerHashJoinStream::next fused: one thread per probe row.
+// Per step of 256 rows a CTA (1) walks every row's probe sequence, counting its matches and
+// keeping the first matching entry in registers, (2) reserves the step's output rows with ONE
+// atomic on the global cursor (block scan of the counts; a per-warp reservation costs millions of
+// same-address atomics per block and was the bottleneck), (3) writes the first match from
+// registers and re-walks the sequence only for rows with several matches.
+__device__ __forceinline__ JoinEntry load_entry(const JoinEntry* e) {
+  JoinEntry r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_last.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(r.key), "=l"(r.row1), "=l"(r.p0), "=l"(r.p1) : "l"(e));
+  return r;
+}
+__device__ __forceinline__ void emit_match(const JoinProbeParams& p, int64_t r, const JoinEntry& e, int64_t pos) {
+  if (pos >= p.out_cap) return;
+  for (int c = 0; c < p.n_probe_cols; ++c) copy_value(p.probe_cols[c], r, pos);
+  for (int c = 0; c < p.n_build_cols; ++c) {
+    const JoinColDev& jc = p.build_cols[c];
+    if (jc.from == 0) copy_value(jc, (int64_t)(e.row1 & kRowMask) - 1, pos);
+    else if (jc.from == 1) store_value(jc, e.key, true, pos);
+    else if (jc.from == 2) store_value(jc, e.p0, (e.row1 >> 62) & 1, pos);
+    else store_value(jc, e.p1, (e.row1 >> 63) & 1, pos);
+  }
+}
 __global__ void __launch_bounds__(kJoinBlock) join_probe_kernel(const __grid_constant__ JoinProbeParams p) {
-  const int lane = threadIdx.x & 31;
-  const int64_t nb_mask = (p.table.cap >> 1) - 1;
+  __shared__ unsigned int s_warp[kJoinBlock / 32];
+  __shared__ unsigned long long s_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t mask = p.table.region - 1;
   const int64_t n_iter = (p.n_rows + (int64_t)gridDim.x * blockDim.x - 1) / ((int64_t)gridDim.x * blockDim.x);
   for (int64_t it = 0; it < n_iter; ++it) {
-    __syncwarp();
-    const int64_t r = it * (int64_t)gridDim.x * blockDim.x + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool live = r < p.n_rows && !(p.key.validity && !bit_test(p.key.validity, p.key.vbit_off + r));
+    const int64_t r = p.row_begin + it * (int64_t)gridDim.x * blockDim.x + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = r < p.row_begin + p.n_rows && !(p.key.validity && !bit_test(p.key.validity, p.key.vbit_off + r));
     uint64_t k = 0;
-    int64_t b = 0;
+    int64_t b0 = 0, rb = 0;
+    unsigned int n_match = 0;
+    JoinEntry first;
+    first.key = first.row1 = first.p0 = first.p1 = 0;
     if (live) {
       k = load_key(p.key, r);
-      b = (int64_t)(agg_hash_u64(k) & (uint64_t)nb_mask);
-    }
-    // all lanes walk their bucket sequences in lock step; a lane retires at the first empty entry
-    while (__any_sync(0xffffffffu, live)) {
-      uint64_t k0 = 0, r0 = 0, k1 = 0, r1 = 0;
-      if (live) {
-        const JoinEntry* e = p.table.entries + 2 * b;
-        asm volatile("ld.global.nc.L1::no_allocate.L2::evict_last.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(k0), "=l"(r0), "=l"(k1), "=l"(r1) : "l"(e));
+      b0 = join_home(p.table, k, &rb);
+      int64_t b = b0;
+      for (;;) {  // an empty entry ends the probe sequence
+        const JoinEntry e = load_entry(p.table.entries + rb + b);
+        if (e.row1 == 0) break;
+        if (e.key == k) { if (n_match == 0) first = e; ++n_match; }
+        b = (b + 1) & mask;
       }
+    }
+    // block-wide exclusive scan of the match counts -> one reservation per CTA and step
+    unsigned int incl = n_match;
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const uint64_t ek = half ? k1 : k0, er = half ? r1 : r0;
-        const bool hit = live && er != 0 && ek == k;
-        const uint32_t bal = __ballot_sync(0xffffffffu, hit);
-        if (bal) {
-          unsigned long long base = 0;
-          if (lane == 0) base = atomicAdd(p.cursor, (unsigned long long)__popc(bal));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (hit) {
-            const int64_t pos = (int64_t)base + __popc(bal & ((1u << lane) - 1));
-            if (pos < p.out_cap) {
-              for (int c = 0; c < p.n_probe_cols; ++c) copy_value(p.probe_cols[c], r, pos);
-              for (int c = 0; c < p.n_build_cols; ++c) copy_value(p.build_cols[c], (int64_t)er - 1, pos);
-            }
-          }
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int tot = 0;
+      for (int w = 0; w < kJoinBlock / 32; ++w) { const unsigned int c = s_warp[w]; s_warp[w] = tot; tot += c; }
+      s_base = tot ? atomicAdd(p.cursor, (unsigned long long)tot) : 0ULL;
+    }
+    __syncthreads();
+    int64_t pos = (int64_t)s_base + s_warp[warp] + incl - n_match;
+    __syncthreads();
+    if (n_match) {
+      emit_match(p, r, first, pos++);
+      if (n_match > 1) {  // duplicates of the key on the build side: walk again, skip the first
+        int64_t b = b0;
+        unsigned int seen = 0;
+        for (;;) {
+          const JoinEntry e = load_entry(p.table.entries + rb + b);
+          if (e.row1 == 0) break;
+          if (e.key == k && seen++ > 0) emit_match(p, r, e, pos++);
+          b = (b + 1) & mask;
         }
       }
-      if (live && (r0 == 0 || r1 == 0)) live = false;  // an empty entry ends the probe sequence
-      b = (b + 1) & nb_mask;
     }
   }
+}
+
+// Pull one table region into L2 with full-line sequential reads before it is probed: the probes
+// themselves would fetch it as scattered 32-byte sectors, which HBM serves an order of magnitude
+// slower than a stream.
+__global__ void l2_prefetch_kernel(const char* base, int64_t bytes) {
+  for (int64_t off = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 128; off < bytes; off += (int64_t)gridDim.x * blockDim.x * 128)
+    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(base + off));
 }
 
 __global__ void pack_bits_kernel(const uint8_t* bytes, int64_t n, uint8_t* bits) {
@@ -193,6 +290,13 @@ class JoinOp : public Op {
   DevBuf table_buf, cursor;
   int64_t table_cap = 0;
   PinnedBuf host;
+  int inline_col[2] = {-1, -1};
+  int n_part = 1;
+  int64_t region = 0;
+  DevBuf part_counters;
+  DevBuf part_cols[kMaxJoinCols];
+  std::vector<int64_t> part_offs;
+  JoinTableDev table_view() const { return JoinTableDev{(JoinEntry*)table_buf.p, table_cap, region, n_part, 0}; }
   std::vector<std::unique_ptr<OwnedBlock>> outputs;  // joined blocks waiting to be pulled (device resident)
   size_t next_out = 0;
 
@@ -266,6 +370,31 @@ class JoinOp : public Op {
   // Join::final_build: size the table for the build row count and insert every row
   int32_t finish() override {
     table_cap = std::max<int64_t>(next_pow2_i64(2 * std::max<int64_t>(build_rows, 1)), 1024);  // with_build_row_num
+    if (build_rows >= (int64_t)kRowMask) { err.set("join: too many build rows"); return DBX_ERR_UNSUPPORTED; }
+    // radix regions: cut a table that is far larger than L2 into pieces of <= 32 MB
+    n_part = 1;
+    {
+      const int64_t bytes = table_cap * (int64_t)sizeof(JoinEntry);
+      int64_t target = 32LL << 20;  // region size; DBX_JOIN_REGION_BYTES overrides (tests), 0 disables
+      if (const char* e = getenv("DBX_JOIN_REGION_BYTES")) target = atoll(e);
+      if (target > 0 && bytes > 3 * target) {
+        while (n_part < kMaxParts && bytes / n_part > target) n_part *= 2;
+      }
+    }
+    region = table_cap / n_part;
+    DBX_CUDA_TRY(err, part_counters.ensure((size_t)kMaxParts * 8));
+    if (n_part > 1) {  // a skewed key distribution could overfill a region: then fall back to one region
+      PartParams cp;
+      memset(&cp, 0, sizeof(cp));
+      cp.key.data = build[prm.build_key_col].data.p;
+      cp.key.dtype = build_dtype[prm.build_key_col];
+      cp.n_cols = 0; cp.n_parts = n_part; cp.n_rows = build_rows;
+      std::vector<int64_t> offs((size_t)n_part + 1);
+      DBX_TRY(hash_partition_device(err, stream, cp, (unsigned long long*)part_counters.p, offs.data()));
+      int64_t worst = 0;
+      for (int i = 0; i < n_part; ++i) worst = std::max(worst, offs[i + 1] - offs[i]);
+      if (worst * 10 > region * 7) { n_part = 1; region = table_cap; }
+    }
     DBX_CUDA_TRY(err, table_buf.ensure((size_t)table_cap * sizeof(JoinEntry)));
     DBX_CUDA_TRY(err, cudaMemsetAsync(table_buf.p, 0, (size_t)table_cap * sizeof(JoinEntry), stream));
     if (build_rows) {
@@ -282,8 +411,21 @@ class JoinOp : public Op {
         count_launch();
         key.validity = (const uint8_t*)kbits.p;
       }
-      JoinTableDev t{(JoinEntry*)table_buf.p, table_cap};
-      join_build_kernel<<<grid_rows(build_rows), kJoinBlock, 0, stream>>>(key, build_rows, 0, t);
+      JoinTableDev t = table_view();
+      // the first two non-key build columns travel inside the entries
+      InlineColDev ic[2];
+      memset(ic, 0, sizeof(ic));
+      inline_col[0] = inline_col[1] = -1;
+      for (int c = 0, k = 0; c < n_build_cols && k < 2; ++c) {
+        if (c == prm.build_key_col) continue;
+        inline_col[k] = c;
+        ic[k].src = build[c].data.p;
+        ic[k].valid_bytes = build[c].nullable ? (const uint8_t*)build[c].valid_bytes.p : nullptr;
+        ic[k].size = build[c].size;
+        ic[k].on = 1;
+        ++k;
+      }
+      join_build_kernel<<<grid_rows(build_rows), kJoinBlock, 0, stream>>>(key, build_rows, 0, t, ic[0], ic[1]);
       count_launch();
       DBX_CUDA_TRY(err, cudaGetLastError());
       DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
@@ -306,13 +448,30 @@ class JoinOp : public Op {
     }
     int64_t out_cap = n + n / 8 + 1024;  // optimistic: about one match per probe row
     DBX_CUDA_TRY(err, cudaEventRecord(ev_k0, stream));
+    // radix probe: reorder the block region by region (row order of a join result is unspecified)
+    bool can_part = n_part > 1 && (n >= (1 << 16) || getenv("DBX_JOIN_REGION_BYTES"));
+    for (int c = 0; c < n_probe_cols && can_part; ++c) can_part = !cols[c].validity;
+    if (can_part) {
+      PartParams pq;
+      memset(&pq, 0, sizeof(pq));
+      pq.key = cols[prm.probe_key_col];
+      pq.n_cols = n_probe_cols; pq.n_parts = n_part; pq.n_rows = n;
+      for (int c = 0; c < n_probe_cols; ++c) {
+        const int sz = dtype_size(probe_dtype[c]);
+        DBX_CUDA_TRY(err, part_cols[c].ensure((size_t)n * sz));
+        pq.cols[c].src = cols[c].data; pq.cols[c].dst = part_cols[c].p; pq.cols[c].size = sz;
+      }
+      part_offs.assign((size_t)n_part + 1, 0);
+      DBX_TRY(hash_partition_device(err, stream, pq, (unsigned long long*)part_counters.p, part_offs.data()));
+      for (int c = 0; c < n_probe_cols; ++c) cols[c].data = part_cols[c].p;
+    }
     for (int attempt = 0; attempt < 2; ++attempt) {
       auto ob = std::make_unique<OwnedBlock>();
       ob->device = device;
       JoinProbeParams pp;
       memset(&pp, 0, sizeof(pp));
       pp.key = cols[prm.probe_key_col];
-      pp.table = JoinTableDev{(JoinEntry*)table_buf.p, table_cap};
+      pp.table = table_view();
       pp.n_probe_cols = n_probe_cols;
       pp.n_build_cols = n_build_cols;
       pp.n_rows = n;
@@ -348,7 +507,8 @@ class JoinOp : public Op {
       DevBuf build_bits[kMaxJoinCols];
       for (int c = 0; c < n_build_cols; ++c) {
         pp.build_cols[c].src = build[c].data.p;
-        if (build[c].nullable) {  // bytes -> use the byte array directly through a 1-byte "bitmap" trick: pack once
+        pp.build_cols[c].from = c == prm.build_key_col ? 1 : (c == inline_col[0] ? 2 : (c == inline_col[1] ? 3 : 0));
+        if (build[c].nullable && pp.build_cols[c].from == 0) {  // bytes -> use the byte array directly through a 1-byte "bitmap" trick: pack once
           DBX_CUDA_TRY(err, build_bits[c].ensure((size_t)(build_rows + 7) / 8 + 8));
           pack_bits_kernel<<<grid_rows((build_rows + 7) / 8), kJoinBlock, 0, stream>>>((const uint8_t*)build[c].valid_bytes.p, build_rows, (uint8_t*)build_bits[c].p);
           count_launch();
@@ -357,8 +517,22 @@ class JoinOp : public Op {
         DBX_TRY(add_out(pp.build_cols[c], build_dtype[c], build_nullable[c]));
       }
       DBX_CUDA_TRY(err, cudaMemsetAsync(cursor.p, 0, 8, stream));
-      join_probe_kernel<<<grid_rows(n), kJoinBlock, 0, stream>>>(pp);
-      count_launch();
+      if (can_part) {  // region by region: stream the region into L2, then probe the rows that hash into it
+        for (int part = 0; part < n_part; ++part) {
+          const int64_t m = part_offs[part + 1] - part_offs[part];
+          if (m == 0) continue;
+          const int64_t bytes = region * (int64_t)sizeof(JoinEntry);
+          l2_prefetch_kernel<<<(int)std::min<int64_t>((bytes / 128 + 255) / 256, (int64_t)kNumSMs * 8), 256, 0, stream>>>(
+              (const char*)table_buf.p + (int64_t)part * bytes, bytes);
+          pp.row_begin = part_offs[part];
+          pp.n_rows = m;
+          join_probe_kernel<<<grid_rows(m), kJoinBlock, 0, stream>>>(pp);
+          count_launch(2);
+        }
+      } else {
+        join_probe_kernel<<<grid_rows(n), kJoinBlock, 0, stream>>>(pp);
+        count_launch();
+      }
       DBX_CUDA_TRY(err, cudaGetLastError());
       DBX_CUDA_TRY(err, cudaMemcpyAsync(host.p, cursor.p, 8, cudaMemcpyDeviceToHost, stream));
       DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));

@@ -136,4 +136,25 @@ inline uint64_t scalar_bits(const dbx_scalar& s, int as_class) {
 
 int32_t fill_owned_block(OwnedBlock* ob, dbx_block* out);
 
+// ---- hash partitioning of device columns (partition.cu)
+constexpr int kMaxParts = 64;
+constexpr int kMaxPartCols = 16;
+struct PartCol {
+  const void* src;
+  void* dst;
+  int32_t size;
+  int32_t pad;
+};
+struct PartParams {
+  DevCol key;
+  PartCol cols[kMaxPartCols];
+  int32_t n_cols, n_parts;
+  int64_t n_rows;
+  unsigned long long* counters;  // [n_parts]: counts (pass 1) / cursors (pass 2)
+};
+// owner of a key (common.cuh: hash_to_part)
+__host__ __device__ __forceinline__ int part_owner(uint64_t key, int n_parts) { return hash_to_part(agg_hash_u64(key), n_parts); }
+int32_t hash_partition_device(ErrorSink& err, cudaStream_t stream, const PartParams& params, unsigned long long* counters,
+                              int64_t* host_offsets);
+
 }  // namespace dbx

@@ -1,6 +1,3 @@
-// stubs.cu — entry points declared in include/dbx.h whose operators are not built yet.
-// They fail loudly (DBX_ERR_UNSUPPORTED); nothing falls back to the CPU.
+// stubs.cu — intentionally empty: every entry point declared in include/dbx.h is implemented
+// (there is no CPU fallback anywhere in the library).
 #include "runtime.h"
-namespace dbx {
-Op* make_filter_op(const dbx_predicate*, const int32_t*, int32_t, int, int32_t* st) { g_create_error.set("DBX_OP_FILTER is not built yet (the filter is fused into DBX_OP_AGG_PARTIAL)"); *st = DBX_ERR_UNSUPPORTED; return nullptr; }
-}

@@ -1,0 +1,110 @@
+"""Multi-GPU drivers for the operators that shard across the GPUs of one box.
+One process per GPU; torch.distributed (NCCL on GPUs, gloo in the CPU tests) is the plumbing,
+every row-touching step is a libdbx kernel.
+
+  hash join   both sides hash-partitioned by key (dbx_hash_partition) -> one all-to-all per side
+              and column -> local DBX_OP_JOIN; the result stays partitioned by key
+              (reference: flight_scatter_hash.rs + physical_hash_join.rs exchange on the join keys)
+  top-k       row-range shards -> local TransformTopN -> all-gather of k candidates per rank ->
+              a final TransformTopN over the gathered candidates (sorts/sort_merge*.rs, top_n/)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import abi
+from .block import Column, DataBlock, np_dtype
+from .lib import check, load
+from .transforms import HashJoin, TransformTopN, schema_types
+
+_TORCH_BYTES = torch.uint8
+
+
+def hash_partition(block: DataBlock, key_col: int, n_parts: int, device: int = 0) -> Tuple[List[torch.Tensor], List[int]]:
+    """dbx_hash_partition over a device-resident block: returns one uint8 tensor per column holding
+    the permuted values, and the partition offsets (n_parts + 1)."""
+    n = block.num_rows
+    outs, ptrs = [], (C.c_void_p * len(block.columns))()
+    for i, c in enumerate(block.columns):
+        t = torch.empty(max(1, n * np_dtype(c.dtype).itemsize), dtype=_TORCH_BYTES, device=f"cuda:{device}")
+        outs.append(t)
+        ptrs[i] = t.data_ptr()
+    offs = (C.c_int64 * (n_parts + 1))()
+    b, keep = block.as_c()
+    check(load().dbx_hash_partition(device, C.byref(b), key_col, n_parts, ptrs, offs))
+    return outs, list(offs)
+
+
+def all_to_all_columns(cols: Sequence[torch.Tensor], widths: Sequence[int], offsets: Sequence[int], group=None):
+    """One all-to-all per column: `cols[i]` holds rows laid out partition after partition
+    (`offsets`), `widths[i]` bytes per value.  Returns (received byte tensors, rows received)."""
+    world = dist.get_world_size(group)
+    send_counts = [offsets[i + 1] - offsets[i] for i in range(world)]
+    dev = cols[0].device
+    sc = torch.tensor(send_counts, dtype=torch.int64, device=dev)
+    rc = torch.empty_like(sc)
+    dist.all_to_all_single(rc, sc, group=group)
+    recv_counts = [int(v) for v in rc.tolist()]
+    n_recv, n_send = sum(recv_counts), sum(send_counts)
+    out = []
+    for t, w in zip(cols, widths):
+        r = torch.empty(max(1, n_recv * w), dtype=_TORCH_BYTES, device=dev)
+        dist.all_to_all_single(r[: n_recv * w], t[: n_send * w], [c * w for c in recv_counts], [c * w for c in send_counts], group=group)
+        out.append(r)
+    return out, n_recv
+
+
+def shuffle_by_key(block: DataBlock, key_col: int, device: int, group=None) -> Tuple[DataBlock, list]:
+    """Hash-partition a device-resident block and exchange the partitions: afterwards this rank
+    holds every row whose key it owns.  Returns the received block (device columns) and the
+    tensors backing it (keep them alive)."""
+    world = dist.get_world_size(group)
+    parts, offs = hash_partition(block, key_col, world, device)
+    widths = [np_dtype(c.dtype).itemsize for c in block.columns]
+    recv, n = all_to_all_columns(parts, widths, offs, group)
+    cols = [Column.device(c.dtype, n, t.data_ptr()) for c, t in zip(block.columns, recv)]
+    return DataBlock(cols, n), recv
+
+
+def partitioned_hash_join(build: DataBlock, probe: DataBlock, build_key: int, probe_key: int, device: int, group=None,
+                          out_mem: int = abi.MEM_HOST):
+    """Inner join of two row-range-sharded tables: shuffle both sides by key, then join locally.
+    Returns the joined blocks of this rank (probe columns then build columns)."""
+    b_local, keep_b = shuffle_by_key(build, build_key, device, group)
+    p_local, keep_p = shuffle_by_key(probe, probe_key, device, group)
+    torch.cuda.synchronize(device)
+    j = HashJoin(schema_types(b_local), schema_types(p_local), build_key, probe_key, device)
+    j.add_block(b_local)
+    j.final_build()
+    out = j.probe_block(p_local, out_mem)
+    return out, j, (keep_b, keep_p)
+
+
+def topk_merge(local: DataBlock, row_base: int, k: int, asc: bool, nulls_first: bool, device: int = 0, group=None) -> DataBlock:
+    """All-gather every rank's top-k block ([key, row id], already in output order) and run the
+    final TransformTopN over the gathered candidates.  Candidates are concatenated in rank order,
+    so equal keys keep ascending GLOBAL row ids (rank r's rows precede rank r+1's)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    keys = local.columns[0]
+    gathered = [None] * world
+    payload = (keys.values().copy(), keys.valid_mask().copy(), local.columns[1].values().astype(np.int64) + row_base)
+    if world > 1:
+        dist.all_gather_object(gathered, payload, group=group)
+    else:
+        gathered = [payload]
+    vals = np.concatenate([g[0] for g in gathered])
+    valid = np.concatenate([g[1] for g in gathered])
+    rows = np.concatenate([g[2] for g in gathered])
+    nullable = keys.validity is not None or not valid.all()
+    cand = DataBlock([Column.from_data(vals, keys.dtype, validity=valid if nullable else None)], len(vals))
+    op = TransformTopN(0, asc, nulls_first, k, schema_types(cand) if nullable else [keys.dtype], device)
+    op.transform(cand)
+    out = op.on_finish()
+    op.close()
+    pos = out.columns[1].values()
+    return DataBlock([out.columns[0], Column.from_data(rows[pos])], out.num_rows)

@@ -70,6 +70,7 @@ def load():
         "dbx_agg_exchange_merge": (i32, [vp, vp]),
         "dbx_agg_exchange_destroy": (i32, [vp]),
         "dbx_agg_exchange_last_error": (C.c_char_p, [vp]),
+        "dbx_hash_partition": (i32, [i32, P(abi.Block), i32, i32, P(vp), P(i64)]),
         "dbx_eval_distance": (i32, [i32, i32, P(abi.Column), P(abi.Column), P(abi.Column)]),
         "dbx_knn_create": (i32, [i32, i32, P(abi.Column), P(vp)]),
         "dbx_knn_search": (i32, [vp, P(abi.Column), i32, i32, vp, vp]),

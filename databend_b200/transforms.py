@@ -82,12 +82,31 @@ def _block_from_c(b: abi.Block, device: int) -> DataBlock:
     for i in range(b.num_cols):
         c = b.cols[i]
         n = c.len
+        if c.is_const:  # BlockEntry::Const stays const
+            k = c.konst
+            if k.is_null:
+                v = None
+            elif c.dtype in (abi.F32, abi.F64):
+                v = k.v.f64
+            elif c.dtype in (abi.U8, abi.U16, abi.U32, abi.U64, abi.BOOL):
+                v = k.v.u64
+            else:
+                v = k.v.i64
+            cols.append(Column.new_const(c.dtype, v, n))
+            continue
         assert c.mem == abi.MEM_HOST
-        nd = np_dtype(c.dtype)
-        arr = np.empty(n, dtype=nd)
-        if n:
-            C.memmove(arr.ctypes.data, c.data, arr.nbytes)
-        col = Column(c.dtype, n, data=arr)
+        if c.dtype == abi.BOOL:
+            nb = (c.data_bit_offset + n + 7) // 8
+            arr = np.zeros(max(nb, 1), dtype=np.uint8)
+            if nb:
+                C.memmove(arr.ctypes.data, c.data, nb)
+            col = Column(abi.BOOL, n, data=arr, data_bit_offset=c.data_bit_offset)
+        else:
+            nd = np_dtype(c.dtype)
+            arr = np.empty(n, dtype=nd)
+            if n:
+                C.memmove(arr.ctypes.data, c.data, arr.nbytes)
+            col = Column(c.dtype, n, data=arr)
         if c.validity:
             nb = (c.validity_bit_offset + n + 7) // 8
             v = np.empty(max(nb, 1), dtype=np.uint8)
@@ -150,6 +169,20 @@ class _Op:
             self.close()
         except Exception:
             pass
+
+
+class TransformFilter(_Op):
+    """TransformFilter (filters/filter_predicate.rs:35-104) = FilterExecutor::filter
+    (filter_executor.rs:82-160): `transform(block)` returns the rows for which the predicate is
+    true, in input order, for every column.  NULL predicate values count as false."""
+
+    def __init__(self, predicate: Optional[E.Node], input_types: Sequence[int], device: int = 0):
+        super().__init__(abi.OP_FILTER, E.build_predicate(predicate), input_types, device)
+
+    def transform(self, block: DataBlock) -> DataBlock:
+        self.push(block)
+        b = self.pull_c(abi.MEM_HOST)
+        return _block_from_c(b, self.device)
 
 
 @dataclass

@@ -290,6 +290,14 @@ int32_t dbx_agg_exchange_merge(dbx_agg_exchange* x, dbx_op* final_op);
 int32_t dbx_agg_exchange_destroy(dbx_agg_exchange* x);
 const char* dbx_agg_exchange_last_error(const dbx_agg_exchange* x);
 
+/* Hash-partition the rows of a device-resident block by the owner of an integer key column
+ * (same owner rule as the aggregate exchange): the step in front of the all-to-all of a
+ * partitioned hash join (flight_scatter_hash.rs).  out_cols[c] are caller-allocated device
+ * buffers of num_rows values; partition p occupies rows [part_offsets[p], part_offsets[p+1])
+ * (part_offsets is HOST memory, n_parts + 1 entries).  Row order inside a partition is unspecified. */
+int32_t dbx_hash_partition(int32_t device, const dbx_block* block, int32_t key_col, int32_t n_parts,
+                           void* const* out_cols, int64_t* part_offsets);
+
 /* ScalarFunction::eval replacement for the vector distances (scalars/vector.rs:497-556):
  * out[i] = distance(lhs[i], rhs[i]) row-wise, either side may be const.  f32 result. */
 int32_t dbx_eval_distance(int32_t kind, int32_t device, const dbx_column* lhs, const dbx_column* rhs,

@@ -78,3 +78,41 @@ def test_two_rank_exchange_matches_single_process(tmp_path):
     np.testing.assert_array_equal(merged[order, 0].view(np.int64), ks)
     np.testing.assert_array_equal(merged[order, 1], cnt)
     np.testing.assert_array_equal(merged[order, 2].view(np.int64), sm)
+
+
+def _join_worker(rank, world, port, out_dir):
+    """Host logic of the partitioned hash join shuffle: rows partitioned by the owner rule (host
+    restatement of dbx_hash_partition), one all-to-all per column, every received key owned here."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from databend_b200.distributed import all_to_all_columns
+    from databend_b200.exchange import owner_of
+    rng = np.random.default_rng(77)
+    n = 30000
+    k_all = rng.integers(-5000, 5000, n).astype(np.int64)
+    v_all = rng.integers(0, 2**31, n).astype(np.int32)
+    lo, hi = n * rank // world, n * (rank + 1) // world
+    k, v = k_all[lo:hi], v_all[lo:hi]
+    own = owner_of(k.view(np.uint64), np.zeros(len(k), np.int64), world)
+    order = np.argsort(own, kind="stable")
+    offs = np.concatenate([[0], np.cumsum(np.bincount(own, minlength=world))]).tolist()
+    cols = [torch.from_numpy(k[order].view(np.uint8).copy()), torch.from_numpy(v[order].view(np.uint8).copy())]
+    recv, n_recv = all_to_all_columns(cols, [8, 4], offs)
+    rk = recv[0].numpy()[: n_recv * 8].view(np.int64)
+    rv = recv[1].numpy()[: n_recv * 4].view(np.int32)
+    assert (owner_of(rk.view(np.uint64), np.zeros(n_recv, np.int64), world) == rank).all()
+    np.save(os.path.join(out_dir, f"j{rank}.npy"), np.stack([rk, rv.astype(np.int64)], axis=1))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_join_shuffle_keeps_every_row(tmp_path):
+    world = 2
+    mp.spawn(_join_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    got = np.concatenate([np.load(os.path.join(tmp_path, f"j{r}.npy")) for r in range(world)])
+    rng = np.random.default_rng(77)
+    k_all = rng.integers(-5000, 5000, 30000).astype(np.int64)
+    v_all = rng.integers(0, 2**31, 30000).astype(np.int64)
+    exp = np.stack([k_all, v_all], axis=1)
+    np.testing.assert_array_equal(got[np.lexsort((got[:, 1], got[:, 0]))], exp[np.lexsort((exp[:, 1], exp[:, 0]))])

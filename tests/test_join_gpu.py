@@ -99,3 +99,35 @@ def test_empty_sides(gpu):
     run_join(build, probe, 0, 0)                       # no matches
     run_join(build.slice(0, 0), probe, 0, 0)           # empty build side
     run_join(build, probe.slice(0, 0), 0, 0)           # empty probe block
+
+
+def test_wide_build_side_inline_and_gather(gpu):
+    """Key in the middle of five build columns: two payload columns ride in the table entries
+    (one of them nullable), the remaining ones are gathered by build row (one nullable, narrow)."""
+    rng = np.random.default_rng(23)
+    nb, npb = 7000, 9000
+    build = DataBlock([Column.from_data(rng.normal(size=nb).astype(np.float32), validity=rng.random(nb) > 0.2),
+                       Column.from_data(rng.integers(-2**62, 2**62, nb).astype(np.int64)),
+                       Column.from_data(rng.integers(0, 3000, nb).astype(np.uint32)),            # key
+                       Column.from_data(rng.integers(0, 60000, nb).astype(np.uint16), validity=rng.random(nb) > 0.5),
+                       Column.from_data(rng.normal(size=nb))])
+    probe = DataBlock([Column.from_data(rng.integers(0, 3500, npb).astype(np.int64)),
+                       Column.from_data(rng.integers(0, 100, npb).astype(np.int8))])
+    run_join(build, probe, 2, 0, build_split=1500, probe_split=2500)
+
+
+def test_radix_partitioned_probe(gpu, monkeypatch):
+    """Force the radix layout (table cut into regions, probe block partitioned the same way) at
+    test size: same multiset of joined rows, incl. duplicate build keys, misses and a skewed build
+    side that must fall back to a single region."""
+    monkeypatch.setenv("DBX_JOIN_REGION_BYTES", str(64 << 10))
+    rng = np.random.default_rng(31)
+    nb, npb = 60_000, 200_000
+    build = DataBlock([Column.from_data(rng.integers(0, 50_000, nb).astype(np.int64)), Column.from_data(rng.integers(-9, 9, nb).astype(np.int64)),
+                       Column.from_data(rng.normal(size=nb))])
+    probe = DataBlock([Column.from_data(rng.integers(-1000, 60_000, npb).astype(np.int64)), Column.from_data(rng.integers(0, 2**31, npb).astype(np.int32))])
+    run_join(build, probe, 0, 0, probe_split=70_000)
+    run_join(build, probe, 0, 0, device_resident=True)
+    skew = DataBlock([Column.from_data(np.full(nb, 7, dtype=np.int64)), Column.from_data(np.arange(nb, dtype=np.int64))])
+    few = DataBlock([Column.from_data(np.array([7, 8, 7], dtype=np.int64))])
+    run_join(skew, few, 0, 0)
