@@ -37,7 +37,7 @@ METRIC = "rows/sec filter->hash-agg (sum,count,avg GROUP BY 1e6 int64 keys) over
 SEEDS = (42, 43, 44)
 N_KEYS = 1_000_000
 BYTES_PER_ROW = 24.0  # three 8-byte columns, each read exactly once
-NCU_TRAFFIC_PER_LAUNCH = 7.070684e9 + 0.526446e9  # bytes; one 2^28-row launch of the fused kernel (r01 capture)
+NCU_TRAFFIC_PER_LAUNCH = 7.094290e9 + 0.544827e9  # bytes; one 2^28-row launch of the fused kernel (profiles/r01b_filter_group_agg_ncu_full.csv)
 
 
 def peaks():
@@ -168,13 +168,15 @@ def run_knn(args, L, dev, rank, world, barrier):
         idx, d = op.search(q, k)
         if world == 1:
             return idx, d
-        ti = torch.from_numpy(idx + r0).to(f"cuda:{dev}")
-        td = torch.from_numpy(d).to(f"cuda:{dev}")
-        gi = [torch.empty_like(ti) for _ in range(world)]
-        gd = [torch.empty_like(td) for _ in range(world)]
-        dist.all_gather(gi, ti)
-        dist.all_gather(gd, td)
-        ai, ad = torch.cat(gi, 1), torch.cat(gd, 1)
+        # one collective: [nq, k] global row ids and the distance bits, packed into one int64 tensor
+        pack = np.empty((2, nq, k), dtype=np.int64)
+        pack[0] = idx + r0
+        pack[1] = d.view(np.int32)
+        t = torch.from_numpy(pack).to(f"cuda:{dev}", non_blocking=True)
+        g = torch.empty((world,) + tuple(t.shape), dtype=torch.int64, device=f"cuda:{dev}")
+        dist.all_gather_into_tensor(g, t)
+        ai = g[:, 0].permute(1, 0, 2).reshape(nq, world * k)
+        ad = g[:, 1].permute(1, 0, 2).reshape(nq, world * k).to(torch.int32).view(torch.float32)
         # merge: ascending (distance, row id); NaN last like OrderedFloat
         key = torch.where(torch.isnan(ad), torch.full_like(ad, float("inf")), ad)
         o1 = torch.argsort(ai, dim=1, stable=True)
@@ -298,6 +300,12 @@ def run_dbx(args):
         xchg = PeerExchange(part, rank, world)
         xchg.connect()
 
+    _k = C.c_float(0)
+
+    def last_kernel_ms():
+        lib.check(L.dbx_op_last_kernel_ms(part.handle, C.byref(_k)), part.handle)
+        return _k.value
+
     def exchange_and_finish(out_mem):
         """partial -> (N>1: hash-partition + exchange) -> final -> result block"""
         part.on_finish()
@@ -331,8 +339,10 @@ def run_dbx(args):
             part.reset()
         fin.reset()
         part.transform(dblock)
-        kernel_ms.append(part.last_kernel_ms())
         out = exchange_and_finish(abi.MEM_DEVICE)
+        # read the kernel's event pair only now: asking earlier blocks the host until the kernel
+        # has finished and exposes the launch latency of everything behind it
+        kernel_ms.append(last_kernel_ms())
         rows_out = out[0].num_rows
         L.dbx_block_release(C.byref(out[0]))
         return rows_out
@@ -473,8 +483,8 @@ def run_dbx(args):
                    "parallelism": f"row-range x{world}" + ("" if world == 1 else (" + peer-memory (NVLink) scatter of partial groups" if use_peer else " + NCCL all-to-all of partial groups"))},
         "wall_ms_per_step": wall_ms, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": NCU_TRAFFIC_PER_LAUNCH, "traffic_note": "dram read+write per 2^28-row launch from profiles/r01_filter_group_agg_ncu_full.csv (ncu --set full)",
-                     "achieved_per_launch_bytes": BYTES_PER_ROW * min(n, 1 << 28), "kernel": "filter_group_agg_kernel<3,FAST=1,INDIRECT=0>", "kernel_ms": k_ms,
+                     "traffic": NCU_TRAFFIC_PER_LAUNCH, "traffic_note": "dram read+write per 2^28-row launch from profiles/r01b_filter_group_agg_ncu_full.csv (ncu --set full)",
+                     "achieved_per_launch_bytes": BYTES_PER_ROW * min(n, 1 << 28), "kernel": "filter_group_agg_kernel<3,FAST=1,INDIRECT=0,BULK=0>", "kernel_ms": k_ms,
                      "algorithmic_bytes_per_row": BYTES_PER_ROW, "peak_source": peak_src},
         "cpu_baseline": cpu, "e2e": e2e, "knn": knn,
     }

@@ -41,29 +41,36 @@ __global__ void __launch_bounds__(256) partition_count_kernel(const __grid_const
   if (threadIdx.x < p.n_parts && s_cnt[threadIdx.x]) atomicAdd(&p.counters[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
 }
 
-// per 256-row step: one reservation per (CTA, owner); the step's values are laid out owner after
-// owner in shared memory and copied out in runs, so the stores are coalesced per partition
+// per step of 1024 rows (4 per thread): one reservation per (CTA, owner); the step's values are
+// laid out owner after owner in shared memory and copied out in runs, so the stores are coalesced
+// per partition and the barriers are amortised over four rows per thread
+constexpr int kPartRows = 4;
 __global__ void __launch_bounds__(256) partition_scatter_kernel(const __grid_constant__ PartParams p) {
   __shared__ unsigned int s_cnt[kMaxParts];
   __shared__ unsigned int s_off[kMaxParts + 1];
   __shared__ unsigned long long s_base[kMaxParts];
-  __shared__ unsigned char s_owner[256];
-  __shared__ unsigned long long s_dst[256];
-  __shared__ uint64_t s_val[256];
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int64_t n_iter = (p.n_rows + stride - 1) / stride;
+  __shared__ unsigned long long s_dst[256 * kPartRows];
+  __shared__ uint64_t s_val[256 * kPartRows];
+  const int64_t step_rows = (int64_t)blockDim.x * kPartRows;
+  const int64_t n_steps = (p.n_rows + step_rows - 1) / step_rows;
 #pragma unroll 1
-  for (int64_t it = 0; it < n_iter; ++it) {
+  for (int64_t st = blockIdx.x; st < n_steps; st += gridDim.x) {
     if (threadIdx.x < kMaxParts) s_cnt[threadIdx.x] = 0;
     __syncthreads();
-    const int64_t i = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool in = i < p.n_rows;
-    int owner = 0;
-    unsigned int local = 0;
-    if (in) {
-      owner = part_owner(part_load_key(p.key, i), p.n_parts);
-      asm volatile("" : "+r"(owner));
-      local = atomicAdd(&s_cnt[owner], 1u);
+    const int64_t i0 = st * step_rows + threadIdx.x;
+    int owner[kPartRows];
+    unsigned int slot[kPartRows];
+#pragma unroll
+    for (int j = 0; j < kPartRows; ++j) {
+      const int64_t i = i0 + (int64_t)j * blockDim.x;
+      owner[j] = -1;
+      slot[j] = 0;
+      if (i < p.n_rows) {
+        int o = part_owner(part_load_key(p.key, i), p.n_parts);
+        asm volatile("" : "+r"(o));
+        owner[j] = o;
+        slot[j] = atomicAdd(&s_cnt[o], 1u);
+      }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -74,28 +81,33 @@ __global__ void __launch_bounds__(256) partition_scatter_kernel(const __grid_con
     if (threadIdx.x < p.n_parts && s_cnt[threadIdx.x])
       s_base[threadIdx.x] = atomicAdd(&p.counters[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
     __syncthreads();
-    unsigned int slot = 0;
-    if (in) {
-      slot = s_off[owner] + local;
-      s_owner[slot] = (unsigned char)owner;
-      s_dst[slot] = s_base[owner] + local;
+#pragma unroll
+    for (int j = 0; j < kPartRows; ++j) {
+      if (owner[j] >= 0) {
+        const unsigned int local = slot[j];
+        slot[j] = s_off[owner[j]] + local;
+        s_dst[slot[j]] = s_base[owner[j]] + local;
+      }
     }
     const unsigned int total = s_off[p.n_parts];
     for (int c = 0; c < p.n_cols; ++c) {
       const PartCol& pc = p.cols[c];
       __syncthreads();
-      if (in) {
+#pragma unroll
+      for (int j = 0; j < kPartRows; ++j) {
+        if (owner[j] < 0) continue;
+        const int64_t i = i0 + (int64_t)j * blockDim.x;
         uint64_t v;
         if (pc.size == 8) v = ((const uint64_t*)pc.src)[i];
         else if (pc.size == 4) v = ((const uint32_t*)pc.src)[i];
         else if (pc.size == 2) v = ((const uint16_t*)pc.src)[i];
         else v = ((const uint8_t*)pc.src)[i];
-        s_val[slot] = v;
+        s_val[slot[j]] = v;
       }
       __syncthreads();
-      if (threadIdx.x < total) {
-        const int64_t o = (int64_t)s_dst[threadIdx.x];
-        const uint64_t v = s_val[threadIdx.x];
+      for (unsigned int t = threadIdx.x; t < total; t += blockDim.x) {
+        const int64_t o = (int64_t)s_dst[t];
+        const uint64_t v = s_val[t];
         if (pc.size == 8) ((uint64_t*)pc.dst)[o] = v;
         else if (pc.size == 4) ((uint32_t*)pc.dst)[o] = (uint32_t)v;
         else if (pc.size == 2) ((uint16_t*)pc.dst)[o] = (uint16_t)v;
@@ -117,7 +129,7 @@ int32_t hash_partition_device(ErrorSink& err, cudaStream_t stream, const PartPar
   PartParams p = params;
   p.counters = counters;
   DBX_CUDA_TRY(err, cudaMemsetAsync(counters, 0, (size_t)kMaxParts * 8, stream));
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((p.n_rows + 255) / 256, (int64_t)kNumSMs * 8));
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((p.n_rows + 1023) / 1024, (int64_t)kNumSMs * 8));
   if (p.n_rows > 0) {
     partition_count_kernel<<<grid, 256, 0, stream>>>(p);
     count_launch();

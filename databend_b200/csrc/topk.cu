@@ -75,16 +75,24 @@ __global__ void __launch_bounds__(kTopkBlock) topk_scan_kernel(const __grid_cons
   const uint64_t pol = make_policy_evict_first();
   const int lane = threadIdx.x & 31;
   const int64_t n_tiles = (n + kTopkBlock * 4 - 1) / (kTopkBlock * 4);
+  u64x4 next_q;
+  next_q.x = next_q.y = next_q.z = next_q.w = 0;
+  bool have_next = false;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     __syncwarp();
     const int64_t r0 = tile * (kTopkBlock * 4) + 4 * (int64_t)threadIdx.x;
     uint64_t v[4];
     uint32_t valid = 0, inr = 0;
     if (FAST && r0 + 4 <= n) {
-      u64x4 q = ld_stream_256((const char*)col.data + r0 * 8);
+      u64x4 q = have_next ? next_q : ld_stream_256((const char*)col.data + r0 * 8);
+      // keep a second tile in flight: one 32-byte load per thread does not cover the HBM latency
+      const int64_t rn = (tile + gridDim.x) * (kTopkBlock * 4) + 4 * (int64_t)threadIdx.x;
+      have_next = tile + gridDim.x < n_tiles && rn + 4 <= n;
+      if (have_next) next_q = ld_stream_256((const char*)col.data + rn * 8);
       v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
       valid = inr = 0xF;
     } else {
+      have_next = false;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         v[j] = 0;

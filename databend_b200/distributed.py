@@ -85,26 +85,52 @@ def partitioned_hash_join(build: DataBlock, probe: DataBlock, build_key: int, pr
     return out, j, (keep_b, keep_p)
 
 
-def topk_merge(local: DataBlock, row_base: int, k: int, asc: bool, nulls_first: bool, device: int = 0, group=None) -> DataBlock:
+def topk_merge(local: DataBlock, row_base: int, k: int, asc: bool, nulls_first: bool, device: int = 0, group=None,
+               final_op: TransformTopN = None) -> DataBlock:
     """All-gather every rank's top-k block ([key, row id], already in output order) and run the
     final TransformTopN over the gathered candidates.  Candidates are concatenated in rank order,
     so equal keys keep ascending GLOBAL row ids (rank r's rows precede rank r+1's)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     keys = local.columns[0]
-    gathered = [None] * world
-    payload = (keys.values().copy(), keys.valid_mask().copy(), local.columns[1].values().astype(np.int64) + row_base)
+    vals_l, valid_l = keys.values(), keys.valid_mask()
+    rows_l = local.columns[1].values().astype(np.int64) + row_base
     if world > 1:
-        dist.all_gather_object(gathered, payload, group=group)
+        # fixed-size tensors (k slots per rank, count in front): one all_gather, no pickling
+        n = len(vals_l)
+        dev = torch.device("cuda", device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        buf = torch.zeros(1 + 3 * k, dtype=torch.int64, device=dev)
+        pack = np.zeros(1 + 3 * k, dtype=np.int64)
+        pack[0] = n
+        pack[1:1 + n] = np.ascontiguousarray(vals_l).view(np.int64) if vals_l.dtype.itemsize == 8 else vals_l.astype(np.float64).view(np.int64) if vals_l.dtype.kind == "f" else vals_l.astype(np.int64)
+        pack[1 + k:1 + k + n] = valid_l.astype(np.int64)
+        pack[1 + 2 * k:1 + 2 * k + n] = rows_l
+        buf.copy_(torch.from_numpy(pack))
+        out = torch.empty(world * (1 + 3 * k), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(out, buf, group=group)
+        g = out.cpu().numpy().reshape(world, 1 + 3 * k)
+        vs, ms, rs = [], [], []
+        for r in range(world):
+            m = int(g[r, 0])
+            raw = g[r, 1:1 + m]
+            if vals_l.dtype.itemsize == 8:
+                vs.append(raw.view(vals_l.dtype))
+            elif vals_l.dtype.kind == "f":
+                vs.append(raw.view(np.float64).astype(vals_l.dtype))
+            else:
+                vs.append(raw.astype(vals_l.dtype))
+            ms.append(g[r, 1 + k:1 + k + m].astype(bool))
+            rs.append(g[r, 1 + 2 * k:1 + 2 * k + m])
+        vals, valid, rows = np.concatenate(vs), np.concatenate(ms), np.concatenate(rs)
     else:
-        gathered = [payload]
-    vals = np.concatenate([g[0] for g in gathered])
-    valid = np.concatenate([g[1] for g in gathered])
-    rows = np.concatenate([g[2] for g in gathered])
+        vals, valid, rows = vals_l, valid_l, rows_l
     nullable = keys.validity is not None or not valid.all()
     cand = DataBlock([Column.from_data(vals, keys.dtype, validity=valid if nullable else None)], len(vals))
-    op = TransformTopN(0, asc, nulls_first, k, schema_types(cand) if nullable else [keys.dtype], device)
+    op = final_op or TransformTopN(0, asc, nulls_first, k, schema_types(cand) if nullable else [keys.dtype], device)
+    if final_op is not None:
+        op.reset()
     op.transform(cand)
     out = op.on_finish()
-    op.close()
+    if final_op is None:
+        op.close()
     pos = out.columns[1].values()
     return DataBlock([out.columns[0], Column.from_data(rows[pos])], out.num_rows)

@@ -141,6 +141,7 @@ if "topk" in ops:
     xb = fill(3, 11, 0, r0, n)
     col = Column.device(abi.F64, n, xb.ptr)
     op = TransformTopN(0, True, False, 1000, [abi.F64], dev)
+    fop = TransformTopN(0, True, False, 1000, [abi.F64], dev) if world > 1 else None
     best, kms = None, None
     for rep in range(a.reps + 1):
         op.reset()
@@ -151,7 +152,7 @@ if "topk" in ops:
         local = op.on_finish()
         if world > 1:
             from databend_b200.distributed import topk_merge
-            res = topk_merge(local, r0, 1000, True, False, dev)
+            res = topk_merge(local, r0, 1000, True, False, dev, final_op=fop)
         else:
             res = local
         sync_all()
