@@ -25,7 +25,7 @@ namespace dbx {
 namespace {
 
 constexpr int kTopkBlock = 256;
-constexpr int64_t kMaxChunk = 1LL << 27;
+constexpr int64_t kMaxChunk = 1LL << 30;
 
 struct TopkDev {
   uint64_t* ord;      // order-preserving image (smaller = earlier in the output)
@@ -318,7 +318,10 @@ class TopkOp : public Op {
       n_cand = cnt;
       done += m;
       // the boundary tightens as rows are seen: later chunks can be geometrically larger
-      if (n_cand > cap / 2 || (boundary == ~0ULL && n_cand > prm.limit)) DBX_TRY(compact());
+      // Cut back after every chunk that left more than 2k candidates: the boundary then reflects
+      // every row seen so far, so the next (8x larger) chunk adds about 8k survivors instead of
+      // overflowing the list and being replayed in smaller pieces.
+      if (n_cand > 2 * prm.limit || n_cand > cap / 2) DBX_TRY(compact());
       next_chunk = std::min<int64_t>(next_chunk * 8, kMaxChunk);
     }
     rows_seen += n;
