@@ -572,21 +572,25 @@ class AggPartialOp : public Op {
   int32_t launch_one(const AggKernelParams& kp) {
     // the TMA bulk-reduction variant exists for the straight-line kernel only; everywhere else
     // paired words are updated with plain REDs
-    if (FAST && !INDIRECT && kp.n_pairs > 0) return launch_kernel<NS, FAST, INDIRECT, true>(kp);
-    return launch_kernel<NS, FAST, INDIRECT, false>(kp);
+    if (FAST && !INDIRECT && kp.n_pairs > 0) return launch_kernel<NS, FAST, INDIRECT, true, 4>(kp);
+    // (occupancy sweep, profiles/r01b_agg_occupancy_sweep.txt: 4 CTAs/SM at 62 registers is the optimum;
+    // 5-6 CTAs spill and queue up behind the L2 atomics, 2-3 CTAs hide less latency)
+    return launch_kernel<NS, FAST, INDIRECT, false, 4>(kp);
   }
-  template <int NS, bool FAST, bool INDIRECT, bool BULK>
+  template <int NS, bool FAST, bool INDIRECT, bool BULK, int MINB>
   int32_t launch_kernel(const AggKernelParams& kp) {
     static bool attr_set[16] = {};
     const size_t smem_rows = (sizeof(StageWarp<NS>) * kWarpsPerBlock + 15) & ~(size_t)15;
     const size_t smem_bulk = (size_t)kWarpsPerBlock * kBulkGen * kMaxPairs * 32 * 16;
     const size_t smem = smem_rows + (BULK ? smem_bulk : 0);
-    auto kern = filter_group_agg_kernel<NS, FAST, INDIRECT, BULK>;
+    auto kern = filter_group_agg_kernel<NS, FAST, INDIRECT, BULK, MINB>;
     if (!attr_set[device]) {
       DBX_CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_set[device] = true;
     }
     int grid = grid_for_rows(kp.n_rows);
+    static const int per_sm = getenv("DBX_AGG_GRID") ? atoi(getenv("DBX_AGG_GRID")) : 0;
+    if (per_sm > 0) grid = (int)std::max<int64_t>(1, std::min<int64_t>((kp.n_rows + kTileRows - 1) / kTileRows, (int64_t)kNumSMs * per_sm));
     kern<<<grid, kBlock, smem, stream>>>(kp);
     count_launch();
     DBX_CUDA_TRY(err, cudaGetLastError());

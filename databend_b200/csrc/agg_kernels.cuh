@@ -410,8 +410,8 @@ __device__ __forceinline__ void prefetch_tile(const AggKernelParams& p, int64_t 
   }
 }
 
-template <int NS, bool FAST, bool INDIRECT, bool BULK = false>
-__global__ void __launch_bounds__(kBlock, 4) filter_group_agg_kernel(const __grid_constant__ AggKernelParams p) {
+template <int NS, bool FAST, bool INDIRECT, bool BULK = false, int MINB = 4>
+__global__ void __launch_bounds__(kBlock, MINB) filter_group_agg_kernel(const __grid_constant__ AggKernelParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   StageWarp<NS>& sw = reinterpret_cast<StageWarp<NS>*>(smem_raw)[warp];
