@@ -51,6 +51,8 @@ struct AggPlan {
   bool grouped = false;
   int key_slot = -1, key_dtype = -1;
   bool key_nullable = false;
+  int n_key_parts = 0;  // > 1: packed multi-column key
+  KeyPartDev key_parts[DBX_MAX_GROUP_COLS];
 
   int n_words = 0;
   WordInit init;
@@ -260,8 +262,35 @@ int32_t build_plan(const dbx_agg_params* p, const int32_t* types, int32_t n_cols
   DBX_TRY(lower_predicate(pl, p->filter, err));
 
   pl->grouped = p->n_group_cols > 0;
-  if (p->n_group_cols > 1) { err->set("multi-column GROUP BY keys are not built yet (SURVEY 8f.1)"); return DBX_ERR_UNSUPPORTED; }
-  if (pl->grouped) {
+  pl->n_key_parts = 0;
+  if (p->n_group_cols > 1) {
+    // several fixed-width integer key columns whose bits (+ one NULL bit per Nullable column) fit
+    // 64 bits are packed into one word, like HashMethodKeysU64 (kernels/group_by.rs:66-79); the
+    // table, exchange and merge code then see an ordinary 64-bit key
+    int bits = 0;
+    for (int g = 0; g < p->n_group_cols; ++g) {
+      const int kc = p->group_cols[g];
+      if (kc < 0 || kc >= n_cols) { err->set("group column outside the input schema"); return DBX_ERR_INVALID; }
+      const int dt = pl->col_dtype[kc];
+      if (dtype_class(dt) == VC_FLT || dt == DBX_BOOL || dtype_size(dt) == 0) { err->set("GROUP BY keys must be integer columns (float/bool keys not built yet)"); return DBX_ERR_UNSUPPORTED; }
+      KeyPartDev& kp = pl->key_parts[g];
+      memset(&kp, 0, sizeof(kp));
+      kp.slot = pl->slot_of(kc, err);
+      if (kp.slot < 0) return DBX_ERR_UNSUPPORTED;
+      kp.dtype = dt;
+      const int w = 8 * dtype_size(dt);
+      kp.shift = bits;
+      kp.mask = w == 64 ? ~0ULL : ((1ULL << w) - 1);
+      bits += w;
+      kp.null_shift = -1;
+      if (pl->col_nullable[kc]) kp.null_shift = bits++;
+    }
+    if (bits > 64) { err->set("multi-column GROUP BY keys wider than 64 bits (incl. NULL flags) need 128-bit packed keys: not built yet (SURVEY 8f.1)"); return DBX_ERR_UNSUPPORTED; }
+    pl->n_key_parts = p->n_group_cols;
+    pl->key_slot = pl->key_parts[0].slot;
+    pl->key_dtype = DBX_U64;
+    pl->key_nullable = false;
+  } else if (pl->grouped) {
     int kc = p->group_cols[0];
     if (kc < 0 || kc >= n_cols) { err->set("group column outside the input schema"); return DBX_ERR_INVALID; }
     int dt = pl->col_dtype[kc];
@@ -680,6 +709,8 @@ class AggPartialOp : public Op {
     kp->n_updates = plan.n_updates;
     kp->key_slot = plan.key_slot;
     kp->key_nullable = plan.key_nullable;
+    kp->n_key_parts = plan.n_key_parts;
+    memcpy(kp->key_parts, plan.key_parts, sizeof(plan.key_parts));
     kp->n_pairs = plan.n_pairs;
     memcpy(kp->pairs, plan.pairs, sizeof(PairDev) * kMaxPairs);
     static const uint32_t bulk_lanes = getenv("DBX_AGG_BULK_LANES") ? (uint32_t)strtoul(getenv("DBX_AGG_BULK_LANES"), nullptr, 16) : 0xFFFFFFFFu;
@@ -979,7 +1010,29 @@ class AggFinalOp : public Op {
       ob->cols.push_back(c);
     }
     fp.key_dtype = -1;
-    if (plan.grouped) {
+    fp.n_key_parts = 0;
+    if (plan.grouped && plan.n_key_parts > 1) {  // packed key -> one output column per group column
+      fp.n_key_parts = plan.n_key_parts;
+      memcpy(fp.key_parts, plan.key_parts, sizeof(plan.key_parts));
+      for (int j = 0; j < plan.n_key_parts; ++j) {
+        const int dt = plan.key_parts[j].dtype;
+        void* kv = nullptr;
+        DBX_TRY(dev_alloc((size_t)cap_rows * dtype_size(dt), &kv));
+        fp.out_keys[j] = kv;
+        uint8_t* vb = nullptr;
+        if (plan.key_parts[j].null_shift >= 0) DBX_TRY(dev_alloc((size_t)cap_rows, (void**)&vb));
+        fp.out_keys_valid[j] = vb;
+        valid_bytes.push_back(vb);
+        dbx_column c;
+        memset(&c, 0, sizeof(c));
+        c.dtype = dt;
+        c.mem = DBX_MEM_DEVICE;
+        c.len = ng;
+        c.data = kv;
+        c.null_count = vb ? -1 : 0;
+        ob->cols.push_back(c);
+      }
+    } else if (plan.grouped) {
       fp.key_dtype = plan.key_dtype;
       void* kv = nullptr;
       DBX_TRY(dev_alloc((size_t)cap_rows * dtype_size(plan.key_dtype), &kv));

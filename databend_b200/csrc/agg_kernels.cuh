@@ -339,11 +339,21 @@ __device__ __forceinline__ void table_phase32(const AggKernelParams& p, const St
   int64_t good_slot = -1;
   uint64_t key = 0;
   uint32_t vm = 0xFF;
+  bool key_null = false;
   if (act) {
-    key = sw.val[p.key_slot][i];
     if (!FAST) vm = sw.vm[i];
+    if (p.n_key_parts > 1) {  // packed multi-column key; NULLs are encoded inside the key
+      for (int j = 0; j < p.n_key_parts; ++j) {
+        const KeyPartDev kp = p.key_parts[j];
+        const bool ok = (vm >> kp.slot) & 1;
+        if (ok) key |= (sw.val[kp.slot][i] & kp.mask) << kp.shift;
+        else key |= 1ULL << kp.null_shift;
+      }
+    } else {
+      key = sw.val[p.key_slot][i];
+      key_null = !((vm >> p.key_slot) & 1);
+    }
   }
-  const bool key_null = !((vm >> p.key_slot) & 1);
   const bool special = key_null || key == kEmptyKey;
   const int64_t b = (int64_t)(agg_hash_u64(key) & (uint64_t)((t.cap >> 2) - 1));
   u64x4 kb;
@@ -973,6 +983,12 @@ struct FinalizeParams {
   int32_t key_dtype;      // -1: no key output
   void* out_key;
   uint8_t* out_key_valid; // byte per group or nullptr
+  // packed multi-column keys (n_key_parts > 1): one output column per part
+  int32_t n_key_parts;
+  int32_t pad;
+  KeyPartDev key_parts[DBX_MAX_GROUP_COLS];
+  void* out_keys[DBX_MAX_GROUP_COLS];
+  uint8_t* out_keys_valid[DBX_MAX_GROUP_COLS];
   unsigned long long* out_count;
   int64_t out_capacity;   // rows the output columns can hold
 };
@@ -1013,7 +1029,15 @@ __global__ void __launch_bounds__(256) table_finalize_kernel(const __grid_consta
     int64_t o = (int64_t)base + __popc(ballot & ((1u << lane) - 1));
     if (o >= fp.out_capacity) continue;  // the host re-runs with a larger output (never silently)
     int key_kind = i >= src.cap ? (int)(i - src.cap) + 1 : 0;
-    if (fp.key_dtype >= 0) {
+    if (fp.n_key_parts > 1) {
+      const uint64_t kb = key_kind == 1 ? kEmptyKey : key;
+      for (int j = 0; j < fp.n_key_parts; ++j) {
+        const KeyPartDev kp = fp.key_parts[j];
+        const bool is_null = kp.null_shift >= 0 && ((kb >> kp.null_shift) & 1);
+        store_narrow(fp.out_keys[j], o, kp.dtype, is_null ? 0 : ((kb >> kp.shift) & kp.mask));
+        if (fp.out_keys_valid[j]) fp.out_keys_valid[j][o] = is_null ? 0 : 1;
+      }
+    } else if (fp.key_dtype >= 0) {
       uint64_t kb = key_kind == 1 ? kEmptyKey : (key_kind == 2 ? 0 : key);
       store_narrow(fp.out_key, o, fp.key_dtype, kb);
       if (fp.out_key_valid) fp.out_key_valid[o] = key_kind == 2 ? 0 : 1;

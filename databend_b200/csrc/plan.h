@@ -145,11 +145,24 @@ __host__ __device__ __forceinline__ uint64_t* word_ptr(const TableDev& t, int64_
   return t.states + t.w_off[w] + slot * t.w_stride[w];
 }
 
+// Multi-column GROUP BY packed into one 64-bit key (the reference's HashMethodKeysU64 idea,
+// kernels/group_by.rs:66-79: fixed-size key columns whose bytes + NULL flags fit one word):
+// column j contributes (value & mask) << shift, a nullable column additionally one NULL bit; a
+// NULL value contributes zero value bits, so (NULL, x) and (0, x) stay different groups.
+struct KeyPartDev {
+  int32_t slot;        // input slot of the column
+  int32_t shift;       // bit position of the value field
+  int32_t null_shift;  // bit position of the NULL flag, -1: column is not Nullable
+  int32_t dtype;
+  uint64_t mask;       // value field mask (unshifted)
+};
+
 struct AggKernelParams {
   DevCol cols[kMaxSlots];
   PredNodeDev nodes[DBX_MAX_PRED_NODES];
   UpdateDev upd[kMaxUpdates];
   PairDev pairs[kMaxPairs];
+  KeyPartDev key_parts[DBX_MAX_GROUP_COLS];
   TableDev table;
   int64_t n_rows;
   const uint32_t* row_index;  // indirect mode: process rows row_index[0..n_rows)
@@ -157,6 +170,8 @@ struct AggKernelParams {
   int32_t n_slots, n_nodes, n_updates;
   int32_t key_slot;     // -1: no GROUP BY
   int32_t key_nullable; // key column may carry a validity bitmap
+  int32_t n_key_parts;  // > 1: the key is packed from key_parts[] (key_slot is unused)
+  int32_t pad3;
   uint32_t row_base;    // added to in-launch row numbers when recording overflow rows
   int32_t n_pairs;      // > 0: paired words go through TMA bulk reductions
   uint32_t bulk_lanes;  // lanes (bit mask) that use the bulk path; the others use REDs for the paired words too
