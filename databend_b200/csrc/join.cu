@@ -84,6 +84,7 @@ struct JoinProbeParams {
   JoinColDev probe_cols[kMaxJoinCols];
   JoinColDev build_cols[kMaxJoinCols];
   int32_t n_probe_cols, n_build_cols;
+  int32_t kind, pad;  // dbx_join_kind
   int64_t row_begin;  // rows [row_begin, row_begin + n_rows) of the (partitioned) probe columns
   int64_t n_rows;
   int64_t out_cap;
@@ -186,7 +187,8 @@ __global__ void __launch_bounds__(kJoinBlock) join_probe_kernel(const __grid_con
   const int64_t n_iter = (p.n_rows + (int64_t)gridDim.x * blockDim.x - 1) / ((int64_t)gridDim.x * blockDim.x);
   for (int64_t it = 0; it < n_iter; ++it) {
     const int64_t r = p.row_begin + it * (int64_t)gridDim.x * blockDim.x + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = r < p.row_begin + p.n_rows && !(p.key.validity && !bit_test(p.key.validity, p.key.vbit_off + r));
+    const bool in_range = r < p.row_begin + p.n_rows;
+    const bool live = in_range && !(p.key.validity && !bit_test(p.key.validity, p.key.vbit_off + r));
     uint64_t k = 0;
     int64_t b0 = 0, rb = 0;
     unsigned int n_match = 0;
@@ -203,6 +205,9 @@ __global__ void __launch_bounds__(kJoinBlock) join_probe_kernel(const __grid_con
         b = (b + 1) & mask;
       }
     }
+    // semi / anti: the probe row itself is the output, at most once (a NULL key counts as no match)
+    if (p.kind == DBX_JOIN_LEFT_SEMI) n_match = n_match ? 1u : 0u;
+    else if (p.kind == DBX_JOIN_LEFT_ANTI) n_match = (in_range && n_match == 0) ? 1u : 0u;
     // block-wide exclusive scan of the match counts -> one reservation per CTA and step
     unsigned int incl = n_match;
 #pragma unroll
@@ -220,7 +225,10 @@ __global__ void __launch_bounds__(kJoinBlock) join_probe_kernel(const __grid_con
     __syncthreads();
     int64_t pos = (int64_t)s_base + s_warp[warp] + incl - n_match;
     __syncthreads();
-    if (n_match) {
+    if (n_match && p.kind != DBX_JOIN_INNER) {
+      if (pos < p.out_cap)
+        for (int c = 0; c < p.n_probe_cols; ++c) copy_value(p.probe_cols[c], r, pos);
+    } else if (n_match) {
       emit_match(p, r, first, pos++);
       if (n_match > 1) {  // duplicates of the key on the build side: walk again, skip the first
         int64_t b = b0;
@@ -304,7 +312,7 @@ class JoinOp : public Op {
   int32_t init(const dbx_join_params* p, const int32_t* types, int32_t n, int dev) {
     DBX_TRY(base_init(dev));
     prm = *p;
-    if (p->kind != DBX_JOIN_INNER) { err.set("only INNER joins are built (SURVEY 8f.3 lists left/semi/anti as next)"); return DBX_ERR_UNSUPPORTED; }
+    if (p->kind != DBX_JOIN_INNER && p->kind != DBX_JOIN_LEFT_SEMI && p->kind != DBX_JOIN_LEFT_ANTI) { err.set("join kind not built (INNER, LEFT SEMI and LEFT ANTI are; outer joins are next, SURVEY 8f.3)"); return DBX_ERR_UNSUPPORTED; }
     n_build_cols = p->n_build_cols;
     n_probe_cols = n - n_build_cols;
     if (n_build_cols <= 0 || n_probe_cols <= 0 || n_build_cols > kMaxJoinCols || n_probe_cols > kMaxJoinCols) {
@@ -473,7 +481,8 @@ class JoinOp : public Op {
       pp.key = cols[prm.probe_key_col];
       pp.table = table_view();
       pp.n_probe_cols = n_probe_cols;
-      pp.n_build_cols = n_build_cols;
+      pp.n_build_cols = prm.kind == DBX_JOIN_INNER ? n_build_cols : 0;
+      pp.kind = prm.kind;
       pp.n_rows = n;
       pp.out_cap = out_cap;
       pp.cursor = (unsigned long long*)cursor.p;
@@ -505,7 +514,7 @@ class JoinOp : public Op {
         DBX_TRY(add_out(pp.probe_cols[c], probe_dtype[c], probe_nullable[c]));
       }
       DevBuf build_bits[kMaxJoinCols];
-      for (int c = 0; c < n_build_cols; ++c) {
+      for (int c = 0; c < pp.n_build_cols; ++c) {
         pp.build_cols[c].src = build[c].data.p;
         pp.build_cols[c].from = c == prm.build_key_col ? 1 : (c == inline_col[0] ? 2 : (c == inline_col[1] ? 3 : 0));
         if (build[c].nullable && pp.build_cols[c].from == 0) {  // bytes -> use the byte array directly through a 1-byte "bitmap" trick: pack once

@@ -131,3 +131,39 @@ def test_radix_partitioned_probe(gpu, monkeypatch):
     skew = DataBlock([Column.from_data(np.full(nb, 7, dtype=np.int64)), Column.from_data(np.arange(nb, dtype=np.int64))])
     few = DataBlock([Column.from_data(np.array([7, 8, 7], dtype=np.int64))])
     run_join(skew, few, 0, 0)
+
+
+@pytest.mark.parametrize("kind_name", ["semi", "anti"])
+def test_left_semi_and_anti(gpu, kind_name, monkeypatch):
+    """LEFT SEMI / LEFT ANTI (left_join_semi.rs, left_join_anti.rs): probe rows with at least one /
+    with no match, probe columns only, each row at most once; a NULL probe key never matches."""
+    rng = np.random.default_rng(41)
+    nb, npb = 20_000, 50_000
+    build = DataBlock([Column.from_data(rng.integers(0, 9000, nb).astype(np.int64), validity=rng.random(nb) > 0.05),
+                       Column.from_data(rng.normal(size=nb))])
+    probe = DataBlock([Column.from_data(rng.integers(-500, 12_000, npb).astype(np.int64), validity=rng.random(npb) > 0.1),
+                       Column.from_data(np.arange(npb, dtype=np.int64))])  # unique row tag
+    pi, _ = oracle().hash_join_inner(build.columns[0], probe.columns[0])
+    matched = np.zeros(npb, dtype=bool)
+    matched[pi] = True
+    expect = np.nonzero(matched if kind_name == "semi" else ~matched)[0]
+    kind = abi.JOIN_LEFT_SEMI if kind_name == "semi" else abi.JOIN_LEFT_ANTI
+    for radix in (False, True):
+        if radix:
+            monkeypatch.setenv("DBX_JOIN_REGION_BYTES", str(64 << 10))
+        j = HashJoin(schema_types(build), schema_types(probe), 0, 0, kind=kind)
+        j.add_block(build)
+        j.final_build()
+        outs = []
+        for p in probe.split_by_rows(17_000):
+            outs.extend(j.probe_block(p))
+        j.close()
+        assert all(o.num_columns() == 2 for o in outs)
+        tags = np.sort(np.concatenate([o.columns[1].values() for o in outs])) if outs else np.empty(0, np.int64)
+        np.testing.assert_array_equal(tags, expect)
+        keys = np.concatenate([o.columns[0].values() for o in outs])
+        kval = np.concatenate([o.columns[0].valid_mask() for o in outs])
+        order = np.argsort(np.concatenate([o.columns[1].values() for o in outs]))
+        np.testing.assert_array_equal(kval[order], probe.columns[0].valid_mask()[expect])
+        m = kval[order]
+        np.testing.assert_array_equal(keys[order][m], probe.columns[0].values()[expect][m])
