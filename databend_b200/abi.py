@@ -27,7 +27,7 @@ AGG_SUM, AGG_COUNT, AGG_AVG, AGG_MIN, AGG_MAX = range(5)
 OP_FILTER, OP_AGG_PARTIAL, OP_AGG_FINAL, OP_TOPK, OP_JOIN = range(5)
 
 DIST_COSINE, DIST_L2 = 0, 1
-JOIN_INNER, JOIN_LEFT_SEMI, JOIN_LEFT_ANTI = 0, 1, 2
+JOIN_INNER, JOIN_LEFT_SEMI, JOIN_LEFT_ANTI, JOIN_LEFT = 0, 1, 2, 3
 
 MAX_PRED_NODES = 16
 MAX_AGGS = 8

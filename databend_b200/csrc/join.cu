@@ -208,6 +208,8 @@ __global__ void __launch_bounds__(kJoinBlock) join_probe_kernel(const __grid_con
     // semi / anti: the probe row itself is the output, at most once (a NULL key counts as no match)
     if (p.kind == DBX_JOIN_LEFT_SEMI) n_match = n_match ? 1u : 0u;
     else if (p.kind == DBX_JOIN_LEFT_ANTI) n_match = (in_range && n_match == 0) ? 1u : 0u;
+    const bool outer_null_row = p.kind == DBX_JOIN_LEFT && in_range && n_match == 0;  // preserved row without a match
+    if (outer_null_row) n_match = 1;
     // block-wide exclusive scan of the match counts -> one reservation per CTA and step
     unsigned int incl = n_match;
 #pragma unroll
@@ -225,7 +227,12 @@ __global__ void __launch_bounds__(kJoinBlock) join_probe_kernel(const __grid_con
     __syncthreads();
     int64_t pos = (int64_t)s_base + s_warp[warp] + incl - n_match;
     __syncthreads();
-    if (n_match && p.kind != DBX_JOIN_INNER) {
+    if (outer_null_row) {
+      if (pos < p.out_cap) {
+        for (int c = 0; c < p.n_probe_cols; ++c) copy_value(p.probe_cols[c], r, pos);
+        for (int c = 0; c < p.n_build_cols; ++c) store_value(p.build_cols[c], 0, false, pos);
+      }
+    } else if (n_match && (p.kind == DBX_JOIN_LEFT_SEMI || p.kind == DBX_JOIN_LEFT_ANTI)) {
       if (pos < p.out_cap)
         for (int c = 0; c < p.n_probe_cols; ++c) copy_value(p.probe_cols[c], r, pos);
     } else if (n_match) {
@@ -312,7 +319,7 @@ class JoinOp : public Op {
   int32_t init(const dbx_join_params* p, const int32_t* types, int32_t n, int dev) {
     DBX_TRY(base_init(dev));
     prm = *p;
-    if (p->kind != DBX_JOIN_INNER && p->kind != DBX_JOIN_LEFT_SEMI && p->kind != DBX_JOIN_LEFT_ANTI) { err.set("join kind not built (INNER, LEFT SEMI and LEFT ANTI are; outer joins are next, SURVEY 8f.3)"); return DBX_ERR_UNSUPPORTED; }
+    if (p->kind < DBX_JOIN_INNER || p->kind > DBX_JOIN_LEFT) { err.set("join kind not built (INNER, LEFT, LEFT SEMI and LEFT ANTI are; right/full joins are next, SURVEY 8f.3)"); return DBX_ERR_UNSUPPORTED; }
     n_build_cols = p->n_build_cols;
     n_probe_cols = n - n_build_cols;
     if (n_build_cols <= 0 || n_probe_cols <= 0 || n_build_cols > kMaxJoinCols || n_probe_cols > kMaxJoinCols) {
@@ -481,7 +488,7 @@ class JoinOp : public Op {
       pp.key = cols[prm.probe_key_col];
       pp.table = table_view();
       pp.n_probe_cols = n_probe_cols;
-      pp.n_build_cols = prm.kind == DBX_JOIN_INNER ? n_build_cols : 0;
+      pp.n_build_cols = (prm.kind == DBX_JOIN_INNER || prm.kind == DBX_JOIN_LEFT) ? n_build_cols : 0;
       pp.kind = prm.kind;
       pp.n_rows = n;
       pp.out_cap = out_cap;
@@ -523,7 +530,7 @@ class JoinOp : public Op {
           count_launch();
           pp.build_cols[c].src_validity = (const uint8_t*)build_bits[c].p;
         }
-        DBX_TRY(add_out(pp.build_cols[c], build_dtype[c], build_nullable[c]));
+        DBX_TRY(add_out(pp.build_cols[c], build_dtype[c], build_nullable[c] || prm.kind == DBX_JOIN_LEFT));
       }
       DBX_CUDA_TRY(err, cudaMemsetAsync(cursor.p, 0, 8, stream));
       if (can_part) {  // region by region: stream the region into L2, then probe the rows that hash into it

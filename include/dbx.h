@@ -191,8 +191,10 @@ typedef struct dbx_topk_params {
 /* INNER: probe columns then build columns per matching pair (inner_join.rs:236-245).
  * LEFT_SEMI / LEFT_ANTI (probe side is "left"): the probe rows with at least one / with no match,
  * probe columns only (left_join_semi.rs, left_join_anti.rs; a NULL probe key never matches, so
- * ANTI keeps the row).  Output row order is unspecified. */
-typedef enum dbx_join_kind { DBX_JOIN_INNER = 0, DBX_JOIN_LEFT_SEMI = 1, DBX_JOIN_LEFT_ANTI = 2 } dbx_join_kind;
+ * ANTI keeps the row).
+ * LEFT (outer, probe side preserved; left_join.rs): every probe row; rows without a match carry
+ * NULL in all build columns, which therefore come back Nullable.  Output row order is unspecified. */
+typedef enum dbx_join_kind { DBX_JOIN_INNER = 0, DBX_JOIN_LEFT_SEMI = 1, DBX_JOIN_LEFT_ANTI = 2, DBX_JOIN_LEFT = 3 } dbx_join_kind;
 typedef struct dbx_join_params {
   int32_t kind;          /* dbx_join_kind */
   int32_t build_key_col; /* key column index in build blocks */

@@ -167,3 +167,46 @@ def test_left_semi_and_anti(gpu, kind_name, monkeypatch):
         np.testing.assert_array_equal(kval[order], probe.columns[0].valid_mask()[expect])
         m = kval[order]
         np.testing.assert_array_equal(keys[order][m], probe.columns[0].values()[expect][m])
+
+
+def test_left_outer(gpu, monkeypatch):
+    """LEFT join (left_join.rs): every probe row; rows without a match carry NULL in all build
+    columns (which come back Nullable).  Compared as a multiset with rows derived from the oracle's
+    inner pairs plus the unmatched probe rows."""
+    rng = np.random.default_rng(43)
+    nb, npb = 8_000, 30_000
+    build = DataBlock([Column.from_data(rng.integers(0, 6000, nb).astype(np.int32)),
+                       Column.from_data(rng.integers(-99, 99, nb).astype(np.int64)),
+                       Column.from_data(rng.normal(size=nb), validity=rng.random(nb) > 0.3),
+                       Column.from_data(rng.integers(0, 200, nb).astype(np.uint8))])
+    probe = DataBlock([Column.from_data(rng.integers(-100, 8000, npb).astype(np.int64), validity=rng.random(npb) > 0.1),
+                       Column.from_data(np.arange(npb, dtype=np.int64))])
+    pi, bi = oracle().hash_join_inner(build.columns[0], probe.columns[0])
+    matched = np.zeros(npb, dtype=bool)
+    matched[pi] = True
+    un = np.nonzero(~matched)[0]
+    exp_cols = []
+    for c in probe.columns:
+        idx = np.concatenate([pi, un])
+        exp_cols.append(Column.from_data(c.values()[idx], c.dtype, validity=c.valid_mask()[idx]))
+    for c in build.columns:
+        vals = np.concatenate([c.values()[bi], np.zeros(len(un), dtype=c.values().dtype)])
+        valid = np.concatenate([c.valid_mask()[bi], np.zeros(len(un), dtype=bool)])
+        exp_cols.append(Column.from_data(vals, c.dtype, validity=valid))
+    for radix in (False, True):
+        if radix:
+            monkeypatch.setenv("DBX_JOIN_REGION_BYTES", str(64 << 10))
+        j = HashJoin(schema_types(build), schema_types(probe), 0, 0, kind=abi.JOIN_LEFT)
+        j.add_block(build)
+        j.final_build()
+        outs = []
+        for p in probe.split_by_rows(11_000):
+            outs.extend(j.probe_block(p))
+        j.close()
+        assert sum(o.num_rows for o in outs) == len(pi) + len(un)
+        got_cols = []
+        for ci in range(6):
+            vals = np.concatenate([o.columns[ci].values() for o in outs])
+            valid = np.concatenate([o.columns[ci].valid_mask() for o in outs])
+            got_cols.append(Column.from_data(vals, outs[0].columns[ci].dtype, validity=valid))
+        np.testing.assert_array_equal(joined_rows_sorted(got_cols), joined_rows_sorted(exp_cols))
