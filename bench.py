@@ -297,8 +297,20 @@ def run_dbx(args):
     xchg = None
     if use_peer:
         from databend_b200.exchange import PeerExchange
-        xchg = PeerExchange(part, rank, world)
-        xchg.connect()
+        ok = 1
+        try:
+            xchg = PeerExchange(part, rank, world)
+            xchg.connect()
+        except Exception as e:  # e.g. no peer access between these GPUs: all ranks fall back together
+            ok = 0
+            print(f"[bench] rank {rank}: peer-memory exchange unavailable ({e}); using the NCCL all-to-all", file=sys.stderr)
+        t_ok = torch.tensor([ok], dtype=torch.int32, device=f"cuda:{dev}")
+        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+        if int(t_ok.item()) == 0:
+            if xchg is not None:
+                xchg.close()
+            xchg = None
+            use_peer = False
 
     _k = C.c_float(0)
 
