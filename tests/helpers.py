@@ -59,3 +59,23 @@ def assert_group_results_equal(gpu, orc, float_exact=True, rtol=0.0):
                                           o.view(np.uint64 if o.itemsize == 8 else np.uint32), err_msg=f"agg {a}")
         else:
             np.testing.assert_array_equal(g, o, err_msg=f"agg {a}")
+
+
+def derive_join_rows(kind: str, probe_key, build_key, pairs):
+    """Expected output row indices of a probe-side ("left") join from the oracle's INNER pairs
+    (probe_idx, build_idx): the same derivation the GPU join tests use.
+      inner -> the pairs;  left -> pairs + (p, None) for unmatched probe rows;
+      semi  -> probe rows with a match, once;  anti -> probe rows without a match (NULL keys too)."""
+    pi, bi = pairs
+    n = len(probe_key)
+    matched = np.zeros(n, dtype=bool)
+    matched[pi] = True
+    if kind == "inner":
+        return [(int(p), int(b)) for p, b in zip(pi, bi)]
+    if kind == "left":
+        return [(int(p), int(b)) for p, b in zip(pi, bi)] + [(int(p), None) for p in np.nonzero(~matched)[0]]
+    if kind == "semi":
+        return [(int(p), None) for p in np.nonzero(matched)[0]]
+    if kind == "anti":
+        return [(int(p), None) for p in np.nonzero(~matched)[0]]
+    raise ValueError(kind)
