@@ -114,10 +114,12 @@ void run(const char* name, const uint64_t* kc, const int64_t* vc, const double* 
 // MODE B0: per surviving row ONE 16-byte TMA bulk reduction (.add.u64 on {cnt, sum_v})
 // MODE B1: B0 + one f64 RED (sum_x)      MODE B2: two bulk reductions (u64 16 B + f64 16 B)
 // AoS entry 32 B: [cnt][sum_v][sum_x][key]
-template <int MODE>
+// round-2 candidates: GEN = staging generations per thread, `lanes` = bit mask of the lanes that use
+// the bulk path (the others update cnt and sum_v with two plain REDs), PROBE = also load the key
+// bucket first (what the real kernel does)
+template <int MODE, int GEN = 2, bool PROBE = false>
 __global__ void __launch_bounds__(256, 4) kbulk(const uint64_t* kc, const int64_t* vc, const double* xc, int64_t n, uint8_t* tab,
-                                                uint64_t mask, uint64_t* sink) {
-  constexpr int GEN = 2;
+                                                uint64_t mask, uint64_t* sink, uint32_t lanes = 0xFFFFFFFFu) {
   constexpr int W = MODE == 2 ? 4 : 2;
   extern __shared__ __align__(16) uint64_t stage_raw[];
   uint64_t (*stage)[256][4][W] = reinterpret_cast<uint64_t (*)[256][4][W]>(stage_raw);
@@ -149,8 +151,13 @@ __global__ void __launch_bounds__(256, 4) kbulk(const uint64_t* kc, const int64_
       if (!((sel >> j) & 1)) continue;
       uint64_t slot = mix(ks[j]) & mask;
       uint8_t* e = tab + slot * 32;
+      if (PROBE && ldtab(e + 24) == 0x1234567) acc += 1;
       uint32_t sa = (uint32_t)__cvta_generic_to_shared(stage[gen][threadIdx.x][j]);
-      asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.u64 [%0], [%1], 16;" ::"l"(e), "r"(sa) : "memory");
+      if ((lanes >> (threadIdx.x & 31)) & 1) {
+        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.u64 [%0], [%1], 16;" ::"l"(e), "r"(sa) : "memory");
+      } else {
+        red64(e, 1); red64(e + 8, (uint64_t)vv[j]);
+      }
       if (MODE == 1) redf64(e + 16, __longlong_as_double((long long)xs[j]));
       if (MODE == 2) asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], 16;" ::"l"(e + 16), "r"(sa + 16) : "memory");
     }
@@ -161,19 +168,20 @@ __global__ void __launch_bounds__(256, 4) kbulk(const uint64_t* kc, const int64_
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   if (acc == 0xdeadbeefULL << 20) *sink = acc;
 }
-template <int MODE>
-void runbulk(const char* name, const uint64_t* kc, const int64_t* vc, const double* xc, int64_t n, uint8_t* tab, uint64_t mask, uint64_t* sink, int grid) {
+template <int MODE, int GEN = 2, bool PROBE = false>
+void runbulk(const char* name, const uint64_t* kc, const int64_t* vc, const double* xc, int64_t n, uint8_t* tab, uint64_t mask, uint64_t* sink, int grid,
+             uint32_t lanes = 0xFFFFFFFFu) {
   cudaEvent_t a, b;
   cudaEventCreate(&a); cudaEventCreate(&b);
-  const int smem = 2 * 256 * 4 * (MODE == 2 ? 4 : 2) * 8;
-  cudaFuncSetAttribute(kbulk<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  kbulk<MODE><<<grid, 256, smem>>>(kc, vc, xc, n, tab, mask, sink);
+  const int smem = GEN * 256 * 4 * (MODE == 2 ? 4 : 2) * 8;
+  cudaFuncSetAttribute(kbulk<MODE, GEN, PROBE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  kbulk<MODE, GEN, PROBE><<<grid, 256, smem>>>(kc, vc, xc, n, tab, mask, sink, lanes);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("%s: CUDA error %s\n", name, cudaGetErrorString(e)); return; }
   float best = 1e9;
   for (int it = 0; it < 3; ++it) {
     cudaEventRecord(a);
-    kbulk<MODE><<<grid, 256, smem>>>(kc, vc, xc, n, tab, mask, sink);
+    kbulk<MODE, GEN, PROBE><<<grid, 256, smem>>>(kc, vc, xc, n, tab, mask, sink, lanes);
     cudaEventRecord(b);
     cudaEventSynchronize(b);
     float ms; cudaEventElapsedTime(&ms, a, b);
@@ -226,6 +234,13 @@ int main(int argc, char** argv) {
   runbulk<0>("B0 stream + 1 bulk-reduce 16B u64x2", kc, vc, xc, n, tab, cap - 1, sink, grid);
   runbulk<1>("B1 stream + bulk u64x2 + RED f64", kc, vc, xc, n, tab, cap - 1, sink, grid);
   runbulk<2>("B2 stream + bulk u64x2 + bulk f64x2", kc, vc, xc, n, tab, cap - 1, sink, grid);
+  // round-2 candidates (not measured yet): deeper staging, RED/TMA lane mixes, with the probe
+  runbulk<1, 4>("B1 GEN=4", kc, vc, xc, n, tab, cap - 1, sink, grid);
+  runbulk<1, 2>("B1 3/4 lanes bulk", kc, vc, xc, n, tab, cap - 1, sink, grid, 0x77777777u);
+  runbulk<1, 2>("B1 1/2 lanes bulk", kc, vc, xc, n, tab, cap - 1, sink, grid, 0x55555555u);
+  runbulk<1, 2>("B1 1/4 lanes bulk", kc, vc, xc, n, tab, cap - 1, sink, grid, 0x11111111u);
+  runbulk<1, 2, true>("B1 + probe", kc, vc, xc, n, tab, cap - 1, sink, grid);
+  runbulk<1, 2, true>("B1 + probe, 1/2 lanes bulk", kc, vc, xc, n, tab, cap - 1, sink, grid, 0x55555555u);
   grid = 148 * 8;
   run<4>("4 (grid x8 -> occupancy-limited to 4/SM)", kc, vc, xc, n, tab, cap - 1, sink, soa, grid);
   return 0;
