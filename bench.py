@@ -135,8 +135,23 @@ def run_reference(args):
         "cpu_baseline": {"value": val, "unit": "rows/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if not args.no_knn:  # second half of the metric, on the same host cores: row-wise cosine_distance + top-k
+        from databend_b200 import abi
+        sn, sq, dim, kk = min(args.knn_rows, args.knn_cpu_rows), 8, args.knn_dim, args.knn_k
+        rng = np.random.default_rng(0)
+        c = rng.standard_normal((sn, dim)).astype(np.float32)
+        qs = rng.standard_normal((sq, dim)).astype(np.float32)
+        orc.distance_rows(abi.DIST_COSINE, c, qs[0], threads=threads)
+        t0 = time.perf_counter()
+        for i in range(sq):
+            d = orc.distance_rows(abi.DIST_COSINE, c, qs[i], threads=threads)
+            np.argpartition(d, min(kk, sn - 1))[:kk]
+        dt_k = time.perf_counter() - t0
+        line["knn"] = {"metric": "kNN QPS @768d (cosine_distance, brute force, exact top-k)", "impl": "reference",
+                       "value": sq / dt_k * sn / args.knn_rows, "unit": "queries/s",
+                       "cpu_baseline": {"value": sq / dt_k * sn / args.knn_rows, "unit": "queries/s", "cores": threads, "kind": "port",
+                                        "sample": f"{sq} queries x {sn} rows x {dim} dims, row-wise cosine_distance (oracle, OpenMP) + top-{kk}, scaled by {sn}/{args.knn_rows} rows"}}
     print(json.dumps(line), flush=True)
-
 
 
 # ---------------------------------------------------------------------------------- kNN leg
@@ -523,6 +538,7 @@ def main():
     ap.add_argument("--knn-dim", type=int, default=768)
     ap.add_argument("--knn-queries", type=int, default=1024)
     ap.add_argument("--knn-k", type=int, default=10)
+    ap.add_argument("--knn-cpu-rows", type=int, default=1_000_000, help="corpus rows of the CPU sample in the reference arm")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
