@@ -61,3 +61,39 @@ def test_product_never_imports_oracle():
                     src = f.read()
                 for pat in (r"^\s*(from|import)\s+oracle", r"libdbx_oracle", r"dbx_oracle\.h", r"\borc_[a-z_]+\s*\("):
                     assert not re.search(pat, src, flags=re.M), f"{fn} uses the oracle ({pat})"
+
+
+def test_ctypes_mirror_matches_the_header_field_by_field(tmp_path):
+    """Compile a probe against include/dbx.h with the system C compiler and compare sizeof / offsetof
+    of every struct that crosses the ABI with the ctypes mirror in databend_b200/abi.py."""
+    import subprocess
+    structs = {
+        "dbx_scalar": (abi.Scalar, ["dtype", "is_null", "v"]),
+        "dbx_column": (abi.Column, ["dtype", "mem", "is_const", "vec_dim", "len", "data", "data_bit_offset", "validity",
+                                    "validity_bit_offset", "null_count", "konst"]),
+        "dbx_block": (abi.Block, ["num_rows", "num_cols", "cols", "meta", "owner"]),
+        "dbx_operand": (abi.Operand, ["is_const", "col", "arith", "c"]),
+        "dbx_pred_node": (abi.PredNode, ["kind", "cmp", "n_children", "value", "lhs", "rhs"]),
+        "dbx_predicate": (abi.Predicate, ["n_nodes", "nodes"]),
+        "dbx_agg_desc": (abi.AggDesc, ["kind", "arg_col"]),
+        "dbx_agg_params": (abi.AggParams, ["n_group_cols", "group_cols", "n_aggs", "aggs", "filter", "expected_groups"]),
+        "dbx_topk_params": (abi.TopkParams, ["key_col", "asc", "nulls_first", "limit"]),
+        "dbx_join_params": (abi.JoinParams, ["kind", "build_key_col", "probe_key_col", "n_build_cols", "expected_build_rows"]),
+    }
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "dbx.h")}"', "int main(void) {"]
+    for cname, (_, fields) in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for f in fields:
+            lines.append(f'  printf("{cname}.{f} %zu\\n", offsetof({cname}, {f}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.check_call(["gcc", "-std=c11", "-o", str(exe), str(src)])
+    out = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, (ctype, fields) in structs.items():
+        assert int(out[cname]) == C.sizeof(ctype), cname
+        for f in fields:
+            assert int(out[f"{cname}.{f}"]) == getattr(ctype, f).offset, f"{cname}.{f}"
+    # enum values the Python side hard-codes
+    assert (abi.JOIN_INNER, abi.JOIN_LEFT_SEMI, abi.JOIN_LEFT_ANTI, abi.JOIN_LEFT) == (0, 1, 2, 3)
