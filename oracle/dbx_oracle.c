@@ -713,6 +713,41 @@ int orc_hash_join_inner(const dbx_column* build_key, const dbx_column* probe_key
   return DBX_OK;
 }
 
+/* Probe-side ("left") join kinds on top of the same table walk
+ * (new_hash_join/memory/left_join.rs, left_join_semi.rs, left_join_anti.rs):
+ *   kind 0 INNER       every (probe, build) match
+ *   kind 1 LEFT SEMI   probe rows with at least one match, once; build index -1
+ *   kind 2 LEFT ANTI   probe rows with no match (a NULL key never matches); build index -1
+ *   kind 3 LEFT        every match, plus (probe, -1) for probe rows with no match
+ * Pairs come out in probe order (the reference's filter_with_bitmap keeps the probe order for
+ * semi/anti; the unmatched rows of a LEFT join follow each probed block: unspecified order). */
+int orc_hash_join(int kind, const dbx_column* build_key, const dbx_column* probe_key, int64_t** out_probe_idx,
+                  int64_t** out_build_idx, int64_t* n_out) {
+  int64_t *ip = NULL, *ib = NULL, ni = 0;
+  int st = orc_hash_join_inner(build_key, probe_key, &ip, &ib, &ni);
+  if (st != DBX_OK) return st;
+  if (kind == 0) { *out_probe_idx = ip; *out_build_idx = ib; *n_out = ni; return DBX_OK; }
+  int64_t np = probe_key->len;
+  int64_t cap = ni + np + 1, no = 0;
+  int64_t* op = (int64_t*)malloc(sizeof(int64_t) * cap);
+  int64_t* ob = (int64_t*)malloc(sizeof(int64_t) * cap);
+  int64_t j = 0; /* inner pairs are in probe order */
+  for (int64_t r = 0; r < np; ++r) {
+    int64_t first = j;
+    while (j < ni && ip[j] == r) ++j;
+    int64_t m = j - first;
+    if (kind == 1) { if (m) { op[no] = r; ob[no] = -1; ++no; } }
+    else if (kind == 2) { if (!m) { op[no] = r; ob[no] = -1; ++no; } }
+    else { /* LEFT */
+      for (int64_t t = first; t < j; ++t) { op[no] = r; ob[no] = ib[t]; ++no; }
+      if (!m) { op[no] = r; ob[no] = -1; ++no; }
+    }
+  }
+  free(ip); free(ib);
+  *out_probe_idx = op; *out_build_idx = ob; *n_out = no;
+  return DBX_OK;
+}
+
 void orc_free(void* p) { free(p); }
 
 /* ------------------------------------------------------------------ sort / top-k */

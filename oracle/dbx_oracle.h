@@ -27,6 +27,8 @@ int orc_filter_group_agg(const dbx_block* blk, const dbx_agg_params* p, int thre
 void orc_agg_result_free(orc_agg_result* r);
 int orc_hash_join_inner(const dbx_column* build_key, const dbx_column* probe_key, int64_t** out_probe_idx,
                         int64_t** out_build_idx, int64_t* n_out);
+int orc_hash_join(int kind, const dbx_column* build_key, const dbx_column* probe_key, int64_t** out_probe_idx,
+                  int64_t** out_build_idx, int64_t* n_out);
 void orc_free(void* p);
 int orc_topk(const dbx_column* key, int asc, int nulls_first, int64_t k, int64_t* out_idx, int64_t* n_out);
 float orc_cosine_distance(const float* a, const float* b, int64_t n);

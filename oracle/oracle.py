@@ -61,6 +61,8 @@ def lib():
         L.orc_hash_join_inner.argtypes = [C.POINTER(abi.Column), C.POINTER(abi.Column),
                                           C.POINTER(C.POINTER(C.c_int64)), C.POINTER(C.POINTER(C.c_int64)),
                                           C.POINTER(C.c_int64)]
+        L.orc_hash_join.argtypes = [C.c_int, C.POINTER(abi.Column), C.POINTER(abi.Column),
+                                    C.POINTER(C.POINTER(C.c_int64)), C.POINTER(C.POINTER(C.c_int64)), C.POINTER(C.c_int64)]
         L.orc_free.argtypes = [C.c_void_p]
         L.orc_topk.argtypes = [C.POINTER(abi.Column), C.c_int, C.c_int, C.c_int64, C.c_void_p, C.POINTER(C.c_int64)]
         L.orc_cosine_distance.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
@@ -163,6 +165,23 @@ def hash_join_inner(build_key: Column, probe_key: Column) -> Tuple[np.ndarray, n
     pp, pb = C.POINTER(C.c_int64)(), C.POINTER(C.c_int64)()
     n = C.c_int64(0)
     st = lib().orc_hash_join_inner(C.byref(bk), C.byref(pk), C.byref(pp), C.byref(pb), C.byref(n))
+    if st != abi.OK:
+        raise OracleError(st)
+    m = n.value
+    probe = np.ctypeslib.as_array(pp, shape=(max(m, 1),))[:m].copy()
+    build = np.ctypeslib.as_array(pb, shape=(max(m, 1),))[:m].copy()
+    lib().orc_free(pp)
+    lib().orc_free(pb)
+    return probe, build
+
+
+def hash_join(kind: int, build_key: Column, probe_key: Column) -> Tuple[np.ndarray, np.ndarray]:
+    """kind: abi.JOIN_INNER / JOIN_LEFT_SEMI / JOIN_LEFT_ANTI / JOIN_LEFT.  Returns (probe_idx, build_idx),
+    build_idx = -1 where the output row carries no build row."""
+    bk, pk = build_key.as_c(), probe_key.as_c()
+    pp, pb = C.POINTER(C.c_int64)(), C.POINTER(C.c_int64)()
+    n = C.c_int64(0)
+    st = lib().orc_hash_join(kind, C.byref(bk), C.byref(pk), C.byref(pp), C.byref(pb), C.byref(n))
     if st != abi.OK:
         raise OracleError(st)
     m = n.value

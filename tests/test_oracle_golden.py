@@ -277,3 +277,19 @@ def test_join_kind_goldens():
     n10 = [Column.from_data(np.arange(10, dtype=np.uint64))]
     assert run("anti", n10, [Column.from_data(np.zeros(0, dtype=np.int32))]) == [(i,) for i in range(10)]
     assert run("semi", n10, [Column.from_data(np.zeros(0, dtype=np.int32))]) == []
+
+
+def test_oracle_join_kinds_agree_with_the_derivation():
+    """The oracle's own LEFT / SEMI / ANTI (orc_hash_join) equals the derivation from its inner
+    pairs that the GPU tests use, on random nullable keys with duplicates and misses."""
+    from helpers import derive_join_rows
+    rng = np.random.default_rng(9)
+    build = Column.from_data(rng.integers(0, 300, 2000).astype(np.int64), validity=rng.random(2000) > 0.1)
+    probe = Column.from_data(rng.integers(-50, 400, 5000).astype(np.int64), validity=rng.random(5000) > 0.1)
+    pairs = orc.hash_join_inner(build, probe)
+    for name, kind in (("inner", abi.JOIN_INNER), ("semi", abi.JOIN_LEFT_SEMI), ("anti", abi.JOIN_LEFT_ANTI), ("left", abi.JOIN_LEFT)):
+        p, b = orc.hash_join(kind, build, probe)
+        got = sorted((int(x), (None if y < 0 else int(y))) for x, y in zip(p, b))
+        exp = sorted(derive_join_rows(name, probe.values(), build.values(), pairs), key=lambda t: (t[0], -1 if t[1] is None else t[1]))
+        got = sorted(got, key=lambda t: (t[0], -1 if t[1] is None else t[1]))
+        assert got == exp, name
