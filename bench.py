@@ -37,7 +37,18 @@ METRIC = "rows/sec filter->hash-agg (sum,count,avg GROUP BY 1e6 int64 keys) over
 SEEDS = (42, 43, 44)
 N_KEYS = 1_000_000
 BYTES_PER_ROW = 24.0  # three 8-byte columns, each read exactly once
-NCU_TRAFFIC_PER_LAUNCH = 7.094290e9 + 0.544827e9  # bytes; one 2^28-row launch of the fused kernel (profiles/r01b_filter_group_agg_ncu_full.csv)
+KERNEL_NAME = "filter_group_agg_ring_kernel<3>"
+
+
+def ncu_traffic():
+    """dram read+write bytes of ONE 2^28-row launch of the fused kernel, from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "r02_agg_kernel_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d["dram_bytes_per_launch"], d["note"]
+    return None, "no ncu capture of this kernel committed yet"
+
 
 
 def peaks():
@@ -55,13 +66,18 @@ class ClockSampler:
         self.rows = []
         self.proc = None
         self.gpu_index = gpu_index
+        self.marks = []
+
+    def mark(self):
+        """Remember how many samples had arrived (called at the start and end of the timed region)."""
+        self.marks.append(len(self.rows))
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -80,7 +96,11 @@ class ClockSampler:
                 pass
         sm, mx, reasons = [], 0.0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows, window = self.rows, "warm-up + timed region (no sample fell inside the timed region alone)"
+        if len(self.marks) >= 2 and self.marks[1] > self.marks[0]:
+            rows, window = self.rows[self.marks[0]:self.marks[1]], "timed region"
+        self.window = window
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx = max(mx, float(r[1]))
@@ -91,7 +111,7 @@ class ClockSampler:
                 continue
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 def make_query():
@@ -263,14 +283,107 @@ def run_knn(args, L, dev, rank, world, barrier):
     return out
 
 # ---------------------------------------------------------------------------------- GPU arm
+def verify_result(out_block, dev, rank, world, cols, n, keys_total, torch, dist):
+    """Full-scale check OUTSIDE the timed region: every group of this rank's result block
+    (host columns [sum(v), count(v), avg(x), k]) against an independent recomputation of the whole
+    query with torch index ops on the same device columns (bincount / index_add_ per key, all-reduced
+    across ranks), plus — rank 0 — the CPU oracle on every row of a key subsample.  Returns a dict."""
+    import numpy as np
+    from databend_b200 import abi
+    kd, vd, xd = cols
+
+    def dev_tensor(ptr, dtype):
+        # wrap the library-owned device column without copying (torch only as the checker)
+        class _Holder:
+            pass
+        h = _Holder()
+        h.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8" if dtype == torch.int64 else "<f8", "data": (ptr, True), "version": 2}
+        return torch.as_tensor(h, device=f"cuda:{dev}")
+
+    k_t, v_t, x_t = dev_tensor(kd, torch.int64), dev_tensor(vd, torch.int64), dev_tensor(xd, torch.float64)
+    cnt = torch.zeros(keys_total, dtype=torch.int64, device=f"cuda:{dev}")
+    sv = torch.zeros(keys_total, dtype=torch.int64, device=f"cuda:{dev}")
+    sx = torch.zeros(keys_total, dtype=torch.float64, device=f"cuda:{dev}")
+    step = 1 << 27
+    sub_keys = 997  # oracle subsample: every row whose key is < sub_keys
+    sub_rows = []
+    for lo in range(0, n, step):
+        hi = min(n, lo + step)
+        kk, vv, xx = k_t[lo:hi], v_t[lo:hi], x_t[lo:hi]
+        m = torch.remainder(vv, 3) == 0  # v % 3 = 0 does not depend on the sign convention of %
+        ks = kk[m]
+        cnt += torch.bincount(ks, minlength=keys_total)
+        sv.index_add_(0, ks, vv[m])  # int64 wrapping add
+        sx.index_add_(0, ks, xx[m])  # integer-valued < 2^20: exact in any order
+        sm = kk < sub_keys
+        sub_rows.append(torch.stack([kk[sm], vv[sm], xx[sm].view(torch.int64)]).cpu())
+    if world > 1:
+        dist.all_reduce(cnt)
+        dist.all_reduce(sv)
+        dist.all_reduce(sx)
+    # this rank's groups against the expectation
+    g_k = torch.from_numpy(out_block.columns[3].values().astype(np.int64)).to(f"cuda:{dev}")
+    g_sv = torch.from_numpy(out_block.columns[0].values().view(np.int64).copy()).to(f"cuda:{dev}")
+    g_cnt = torch.from_numpy(out_block.columns[1].values().astype(np.int64)).to(f"cuda:{dev}")
+    g_avg = torch.from_numpy(out_block.columns[2].values().copy()).to(f"cuda:{dev}")
+    bad = int((g_cnt != cnt[g_k]).sum() + (g_sv != sv[g_k]).sum() + (g_avg != sx[g_k] / cnt[g_k].to(torch.float64)).sum())
+    dup = int(g_k.numel() - torch.unique(g_k).numel())
+    t = torch.tensor([g_k.numel(), bad, dup, int(g_cnt.sum())], dtype=torch.int64, device=f"cuda:{dev}")
+    if world > 1:
+        dist.all_reduce(t)
+    groups_total, bad_total, dup_total, rows_selected = [int(v) for v in t.tolist()]
+    expected_groups = int((cnt > 0).sum())
+    res = {"groups": groups_total, "expected_groups": expected_groups, "mismatching_values": bad_total, "duplicate_keys": dup_total,
+           "selected_rows": rows_selected, "expected_selected_rows": int(cnt.sum()),
+           "how": "every group vs torch bincount/index_add_ over all rows (all-reduced across ranks)"}
+    ok = groups_total == expected_groups and bad_total == 0 and dup_total == 0 and rows_selected == int(cnt.sum())
+    # oracle on the key subsample (rank 0 gathers the subsample rows of every rank)
+    sub = torch.cat(sub_rows, dim=1)
+    if world > 1:
+        sizes = [None] * world
+        dist.all_gather_object(sizes, int(sub.shape[1]))
+        pad = torch.zeros((3, max(sizes)), dtype=torch.int64, device=f"cuda:{dev}")
+        pad[:, : sub.shape[1]] = sub.to(f"cuda:{dev}")
+        gp = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(gp, pad)
+        sub = torch.cat([g[:, :s_].cpu() for g, s_ in zip(gp, sizes)], dim=1)
+        # every rank's owned subsample groups -> all ranks (rank 0 checks)
+        mine = (g_k < sub_keys)
+        loc = torch.stack([g_k[mine], g_sv[mine], g_cnt[mine], g_avg[mine].view(torch.int64)]).cpu()
+        parts = [None] * world
+        dist.all_gather_object(parts, loc.numpy())
+        got = np.concatenate(parts, axis=1)
+    else:
+        mine = (g_k < sub_keys)
+        got = torch.stack([g_k[mine], g_sv[mine], g_cnt[mine], g_avg[mine].view(torch.int64)]).cpu().numpy()
+    if rank == 0:
+        from databend_b200.block import Column, DataBlock
+        from oracle import oracle as orc
+        sn = sub.numpy()
+        sblk = DataBlock([Column.from_data(np.ascontiguousarray(sn[0])), Column.from_data(np.ascontiguousarray(sn[1])),
+                          Column.from_data(np.ascontiguousarray(sn[2]).view(np.float64))])
+        params, filt = make_query()
+        okeys, _, oaggs, _, _ = orc.filter_group_agg(sblk, params.to_c(filt), threads=len(os.sched_getaffinity(0)))
+        oo = np.argsort(okeys[0].view(np.int64))
+        go = np.argsort(got[0])
+        same = (len(oo) == len(go) and np.array_equal(okeys[0].view(np.int64)[oo], got[0][go])
+                and np.array_equal(oaggs[0].view(np.int64)[oo], got[1][go]) and np.array_equal(oaggs[1].view(np.int64)[oo], got[2][go])
+                and np.array_equal(oaggs[2].view(np.int64)[oo], got[3][go]))
+        res["oracle_subsample"] = {"keys_below": sub_keys, "rows": int(sn.shape[1]), "groups": int(len(oo)), "bit_exact": bool(same)}
+        ok = ok and same
+    res["ok"] = bool(ok)
+    return res
+
+
 def run_dbx(args):
+    import gc
     import numpy as np
     import torch
     import torch.distributed as dist
     from databend_b200 import abi, build, lib
     from databend_b200.block import Column, DataBlock
     from databend_b200.exchange import all_to_all_rows
-    from databend_b200.transforms import (DeviceBuffer, TransformFinalAggregate, TransformPartialAggregate)
+    from databend_b200.transforms import (DeviceBuffer, TransformFinalAggregate, TransformPartialAggregate, _block_from_c)
 
     build.build()
     L = lib.load()
@@ -306,8 +419,6 @@ def run_dbx(args):
     lib.check(L.dbx_op_stream(fin.handle, C.byref(sp)))
     fin_stream = torch.cuda.ExternalStream(sp.value, device=dev)
 
-    kernel_ms = []
-
     use_peer = world > 1 and os.environ.get("DBX_EXCHANGE", "peer") == "peer"
     xchg = None
     if use_peer:
@@ -326,23 +437,22 @@ def run_dbx(args):
                 xchg.close()
             xchg = None
             use_peer = False
+    # Software pipelining across the two operators (they are different Processors in the reference
+    # too): the partial operator starts scanning the next query's input while the final operator
+    # still merges / materialises the current one.  Every query's full work stays inside the timed
+    # region: the first timed step enqueues its own scan, the last one enqueues none.
+    pipeline = use_peer and os.environ.get("DBX_BENCH_PIPELINE", "1") != "0"
 
-    _k = C.c_float(0)
-
-    def last_kernel_ms():
-        lib.check(L.dbx_op_last_kernel_ms(part.handle, C.byref(_k)), part.handle)
-        return _k.value
-
-    def exchange_and_finish(out_mem):
-        """partial -> (N>1: hash-partition + exchange) -> final -> result block"""
+    def exchange(out_mem):
+        """partial -> (N>1: hash-partition + exchange) -> final merge (no host sync on the peer path)"""
         part.on_finish()
         if world == 1:
             fin.transform(part)
         elif use_peer:
-            # rows go straight into the owners' HBM over NVLink; the merge kernel waits on the
-            # sources' flags on the device: no NCCL call, staging copy or host sync in between
+            # rows go straight into the owners' HBM over NVLink (the same pass re-arms the partial's
+            # table); a one-warp kernel waits for the sources' flags on the device, then the merge
             xchg.scatter(part)
-            part.reset()  # re-arm the partial now: its table is cleared while the owners merge
+            part.reset()
             xchg.merge(fin)
         else:
             rows_ptr = C.c_void_p()
@@ -359,20 +469,31 @@ def run_dbx(args):
             recv, recv_counts = all_to_all_rows(send, send_counts, row_bytes)
             torch.cuda.current_stream().synchronize()
             fin.merge_rows(recv.data_ptr(), sum(recv_counts))
-        return fin.on_finish(out_mem)
 
-    def step_device():
-        if not use_peer:
-            part.reset()
-        fin.reset()
-        part.transform(dblock)
-        out = exchange_and_finish(abi.MEM_DEVICE)
+    state = {"queued": False}
+    kernel_ms, phases, step_walls = [], [], []
+
+    def step_device(input_blocks, out_mem, prefetch_next):
+        """one query: scan (+filter+partial agg) -> exchange -> final -> result block"""
+        if not state["queued"]:
+            if not use_peer:
+                part.reset()
+            for b in input_blocks:
+                part.transform(b)
+        state["queued"] = False
+        exchange(out_mem)
+        if pipeline and prefetch_next:  # the next query's scan runs while this one is merged and materialised
+            for b in input_blocks:
+                part.transform(b)
+            state["queued"] = True
+        out = fin.on_finish(out_mem)
         # read the kernel's event pair only now: asking earlier blocks the host until the kernel
         # has finished and exposes the launch latency of everything behind it
-        kernel_ms.append(last_kernel_ms())
-        rows_out = out[0].num_rows
-        L.dbx_block_release(C.byref(out[0]))
-        return rows_out
+        kernel_ms.append(part.kernel_ms(1 if state["queued"] else 0))
+        if xchg is not None:
+            phases.append(xchg.phase_ms())
+        fin.reset()
+        return out[0]
 
     def barrier():
         torch.cuda.synchronize()
@@ -380,23 +501,38 @@ def run_dbx(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        groups = step_device()
-    kernel_ms.clear()
-    barrier()
+    def run_steps(blocks, steps, out_mem, timed):
+        res = None
+        for i in range(steps):
+            res = step_device(blocks, out_mem, prefetch_next=(i + 1 < steps))
+            if timed:
+                step_walls.append(time.perf_counter())
+            if out_mem == abi.MEM_DEVICE:
+                rows_out = res.num_rows
+                L.dbx_block_release(C.byref(res))
+                res = rows_out
+        return res
+
     sampler = ClockSampler(dev)
     if rank == 0:
-        sampler.start()
+        sampler.start()  # before the warm-up: nvidia-smi's start-up must not fall into the timed region
+    groups = run_steps([dblock], args.warmup, abi.MEM_DEVICE, False)
+    kernel_ms.clear()
+    phases.clear()
+    barrier()
+    gc.disable()
+    sampler.mark()
     launches0 = L.dbx_kernel_launch_count()
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
     ev0.record(part_stream)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        groups = step_device()
+    groups = run_steps([dblock], args.steps, abi.MEM_DEVICE, True)
     ev1.record(fin_stream)
     barrier()
     wall = time.perf_counter() - t0
+    sampler.mark()
+    gc.enable()
     dev_ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     launches = L.dbx_kernel_launch_count() - launches0
@@ -406,6 +542,26 @@ def run_dbx(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     step_ms, wall_ms = t.tolist()
     k_ms = sum(kernel_ms) / max(1, len(kernel_ms))
+    per_step = np.diff(np.array([t0] + step_walls)) * 1e3
+    phase_avg = None
+    if phases:
+        phase_avg = {k: float(np.mean([p_[k] for p_ in phases])) for k in phases[0]}
+        phase_avg["partial_kernel"] = k_ms
+        pt = torch.tensor([phase_avg[k] for k in sorted(phase_avg)], dtype=torch.float64, device=f"cuda:{dev}")
+        dist.all_reduce(pt, op=dist.ReduceOp.MAX)
+        phase_avg = {k: v for k, v in zip(sorted(phase_avg), pt.tolist())}
+        phase_avg["note"] = "device ms per query, mean over the timed steps, max over ranks (CUDA events; wait_spin = the wait kernel's own globaltimer measure)"
+
+    # ---- verification (outside the timed region): the whole result, at full size
+    verify = None
+    if not args.no_verify:
+        res_host = step_device([dblock], abi.MEM_HOST, prefetch_next=False)
+        try:
+            verify = verify_result(res_host, dev, rank, world, [b_.ptr for b_ in bufs], n, args.keys, torch, dist)
+        except Exception as e:  # the checker itself failed: say so, never claim a verified result
+            verify = {"ok": False, "groups": None, "error": f"{type(e).__name__}: {e}"}
+        if rank == 0 and not verify["ok"]:
+            print(f"[bench] VERIFICATION FAILED: {verify}", file=sys.stderr)
 
     # ---- e2e: host (pinned) columns pushed through the operator API, result pulled to the host
     e2e = None
@@ -414,7 +570,7 @@ def run_dbx(args):
         try:
             import psutil
             avail = psutil.virtual_memory().available
-            while e_rows * 24 > 0.5 * avail and e_rows > 1_000_000:
+            while e_rows * 24 * world > 0.5 * avail and e_rows > 1_000_000:
                 e_rows //= 2
         except Exception:
             pass
@@ -424,40 +580,34 @@ def run_dbx(args):
             lib.check(L.dbx_host_alloc(e_rows * 8, C.byref(p)))
             lib.check(L.dbx_memcpy_d2h(dev, p, bufs[i].ptr, e_rows * 8))
             hp.append(p)
-        nd = [np.int64, np.int64, np.float64]
         harr = [np.ctypeslib.as_array(C.cast(hp[i], C.POINTER(C.c_int64 if i < 2 else C.c_double)), shape=(e_rows,)) for i in range(3)]
         hblock = DataBlock([Column.from_data(harr[0]), Column.from_data(harr[1]), Column.from_data(harr[2])], e_rows)
-        hblocks = hblock.split_by_rows(args.block_rows)
 
-        def step_host():
-            if not use_peer:
-                part.reset()
-            fin.reset()
-            for b in hblocks:
-                part.transform(b)
-            out = exchange_and_finish(abi.MEM_HOST)
-            return out[0]
+        def e2e_leg(block_rows, steps):
+            hblocks = hblock.split_by_rows(block_rows)
+            res = None
+            for _ in range(max(1, min(2, args.warmup - 1))):
+                res = run_steps(hblocks, 1, abi.MEM_HOST, False)
+            barrier()
+            t0 = time.perf_counter()
+            res = run_steps(hblocks, steps, abi.MEM_HOST, False)
+            barrier()
+            ms = (time.perf_counter() - t0) * 1e3 / steps
+            te = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{dev}")
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            return te.item(), res
 
-        res = None
-        for _ in range(max(1, args.warmup - 1)):
-            res = step_host()
-        barrier()
         e_steps = max(1, min(args.steps, 3))
-        ev0.record(part_stream)
-        t0 = time.perf_counter()
-        for _ in range(e_steps):
-            res = step_host()
-        ev1.record(fin_stream)
-        barrier()
-        e_wall_ms = (time.perf_counter() - t0) * 1e3 / e_steps
-        te = torch.tensor([e_wall_ms], dtype=torch.float64, device=f"cuda:{dev}")
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e_wall_ms = te.item()
+        e_wall_ms, res = e2e_leg(args.block_rows, e_steps)
         d2h = sum(c.data.nbytes for c in res.columns)
         e2e = {"value": (e_rows * world) / (e_wall_ms * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": int(e_rows * 24),
                "d2h_bytes_per_step": int(d2h), "rows": int(e_rows * world), "block_rows": args.block_rows,
                "ms_per_step": e_wall_ms, "timing": "host wall clock around push..pull incl. stream sync, max over ranks"}
+        if args.small_block_rows:
+            s_ms, _ = e2e_leg(args.small_block_rows, 1)
+            e2e["small_blocks"] = {"block_rows": args.small_block_rows, "value": (e_rows * world) / (s_ms * 1e-3), "unit": "rows/s",
+                                   "ms_per_step": s_ms, "note": "the reference's max_block_size (settings_default.rs:142)"}
         for p in hp:
             L.dbx_host_free(p)
 
@@ -465,11 +615,11 @@ def run_dbx(args):
     if xchg is not None:
         barrier()
         xchg.close()
+    part.close()
+    fin.close()
+    for b_ in bufs:
+        b_.free()
     if not args.no_knn:
-        part.close()
-        fin.close()
-        for b_ in bufs:
-            b_.free()
         knn = run_knn(args, L, dev, rank, world, barrier)
 
     if rank != 0:
@@ -495,24 +645,30 @@ def run_dbx(args):
             orc.filter_group_agg(cblk, cp, threads=threads)
         cdt = (time.perf_counter() - t0) / reps
         cpu = {"value": cn / cdt, "unit": "rows/s", "cores": threads, "kind": "port",
-               "sample": f"first {cn} rows of the same columns, reference-algorithm C/OpenMP restatement (oracle), {reps} reps"}
+               "sample": f"first {cn} rows of the same columns, reference-algorithm C/OpenMP restatement (oracle), {reps} reps",
+               "note": "a restatement, not Databend's executor: reported baseline only (its per-bucket final merge is not tuned)"}
 
     peak, peak_src = peaks()
     achieved = BYTES_PER_ROW * n / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    traffic, traffic_note = ncu_traffic()
     line = {
         "metric": METRIC, "value": total_rows / (step_ms * 1e-3), "unit": "rows/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "int64", "data": "synthetic",
         "config": {"workload": "configs[1]: filter(v%3=0) + hash-agg sum(v),count(v),avg(x) GROUP BY k; 1e6 int64 keys",
-                   "rows": total_rows, "rows_per_gpu": n, "groups_out": int(groups) * (1 if world == 1 else world),
+                   "rows": total_rows, "rows_per_gpu": n, "groups_out": verify["groups"] if verify else None,
+                   "groups_out_rank0": int(groups),
                    "columns": "k:int64 v:int64 x:float64", "l2": "inputs (24 B/row x rows) far larger than the 126 MB L2",
-                   "timing": "CUDA events on the operators' stream, max over ranks; wall_ms_per_step alongside",
+                   "timing": "CUDA events on the operators' streams around the K steps, max over ranks; wall_ms_per_step alongside",
+                   "pipelining": ("partial operator scans query i+1 while the final operator merges/materialises query i (every query's work inside the timed region)" if pipeline else "none"),
+                   "per_step_wall_ms": {"min": float(per_step.min()), "median": float(np.median(per_step)), "max": float(per_step.max())},
                    "parallelism": f"row-range x{world}" + ("" if world == 1 else (" + peer-memory (NVLink) scatter of partial groups" if use_peer else " + NCCL all-to-all of partial groups"))},
         "wall_ms_per_step": wall_ms, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": NCU_TRAFFIC_PER_LAUNCH, "traffic_note": "dram read+write per 2^28-row launch from profiles/r01b_filter_group_agg_ncu_full.csv (ncu --set full)",
-                     "achieved_per_launch_bytes": BYTES_PER_ROW * min(n, 1 << 28), "kernel": "filter_group_agg_kernel<3,FAST=1,INDIRECT=0,BULK=0>", "kernel_ms": k_ms,
+                     "traffic": traffic, "traffic_note": traffic_note,
+                     "achieved_per_launch_bytes": BYTES_PER_ROW * min(n, 1 << 28), "kernel": KERNEL_NAME, "kernel_ms": k_ms,
                      "algorithmic_bytes_per_row": BYTES_PER_ROW, "peak_source": peak_src},
+        "phases": phase_avg, "verify": verify,
         "cpu_baseline": cpu, "e2e": e2e, "knn": knn,
     }
     print(json.dumps(line), flush=True)
@@ -531,6 +687,8 @@ def main():
     ap.add_argument("--block-rows", type=int, default=1 << 22, help="rows per pushed host block in the e2e leg (max_block_size)")
     ap.add_argument("--cpu-rows", type=int, default=50_000_000)
     ap.add_argument("--keys", type=int, default=N_KEYS, help="distinct group keys (the named config uses 1e6)")
+    ap.add_argument("--small-block-rows", type=int, default=0, help="also time the e2e leg with blocks of this many rows (65536 = the reference's max_block_size)")
+    ap.add_argument("--no-verify", action="store_true", help="skip the full-size result verification (outside the timed region)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-knn", action="store_true", help="skip the kNN leg (second half of BASELINE.json's metric)")

@@ -140,5 +140,6 @@ EXPORTS = [
     "dbx_agg_exchange_merge", "dbx_agg_exchange_destroy", "dbx_agg_exchange_last_error",
     "dbx_hash_partition",
     "dbx_eval_distance", "dbx_knn_create", "dbx_knn_search", "dbx_knn_destroy", "dbx_knn_last_error", "dbx_knn_last_gemm_ms", "dbx_knn_last_stats",
-    "dbx_synth_fill", "dbx_kernel_launch_count", "dbx_op_last_kernel_ms", "dbx_op_stream",
+    "dbx_synth_fill", "dbx_kernel_launch_count", "dbx_op_last_kernel_ms", "dbx_op_kernel_ms", "dbx_op_stream",
+    "dbx_op_inputs_consumed", "dbx_agg_exchange_phase_ms",
 ]

@@ -23,6 +23,7 @@ namespace {
 constexpr int64_t kChunkRows = 1LL << 28;        // rows per kernel launch (u32 overflow row ids)
 constexpr int64_t kDefaultTableBytes = 64 << 20; // default table = half of the 126 MB L2
 constexpr int kProbeLimit = 64;  // buckets (x4 slots)
+constexpr uint32_t kDefaultBulkLanes = 0x6DB6DB6Du;  // 21 of 32 lanes on the TMA unit
 
 inline int grid_for_rows(int64_t n_rows) {
   int64_t tiles = (n_rows + kTileRows - 1) / kTileRows;
@@ -66,6 +67,11 @@ struct AggPlan {
   PairDev pairs[kMaxPairs];
   int w_pair[kMaxWords];
   int w_pos[kMaxWords];
+  // tuning knobs, read from the environment once per operator (experiments sweep them in one process)
+  uint32_t bulk_lanes = 0;   // lanes of a warp that update pairs through the TMA unit (the rest use REDs)
+  bool use_ring = true;      // ring kernel for the straight-line case with pairs
+  bool l2_persist = true;    // persisting L2 access-policy window over the table
+  int debug_flags = 0;
 
   int slot_of(int col, ErrorSink* err) {
     for (int s = 0; s < n_slots; ++s)
@@ -371,7 +377,9 @@ int32_t build_plan(const dbx_agg_params* p, const int32_t* types, int32_t n_cols
   // bound by L2 atomic operations per row, not by bytes).
   for (int w = 0; w < kMaxWords; ++w) { pl->w_pair[w] = -1; pl->w_pos[w] = 0; }
   pl->n_pairs = 0;
-  if (pl->grouped && getenv("DBX_AGG_BULK")) {  // opt-in: measured slower than REDs in the full kernel
+  // (DBX_AGG_BULK=0 turns pairing off: every word is then updated by its own RED)
+  const char* bulk_env = getenv("DBX_AGG_BULK");
+  if (pl->grouped && !(bulk_env && atoi(bulk_env) == 0)) {
     for (int cls = 0; cls < 2 && pl->n_pairs < kMaxPairs; ++cls) {
       int pending = -1;
       for (int u = 0; u < pl->n_updates && pl->n_pairs < kMaxPairs; ++u) {
@@ -391,12 +399,21 @@ int32_t build_plan(const dbx_agg_params* p, const int32_t* types, int32_t n_cols
       }
     }
   }
+  // Lane split between the TMA unit and the RED path, measured with experiments/agg_sweep.py
+  // (profiles/r02_agg_lane_sweep.txt).
+  pl->bulk_lanes = getenv("DBX_AGG_BULK_LANES") ? (uint32_t)strtoul(getenv("DBX_AGG_BULK_LANES"), nullptr, 16) : kDefaultBulkLanes;
+  pl->use_ring = !(getenv("DBX_AGG_RING") && atoi(getenv("DBX_AGG_RING")) == 0);
+  pl->debug_flags = getenv("DBX_AGG_DEBUG") ? atoi(getenv("DBX_AGG_DEBUG")) : 0;
+  pl->l2_persist = !(getenv("DBX_AGG_L2_PERSIST") && atoi(getenv("DBX_AGG_L2_PERSIST")) == 0);
   return DBX_OK;
 }
 
 // ---------------------------------------------------------------- device table
 struct DeviceTable {
-  DevBuf keys, states;
+  DevBuf mem;       // one allocation: [keys: (cap + 2) u64, padded to 256 B][states: (cap + 2) * n_words u64]
+                    // (contiguous so ONE L2 access-policy window can cover the whole table)
+  void* keys_p = nullptr;
+  void* states_p = nullptr;
   DevBuf counters;  // [0] n_groups, [1] n_overflow
   int64_t cap = 0;
   int n_words = 0;
@@ -414,8 +431,10 @@ struct DeviceTable {
     n_pairs = pl.n_pairs;
     memcpy(w_pair, pl.w_pair, sizeof(w_pair));
     memcpy(w_pos, pl.w_pos, sizeof(w_pos));
-    DBX_CUDA_TRY(*err, keys.ensure((size_t)(cap + 2) * 8 + 32));
-    DBX_CUDA_TRY(*err, states.ensure((size_t)(cap + 2) * 8 * n_words));
+    const size_t kbytes = ((size_t)(cap + 2) * 8 + 32 + 255) & ~(size_t)255;
+    DBX_CUDA_TRY(*err, mem.ensure(kbytes + (size_t)(cap + 2) * 8 * n_words));
+    keys_p = mem.p;
+    states_p = (char*)mem.p + kbytes;
     DBX_CUDA_TRY(*err, counters.ensure(64));
     return clear(pl, stream, err);
   }
@@ -428,7 +447,7 @@ struct DeviceTable {
     DBX_CUDA_TRY(*err, cudaGetLastError());
     if (!pl.grouped) {  // the single state is slot 0 (key 0) and always exists
       uint64_t zero = 0;
-      DBX_CUDA_TRY(*err, cudaMemcpyAsync(keys.p, &zero, 8, cudaMemcpyHostToDevice, stream));
+      DBX_CUDA_TRY(*err, cudaMemcpyAsync(keys_p, &zero, 8, cudaMemcpyHostToDevice, stream));
       unsigned long long one = 1;
       DBX_CUDA_TRY(*err, cudaMemcpyAsync(counters.p, &one, 8, cudaMemcpyHostToDevice, stream));
     }
@@ -436,8 +455,8 @@ struct DeviceTable {
   }
   TableDev view(uint32_t* overflow_rows) const {
     TableDev t;
-    t.keys = (uint64_t*)keys.p;
-    t.states = (uint64_t*)states.p;
+    t.keys = (uint64_t*)keys_p;
+    t.states = (uint64_t*)states_p;
     t.cap = cap;
     t.n_words = n_words;
     // pair arrays first (16-byte aligned: every region has an even number of words), then the
@@ -463,8 +482,9 @@ struct DeviceTable {
     return t;
   }
   void swap(DeviceTable& o) {
-    std::swap(keys, o.keys);
-    std::swap(states, o.states);
+    std::swap(mem, o.mem);
+    std::swap(keys_p, o.keys_p);
+    std::swap(states_p, o.states_p);
     std::swap(counters, o.counters);
     std::swap(cap, o.cap);
     std::swap(n_words, o.n_words);
@@ -539,6 +559,17 @@ class AggPartialOp : public Op {
   int64_t rows_in = 0;
   int64_t initial_cap = 0;
   bool table_ready = false;
+  bool ring_ok = false;
+  bool table_clean = false;  // the exchange scatter left the table empty (fused clear): reset costs no kernel
+  void* window_base = nullptr;  // L2 access-policy window currently set on the stream
+  size_t window_bytes = 0;
+  ~AggPartialOp() override {
+    if (window_base) {  // give the persisting L2 lines back (other operators / the kNN GEMM want the whole L2)
+      cudaSetDevice(device);
+      if (stream) cudaStreamSynchronize(stream);
+      cudaCtxResetPersistingL2Cache();
+    }
+  }
 
   int32_t init(const dbx_agg_params* p, const int32_t* types, int32_t n, int dev) {
     DBX_TRY(base_init(dev));
@@ -554,11 +585,43 @@ class AggPartialOp : public Op {
     return DBX_OK;
   }
 
+  // Pin the hash table in L2 while the column stream passes through: a persisting access-policy
+  // window over the table's allocation on this operator's stream (the column loads are outside
+  // the window and carry evict_first).  DBX_AGG_L2_PERSIST=0 turns it off.
+  int32_t apply_l2_window() {
+    if (!plan.l2_persist || !plan.grouped) return DBX_OK;
+    if (table.mem.p == window_base && table.bytes() == window_bytes) return DBX_OK;
+    window_base = table.mem.p;
+    window_bytes = table.bytes();
+    int max_persist = 0, max_window = 0;
+    DBX_CUDA_TRY(err, cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device));
+    DBX_CUDA_TRY(err, cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device));
+    if (max_persist <= 0 || max_window <= 0) return DBX_OK;
+    const size_t bytes = std::min<size_t>(table.bytes() + 512, (size_t)max_window);
+    static std::atomic<size_t> limit_set[64];
+    const size_t want = std::min<size_t>(bytes, (size_t)max_persist);
+    if (limit_set[device] < want) {
+      DBX_CUDA_TRY(err, cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+      limit_set[device] = want;
+    }
+    cudaStreamAttrValue av;
+    memset(&av, 0, sizeof(av));
+    av.accessPolicyWindow.base_ptr = table.mem.p;
+    av.accessPolicyWindow.num_bytes = bytes;
+    av.accessPolicyWindow.hitRatio = bytes <= want ? 1.0f : (float)want / (float)bytes;
+    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    av.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    DBX_CUDA_TRY(err, cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av));
+    return DBX_OK;
+  }
+
   // (Re-)create or clear the table lazily: after a final operator adopted it, or after reset().
   int32_t ensure_table() {
     if (table_ready) return DBX_OK;
-    if (table.cap != initial_cap || !table.keys.p) DBX_TRY(table.create(initial_cap, plan, stream, &err));
-    else DBX_TRY(table.clear(plan, stream, &err));
+    if (table.cap != initial_cap || !table.keys_p) DBX_TRY(table.create(initial_cap, plan, stream, &err));
+    else if (!table_clean) DBX_TRY(table.clear(plan, stream, &err));
+    table_clean = false;
+    DBX_TRY(apply_l2_window());
     table_ready = true;
     groups_known = plan.grouped ? 0 : 1;
     rows_since_read = 0;
@@ -594,21 +657,44 @@ class AggPartialOp : public Op {
     DBX_CUDA_TRY(err, cudaGetLastError());
     DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));  // old table is freed below
     table.swap(nt);
+    DBX_TRY(apply_l2_window());
     return DBX_OK;
   }
 
+  // ring kernel: whole tiles of plain 8-byte columns, pairs present, table provably large enough
+  template <int NS>
+  int32_t launch_ring(const AggKernelParams& kp) {
+    static std::atomic<bool> attr_set[64];
+    if (device < 0 || device >= 64) { err.set("device index out of range"); return DBX_ERR_INVALID; }
+    const size_t smem = (size_t)kWarpsPerBlock * kRingCap * (16 * kp.n_pairs + 8 * kp.ring_nsv);
+    auto kern = filter_group_agg_ring_kernel<NS, 4>;
+    if (!attr_set[device]) {  // upper bound over every plan this instantiation can serve
+      const size_t smem_max = (size_t)kWarpsPerBlock * kRingCap * (16 * kMaxPairs + 8 * NS);
+      DBX_CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+      attr_set[device] = true;
+    }
+    int grid = grid_for_rows(kp.n_rows);
+    const int per_sm = getenv("DBX_AGG_GRID") ? atoi(getenv("DBX_AGG_GRID")) : 0;
+    if (per_sm > 0) grid = (int)std::max<int64_t>(1, std::min<int64_t>(kp.n_rows / kTileRows, (int64_t)kNumSMs * per_sm));
+    kern<<<grid, kBlock, smem, stream>>>(kp);
+    count_launch();
+    DBX_CUDA_TRY(err, cudaGetLastError());
+    return DBX_OK;
+  }
   template <int NS, bool FAST, bool INDIRECT>
   int32_t launch_one(const AggKernelParams& kp) {
-    // the TMA bulk-reduction variant exists for the straight-line kernel only; everywhere else
+    // the TMA bulk-reduction variants exist for the straight-line kernel only; everywhere else
     // paired words are updated with plain REDs
-    if (FAST && !INDIRECT && kp.n_pairs > 0) return launch_kernel<NS, FAST, INDIRECT, true, 4>(kp);
+    if (FAST && !INDIRECT && kp.n_pairs > 0 && plan.use_ring && ring_ok) return launch_ring<NS>(kp);
+    if (FAST && !INDIRECT && kp.n_pairs > 0 && getenv("DBX_AGG_BULK_OLD")) return launch_kernel<NS, FAST, INDIRECT, true, 4>(kp);
     // (occupancy sweep, profiles/r01b_agg_occupancy_sweep.txt: 4 CTAs/SM at 62 registers is the optimum;
     // 5-6 CTAs spill and queue up behind the L2 atomics, 2-3 CTAs hide less latency)
     return launch_kernel<NS, FAST, INDIRECT, false, 4>(kp);
   }
   template <int NS, bool FAST, bool INDIRECT, bool BULK, int MINB>
   int32_t launch_kernel(const AggKernelParams& kp) {
-    static bool attr_set[16] = {};
+    static std::atomic<bool> attr_set[64];
+    if (device < 0 || device >= 64) { err.set("device index out of range"); return DBX_ERR_INVALID; }
     const size_t smem_rows = (sizeof(StageWarp<NS>) * kWarpsPerBlock + 15) & ~(size_t)15;
     const size_t smem_bulk = (size_t)kWarpsPerBlock * kBulkGen * kMaxPairs * 32 * 16;
     const size_t smem = smem_rows + (BULK ? smem_bulk : 0);
@@ -713,10 +799,18 @@ class AggPartialOp : public Op {
     memcpy(kp->key_parts, plan.key_parts, sizeof(plan.key_parts));
     kp->n_pairs = plan.n_pairs;
     memcpy(kp->pairs, plan.pairs, sizeof(PairDev) * kMaxPairs);
-    static const uint32_t bulk_lanes = getenv("DBX_AGG_BULK_LANES") ? (uint32_t)strtoul(getenv("DBX_AGG_BULK_LANES"), nullptr, 16) : 0xFFFFFFFFu;
-    kp->bulk_lanes = bulk_lanes;
-    static const int dbg = getenv("DBX_AGG_DEBUG") ? atoi(getenv("DBX_AGG_DEBUG")) : 0;
-    kp->debug_flags = dbg;
+    kp->bulk_lanes = plan.bulk_lanes;
+    kp->debug_flags = plan.debug_flags;
+    // ring kernel: slots the table phase reads back from the ring = key parts + arguments of unpaired updates
+    bool need[kMaxSlots] = {};
+    if (plan.n_key_parts > 1) for (int j = 0; j < plan.n_key_parts; ++j) need[plan.key_parts[j].slot] = true;
+    else if (plan.key_slot >= 0) need[plan.key_slot] = true;
+    for (int u = 0; u < plan.n_updates; ++u) {
+      const UpdateDev& ud = plan.upd[u];
+      if (!ud.paired && ud.op != UPD_INC && ud.op != UPD_INC_VALID) need[ud.slot] = true;
+    }
+    kp->ring_nsv = 0;
+    for (int s = 0; s < kMaxSlots; ++s) kp->ring_sidx[s] = (s < plan.n_slots && need[s]) ? (int8_t)kp->ring_nsv++ : (int8_t)-1;
   }
 
   int32_t push(const dbx_block* b) override {
@@ -733,25 +827,27 @@ class AggPartialOp : public Op {
       return DBX_ERR_BAD_ARGUMENTS;
     }
     DBX_TRY(ensure_table());
+    table_clean = false;
     DevCol cols[kMaxSlots];
     DBX_TRY(stager.begin());
     for (int s = 0; s < plan.n_slots; ++s) DBX_TRY(stager.stage(b->cols[plan.slot_col[s]], s, &cols[s]));
     rows_in += n;
 
-    DBX_CUDA_TRY(err, cudaEventRecord(ev_k0, stream));
+    DBX_TRY(timing_begin());
     for (int64_t row0 = 0; row0 < n; row0 += kChunkRows) {
       const int64_t m = std::min(kChunkRows, n - row0);
       AggKernelParams kp;
       fill_params(&kp, cols, row0, m);
       if (!plan.grouped) {
         kp.table = table.view(nullptr);
-        kp.single_state = (unsigned long long*)table.states.p;
+        kp.single_state = (unsigned long long*)table.states_p;
         DBX_TRY(launch_single(kp));
         continue;
       }
       // Insertions are provably within the load-factor budget when even "every row is a new
       // group" keeps the table at most half full: no overflow list, no host sync.
       const bool safe = (groups_known + rows_since_read + m) * 2 <= table.cap;
+      ring_ok = safe;  // the ring kernel does not record overflow rows
       if (safe) {
         kp.table = table.view(nullptr);
         DBX_TRY(launch_grouped(kp, false));
@@ -779,8 +875,7 @@ class AggPartialOp : public Op {
       }
       if ((int64_t)ng * 2 > table.cap) DBX_TRY(grow_to(next_pow2(4 * (int64_t)ng)));
     }
-    DBX_CUDA_TRY(err, cudaEventRecord(ev_k1, stream));
-    timed = true;
+    DBX_TRY(timing_end());
     DBX_TRY(stager.end());
     return DBX_OK;
   }
@@ -825,11 +920,15 @@ class AggFinalOp : public Op {
   unsigned long long* exchange_status = nullptr;  // device: set by a peer-memory exchange merge
   dbx_agg_exchange* exchange_src = nullptr;       // the exchange whose regions this table was merged from
   int64_t last_groups = 0;                        // result size of the previous query (sizing hint, survives reset)
+  cudaEvent_t ev_fin_end = nullptr;               // recorded behind the finalize kernels (per-phase timing)
+  bool fin_timed = false;
+  ~AggFinalOp() override { if (ev_fin_end) cudaEventDestroy(ev_fin_end); }
 
   int32_t init(const dbx_agg_params* p, const int32_t* types, int32_t n, int dev) {
     DBX_TRY(base_init(dev));
     DBX_TRY(build_plan(p, types, n, &plan, &err));
     DBX_CUDA_TRY(err, host_counters.ensure(64));
+    DBX_CUDA_TRY(err, cudaEventCreate(&ev_fin_end));
     return DBX_OK;
   }
   int32_t reset() override {
@@ -900,6 +999,7 @@ class AggFinalOp : public Op {
       table.swap(part->table);
       has_table = true;
       part->table_ready = false;  // whatever buffer it now holds is re-created / cleared lazily
+      part->table_clean = false;
       return DBX_OK;
     }
     int64_t pg = 0;
@@ -921,7 +1021,11 @@ class AggFinalOp : public Op {
     if (finished) { err.set("merge after finish"); return DBX_ERR_STATE; }
     DBX_TRY(ensure_capacity(n_rows));
     if (n_rows == 0) return DBX_OK;
-    rows_merge_kernel<<<grid_for_entries(n_rows), 256, 0, stream>>>((const uint64_t*)dev_rows, n_rows, table.view(nullptr), plan.kinds);
+    // no GROUP BY: the rows are per-rank single states (FinalSingleStateAggregator,
+    // transform_single_key.rs:232-278): merged by ONE thread in row (= rank) order, so f64 sums
+    // are reproducible; grouped rows merge concurrently with REDs
+    if (!plan.grouped) rows_merge_ordered_kernel<<<1, 32, 0, stream>>>((const uint64_t*)dev_rows, n_rows, table.view(nullptr), plan.kinds);
+    else rows_merge_kernel<<<grid_for_entries(n_rows), 256, 0, stream>>>((const uint64_t*)dev_rows, n_rows, table.view(nullptr), plan.kinds);
     count_launch();
     DBX_CUDA_TRY(err, cudaGetLastError());
     int64_t ng, no;
@@ -960,6 +1064,7 @@ class AggFinalOp : public Op {
       // the table was sized from the previous query's result and this one has more groups: the
       // received regions are still intact, so merge them again into a worst-case table
       result_dev.reset();
+      has_table = false;
       DBX_TRY(exchange_launch_merge(exchange_src, this, 0));
       DBX_TRY(finalize_pass(table.cap / 2 + 2, &ng, &no));
     }
@@ -1070,6 +1175,8 @@ class AggFinalOp : public Op {
       ob->cols[i].validity_bit_offset = 0;
     }
     result_dev = std::move(ob);
+    DBX_CUDA_TRY(err, cudaEventRecord(ev_fin_end, stream));
+    fin_timed = true;
     return read_groups(ng_out, no_out);  // the one synchronisation: also completes the kernels above
   }
 
@@ -1155,7 +1262,7 @@ class FilterOp : public Op {
       memcpy(kp.nodes, plan.nodes, sizeof(PredNodeDev) * plan.n_nodes);
       kp.n_rows = n; kp.n_slots = plan.n_slots; kp.n_nodes = plan.n_nodes; kp.key_slot = -1;
       const int grid = grid_for_rows(n);
-      DBX_CUDA_TRY(err, cudaEventRecord(ev_k0, stream));
+      DBX_TRY(timing_begin());
       switch (plan.n_slots) {
         case 1: launch_select<1>(kp, grid); break;
         case 2: launch_select<2>(kp, grid); break;
@@ -1235,8 +1342,7 @@ class FilterOp : public Op {
       }
     }
     if (n > 0) {
-      DBX_CUDA_TRY(err, cudaEventRecord(ev_k1, stream));
-      timed = true;
+      DBX_TRY(timing_end());
       DBX_TRY(stager.end());
     }
     out_q.push_back(std::move(ob));
@@ -1348,8 +1454,14 @@ struct dbx_agg_exchange {
   void* peer_base[dbx::kMaxRanks] = {};
   bool peer_is_ipc[dbx::kMaxRanks] = {};
   bool connected = false;
+  bool fused_clear = true;
+  long long spin_limit_ns = 5000LL * 1000 * 1000;
   unsigned long long epoch = 0;
-  cudaEvent_t ev_scatter = nullptr, ev_merge = nullptr;
+  cudaEvent_t ev_scatter = nullptr, ev_merge = nullptr;  // cross-stream ordering (no timing)
+  // per-phase timing of the last query: [0] scatter begin, [1] scatter end (partial's stream);
+  // [2] wait begin, [3] wait end = merge begin, [4] merge end (final's stream)
+  cudaEvent_t ev_t[5] = {};
+  dbx::AggFinalOp* last_final = nullptr;
   size_t recv_bytes() const {
     return sizeof(dbx::ExchangeHeader) + (size_t)2 * n_ranks * region_rows * row_words * 8;
   }
@@ -1365,13 +1477,15 @@ int32_t dbx_agg_exchange_create(dbx_op* partial_op, int32_t rank, int32_t n_rank
   Op* o = reinterpret_cast<Op*>(partial_op);
   if (o->kind != DBX_OP_AGG_PARTIAL) { g_create_error.set("dbx_agg_exchange_create: not a partial aggregate operator"); return DBX_ERR_INVALID; }
   AggPartialOp* p = static_cast<AggPartialOp*>(o);
-  if (!p->plan.grouped) { g_create_error.set("dbx_agg_exchange_create: aggregation without GROUP BY needs no exchange (all-reduce the single state)"); return DBX_ERR_UNSUPPORTED; }
+  if (!p->plan.grouped) { g_create_error.set("dbx_agg_exchange_create: aggregation without GROUP BY has no key to partition by: use dbx_agg_single_allreduce"); return DBX_ERR_UNSUPPORTED; }
   ErrorSink& err = g_create_error;
   std::unique_ptr<dbx_agg_exchange> x(new dbx_agg_exchange());
   x->device = p->device; x->rank = rank; x->n_ranks = n_ranks; x->row_words = 2 + p->plan.n_words;
   // a source can send at most all of its groups to one owner; a partial table holds at most cap/2
   x->region_rows = region_rows > 0 ? region_rows : std::max<int64_t>(p->initial_cap / 2 + 2, 1024);
   x->table_cap = std::max<int64_t>(p->initial_cap, next_pow2(2 * x->region_rows - 4));
+  x->fused_clear = !(getenv("DBX_EXCH_FUSED_CLEAR") && atoi(getenv("DBX_EXCH_FUSED_CLEAR")) == 0);
+  if (getenv("DBX_EXCH_SPIN_MS")) x->spin_limit_ns = atoll(getenv("DBX_EXCH_SPIN_MS")) * 1000000LL;
   DBX_CUDA_TRY(err, cudaSetDevice(x->device));
   DBX_CUDA_TRY(err, x->recv.ensure(x->recv_bytes()));
   DBX_CUDA_TRY(err, cudaMemset(x->recv.p, 0, sizeof(ExchangeHeader)));
@@ -1381,6 +1495,7 @@ int32_t dbx_agg_exchange_create(dbx_op* partial_op, int32_t rank, int32_t n_rank
   DBX_CUDA_TRY(err, x->host_status.ensure(64));
   DBX_CUDA_TRY(err, cudaEventCreateWithFlags(&x->ev_scatter, cudaEventDisableTiming));
   DBX_CUDA_TRY(err, cudaEventCreateWithFlags(&x->ev_merge, cudaEventDisableTiming));
+  for (auto& e : x->ev_t) DBX_CUDA_TRY(err, cudaEventCreate(&e));
   if (ipc_handle_out) {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     cudaIpcMemHandle_t hd;
@@ -1419,7 +1534,9 @@ int32_t dbx_agg_exchange_connect(dbx_agg_exchange* x, const void* all_handles, v
 }
 
 /* Hash-partition the finished partial's groups by owner and store every row straight into the
- * owner's receive region (peer memory).  Enqueued on the partial's stream; no host sync. */
+ * owner's receive region (peer memory).  Enqueued on the partial's stream; no host sync.  The
+ * same pass re-initialises the partial's table, so the operator is re-armed for the next query
+ * without a separate clear (dbx_op_reset on it then costs no kernel). */
 int32_t dbx_agg_exchange_scatter(dbx_agg_exchange* x, dbx_op* partial_op) {
   if (!x || !partial_op) return DBX_ERR_INVALID;
   if (!x->connected) { x->err.set("exchange: scatter before connect"); return DBX_ERR_STATE; }
@@ -1430,6 +1547,7 @@ int32_t dbx_agg_exchange_scatter(dbx_agg_exchange* x, dbx_op* partial_op) {
   x->epoch += 1;
   // region reuse: this rank's merge of the previous epoch must precede the scatter that lets peers move on
   DBX_CUDA_TRY(x->err, cudaStreamWaitEvent(p->stream, x->ev_merge, 0));
+  DBX_CUDA_TRY(x->err, cudaEventRecord(x->ev_t[0], p->stream));
   DBX_CUDA_TRY(x->err, cudaMemsetAsync(x->scratch.p, 0, 8 * (kMaxRanks + 2), p->stream));
   ExchangeScatterParams sp;
   memset(&sp, 0, sizeof(sp));
@@ -1440,15 +1558,23 @@ int32_t dbx_agg_exchange_scatter(dbx_agg_exchange* x, dbx_op* partial_op) {
   sp.region_rows = x->region_rows;
   sp.epoch = x->epoch;
   sp.n_ranks = x->n_ranks; sp.rank = x->rank; sp.row_words = x->row_words; sp.parity = (int)(x->epoch & 1);
+  sp.clear_src = x->fused_clear ? 1 : 0;
+  sp.init = p->plan.init;
   exchange_scatter_kernel<<<grid_for_entries(sp.src.cap + 2), 256, (size_t)256 * x->row_words * 8, p->stream>>>(sp);
   count_launch();
   DBX_CUDA_TRY(x->err, cudaGetLastError());
+  if (x->fused_clear) {  // the table is empty again: only the counters are left to reset
+    DBX_CUDA_TRY(x->err, cudaMemsetAsync(p->table.counters.p, 0, 64, p->stream));
+    p->table_clean = true;
+  }
+  DBX_CUDA_TRY(x->err, cudaEventRecord(x->ev_t[1], p->stream));
   DBX_CUDA_TRY(x->err, cudaEventRecord(x->ev_scatter, p->stream));
   return DBX_OK;
 }
 
-/* Merge every source's region of the current epoch into the final operator's table; the kernel
- * waits on the sources' release flags (device side).  Enqueued on the final's stream. */
+/* Merge every source's region of the current epoch into the final operator's table; a one-warp
+ * kernel waits on the sources' release flags (device side), the merge grid follows it in stream
+ * order.  Enqueued on the final's stream; no host sync. */
 int32_t dbx_agg_exchange_merge(dbx_agg_exchange* x, dbx_op* final_op) {
   if (!x || !final_op) return DBX_ERR_INVALID;
   Op* o = reinterpret_cast<Op*>(final_op);
@@ -1456,13 +1582,36 @@ int32_t dbx_agg_exchange_merge(dbx_agg_exchange* x, dbx_op* final_op) {
   AggFinalOp* f = static_cast<AggFinalOp*>(o);
   DBX_CUDA_TRY(x->err, cudaSetDevice(x->device));
   if (f->finished) { x->err.set("merge after finish"); return DBX_ERR_STATE; }
+  if (f->has_table) { x->err.set("exchange: the final operator already holds merged state (reset it first; an exchange merge always starts a fresh table)"); return DBX_ERR_STATE; }
   // table size: from the previous query's result when there is one (an owner holds ~1/n_ranks of
   // the groups, so this is far smaller than the worst case and cheaper to clear and scan); finish()
   // falls back to the worst-case size if it turns out too small
   int64_t cap = 0;
   if (f->last_groups > 0) cap = std::min<int64_t>(x->table_cap, next_pow2(std::max<int64_t>(4 * f->last_groups, 1024)));
   DBX_TRY(exchange_launch_merge(x, f, cap));
-  f->exchange_status = (unsigned long long*)x->status.p;
+  return DBX_OK;
+}
+
+/* Per-phase device times (ms, CUDA events) of the last scatter/merge pair, for bench.py's N > 1
+ * line: out8[0] scatter kernel, [1] wait for the peers' flags (wait kernel, event-timed),
+ * [2] merge kernel, [3] finalize (merge end -> result columns ready), [4] the wait kernel's own
+ * measure of its spin (globaltimer), [5..7] reserved (0).  Call after the final's finish(). */
+int32_t dbx_agg_exchange_phase_ms(dbx_agg_exchange* x, float* out8) {
+  if (!x || !out8) return DBX_ERR_INVALID;
+  DBX_CUDA_TRY(x->err, cudaSetDevice(x->device));
+  for (int i = 0; i < 8; ++i) out8[i] = 0.f;
+  if (x->epoch == 0) { x->err.set("exchange: no query timed yet"); return DBX_ERR_STATE; }
+  DBX_CUDA_TRY(x->err, cudaEventSynchronize(x->ev_t[1]));
+  DBX_CUDA_TRY(x->err, cudaEventSynchronize(x->ev_t[4]));
+  DBX_CUDA_TRY(x->err, cudaEventElapsedTime(&out8[0], x->ev_t[0], x->ev_t[1]));
+  DBX_CUDA_TRY(x->err, cudaEventElapsedTime(&out8[1], x->ev_t[2], x->ev_t[3]));
+  DBX_CUDA_TRY(x->err, cudaEventElapsedTime(&out8[2], x->ev_t[3], x->ev_t[4]));
+  if (x->last_final && x->last_final->fin_timed) {
+    DBX_CUDA_TRY(x->err, cudaEventSynchronize(x->last_final->ev_fin_end));
+    DBX_CUDA_TRY(x->err, cudaEventElapsedTime(&out8[3], x->ev_t[4], x->last_final->ev_fin_end));
+  }
+  DBX_CUDA_TRY(x->err, cudaMemcpy(x->host_status.p, x->status.p, 32, cudaMemcpyDeviceToHost));
+  out8[4] = (float)(((unsigned long long*)x->host_status.p)[2] * 1e-6);
   return DBX_OK;
 }
 
@@ -1486,14 +1635,19 @@ int32_t exchange_launch_merge(dbx_agg_exchange* x, AggFinalOp* f, int64_t cap) {
   mp.status = (unsigned long long*)x->status.p;
   mp.region_rows = x->region_rows;
   mp.epoch = x->epoch;
-  mp.spin_limit_cycles = 20LL * 1000 * 1000 * 1000;  // ~10 s: a peer that never arrives must not hang the GPU
+  mp.spin_limit_ns = x->spin_limit_ns;  // a peer that never arrives must not hang the GPU
   mp.n_ranks = x->n_ranks; mp.row_words = x->row_words; mp.parity = (int)(x->epoch & 1);
+  DBX_CUDA_TRY(x->err, cudaEventRecord(x->ev_t[2], f->stream));
+  exchange_wait_kernel<<<1, 32, 0, f->stream>>>(mp);
+  DBX_CUDA_TRY(x->err, cudaEventRecord(x->ev_t[3], f->stream));
   exchange_merge_kernel<<<grid_for_entries(x->region_rows), 256, 0, f->stream>>>(mp);
-  count_launch();
+  count_launch(2);
   DBX_CUDA_TRY(x->err, cudaGetLastError());
+  DBX_CUDA_TRY(x->err, cudaEventRecord(x->ev_t[4], f->stream));
   DBX_CUDA_TRY(x->err, cudaEventRecord(x->ev_merge, f->stream));
   f->exchange_status = (unsigned long long*)x->status.p;
   f->exchange_src = x;
+  x->last_final = f;
   return DBX_OK;
 }
 }  // namespace dbx
@@ -1508,6 +1662,8 @@ int32_t dbx_agg_exchange_destroy(dbx_agg_exchange* x) {
     if (x->peer_is_ipc[r] && x->peer_base[r]) cudaIpcCloseMemHandle(x->peer_base[r]);
   if (x->ev_scatter) cudaEventDestroy(x->ev_scatter);
   if (x->ev_merge) cudaEventDestroy(x->ev_merge);
+  for (auto& e : x->ev_t)
+    if (e) cudaEventDestroy(e);
   delete x;
   return DBX_OK;
 }

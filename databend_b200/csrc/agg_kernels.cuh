@@ -502,6 +502,157 @@ __global__ void __launch_bounds__(kBlock, MINB) filter_group_agg_kernel(const __
   if (lane == 0 && new_groups) atomicAdd(p.table.n_groups, (unsigned long long)new_groups);
 }
 
+// ---------------------------------------------------------------- fused kernel, ring variant
+// Same front end as the FAST kernel above; the table phase differs in how the state words are
+// updated.  The plain kernel is bound by the NUMBER of L2 reduction requests (~150 G RED/s
+// chip-wide, profiles/r01b_atomics_microbench.txt), three per surviving row for config 2.  Here
+// adjacent additive words (e.g. {row count, wrapping integer sum}) are one 16-byte pair and a
+// share of the lanes updates the pair with ONE TMA bulk reduction (cp.reduce.async.bulk, a
+// separate unit that sustains ~1 small op / 5 clk / SM) while the other lanes keep using REDs,
+// so both units run side by side.  The surviving rows are compacted into a warp-private
+// shared-memory RING (FIFO) whose pair records {contribution0, contribution1} are the TMA source
+// directly — no second staging copy; a ring position is rewritten only after the bulk group that
+// read it has drained (cp.async.bulk.wait_group.read).
+//
+// Ring capacity: a tile adds <= 128 rows per warp behind < 32 carried ones, and the most recent
+// K = 1 table phases (32 rows each) may still be read by the TMA unit: R >= 128 + 31 + 32 K.
+constexpr int kRingCap = 192;
+
+template <int NS>
+__device__ __forceinline__ void ring_table_phase(const AggKernelParams& p, const uint64_t* pair_base, const uint64_t* val_base,
+                                                 int head, int count, int lane, uint32_t& new_groups) {
+  const TableDev& t = p.table;
+  const bool act = lane < count;
+  int pos = head + lane;
+  if (pos >= kRingCap) pos -= kRingCap;
+  uint64_t key = 0;
+  if (act) {
+    if (p.n_key_parts > 1) {
+      for (int j = 0; j < p.n_key_parts; ++j) {
+        const KeyPartDev kp = p.key_parts[j];
+        key |= (val_base[p.ring_sidx[kp.slot] * kRingCap + pos] & kp.mask) << kp.shift;
+      }
+    } else {
+      key = val_base[p.ring_sidx[p.key_slot] * kRingCap + pos];
+    }
+  }
+  const bool special = key == kEmptyKey;
+  const int64_t b = (int64_t)(agg_hash_u64(key) & (uint64_t)((t.cap >> 2) - 1));
+  u64x4 kb;
+  kb.x = kb.y = kb.z = kb.w = 0;
+  if (act && !special) kb = ld_bucket(t.keys + 4 * b);
+  if (act) {
+    int64_t slot;
+    if (special) {
+      slot = special_slot(t, false, new_groups);
+    } else {
+      int m = bucket_match(kb, key);
+      slot = m >= 0 ? 4 * b + m : find_or_insert_slow(t, key, b, kb, new_groups);
+    }
+    if (slot < 0) {
+      atomicAdd(t.n_overflow, 1ULL);  // ring kernel runs in "safe" mode only: counted, reported loudly by the host
+    } else if (!(p.debug_flags & 1)) {
+      const bool use_bulk = (p.bulk_lanes >> lane) & 1;
+      uint64_t* row = t.states + t.row_base + slot * t.n_single;
+      for (int u = 0; u < p.n_updates; ++u) {
+        const UpdateDev ud = p.upd[u];
+        if (ud.paired) continue;
+        apply_update(ud.op, row + ud.ridx, (ud.op == UPD_INC || ud.op == UPD_INC_VALID) ? 0 : val_base[p.ring_sidx[ud.slot] * kRingCap + pos], true);
+      }
+      for (int pr = 0; pr < p.n_pairs; ++pr) {
+        const PairDev pd = p.pairs[pr];
+        const uint64_t* src = pair_base + ((size_t)pr * kRingCap + pos) * 2;
+        uint64_t* dst = word_ptr(t, slot, p.upd[pd.upd0].word);
+        if (use_bulk) {
+          const uint32_t sa = (uint32_t)__cvta_generic_to_shared(src);
+          if (pd.is_f64) asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], 16;" ::"l"(dst), "r"(sa) : "memory");
+          else asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.u64 [%0], [%1], 16;" ::"l"(dst), "r"(sa) : "memory");
+        } else {
+          const uint64_t c0 = src[0], c1 = src[1];
+          if (pd.is_f64) {
+            if (c0) red_add_f64(dst, __longlong_as_double((long long)c0));
+            if (c1) red_add_f64(dst + 1, __longlong_as_double((long long)c1));
+          } else {
+            if (c0) red_add_u64(dst, c0);
+            if (c1) red_add_u64(dst + 1, c1);
+          }
+        }
+      }
+    }
+  }
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");  // every lane, every call: group counts stay aligned
+  __syncwarp();
+}
+
+template <int NS, int MINB = 4>
+__global__ void __launch_bounds__(kBlock, MINB) filter_group_agg_ring_kernel(const __grid_constant__ AggKernelParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int np = p.n_pairs, nsv = p.ring_nsv;
+  const size_t warp_bytes = (size_t)kRingCap * (16 * np + 8 * nsv);
+  uint64_t* pair_base = reinterpret_cast<uint64_t*>(smem_raw + warp * warp_bytes);  // [np][kRingCap][2]
+  uint64_t* val_base = pair_base + (size_t)np * kRingCap * 2;                       // [nsv][kRingCap]
+  const int64_t n_tiles = p.n_rows / kTileRows;  // whole tiles only (the generic kernel takes the remainder)
+  const uint32_t lt_mask = (1u << lane) - 1;
+  uint32_t new_groups = 0;
+  int head = 0, cnt = 0;  // warp-uniform: the ring holds rows [head, head + cnt)
+
+  RowVals vals[NS];
+  int64_t tile = blockIdx.x;
+  if (tile < n_tiles) prefetch_tile<NS>(p, tile, vals);
+  for (; tile < n_tiles; tile += gridDim.x) {
+    __syncwarp();
+    uint32_t sel = 0xF;
+    if (p.n_nodes) {
+      const PredNodeDev& nd = p.nodes[0];
+#pragma unroll
+      for (int j = 0; j < kRowsPerThread; ++j)
+        if (!eval_cmp(nd, pick<NS>(vals, nd.l_slot, j), nd.r_const)) sel &= ~(1u << j);
+    }
+    if (p.debug_flags & 2) sel = 0;
+    // the positions written below were last handed to the TMA unit >= 2 table phases ago
+    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < kRowsPerThread; ++j) {
+      const bool on = (sel >> j) & 1;
+      const uint32_t bal = __ballot_sync(0xffffffffu, on);
+      if (on) {
+        int o = head + cnt + __popc(bal & lt_mask);
+        if (o >= kRingCap) o -= kRingCap;
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+          if (p.ring_sidx[s] >= 0) val_base[p.ring_sidx[s] * kRingCap + o] = vals[s].v[j];
+        for (int pr = 0; pr < np; ++pr) {
+          const UpdateDev u0 = p.upd[p.pairs[pr].upd0], u1 = p.upd[p.pairs[pr].upd1];
+          uint64_t* d = pair_base + ((size_t)pr * kRingCap + o) * 2;
+          d[0] = (u0.op == UPD_INC || u0.op == UPD_INC_VALID) ? 1 : pick<NS>(vals, u0.slot, j);
+          d[1] = (u1.op == UPD_INC || u1.op == UPD_INC_VALID) ? 1 : pick<NS>(vals, u1.slot, j);
+        }
+      }
+      cnt += __popc(bal);
+    }
+    {  // prefetch the next tile: the loads fly while this warp works on the table
+      const int64_t nt = tile + gridDim.x;
+      if (nt < n_tiles) prefetch_tile<NS>(p, nt, vals);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // ring writes -> visible to the TMA unit
+    __syncwarp();
+    while (cnt >= 32) {
+      ring_table_phase<NS>(p, pair_base, val_base, head, 32, lane, new_groups);
+      head += 32;
+      if (head >= kRingCap) head -= kRingCap;
+      cnt -= 32;
+    }
+  }
+  __syncwarp();
+  if (cnt > 0) ring_table_phase<NS>(p, pair_base, val_base, head, cnt, lane, new_groups);
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) new_groups += __shfl_xor_sync(0xffffffffu, new_groups, o);
+  if (lane == 0 && new_groups) atomicAdd(p.table.n_groups, (unsigned long long)new_groups);
+}
+
 // ---------------------------------------------------------------- fused kernel (no GROUP BY)
 // PartialSingleStateAggregator (transform_single_key.rs:93-141): a pure streaming reduce.
 // Per-thread accumulators -> warp shuffle -> one atomic per warp into the single state.
@@ -814,6 +965,25 @@ __global__ void rows_merge_kernel(const uint64_t* rows, int64_t n_rows, const __
   if ((threadIdx.x & 31) == 0 && new_groups) atomicAdd(dst.n_groups, (unsigned long long)new_groups);
 }
 
+// Same, but ONE thread merges the rows in the order given: used for per-rank single states
+// (no GROUP BY), where the row order is the rank order and f64 sums must be reproducible.
+__global__ void rows_merge_ordered_kernel(const uint64_t* rows, int64_t n_rows, const __grid_constant__ TableDev dst,
+                                          const __grid_constant__ WordKinds kinds) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  uint32_t new_groups = 0;
+  const int row_words = 2 + dst.n_words;
+  for (int64_t i = 0; i < n_rows; ++i) {
+    const uint64_t* r = rows + i * row_words;
+    int64_t d = resolve_slot(dst, r[0], (int)r[1], new_groups);
+    if (d < 0) { atomicAdd(dst.n_overflow, 1ULL); continue; }
+    for (int w = 0; w < dst.n_words; ++w) {
+      merge_word(kinds.op[w], word_ptr(dst, d, w), r[2 + w]);
+      __threadfence();  // keep the order of the f64 additions to one word
+    }
+  }
+  if (new_groups) atomicAdd(dst.n_groups, (unsigned long long)new_groups);
+}
+
 // ---------------------------------------------------------------- partial -> final exchange over peer memory
 // One process per GPU; every rank owns a receive buffer in its HBM that all peers map (CUDA IPC
 // over NVLink / NVSwitch).  The partial's groups are hash-partitioned by owner and each row is
@@ -825,7 +995,7 @@ constexpr int kMaxRanks = 16;
 struct ExchangeHeader {
   unsigned long long count[2][kMaxRanks];  // [parity][source rank]: rows that source wrote
   unsigned long long flag[kMaxRanks];      // [source rank]: last epoch the source completed
-  unsigned long long overflow[kMaxRanks];  // [source rank]: epoch in which the region was too small
+  unsigned long long overflow[2][kMaxRanks];  // [parity][source rank]: epoch in which the region was too small
   unsigned long long pad[16];
 };
 struct ExchangeScatterParams {
@@ -836,6 +1006,9 @@ struct ExchangeScatterParams {
   int64_t region_rows;
   unsigned long long epoch;
   int32_t n_ranks, rank, row_words, parity;
+  int32_t clear_src;  // 1: re-initialise every source slot once it was read (fused table clear)
+  int32_t pad;
+  WordInit init;
 };
 __device__ __forceinline__ uint64_t* exchange_region(void* base, int n_ranks, int parity, int src, int64_t region_rows, int row_words) {
   return reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(base) + sizeof(ExchangeHeader)) +
@@ -886,6 +1059,10 @@ __global__ void __launch_bounds__(256) exchange_scatter_kernel(const __grid_cons
       r[0] = key_kind ? 0 : key;
       r[1] = (uint64_t)key_kind;
       for (int w = 0; w < src.n_words; ++w) r[2 + w] = *word_ptr(src, i, w);
+      if (x.clear_src) {  // the slot is read by this thread only: leave the table ready for the next query
+        src.keys[i] = kEmptyKey;
+        for (int w = 0; w < src.n_words; ++w) *word_ptr(src, i, w) = x.init.w[w];
+      }
     }
     __syncthreads();
     for (int o = 0; o < x.n_ranks; ++o) {
@@ -912,7 +1089,7 @@ __global__ void __launch_bounds__(256) exchange_scatter_kernel(const __grid_cons
     ExchangeHeader* h = reinterpret_cast<ExchangeHeader*>(x.peer_base[threadIdx.x]);
     const bool over = (int64_t)cnt > x.region_rows;
     h->count[x.parity][x.rank] = over ? (unsigned long long)x.region_rows : cnt;
-    if (over) h->overflow[x.rank] = x.epoch;
+    if (over) h->overflow[x.parity][x.rank] = x.epoch;
     __threadfence_system();
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&h->flag[x.rank]), "l"(x.epoch) : "memory");
   }
@@ -922,36 +1099,51 @@ struct ExchangeMergeParams {
   TableDev dst;
   WordKinds kinds;
   void* base;  // this rank's receive buffer
-  unsigned long long* status;  // [0] != 0: timed out waiting for a peer; [1] != 0: a region overflowed
+  unsigned long long* status;  // [0] != 0: timed out waiting for a peer; [1] != 0: a region overflowed;
+                               // [2] nanoseconds the wait kernel spent until every source had released
   int64_t region_rows;
   unsigned long long epoch;
-  long long spin_limit_cycles;
+  long long spin_limit_ns;
   int32_t n_ranks, row_words, parity, pad;
 };
-__global__ void __launch_bounds__(256) exchange_merge_kernel(const __grid_constant__ ExchangeMergeParams x) {
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// One warp waits until every source has released its region for this epoch (one lane per
+// source, acquire loads at system scope on flags in LOCAL memory that the peers store to over
+// NVLink).  A separate 1-CTA kernel in front of the merge: nothing else spins, the merge grid
+// starts only when its input is complete, and a peer that never arrives costs `spin_limit_ns`,
+// not a hung GPU.
+__global__ void __launch_bounds__(32) exchange_wait_kernel(const __grid_constant__ ExchangeMergeParams x) {
   ExchangeHeader* h = reinterpret_cast<ExchangeHeader*>(x.base);
-  __shared__ int s_fail;
-  if (threadIdx.x == 0) s_fail = 0;
-  __syncthreads();
-  if (threadIdx.x < x.n_ranks) {  // wait until every source has released its region for this epoch
-    const long long t0 = clock64();
+  const unsigned long long t0 = globaltimer_ns();
+  bool fail = false;
+  if ((int)threadIdx.x < x.n_ranks) {
     while (true) {
       unsigned long long f;
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(&h->flag[threadIdx.x]) : "memory");
       if (f >= x.epoch) break;
-      if (clock64() - t0 > x.spin_limit_cycles) { s_fail = 1; break; }
-      __nanosleep(200);
+      if ((long long)(globaltimer_ns() - t0) > x.spin_limit_ns) { fail = true; break; }
+      __nanosleep(100);
     }
+    if (!fail && h->overflow[x.parity][threadIdx.x] == x.epoch) atomicExch(&x.status[1], 1ULL);
   }
-  __syncthreads();
-  if (s_fail) {
-    if (threadIdx.x == 0) atomicExch(&x.status[0], 1ULL);
-    return;
+  const unsigned any_fail = __ballot_sync(0xffffffffu, fail);
+  if (threadIdx.x == 0) {
+    if (any_fail) atomicExch(&x.status[0], 1ULL);
+    x.status[2] = globaltimer_ns() - t0;
   }
+}
+// TransformFinalAggregate over the received regions (transform_aggregate_final.rs:201-303):
+// every row of every source is found-or-inserted in the final table and its words merged.
+__global__ void __launch_bounds__(256) exchange_merge_kernel(const __grid_constant__ ExchangeMergeParams x) {
+  const ExchangeHeader* h = reinterpret_cast<const ExchangeHeader*>(x.base);
+  if (*reinterpret_cast<volatile unsigned long long*>(&x.status[0])) return;  // a peer never arrived: reported by the host
   uint32_t new_groups = 0;
   for (int s = 0; s < x.n_ranks; ++s) {
     const int64_t cnt = (int64_t)h->count[x.parity][s];
-    if (blockIdx.x == 0 && threadIdx.x == 0 && h->overflow[s] == x.epoch) atomicExch(&x.status[1], 1ULL);
     const uint64_t* rows = exchange_region(x.base, x.n_ranks, x.parity, s, x.region_rows, x.row_words);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (int64_t)gridDim.x * blockDim.x) {
       const uint64_t* r = rows + i * x.row_words;

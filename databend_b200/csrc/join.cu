@@ -462,7 +462,7 @@ class JoinOp : public Op {
       DBX_TRY(stager.stage(col, c, &cols[c]));
     }
     int64_t out_cap = n + n / 8 + 1024;  // optimistic: about one match per probe row
-    DBX_CUDA_TRY(err, cudaEventRecord(ev_k0, stream));
+    DBX_TRY(timing_begin());
     // radix probe: reorder the block region by region (row order of a join result is unspecified)
     bool can_part = n_part > 1 && (n >= (1 << 16) || getenv("DBX_JOIN_REGION_BYTES"));
     for (int c = 0; c < n_probe_cols && can_part; ++c) can_part = !cols[c].validity;
@@ -572,8 +572,7 @@ class JoinOp : public Op {
       if (matches > 0) outputs.push_back(std::move(ob));
       break;
     }
-    DBX_CUDA_TRY(err, cudaEventRecord(ev_k1, stream));
-    timed = true;
+    DBX_TRY(timing_end());
     DBX_TRY(stager.end());
     return DBX_OK;
   }

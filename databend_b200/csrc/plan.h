@@ -176,6 +176,10 @@ struct AggKernelParams {
   int32_t n_pairs;      // > 0: paired words go through TMA bulk reductions
   uint32_t bulk_lanes;  // lanes (bit mask) that use the bulk path; the others use REDs for the paired words too
   int32_t debug_flags;  // perf bisecting only (env DBX_AGG_DEBUG): 1 = skip state updates, 2 = skip table probe
+  // ring kernel (filter_group_agg_ring_kernel): which input slots the table phase still needs after
+  // the predicate (key parts + arguments of unpaired updates) and where they are stored in the ring
+  int32_t ring_nsv;                 // number of stored slot arrays
+  int8_t ring_sidx[kMaxSlots];      // slot -> storage index, -1: not stored
 };
 
 }  // namespace dbx

@@ -160,14 +160,25 @@ int32_t Op::base_init(int dev) {
   device = dev;
   DBX_CUDA_TRY(err, cudaSetDevice(device));
   DBX_CUDA_TRY(err, cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-  DBX_CUDA_TRY(err, cudaEventCreate(&ev_k0));
-  DBX_CUDA_TRY(err, cudaEventCreate(&ev_k1));
+  for (auto& pr : ev_ring)
+    for (auto& e : pr) DBX_CUDA_TRY(err, cudaEventCreate(&e));
   return DBX_OK;
 }
 Op::~Op() {
-  if (ev_k0) cudaEventDestroy(ev_k0);
-  if (ev_k1) cudaEventDestroy(ev_k1);
+  for (auto& pr : ev_ring)
+    for (auto& e : pr)
+      if (e) cudaEventDestroy(e);
   if (stream) cudaStreamDestroy(stream);
+}
+int32_t Op::timing_begin() {
+  ev_idx += 1;
+  DBX_CUDA_TRY(err, cudaEventRecord(ev_ring[ev_idx % kEvRing][0], stream));
+  return DBX_OK;
+}
+int32_t Op::timing_end() {
+  DBX_CUDA_TRY(err, cudaEventRecord(ev_ring[ev_idx % kEvRing][1], stream));
+  timed = true;
+  return DBX_OK;
 }
 
 int32_t fill_owned_block(OwnedBlock* ob, dbx_block* out) {
@@ -335,17 +346,23 @@ int32_t dbx_block_release(dbx_block* block) {
 
 int64_t dbx_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
-int32_t dbx_op_last_kernel_ms(dbx_op* op, float* ms) {
+int32_t dbx_op_kernel_ms(dbx_op* op, int32_t back, float* ms) {
   DBX_OP_ENTER(op);
-  if (!o->timed) { o->err.set("no timed kernel on this handle yet"); return DBX_ERR_STATE; }
-  DBX_CUDA_TRY(o->err, cudaEventSynchronize(o->ev_k1));
-  DBX_CUDA_TRY(o->err, cudaEventElapsedTime(ms, o->ev_k0, o->ev_k1));
+  if (!o->timed || back < 0 || back >= Op::kEvRing || back > o->ev_idx) { o->err.set("no timed kernel that far back on this handle"); return DBX_ERR_STATE; }
+  cudaEvent_t* pr = o->ev_ring[(o->ev_idx - back) % Op::kEvRing];
+  DBX_CUDA_TRY(o->err, cudaEventSynchronize(pr[1]));
+  DBX_CUDA_TRY(o->err, cudaEventElapsedTime(ms, pr[0], pr[1]));
   return DBX_OK;
 }
+int32_t dbx_op_last_kernel_ms(dbx_op* op, float* ms) { return dbx_op_kernel_ms(op, 0, ms); }
 int32_t dbx_op_stream(dbx_op* op, void** stream) {
   DBX_OP_ENTER(op);
   *stream = (void*)o->stream;
   return DBX_OK;
+}
+int32_t dbx_op_inputs_consumed(dbx_op* op) {
+  DBX_OP_ENTER(op);
+  return o->wait_inputs();
 }
 int32_t dbx_op_synchronize(dbx_op* op) {
   DBX_OP_ENTER(op);

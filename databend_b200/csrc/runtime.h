@@ -112,12 +112,24 @@ class Op {
   virtual int32_t finish() = 0;
   virtual int32_t pull(int32_t out_mem, dbx_block* out, int32_t* has_block) = 0;
   virtual int32_t reset() { err.set("reset not supported by this operator"); return DBX_ERR_UNSUPPORTED; }
+  // Block until every pushed block has been read completely (see dbx_op_inputs_consumed).  The
+  // consumers of a pushed block are all enqueued on `stream` before push returns.
+  virtual int32_t wait_inputs() {
+    DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
+    return DBX_OK;
+  }
 
   int kind = -1;
   int device = 0;
   cudaStream_t stream = nullptr;
   ErrorSink err;
-  cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // bracket the dominant kernel(s) of the last push
+  // event pairs bracketing the dominant kernel(s) of the most recent pushes (a small ring, so the
+  // kernel of push i can still be read after push i+1 was enqueued)
+  static constexpr int kEvRing = 8;
+  cudaEvent_t ev_ring[kEvRing][2] = {};
+  int64_t ev_idx = -1;
+  int32_t timing_begin();
+  int32_t timing_end();
   bool timed = false;
   bool finished = false;
 };

@@ -282,7 +282,7 @@ class TopkOp : public Op {
     DevCol col;
     DBX_TRY(stager.begin());
     DBX_TRY(stager.stage(kc, 0, &col));
-    DBX_CUDA_TRY(err, cudaEventRecord(ev_k0, stream));
+    DBX_TRY(timing_begin());
     const int esz = dtype_size(key_dtype);
     int64_t done = 0;
     while (done < n) {
@@ -325,8 +325,7 @@ class TopkOp : public Op {
       next_chunk = std::min<int64_t>(next_chunk * 8, kMaxChunk);
     }
     rows_seen += n;
-    DBX_CUDA_TRY(err, cudaEventRecord(ev_k1, stream));
-    timed = true;
+    DBX_TRY(timing_end());
     DBX_TRY(stager.end());
     return DBX_OK;
   }

@@ -134,3 +134,41 @@ def topk_merge(local: DataBlock, row_base: int, k: int, asc: bool, nulls_first: 
         op.close()
     pos = out.columns[1].values()
     return DataBlock([out.columns[0], Column.from_data(rows[pos])], out.num_rows)
+
+
+def allreduce_single_state(partial, final, device: int = 0, group=None, out_mem: int = abi.MEM_HOST) -> DataBlock:
+    """Aggregation WITHOUT GROUP BY across ranks (PartialSingleStateAggregator ->
+    FinalSingleStateAggregator, transform_single_key.rs:93-141,232-278): every rank's partial state is
+    one fixed-width row [key][kind][state words]; the rows are all-gathered (a few dozen bytes per
+    rank — the reference's `allReduce` of 1-2 scalars) and every rank merges ALL of them in rank
+    order with one device thread (dbx_agg_final_merge_rows on a no-GROUP-BY plan), so integer
+    results are exact and f64 sums are reproducible and identical on every rank."""
+    L = load()
+    partial.on_finish()
+    rows_ptr, offs, rb = C.c_void_p(), (C.c_int64 * 2)(), C.c_int32(0)
+    check(L.dbx_agg_partial_partition(partial.handle, 1, C.byref(rows_ptr), offs, C.byref(rb)), partial.handle)
+    n_rows, row_bytes = offs[1], rb.value
+    assert n_rows == 1, "a no-GROUP-BY partial holds exactly one state row"
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    host = np.empty(row_bytes // 8, dtype=np.int64)
+    check(L.dbx_memcpy_d2h(device, host.ctypes.data, rows_ptr, row_bytes))
+    check(L.dbx_device_free(device, rows_ptr))
+    if world > 1:
+        nccl = dist.get_backend(group) == "nccl"
+        t = torch.from_numpy(host)
+        if nccl:
+            t = t.to(f"cuda:{device}")
+        g = torch.empty(world * len(host), dtype=torch.int64, device=t.device)
+        dist.all_gather_into_tensor(g, t, group=group)
+        allrows = g.cpu().numpy()
+    else:
+        allrows = host
+    buf = C.c_void_p()
+    check(L.dbx_device_alloc(device, allrows.nbytes, C.byref(buf)))
+    try:
+        check(L.dbx_memcpy_h2d(device, buf, allrows.ctypes.data, allrows.nbytes))
+        final.merge_rows(buf.value, world)
+        out = final.on_finish(out_mem)
+    finally:
+        check(L.dbx_device_free(device, buf))
+    return out[0]

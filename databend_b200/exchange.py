@@ -112,6 +112,12 @@ class PeerExchange:
     def merge(self, final):
         self._check(load().dbx_agg_exchange_merge(self._h, final.handle))
 
+    def phase_ms(self) -> dict:
+        """Device times (ms) of the last scatter / wait / merge / finalize (call after the final's on_finish)."""
+        out = (C.c_float * 8)()
+        self._check(load().dbx_agg_exchange_phase_ms(self._h, out))
+        return {"scatter": out[0], "wait_flags": out[1], "merge": out[2], "finalize": out[3], "wait_spin": out[4]}
+
     def close(self):
         if self._h:
             load().dbx_agg_exchange_destroy(self._h)

@@ -82,6 +82,9 @@ def load():
         "dbx_kernel_launch_count": (i64, []),
         "dbx_op_last_kernel_ms": (i32, [vp, P(C.c_float)]),
         "dbx_op_stream": (i32, [vp, P(vp)]),
+        "dbx_op_kernel_ms": (i32, [vp, i32, P(C.c_float)]),
+        "dbx_op_inputs_consumed": (i32, [vp]),
+        "dbx_agg_exchange_phase_ms": (i32, [vp, P(C.c_float)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError = the library does not export a declared symbol

@@ -159,6 +159,16 @@ class _Op:
         check(load().dbx_op_last_kernel_ms(self._h, C.byref(ms)), self._h)
         return ms.value
 
+    def kernel_ms(self, back: int = 0) -> float:
+        """Device time of the dominant kernel(s) of an earlier push (0 = last, 1 = the one before ...)."""
+        ms = C.c_float(0)
+        check(load().dbx_op_kernel_ms(self._h, back, C.byref(ms)), self._h)
+        return ms.value
+
+    def inputs_consumed(self):
+        """Block until every pushed block has been read completely (pinned/device inputs may be reused)."""
+        check(load().dbx_op_inputs_consumed(self._h), self._h)
+
     def close(self):
         if self._h:
             load().dbx_op_destroy(self._h)

@@ -28,7 +28,11 @@
  *     error of the failed create call).  Nothing aborts or throws across the ABI;
  *   - a handle is thread-compatible (one caller at a time, may migrate between
  *     threads), distinct handles are fully concurrent: each owns one CUDA stream;
- *   - input blocks are borrowed for the duration of the call only;
+ *   - input blocks are borrowed until the operator has consumed them.  Pageable host memory is
+ *     consumed before push returns.  PINNED host memory (dbx_host_alloc / dbx_host_register) and
+ *     DEVICE memory are read asynchronously on the handle's stream: the caller must not modify or
+ *     recycle those buffers before dbx_op_inputs_consumed(op) (or any later dbx_op_finish /
+ *     dbx_op_synchronize on the handle) has returned;
  *   - output blocks are owned by the library until dbx_block_release().
  */
 #ifndef DBX_H_
@@ -257,6 +261,10 @@ int32_t dbx_block_release(dbx_block* block);
 int32_t dbx_op_reset(dbx_op* op);
 /* Block until everything enqueued on the handle's stream has completed. */
 int32_t dbx_op_synchronize(dbx_op* op);
+/* Block until every block pushed so far has been read completely (host->device copies done,
+ * kernels that read device-resident inputs finished): the point after which the caller may
+ * reuse pinned-host / device input buffers (the Arc<Buffer> of the reference can be dropped). */
+int32_t dbx_op_inputs_consumed(dbx_op* op);
 
 /* Join probe side: Join::probe_block(block) -> JoinStream::next()* ; output blocks are
  * pulled with dbx_op_pull until drained.  Join::final_probe is a no-op for inner joins. */
@@ -293,6 +301,11 @@ int32_t dbx_agg_exchange_connect(dbx_agg_exchange* x, const void* all_handles /*
                                  void* const* same_process_ptrs /* or the buffers themselves */);
 int32_t dbx_agg_exchange_scatter(dbx_agg_exchange* x, dbx_op* partial_op);
 int32_t dbx_agg_exchange_merge(dbx_agg_exchange* x, dbx_op* final_op);
+/* Per-phase device times (ms, CUDA events) of the last scatter/merge pair: out8[0] scatter kernel,
+ * [1] wait for the peers' release flags, [2] merge kernel, [3] finalize (merge end -> result
+ * columns ready), [4] the wait kernel's own measure of its spin; [5..7] reserved.  Call after the
+ * final operator's finish(). */
+int32_t dbx_agg_exchange_phase_ms(dbx_agg_exchange* x, float* out8);
 int32_t dbx_agg_exchange_destroy(dbx_agg_exchange* x);
 const char* dbx_agg_exchange_last_error(const dbx_agg_exchange* x);
 
@@ -346,6 +359,9 @@ int64_t dbx_kernel_launch_count(void);
 /* Device time (ms) of the dominant kernel of the last push on this handle, measured
  * with CUDA events on the handle's stream (roofline.achieved in bench.py). */
 int32_t dbx_op_last_kernel_ms(dbx_op* op, float* ms);
+/* Same for an earlier push: back = 0 is the last push, 1 the one before, ... (a ring of 8), so
+ * the kernel of query i can be read after query i+1 was enqueued without waiting for it. */
+int32_t dbx_op_kernel_ms(dbx_op* op, int32_t back, float* ms);
 /* Stream of a handle as a cudaStream_t value (for external event timing). */
 int32_t dbx_op_stream(dbx_op* op, void** stream);
 

@@ -456,3 +456,74 @@ def test_multi_column_keys_too_wide_is_loud(gpu):
     blk = DataBlock([Column.from_data(np.arange(4, dtype=np.int64)), Column.from_data(np.arange(4, dtype=np.int64))])
     with pytest.raises(DbxError, match="128-bit"):
         TransformPartialAggregate(AggregatorParams([0, 1], [("count", None)]), schema_types(blk))
+
+
+@pytest.mark.parametrize("lanes", [None, "FFFFFFFF", "00000000", "55555555", "0000FFFF"])
+def test_ring_kernel_lane_splits(gpu, monkeypatch, lanes):
+    """The straight-line ring kernel (device-resident 8-byte columns, whole tiles): pairs of additive
+    state words updated by TMA bulk reductions on some lanes and by REDs on the others.  Every split
+    must give the oracle's result bit for bit (incl. the sentinel-valued key and a ragged tail that
+    the generic kernel finishes)."""
+    if lanes is not None:
+        monkeypatch.setenv("DBX_AGG_BULK_LANES", lanes)
+    blk = config2_block(3_000_017, n_keys=70_000)
+    blk.columns[0].data[:5] = -(2**63)
+    run_both(blk, CONFIG2, V_MOD3, device_resident=True)
+
+
+def test_ring_kernel_two_pairs_and_minmax(gpu):
+    """sum(v), count(*), sum(x), avg(x2), min(v), max(x) over device columns: two pairs (integer and
+    f64) go through the bulk path, min/max and the leftovers through REDs."""
+    rng = np.random.default_rng(3)
+    n = 1_500_000
+    k = rng.integers(0, 20_000, n).astype(np.int64)
+    v = rng.integers(-2**40, 2**40, n).astype(np.int64)
+    x = rng.integers(0, 1 << 20, n).astype(np.float64)
+    x2 = rng.integers(0, 1 << 18, n).astype(np.float64)
+    blk = DataBlock([Column.from_data(k), Column.from_data(v), Column.from_data(x), Column.from_data(x2)])
+    params = AggregatorParams([0], [("sum", 1), ("count", None), ("sum", 2), ("avg", 3), ("min", 1), ("max", 2)])
+    run_both(blk, params, E.ne(E.col(1) % E.lit(7), E.lit(0)), device_resident=True)
+    run_both(blk, params, None, device_resident=True, split=400_000, n_partials=2)
+
+
+def test_pairs_layout_off_matches(gpu, monkeypatch):
+    monkeypatch.setenv("DBX_AGG_BULK", "0")
+    run_both(config2_block(1_200_000, n_keys=30_000), CONFIG2, V_MOD3, device_resident=True)
+
+
+def test_full_size_query_verified(gpu):
+    """BASELINE.json configs[1] at its full size (1e9 rows, 1e6 keys; a quarter of it if HBM is
+    short): EVERY group of the result against an independent recomputation of the query (torch
+    bincount / index_add_ over all rows) and the CPU oracle on every row of a key subsample —
+    the check bench.py runs outside its timed region."""
+    import ctypes as C
+    import sys
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
+    import bench
+    from databend_b200 import lib
+    from databend_b200.transforms import DeviceBuffer
+    L = lib.load()
+    free, _total = torch.cuda.mem_get_info(0)
+    n = 1_000_000_000 if free > 60e9 else 250_000_000
+    n_keys = 1_000_000
+    bufs = [DeviceBuffer(n * 8, 0) for _ in range(3)]
+    lib.check(L.dbx_synth_fill(0, 0, bench.SEEDS[0], n_keys, 0, n, bufs[0].ptr))
+    lib.check(L.dbx_synth_fill(0, 1, bench.SEEDS[1], 0, 0, n, bufs[1].ptr))
+    lib.check(L.dbx_synth_fill(0, 2, bench.SEEDS[2], 20, 0, n, bufs[2].ptr))
+    blk = DataBlock([Column.device(abi.I64, n, bufs[0].ptr), Column.device(abi.I64, n, bufs[1].ptr),
+                     Column.device(abi.F64, n, bufs[2].ptr)], n)
+    types = [abi.I64, abi.I64, abi.F64]
+    part = TransformPartialAggregate(CONFIG2, types, V_MOD3)
+    fin = TransformFinalAggregate(CONFIG2, types)
+    part.transform(blk)
+    fin.transform(part.on_finish())
+    out = fin.on_finish()[0]
+    v = bench.verify_result(out, 0, 0, 1, [b.ptr for b in bufs], n, n_keys, torch, dist)
+    part.close(); fin.close()
+    for b in bufs:
+        b.free()
+    assert v["ok"], v
+    assert v["groups"] == v["expected_groups"] == n_keys
+    assert v["oracle_subsample"]["bit_exact"]
