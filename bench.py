@@ -37,7 +37,7 @@ METRIC = "rows/sec filter->hash-agg (sum,count,avg GROUP BY 1e6 int64 keys) over
 SEEDS = (42, 43, 44)
 N_KEYS = 1_000_000
 BYTES_PER_ROW = 24.0  # three 8-byte columns, each read exactly once
-KERNEL_NAME = "filter_group_agg_ring_kernel<3>"
+KERNEL_NAME = "filter_group_agg_kernel<3,FAST=1,INDIRECT=0,BULK=0>"
 
 
 def ncu_traffic():
@@ -297,7 +297,7 @@ def verify_result(out_block, dev, rank, world, cols, n, keys_total, torch, dist)
         class _Holder:
             pass
         h = _Holder()
-        h.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8" if dtype == torch.int64 else "<f8", "data": (ptr, True), "version": 2}
+        h.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8" if dtype == torch.int64 else "<f8", "data": (ptr, False), "version": 2}
         return torch.as_tensor(h, device=f"cuda:{dev}")
 
     k_t, v_t, x_t = dev_tensor(kd, torch.int64), dev_tensor(vd, torch.int64), dev_tensor(xd, torch.float64)

@@ -142,4 +142,7 @@ EXPORTS = [
     "dbx_eval_distance", "dbx_knn_create", "dbx_knn_search", "dbx_knn_destroy", "dbx_knn_last_error", "dbx_knn_last_gemm_ms", "dbx_knn_last_stats",
     "dbx_synth_fill", "dbx_kernel_launch_count", "dbx_op_last_kernel_ms", "dbx_op_kernel_ms", "dbx_op_stream",
     "dbx_op_inputs_consumed", "dbx_agg_exchange_phase_ms",
+    "dbx_shuffle_create", "dbx_shuffle_local_buffer", "dbx_shuffle_connect", "dbx_shuffle_send", "dbx_shuffle_recv", "dbx_shuffle_last_ms",
+    "dbx_shuffle_destroy", "dbx_shuffle_last_error",
+    "dbx_block_take", "dbx_block_take_ranges", "dbx_block_scatter", "dbx_block_concat",
 ]

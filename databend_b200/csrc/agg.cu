@@ -52,6 +52,7 @@ struct AggPlan {
   bool grouped = false;
   int key_slot = -1, key_dtype = -1;
   bool key_nullable = false;
+  bool key_is_float = false;
   int n_key_parts = 0;  // > 1: packed multi-column key
   KeyPartDev key_parts[DBX_MAX_GROUP_COLS];
 
@@ -300,7 +301,8 @@ int32_t build_plan(const dbx_agg_params* p, const int32_t* types, int32_t n_cols
     int kc = p->group_cols[0];
     if (kc < 0 || kc >= n_cols) { err->set("group column outside the input schema"); return DBX_ERR_INVALID; }
     int dt = pl->col_dtype[kc];
-    if (dtype_class(dt) == VC_FLT || dt == DBX_BOOL || dtype_size(dt) == 0) { err->set("GROUP BY key must be an integer column (float/bool keys not built yet)"); return DBX_ERR_UNSUPPORTED; }
+    if (dt == DBX_BOOL || dtype_size(dt) == 0) { err->set("GROUP BY key must be a numeric column (bool/string keys not built yet)"); return DBX_ERR_UNSUPPORTED; }
+    pl->key_is_float = dtype_class(dt) == VC_FLT;
     pl->key_slot = pl->slot_of(kc, err);
     if (pl->key_slot < 0) return DBX_ERR_UNSUPPORTED;
     pl->key_dtype = dt;
@@ -377,9 +379,14 @@ int32_t build_plan(const dbx_agg_params* p, const int32_t* types, int32_t n_cols
   // bound by L2 atomic operations per row, not by bytes).
   for (int w = 0; w < kMaxWords; ++w) { pl->w_pair[w] = -1; pl->w_pos[w] = 0; }
   pl->n_pairs = 0;
-  // (DBX_AGG_BULK=0 turns pairing off: every word is then updated by its own RED)
+  // Measured on B200 (profiles/r02_agg_lane_sweep.txt): the TMA bulk-reduction path does NOT lift
+  // the bound — a 16-byte bulk reduction is split into two 8-byte L2 atomic operations, and the L2
+  // atomic units (~157 G op/s chip-wide) are what the kernel is bound by; every lane split between
+  // TMA and REDs lands on the same 8.05 ms as the plain RED kernel (7.92 ms with the L2 window).
+  // The pair layout and the ring kernel therefore stay opt-in (DBX_AGG_BULK=1) as a documented
+  // negative result; the default is one RED per state word.
   const char* bulk_env = getenv("DBX_AGG_BULK");
-  if (pl->grouped && !(bulk_env && atoi(bulk_env) == 0)) {
+  if (pl->grouped && bulk_env && atoi(bulk_env) != 0) {
     for (int cls = 0; cls < 2 && pl->n_pairs < kMaxPairs; ++cls) {
       int pending = -1;
       for (int u = 0; u < pl->n_updates && pl->n_pairs < kMaxPairs; ++u) {
@@ -500,49 +507,6 @@ inline int64_t next_pow2(int64_t x) {
   return p;
 }
 
-// Hand a finished device-resident result to the caller: as is (device), or copied into pinned
-// host memory (zero-copy wrappable by the caller, released through dbx_block_release).
-// BOOL columns hold packed bits (like validity).
-int32_t pull_owned_block(std::unique_ptr<OwnedBlock>& result_dev, int device, cudaStream_t stream, ErrorSink& err, int32_t out_mem,
-                         dbx_block* out) {
-  if (out_mem == DBX_MEM_DEVICE) {
-    DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
-    OwnedBlock* ob = result_dev.release();
-    return fill_owned_block(ob, out);
-  }
-  auto hb = std::make_unique<OwnedBlock>();
-  hb->device = device;
-  for (const dbx_column& dc : result_dev->cols) {
-    dbx_column c = dc;
-    c.mem = DBX_MEM_HOST;
-    if (dc.is_const) { hb->cols.push_back(c); continue; }
-    size_t bytes = dc.dtype == DBX_BOOL ? (size_t)(dc.len + 7) / 8 : (size_t)dc.len * dtype_size(dc.dtype);
-    void* hp = nullptr;
-    DBX_CUDA_TRY(err, pinned_alloc(bytes, &hp));
-    hb->host_allocs.push_back(hp);
-    if (bytes) DBX_CUDA_TRY(err, cudaMemcpyAsync(hp, dc.data, bytes, cudaMemcpyDeviceToHost, stream));
-    c.data = hp;
-    if (dc.validity) {
-      size_t vb = (size_t)(dc.len + 7) / 8;
-      void* hv = nullptr;
-      DBX_CUDA_TRY(err, pinned_alloc(vb, &hv));
-      hb->host_allocs.push_back(hv);
-      if (vb) DBX_CUDA_TRY(err, cudaMemcpyAsync(hv, dc.validity, vb, cudaMemcpyDeviceToHost, stream));
-      c.validity = (const uint8_t*)hv;
-    }
-    hb->cols.push_back(c);
-  }
-  DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
-  for (dbx_column& c : hb->cols) {
-    if (!c.validity) continue;
-    int64_t nulls = 0;
-    for (int64_t i = 0; i < c.len; ++i) nulls += !((c.validity[i >> 3] >> (i & 7)) & 1);
-    c.null_count = nulls;
-  }
-  result_dev.reset();
-  return fill_owned_block(hb.release(), out);
-}
-
 }  // namespace
 
 // ================================================================ partial
@@ -629,6 +593,7 @@ class AggPartialOp : public Op {
   }
 
   int32_t reset() override {
+    if (batch_open) { batch_open = false; batch_rows = 0; DBX_TRY(stager.end()); }
     table_ready = false;
     DBX_TRY(ensure_table());
     groups_known = plan.grouped ? 0 : 1;
@@ -795,6 +760,7 @@ class AggPartialOp : public Op {
     kp->n_updates = plan.n_updates;
     kp->key_slot = plan.key_slot;
     kp->key_nullable = plan.key_nullable;
+    kp->key_is_float = plan.key_is_float ? 1 : 0;
     kp->n_key_parts = plan.n_key_parts;
     memcpy(kp->key_parts, plan.key_parts, sizeof(plan.key_parts));
     kp->n_pairs = plan.n_pairs;
@@ -828,11 +794,53 @@ class AggPartialOp : public Op {
     }
     DBX_TRY(ensure_table());
     table_clean = false;
+    // Small host blocks (the reference pushes 65 536-row DataBlocks, settings_default.rs:142) are
+    // coalesced: their columns are DMA'd back to back into one staging generation and the fused
+    // kernel runs once per ~4 Mi rows instead of once per block.
+    if (batchable(b)) {
+      if (batch_open && batch_rows + n > kBatchCapRows) DBX_TRY(flush_batch());
+      if (!batch_open) { DBX_TRY(stager.begin()); batch_open = true; batch_rows = 0; }
+      for (int s = 0; s < plan.n_slots; ++s) DBX_TRY(stager.stage_at(b->cols[plan.slot_col[s]], s, batch_rows, kBatchCapRows, &batch_cols[s]));
+      batch_rows += n;
+      rows_in += n;
+      return DBX_OK;
+    }
+    DBX_TRY(flush_batch());
     DevCol cols[kMaxSlots];
     DBX_TRY(stager.begin());
     for (int s = 0; s < plan.n_slots; ++s) DBX_TRY(stager.stage(b->cols[plan.slot_col[s]], s, &cols[s]));
     rows_in += n;
+    DBX_TRY(process_rows(cols, n));
+    DBX_TRY(stager.end());
+    return DBX_OK;
+  }
 
+  // ---- coalescing of small pushes
+  static constexpr int64_t kBatchCapRows = 4 << 20;
+  static constexpr int64_t kBatchMaxBlockRows = 1 << 20;
+  bool batch_open = false;
+  int64_t batch_rows = 0;
+  DevCol batch_cols[kMaxSlots];
+  bool batchable(const dbx_block* b) const {
+    if (no_batching || b->num_rows > kBatchMaxBlockRows) return false;
+    for (int s = 0; s < plan.n_slots; ++s) {
+      const dbx_column& c = b->cols[plan.slot_col[s]];
+      if (c.mem != DBX_MEM_HOST || c.is_const || c.validity || c.dtype == DBX_BOOL) return false;
+    }
+    return true;
+  }
+  int32_t flush_batch() {
+    if (!batch_open) return DBX_OK;
+    batch_open = false;
+    if (batch_rows > 0) DBX_TRY(process_rows(batch_cols, batch_rows));
+    batch_rows = 0;
+    DBX_TRY(stager.end());
+    return DBX_OK;
+  }
+  bool no_batching = getenv("DBX_AGG_NO_BATCH") != nullptr;
+
+  // the fused kernel(s) over n rows whose needed columns are on the device
+  int32_t process_rows(const DevCol* cols, int64_t n) {
     DBX_TRY(timing_begin());
     for (int64_t row0 = 0; row0 < n; row0 += kChunkRows) {
       const int64_t m = std::min(kChunkRows, n - row0);
@@ -876,11 +884,10 @@ class AggPartialOp : public Op {
       if ((int64_t)ng * 2 > table.cap) DBX_TRY(grow_to(next_pow2(4 * (int64_t)ng)));
     }
     DBX_TRY(timing_end());
-    DBX_TRY(stager.end());
     return DBX_OK;
   }
 
-  int32_t finish() override { return DBX_OK; }
+  int32_t finish() override { return flush_batch(); }
 
   // The partial emits one metadata-only block (AggregateMeta::AggregatePayload): the payload
   // stays in HBM and is referenced through block.meta.
@@ -896,6 +903,7 @@ class AggPartialOp : public Op {
 
   int32_t exact_groups(int64_t* n) {
     unsigned long long ng, no;
+    DBX_TRY(flush_batch());
     DBX_TRY(ensure_table());
     DBX_TRY(read_counters(&ng, &no));
     if (no) { err.set("internal: rows were dropped by the partial table (overflow in safe mode)"); return DBX_ERR_CUDA; }
@@ -987,7 +995,8 @@ class AggFinalOp : public Op {
       return DBX_ERR_INVALID;
     }
     {
-      int32_t st = part->ensure_table();
+      int32_t st = part->flush_batch();
+      if (st == DBX_OK) st = part->ensure_table();
       if (st != DBX_OK) { err.set(part->err.msg); return st; }
     }
     DBX_CUDA_TRY(err, cudaStreamSynchronize(part->stream));  // partial's kernels precede the merge
@@ -1406,6 +1415,7 @@ int32_t dbx_agg_partial_partition(dbx_op* partial_op, int32_t n_parts, void** de
   if (o->kind != DBX_OP_AGG_PARTIAL) { o->err.set("partition: not a partial aggregate operator"); return DBX_ERR_INVALID; }
   AggPartialOp* p = static_cast<AggPartialOp*>(o);
   DBX_CUDA_TRY(p->err, cudaSetDevice(p->device));
+  DBX_TRY(p->flush_batch());
   DevBuf counts;
   DBX_CUDA_TRY(p->err, counts.ensure((size_t)n_parts * 8));
   DBX_CUDA_TRY(p->err, cudaMemsetAsync(counts.p, 0, (size_t)n_parts * 8, p->stream));
@@ -1542,7 +1552,7 @@ int32_t dbx_agg_exchange_scatter(dbx_agg_exchange* x, dbx_op* partial_op) {
   if (!x->connected) { x->err.set("exchange: scatter before connect"); return DBX_ERR_STATE; }
   AggPartialOp* p = static_cast<AggPartialOp*>(reinterpret_cast<Op*>(partial_op));
   DBX_CUDA_TRY(x->err, cudaSetDevice(x->device));
-  { int32_t st = p->ensure_table(); if (st != DBX_OK) { x->err.set(p->err.msg); return st; } }
+  { int32_t st = p->flush_batch(); if (st == DBX_OK) st = p->ensure_table(); if (st != DBX_OK) { x->err.set(p->err.msg); return st; } }
   if (2 + p->plan.n_words != x->row_words) { x->err.set("exchange: operator state layout differs from the exchange's"); return DBX_ERR_INVALID; }
   x->epoch += 1;
   // region reuse: this rank's merge of the previous epoch must precede the scatter that lets peers move on

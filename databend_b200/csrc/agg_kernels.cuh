@@ -237,6 +237,14 @@ __device__ __forceinline__ uint32_t eval_predicate(const AggKernelParams& p, con
   return sel & in_range;
 }
 
+// Float group keys (group_hash.rs:599-619, payload_row.rs match_column_type on OrderedFloat): rows
+// group by the value's bit pattern, except that every NaN is ONE group (canonical NaN); -0.0 and
+// +0.0 hash differently in the reference and are separate groups here too.
+__device__ __forceinline__ uint64_t canonical_float_key(uint64_t bits) {
+  const double d = __longlong_as_double((long long)bits);
+  return d != d ? 0x7FF8000000000000ULL : bits;
+}
+
 // ---------------------------------------------------------------- table
 // 256-bit coherent load of one bucket (4 keys): goes to L2, the point of coherence of the CAS.
 __device__ __forceinline__ u64x4 ld_bucket(const uint64_t* p) {
@@ -351,6 +359,7 @@ __device__ __forceinline__ void table_phase32(const AggKernelParams& p, const St
       }
     } else {
       key = sw.val[p.key_slot][i];
+      if (p.key_is_float) key = canonical_float_key(key);
       key_null = !((vm >> p.key_slot) & 1);
     }
   }
@@ -534,6 +543,7 @@ __device__ __forceinline__ void ring_table_phase(const AggKernelParams& p, const
       }
     } else {
       key = val_base[p.ring_sidx[p.key_slot] * kRingCap + pos];
+      if (p.key_is_float) key = canonical_float_key(key);
     }
   }
   const bool special = key == kEmptyKey;

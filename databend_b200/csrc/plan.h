@@ -171,7 +171,7 @@ struct AggKernelParams {
   int32_t key_slot;     // -1: no GROUP BY
   int32_t key_nullable; // key column may carry a validity bitmap
   int32_t n_key_parts;  // > 1: the key is packed from key_parts[] (key_slot is unused)
-  int32_t pad3;
+  int32_t key_is_float; // 1: the (single) key is a float column: every NaN is one group (group_hash.rs:599-619)
   uint32_t row_base;    // added to in-launch row numbers when recording overflow rows
   int32_t n_pairs;      // > 0: paired words go through TMA bulk reductions
   uint32_t bulk_lanes;  // lanes (bit mask) that use the bulk path; the others use REDs for the paired words too

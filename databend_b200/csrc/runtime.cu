@@ -148,6 +148,27 @@ int32_t Stager::stage(const dbx_column& c, int slot, DevCol* out) {
   }
   return DBX_OK;
 }
+// Append `c` (a HOST column without validity) at row `row_off` of the generation's buffer for `slot`;
+// the buffer holds `cap_rows` rows.  `out->data` is the buffer base (rows [0, row_off + c.len) valid).
+int32_t Stager::stage_at(const dbx_column& c, int slot, int64_t row_off, int64_t cap_rows, DevCol* out) {
+  Gen& g = gens_[cur_];
+  const int esz = dtype_size(c.dtype);
+  if (esz == 0 || c.is_const || c.validity || c.mem != DBX_MEM_HOST || row_off + c.len > cap_rows) {
+    err_->set("internal: stage_at on a column that cannot be coalesced");
+    return DBX_ERR_INVALID;
+  }
+  if ((int)g.data.size() <= slot) { g.data.resize(slot + 1); g.validity.resize(slot + 1); }
+  if (g.data[slot].bytes < (size_t)cap_rows * esz) {
+    if (row_off != 0) { err_->set("internal: staging buffer too small in the middle of a batch"); return DBX_ERR_INVALID; }
+    DBX_CUDA_TRY(*err_, g.data[slot].ensure((size_t)cap_rows * esz));
+  }
+  if (c.len) DBX_CUDA_TRY(*err_, cudaMemcpyAsync((char*)g.data[slot].p + (size_t)row_off * esz, c.data, (size_t)c.len * esz, cudaMemcpyHostToDevice, stream_));
+  h2d_bytes += (size_t)c.len * esz;
+  memset(out, 0, sizeof(*out));
+  out->dtype = c.dtype;
+  out->data = g.data[slot].p;
+  return DBX_OK;
+}
 int32_t Stager::end() {
   Gen& g = gens_[cur_];
   DBX_CUDA_TRY(*err_, cudaEventRecord(g.done, stream_));
@@ -190,6 +211,51 @@ int32_t fill_owned_block(OwnedBlock* ob, dbx_block* out) {
   out->reserved = 0;
   return DBX_OK;
 }
+
+// Hand a finished device-resident result to the caller: as is (device), or copied into pinned
+// host memory (zero-copy wrappable by the caller, released through dbx_block_release).
+// BOOL columns hold packed bits (like validity).
+int32_t pull_owned_block(std::unique_ptr<OwnedBlock>& result_dev, int device, cudaStream_t stream, ErrorSink& err, int32_t out_mem,
+                         dbx_block* out) {
+  if (out_mem == DBX_MEM_DEVICE) {
+    DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
+    OwnedBlock* ob = result_dev.release();
+    return fill_owned_block(ob, out);
+  }
+  auto hb = std::make_unique<OwnedBlock>();
+  hb->device = device;
+  for (const dbx_column& dc : result_dev->cols) {
+    dbx_column c = dc;
+    c.mem = DBX_MEM_HOST;
+    if (dc.is_const) { hb->cols.push_back(c); continue; }
+    size_t bytes = dc.dtype == DBX_BOOL ? (size_t)(dc.data_bit_offset + dc.len + 7) / 8
+                 : dc.dtype == DBX_VEC_F32 ? (size_t)dc.len * 4 * dc.vec_dim : (size_t)dc.len * dtype_size(dc.dtype);
+    void* hp = nullptr;
+    DBX_CUDA_TRY(err, pinned_alloc(bytes, &hp));
+    hb->host_allocs.push_back(hp);
+    if (bytes) DBX_CUDA_TRY(err, cudaMemcpyAsync(hp, dc.data, bytes, cudaMemcpyDeviceToHost, stream));
+    c.data = hp;
+    if (dc.validity) {
+      size_t vb = (size_t)(dc.len + 7) / 8;
+      void* hv = nullptr;
+      DBX_CUDA_TRY(err, pinned_alloc(vb, &hv));
+      hb->host_allocs.push_back(hv);
+      if (vb) DBX_CUDA_TRY(err, cudaMemcpyAsync(hv, dc.validity, vb, cudaMemcpyDeviceToHost, stream));
+      c.validity = (const uint8_t*)hv;
+    }
+    hb->cols.push_back(c);
+  }
+  DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
+  for (dbx_column& c : hb->cols) {
+    if (!c.validity) continue;
+    int64_t nulls = 0;
+    for (int64_t i = 0; i < c.len; ++i) nulls += !((c.validity[i >> 3] >> (i & 7)) & 1);
+    c.null_count = nulls;
+  }
+  result_dev.reset();
+  return fill_owned_block(hb.release(), out);
+}
+
 
 // factories implemented next to each operator
 Op* make_agg_partial_op(const dbx_agg_params* p, const int32_t* types, int32_t n, int device, int32_t* st);

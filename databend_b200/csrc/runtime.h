@@ -85,6 +85,8 @@ class Stager {
   // Make column `c` of the pushed block available on the device (copying if it lives on the
   // host) and describe it as a DevCol.  `slot` indexes the per-generation buffers.
   int32_t stage(const dbx_column& c, int slot, DevCol* out);
+  // Coalescing of small host blocks: append the column at row `row_off` of a `cap_rows`-row buffer.
+  int32_t stage_at(const dbx_column& c, int slot, int64_t row_off, int64_t cap_rows, DevCol* out);
   // Record that all kernels consuming this generation have been enqueued.
   int32_t end();
   int64_t h2d_bytes = 0;  // instrumentation
@@ -147,6 +149,10 @@ inline uint64_t scalar_bits(const dbx_scalar& s, int as_class) {
 }
 
 int32_t fill_owned_block(OwnedBlock* ob, dbx_block* out);
+// Hand a finished device-resident block to the caller: as is (device), or copied into pinned host
+// memory (zero-copy wrappable by the caller, released through dbx_block_release).
+int32_t pull_owned_block(std::unique_ptr<OwnedBlock>& result_dev, int device, cudaStream_t stream, ErrorSink& err, int32_t out_mem,
+                         dbx_block* out);
 
 // ---- hash partitioning of device columns (partition.cu)
 constexpr int kMaxParts = 64;

@@ -1,43 +1,37 @@
-// topk.cu — DBX_OP_TOPK: `ORDER BY key [ASC|DESC] [NULLS FIRST|LAST] LIMIT k` as a streaming
-// device top-k.
+// sort.cu — DBX_OP_TOPK: `ORDER BY key [ASC|DESC] [NULLS FIRST|LAST] [LIMIT k]` on the device.
 //
 // Reference pipeline replaced (paths relative to /root/reference):
 //   TransformSortPartial (per block sort + limit)   src/query/pipeline/transforms/src/processors/transforms/sorts/sort_partial.rs:24-60
 //     DataBlock::sort_with_type / SortCompare       src/query/expression/src/kernels/sort.rs:91-111, sort_compare.rs:197-296
-//   limit-aware merge                               sorts/sort_merge*.rs, sorts/core/merger.rs
+//   limit-aware k-way merge                         sorts/sort_merge*.rs, sorts/core/{merger,loser_tree}.rs
 //   fused TopN with a runtime boundary filter       src/query/service/src/pipelines/processors/transforms/top_n/transform_partial_top_n.rs:73-130
 //
-// B200 design: the column is read ONCE (8 B/row, 256-bit streaming loads).  Each key is mapped
-// to an order-preserving u64 (OrderedFloat order: NaN greatest, -0 == +0,
-// src/common/base/src/base/ordered_float.rs:147-201); a row survives only if it beats the
-// current boundary (the k-th best key so far — the reference's TopN boundary filter), and
-// survivors are appended to a small candidate list with one warp-aggregated atomic.  The
-// candidate list is periodically cut back to k (radix sort, tiny), tightening the boundary.
-// Ties are broken by ascending row id, as in the oracle.
-#include <cub/device/device_radix_sort.cuh>
-
+// Every key is mapped to an order-preserving u64 (OrderedFloat order: NaN greatest, -0 == +0,
+// src/common/base/src/base/ordered_float.rs:147-201); ties are broken by ascending row id, as in
+// the oracle.  Everything below is hand-written (no CUB):
+//
+//   LIMIT k (k <= 4 Mi)   streaming top-k: the column is read ONCE (8 B/row, 256-bit streaming
+//                         loads); a row survives only if it beats the boundary (the k-th best key
+//                         so far — the reference's TopN boundary filter), kept in DEVICE memory and
+//                         tightened by a one-CTA radix-select ("cut") kernel that runs between
+//                         scan launches.  No host synchronisation between chunks: the host only
+//                         chooses chunk sizes that provably fit the candidate list, or launches
+//                         one optimistic scan over the rest and checks an overflow flag once.
+//   no LIMIT (limit = 0)  full sort: (ordered key, row id) pairs are radix-sorted with a
+//                         onesweep-style LSD sort (one global histogram pass for all digits, then
+//                         one read+write pass per 8-bit digit with decoupled look-back between
+//                         tiles); LSD passes are stable, so equal keys stay in row order.
 #include <algorithm>
+#include <vector>
 
+#include "radix_sort.cuh"
 #include "runtime.h"
 
 namespace dbx {
 
 namespace {
 
-constexpr int kTopkBlock = 256;
-constexpr int64_t kMaxChunk = 1LL << 30;
-
-struct TopkDev {
-  uint64_t* ord;      // order-preserving image (smaller = earlier in the output)
-  uint64_t* rowid;    // global row ordinal
-  uint64_t* bits;     // original value bits (widened to 64)
-  unsigned long long* count;     // appended candidates
-  unsigned long long* n_null;    // NULL rows seen
-  uint64_t* null_rowid;          // first rows with NULL key (up to k, by append order)
-  int64_t cap;
-  int64_t k;
-};
-
+// ================================================================ key images
 __device__ __forceinline__ uint64_t key_to_ord(uint64_t bits, int cls, bool asc) {
   uint64_t o;
   if (cls == VC_FLT) {
@@ -66,27 +60,72 @@ __device__ __forceinline__ uint64_t load_widened(const DevCol& c, int64_t row, u
   }
 }
 
-// One pass over `n` rows of the key column.  boundary: only ord <= boundary can still be in
-// the top k.  FAST: 8-byte column, 32 B aligned, no validity -> one 256-bit load per 4 rows.
+__device__ __forceinline__ void store_narrow_key(void* out, int64_t i, int dtype, uint64_t b) {
+  switch (dtype) {
+    case DBX_I8: case DBX_U8: ((uint8_t*)out)[i] = (uint8_t)b; break;
+    case DBX_I16: case DBX_U16: ((uint16_t*)out)[i] = (uint16_t)b; break;
+    case DBX_I32: case DBX_U32: ((uint32_t*)out)[i] = (uint32_t)b; break;
+    case DBX_F32: ((float*)out)[i] = (float)__longlong_as_double((long long)b); break;
+    default: ((uint64_t*)out)[i] = b; break;
+  }
+}
+
+inline int grid_1d(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)kNumSMs * 8)); }
+
+// (the radix sort lives in radix_sort.cuh)
+// ================================================================ streaming top-k
+// Device state words of one candidate list
+enum : int { ST_COUNT = 0, ST_BOUND = 1, ST_OVERFLOW = 2, ST_WORDS = 4 };
+
+struct CandList {
+  uint64_t* ord;    // order-preserving image (nullptr: list keyed by row id only — the NULL rows)
+  uint64_t* rowid;  // global row ordinal
+  uint64_t* bits;   // original value bits (nullptr for the NULL list)
+  unsigned long long* state;  // [ST_WORDS]
+  int64_t cap;
+};
+
+__device__ __forceinline__ void cand_append_warp(const CandList& l, bool keep, uint64_t o, uint64_t rid, uint64_t b, int lane) {
+  const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+  if (!bal) return;
+  unsigned long long base = 0;
+  if (lane == __ffs(bal) - 1) base = atomicAdd(&l.state[ST_COUNT], (unsigned long long)__popc(bal));
+  base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+  if (keep) {
+    const unsigned long long pos = base + __popc(bal & ((1u << lane) - 1));
+    if ((int64_t)pos < l.cap) {
+      if (l.ord) l.ord[pos] = o;
+      l.rowid[pos] = rid;
+      if (l.bits) l.bits[pos] = b;
+    } else {
+      l.state[ST_OVERFLOW] = 1;  // never silently: the host replays the chunk in pieces that fit
+    }
+  }
+}
+
+// One pass over `n` rows of the key column.  Only ord <= boundary (read from device memory) can
+// still be in the top k.  FAST: 8-byte column, 32 B aligned, no validity -> one 256-bit load per 4 rows.
 template <bool FAST>
-__global__ void __launch_bounds__(kTopkBlock) topk_scan_kernel(const __grid_constant__ DevCol col, int64_t n,
-                                                               int64_t row_base, int cls, int asc, uint64_t boundary,
-                                                               const __grid_constant__ TopkDev t) {
+__global__ void __launch_bounds__(256) topk_scan_kernel(const __grid_constant__ DevCol col, int64_t n, int64_t row_base, int cls,
+                                                        int asc, const __grid_constant__ CandList cand,
+                                                        const __grid_constant__ CandList nulls) {
   const uint64_t pol = make_policy_evict_first();
   const int lane = threadIdx.x & 31;
-  const int64_t n_tiles = (n + kTopkBlock * 4 - 1) / (kTopkBlock * 4);
+  const uint64_t boundary = cand.state[ST_BOUND];
+  const uint64_t null_boundary = nulls.rowid ? nulls.state[ST_BOUND] : 0;
+  const int64_t n_tiles = (n + 1023) / 1024;
   u64x4 next_q;
   next_q.x = next_q.y = next_q.z = next_q.w = 0;
   bool have_next = false;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     __syncwarp();
-    const int64_t r0 = tile * (kTopkBlock * 4) + 4 * (int64_t)threadIdx.x;
+    const int64_t r0 = tile * 1024 + 4 * (int64_t)threadIdx.x;
     uint64_t v[4];
     uint32_t valid = 0, inr = 0;
     if (FAST && r0 + 4 <= n) {
       u64x4 q = have_next ? next_q : ld_stream_256((const char*)col.data + r0 * 8);
       // keep a second tile in flight: one 32-byte load per thread does not cover the HBM latency
-      const int64_t rn = (tile + gridDim.x) * (kTopkBlock * 4) + 4 * (int64_t)threadIdx.x;
+      const int64_t rn = (tile + gridDim.x) * 1024 + 4 * (int64_t)threadIdx.x;
       have_next = tile + gridDim.x < n_tiles && rn + 4 <= n;
       if (have_next) next_q = ld_stream_256((const char*)col.data + rn * 8);
       v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
@@ -107,59 +146,226 @@ __global__ void __launch_bounds__(kTopkBlock) topk_scan_kernel(const __grid_cons
     for (int j = 0; j < 4; ++j) {
       const bool in = (inr >> j) & 1, ok = (valid >> j) & 1;
       const uint64_t o = key_to_ord(v[j], cls, asc != 0);
-      const bool keep = in && ok && o <= boundary;
-      const bool is_null = in && !ok;
-      const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-      if (bal) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(t.count, (unsigned long long)__popc(bal));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (keep) {
-          unsigned long long pos = base + __popc(bal & ((1u << lane) - 1));
-          if ((int64_t)pos < t.cap) {
-            t.ord[pos] = o;
-            t.rowid[pos] = (uint64_t)(row_base + r0 + j);
-            t.bits[pos] = v[j];
-          }
-        }
-      }
-      const uint32_t nb = __ballot_sync(0xffffffffu, is_null);
-      if (nb) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(t.n_null, (unsigned long long)__popc(nb));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (is_null) {
-          unsigned long long pos = base + __popc(nb & ((1u << lane) - 1));
-          if ((int64_t)pos < t.k) t.null_rowid[pos] = (uint64_t)(row_base + r0 + j);
-        }
-      }
+      const uint64_t rid = (uint64_t)(row_base + r0 + j);
+      cand_append_warp(cand, in && ok && o <= boundary, o, rid, v[j], lane);
+      if (nulls.rowid) cand_append_warp(nulls, in && !ok && rid <= null_boundary, 0, rid, 0, lane);
     }
   }
 }
 
-__global__ void iota_kernel(uint32_t* p, int64_t n) {
+// Radix select inside ONE CTA: keep the k smallest entries of a candidate list under the
+// (ord, rowid) order, compact them to the front and publish the new boundary (the k-th entry's
+// ord; for the NULL list its row id).  MSD passes over 8-bit digits of the 128-bit key only build
+// a 256-bin histogram of the entries that still match the prefix found so far; the loop ends as
+// soon as the bucket that contains the k-th entry is taken whole.  Does nothing when the list
+// holds <= threshold entries.
+struct CutArgs {
+  CandList l;
+  uint64_t* alt_ord;    // [k] scratch
+  uint64_t* alt_rowid;
+  uint64_t* alt_bits;
+  int64_t k;
+  int64_t threshold;
+};
+__global__ void __launch_bounds__(1024) topk_cut_kernel(const __grid_constant__ CutArgs a) {
+  __shared__ unsigned int s_hist[256];
+  __shared__ unsigned int s_b, s_cum, s_c, s_out;
+  const CandList& l = a.l;
+  const int64_t cnt = (int64_t)l.state[ST_COUNT];
+  const int64_t n = cnt < l.cap ? cnt : l.cap;
+  if (n <= a.threshold || n <= a.k) return;
+  const int tid = threadIdx.x, lane = tid & 31;
+  uint64_t th_hi = 0, th_lo = 0;  // prefix of the threshold key (ord, rowid)
+  int64_t k_rem = a.k;
+  bool closed = false;
+  for (int p = l.ord ? 0 : 8; p < 16 && !closed; ++p) {
+    if (tid < 256) s_hist[tid] = 0;
+    __syncthreads();
+    const int sh = 56 - 8 * (p & 7);
+    for (int64_t i0 = tid - lane; i0 < n; i0 += 1024) {
+      const int64_t i = i0 + lane;
+      bool m = i < n;
+      int d = 0;
+      if (m) {
+        const uint64_t o = l.ord ? l.ord[i] : 0, r = l.rowid[i];
+        if (p < 8) {
+          m = p == 0 || (o >> (sh + 8)) == (th_hi >> (sh + 8));
+          d = (int)((o >> sh) & 255);
+        } else {
+          m = o == th_hi && (p == 8 || (r >> (sh + 8)) == (th_lo >> (sh + 8)));
+          d = (int)((r >> sh) & 255);
+        }
+      }
+      const unsigned peers = __match_any_sync(0xffffffffu, m ? d : 256 + lane);
+      if (m && lane == __ffs(peers) - 1) atomicAdd(&s_hist[d], (unsigned)__popc(peers));
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned int cum = 0;
+      int b = 0;
+      for (; b < 255; ++b) {
+        if ((int64_t)cum + s_hist[b] >= k_rem) break;
+        cum += s_hist[b];
+      }
+      s_b = b; s_cum = cum; s_c = s_hist[b];
+    }
+    __syncthreads();
+    const uint64_t b = s_b;
+    if (p < 8) th_hi |= b << sh; else th_lo |= b << sh;
+    k_rem -= s_cum;
+    if ((int64_t)s_c == k_rem) {  // the whole bucket is in: every key with this prefix passes
+      const uint64_t low = sh ? ((1ULL << sh) - 1) : 0;
+      if (p < 8) { th_hi |= low; th_lo = ~0ULL; } else { th_lo |= low; }
+      closed = true;
+    }
+    __syncthreads();
+  }
+  // compaction of the entries <= threshold into the scratch arrays (at most k of them)
+  if (tid == 0) s_out = 0;
+  __syncthreads();
+  for (int64_t i0 = tid - lane; i0 < n; i0 += 1024) {
+    const int64_t i = i0 + lane;
+    uint64_t o = 0, r = 0;
+    bool keep = false;
+    if (i < n) {
+      o = l.ord ? l.ord[i] : 0;
+      r = l.rowid[i];
+      keep = o < th_hi || (o == th_hi && r <= th_lo);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (!bal) continue;
+    unsigned int base = 0;
+    if (lane == __ffs(bal) - 1) base = atomicAdd(&s_out, (unsigned)__popc(bal));
+    base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+    if (keep) {
+      const unsigned int q = base + __popc(bal & ((1u << lane) - 1));
+      if ((int64_t)q < a.k) {
+        if (l.ord) a.alt_ord[q] = o;
+        a.alt_rowid[q] = r;
+        if (l.bits) a.alt_bits[q] = l.bits[i];
+      }
+    }
+  }
+  __syncthreads();
+  const int64_t kept = (int64_t)s_out < a.k ? (int64_t)s_out : a.k;
+  for (int64_t i = tid; i < kept; i += 1024) {
+    if (l.ord) l.ord[i] = a.alt_ord[i];
+    l.rowid[i] = a.alt_rowid[i];
+    if (l.bits) l.bits[i] = a.alt_bits[i];
+  }
+  if (tid == 0) {
+    l.state[ST_COUNT] = (unsigned long long)kept;
+    l.state[ST_BOUND] = l.ord ? th_hi : th_lo;
+  }
+}
+
+// Sort n <= 4096 candidates by (ord, rowid) inside one CTA by counting, for every entry, the
+// entries that precede it (n^2 / 1024 comparisons per thread out of shared memory).
+__global__ void __launch_bounds__(1024) small_rank_sort_kernel(const uint64_t* ord, const uint64_t* rowid, const uint64_t* bits, int n,
+                                                               uint64_t* out_rowid, uint64_t* out_bits) {
+  extern __shared__ __align__(16) uint64_t s_kr[];  // [n] ord, [n] rowid
+  uint64_t* s_o = s_kr;
+  uint64_t* s_r = s_kr + n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { s_o[i] = ord ? ord[i] : 0; s_r[i] = rowid[i]; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint64_t o = s_o[i], r = s_r[i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += (s_o[j] < o) || (s_o[j] == o && s_r[j] < r);
+    out_rowid[rank] = r;
+    if (bits) out_bits[rank] = bits[i];
+  }
+}
+
+__global__ void iota_u32_kernel(uint32_t* p, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = (uint32_t)i;
 }
 __global__ void gather_u64_kernel(const uint64_t* src, const uint32_t* idx, uint64_t* dst, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[idx[i]];
 }
-__global__ void narrow_store_kernel(const uint64_t* bits, int64_t n, int dtype, void* out) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    uint64_t b = bits[i];
-    switch (dtype) {
-      case DBX_I8: case DBX_U8: ((uint8_t*)out)[i] = (uint8_t)b; break;
-      case DBX_I16: case DBX_U16: ((uint16_t*)out)[i] = (uint16_t)b; break;
-      case DBX_I32: case DBX_U32: ((uint32_t*)out)[i] = (uint32_t)b; break;
-      case DBX_F32: ((float*)out)[i] = (float)__longlong_as_double((long long)b); break;
-      default: ((uint64_t*)out)[i] = b; break;
+
+// Assemble the result block on the device: [key (original dtype, Nullable), row_id Int64].
+struct EmitArgs {
+  const uint64_t* bits;    // sorted valid rows: original value bits
+  const uint64_t* rowid;   // sorted valid rows
+  const uint64_t* null_rowid;  // sorted NULL rows
+  int64_t take_valid, take_null;
+  int32_t nulls_first, dtype;
+  void* out_key;
+  int64_t* out_row;
+  uint8_t* out_valid_bytes;  // one byte per row
+};
+__global__ void topk_emit_kernel(const __grid_constant__ EmitArgs a) {
+  const int64_t n_out = a.take_valid + a.take_null;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t first = a.nulls_first ? a.take_null : a.take_valid;
+    const bool in_first = i < first;
+    const bool is_null = a.nulls_first ? in_first : !in_first;
+    const int64_t j = in_first ? i : i - first;
+    if (is_null) {
+      store_narrow_key(a.out_key, i, a.dtype, 0);
+      a.out_row[i] = (int64_t)a.null_rowid[j];
+      a.out_valid_bytes[i] = 0;
+    } else {
+      store_narrow_key(a.out_key, i, a.dtype, a.bits[j]);
+      a.out_row[i] = (int64_t)a.rowid[j];
+      a.out_valid_bytes[i] = 1;
     }
   }
 }
+__global__ void pack_bits_kernel(const uint8_t* bytes, int64_t n, uint8_t* bits) {
+  const int64_t nb = (n + 7) / 8;
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t v = 0;
+    for (int k = 0; k < 8; ++k) {
+      const int64_t i = b * 8 + k;
+      if (i < n && bytes[i]) v |= 1u << k;
+    }
+    bits[b] = (uint8_t)v;
+  }
+}
 
-inline int grid_1d(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)kNumSMs * 8)); }
+// ================================================================ full sort: ingest
+// Appends one chunk of the key column to the (ord, row id | NULL flag, original bits) arrays.
+__global__ void __launch_bounds__(256) sort_ingest_kernel(const __grid_constant__ DevCol col, int64_t n, int64_t row_base, int cls, int asc,
+                                                          uint64_t* ord, uint32_t* rid, uint64_t* bits, unsigned long long* n_null) {
+  const uint64_t pol = make_policy_evict_first();
+  unsigned int nulls = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const bool ok = !col.validity || bit_test(col.validity, col.vbit_off + i);
+    const uint64_t v = ok ? load_widened(col, i, pol) : 0;
+    ord[row_base + i] = ok ? key_to_ord(v, cls, asc != 0) : 0;  // NULL rows: placed by the extra pass on the flag
+    rid[row_base + i] = (uint32_t)(row_base + i) | (ok ? 0u : 0x80000000u);
+    bits[row_base + i] = v;
+    nulls += !ok;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nulls += __shfl_xor_sync(0xffffffffu, nulls, o);
+  if ((threadIdx.x & 31) == 0 && nulls) atomicAdd(n_null, (unsigned long long)nulls);
+}
+struct SortEmitArgs {
+  const uint32_t* rid;   // sorted: row id | NULL flag
+  const uint64_t* bits;  // by original row id
+  int64_t n;
+  int32_t dtype;
+  void* out_key;
+  int64_t* out_row;
+  uint8_t* out_valid_bytes;  // nullptr: key not nullable
+};
+__global__ void sort_emit_kernel(const __grid_constant__ SortEmitArgs a) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t r = a.rid[i];
+    const uint32_t row = r & 0x7FFFFFFFu;
+    const bool is_null = r >> 31;
+    store_narrow_key(a.out_key, i, a.dtype, is_null ? 0 : a.bits[row]);
+    a.out_row[i] = (int64_t)row;
+    if (a.out_valid_bytes) a.out_valid_bytes[i] = is_null ? 0 : 1;
+  }
+}
 
 }  // namespace
 
+// ================================================================ operator
 class TopkOp : public Op {
  public:
   dbx_topk_params prm;
@@ -167,16 +373,20 @@ class TopkOp : public Op {
   int key_dtype = 0;
   bool key_nullable = false;
   int cls = 0;
+  bool full_sort = false;
   Stager stager;
-  DevBuf ord, rowid, bits, counters, null_rowid;
-  DevBuf s_ord, s_rowid, s_bits, idx_a, idx_b, key_tmp, key_tmp2, cub_tmp;
+  RadixSorter sorter;
+  // ---- top-k mode
+  DevBuf ord, rowid, bits, null_rowid, state, alt_ord, alt_rowid, alt_bits, alt_null;
+  DevBuf f_idx0, f_idx1, f_key0, f_key1, f_rowid, f_bits, f_null;  // finish(): sorted candidates
   PinnedBuf host;
   int64_t cap = 0;
-  int64_t n_cand = 0;        // exact candidate count (host knowledge)
-  uint64_t boundary = ~0ULL; // ord of the k-th best so far
+  int64_t count_ub = 0, null_ub = 0;   // upper bounds on the list sizes known to the host without a sync
   int64_t rows_seen = 0;
-  int64_t next_chunk = 0;
-  int64_t n_null_seen = 0;
+  int64_t rows_at_last_cut = 0;
+  // ---- full-sort mode
+  DevBuf s_ord[2], s_rid[2], s_bits;
+  int64_t s_cap = 0;
   std::unique_ptr<OwnedBlock> result;
   bool pulled = false;
 
@@ -185,90 +395,198 @@ class TopkOp : public Op {
     prm = *p;
     n_cols = n;
     if (p->key_col < 0 || p->key_col >= n) { err.set("top-k: key column outside the input schema"); return DBX_ERR_INVALID; }
-    if (p->limit <= 0 || p->limit > (1 << 22)) { err.set("top-k: limit must be in [1, 4194304]"); return DBX_ERR_UNSUPPORTED; }
+    if (p->limit < 0) { err.set("top-k: negative limit"); return DBX_ERR_INVALID; }
     key_dtype = types[p->key_col] & 0xFF;
     key_nullable = (types[p->key_col] & DBX_NULLABLE) != 0;
     if (dtype_size(key_dtype) == 0) { err.set("top-k: key must be a numeric column"); return DBX_ERR_UNSUPPORTED; }
     cls = key_dtype == DBX_U64 ? VC_UINT : (dtype_class(key_dtype) == VC_FLT ? VC_FLT : VC_INT);
-    cap = std::max<int64_t>(1 << 16, 16 * p->limit);
+    full_sort = p->limit == 0 || p->limit > (1 << 22);  // no LIMIT (or one too large for the candidate list): sort everything
     DBX_TRY(stager.init(dev, stream, &err));
-    DBX_CUDA_TRY(err, ord.ensure(cap * 8));
-    DBX_CUDA_TRY(err, rowid.ensure(cap * 8));
-    DBX_CUDA_TRY(err, bits.ensure(cap * 8));
-    DBX_CUDA_TRY(err, s_ord.ensure(cap * 8));
-    DBX_CUDA_TRY(err, s_rowid.ensure(cap * 8));
-    DBX_CUDA_TRY(err, s_bits.ensure(cap * 8));
-    DBX_CUDA_TRY(err, idx_a.ensure(cap * 4));
-    DBX_CUDA_TRY(err, idx_b.ensure(cap * 4));
-    DBX_CUDA_TRY(err, key_tmp.ensure(cap * 8));
-    DBX_CUDA_TRY(err, key_tmp2.ensure(cap * 8));
-    DBX_CUDA_TRY(err, null_rowid.ensure(p->limit * 8));
-    DBX_CUDA_TRY(err, counters.ensure(64));
-    DBX_CUDA_TRY(err, host.ensure(64));
-    size_t tmp = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint32_t*)nullptr,
-                                    (uint32_t*)nullptr, (int)cap, 0, 64, stream);
-    DBX_CUDA_TRY(err, cub_tmp.ensure(tmp + 256));
+    DBX_CUDA_TRY(err, host.ensure(256));
+    DBX_CUDA_TRY(err, state.ensure(8 * ST_WORDS * 2 + 64));
+    if (!full_sort) {
+      const int64_t k = p->limit;
+      // candidate list: large enough that a whole device-resident column usually fits behind the
+      // boundary of its first few million rows; 3 x 8 B per entry
+      static const int64_t cap_env = getenv("DBX_TOPK_CAP") ? atoll(getenv("DBX_TOPK_CAP")) : 0;
+      cap = cap_env > 0 ? cap_env : std::max<int64_t>(1 << 22, 8 * k);
+      cap = std::max<int64_t>(cap, 4 * k + 4096);
+      DBX_CUDA_TRY(err, ord.ensure(cap * 8));
+      DBX_CUDA_TRY(err, rowid.ensure(cap * 8));
+      DBX_CUDA_TRY(err, bits.ensure(cap * 8));
+      DBX_CUDA_TRY(err, alt_ord.ensure(k * 8));
+      DBX_CUDA_TRY(err, alt_rowid.ensure(k * 8));
+      DBX_CUDA_TRY(err, alt_bits.ensure(k * 8));
+      if (key_nullable) {
+        DBX_CUDA_TRY(err, null_rowid.ensure(cap * 8));
+        DBX_CUDA_TRY(err, alt_null.ensure(k * 8));
+      }
+    }
     return reset();
   }
 
   int32_t reset() override {
-    DBX_CUDA_TRY(err, cudaMemsetAsync(counters.p, 0, 64, stream));
-    n_cand = 0;
-    boundary = ~0ULL;
+    unsigned long long init_state[2 * ST_WORDS] = {0, ~0ULL, 0, 0, 0, ~0ULL, 0, 0};
+    memcpy(host.p, init_state, sizeof(init_state));
+    DBX_CUDA_TRY(err, cudaMemcpyAsync(state.p, host.p, sizeof(init_state), cudaMemcpyHostToDevice, stream));
+    DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
+    count_ub = null_ub = 0;
     rows_seen = 0;
-    n_null_seen = 0;
-    next_chunk = std::max<int64_t>(cap / 4, 1024);
+    rows_at_last_cut = 0;
     result.reset();
     pulled = false;
     return DBX_OK;
   }
 
-  TopkDev view() const {
-    TopkDev t;
-    t.ord = (uint64_t*)ord.p; t.rowid = (uint64_t*)rowid.p; t.bits = (uint64_t*)bits.p;
-    t.count = (unsigned long long*)counters.p;
-    t.n_null = (unsigned long long*)counters.p + 1;
-    t.null_rowid = (uint64_t*)null_rowid.p;
-    t.cap = cap; t.k = prm.limit;
-    return t;
+  CandList cand_list() const {
+    CandList l;
+    l.ord = (uint64_t*)ord.p; l.rowid = (uint64_t*)rowid.p; l.bits = (uint64_t*)bits.p;
+    l.state = (unsigned long long*)state.p;
+    l.cap = cap;
+    return l;
+  }
+  CandList null_list() const {
+    CandList l;
+    l.ord = nullptr; l.rowid = (uint64_t*)null_rowid.p; l.bits = nullptr;  // rowid == nullptr: key not nullable
+    l.state = (unsigned long long*)state.p + ST_WORDS;
+    l.cap = cap;
+    return l;
   }
 
-  // Sort the first n candidates by (ord, rowid) into s_ord/s_rowid/s_bits (two stable passes).
-  int32_t sort_candidates(int64_t n) {
-    if (n == 0) return DBX_OK;
-    size_t tmp = cub_tmp.bytes;
-    iota_kernel<<<grid_1d(n), 256, 0, stream>>>((uint32_t*)idx_a.p, n);
+  // cut both lists back to k when they hold more than `threshold` entries (device decides)
+  int32_t launch_cuts(int64_t threshold, int64_t rows_so_far) {
+    CutArgs a;
+    a.l = cand_list();
+    a.alt_ord = (uint64_t*)alt_ord.p; a.alt_rowid = (uint64_t*)alt_rowid.p; a.alt_bits = (uint64_t*)alt_bits.p;
+    a.k = prm.limit; a.threshold = threshold;
+    topk_cut_kernel<<<1, 1024, 0, stream>>>(a);
     count_launch();
-    DBX_CUDA_TRY(err, cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp, (const uint64_t*)rowid.p, (uint64_t*)key_tmp.p,
-                                                      (const uint32_t*)idx_a.p, (uint32_t*)idx_b.p, (int)n, 0, 64, stream));
-    gather_u64_kernel<<<grid_1d(n), 256, 0, stream>>>((const uint64_t*)ord.p, (const uint32_t*)idx_b.p, (uint64_t*)key_tmp.p, n);
+    if (key_nullable) {
+      CutArgs b;
+      b.l = null_list();
+      b.alt_ord = nullptr; b.alt_rowid = (uint64_t*)alt_null.p; b.alt_bits = nullptr;
+      b.k = prm.limit; b.threshold = threshold;
+      topk_cut_kernel<<<1, 1024, 0, stream>>>(b);
+      count_launch();
+    }
+    DBX_CUDA_TRY(err, cudaGetLastError());
+    count_ub = std::min(count_ub, std::max(threshold, prm.limit));
+    null_ub = std::min(null_ub, std::max(threshold, prm.limit));
+    rows_at_last_cut = rows_so_far;
+    return DBX_OK;
+  }
+
+  int32_t launch_scan(const DevCol& col, int64_t off, int64_t m, int64_t row_base) {
+    DevCol c = col;
+    const int esz = dtype_size(key_dtype);
+    c.data = (const char*)col.data + off * esz;
+    if (c.validity) c.vbit_off += off;
+    const bool fast = esz == 8 && !c.validity && ((reinterpret_cast<uintptr_t>(c.data) & 31) == 0);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((m + 1023) / 1024, (int64_t)kNumSMs * 8));
+    CandList nl = null_list();
+    if (!key_nullable) nl.rowid = nullptr;
+    if (fast) topk_scan_kernel<true><<<grid, 256, 0, stream>>>(c, m, row_base, cls, prm.asc, cand_list(), nl);
+    else topk_scan_kernel<false><<<grid, 256, 0, stream>>>(c, m, row_base, cls, prm.asc, cand_list(), nl);
     count_launch();
-    tmp = cub_tmp.bytes;
-    DBX_CUDA_TRY(err, cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp, (const uint64_t*)key_tmp.p, (uint64_t*)key_tmp2.p,
-                                                      (const uint32_t*)idx_b.p, (uint32_t*)idx_a.p, (int)n, 0, 64, stream));
-    gather_u64_kernel<<<grid_1d(n), 256, 0, stream>>>((const uint64_t*)ord.p, (const uint32_t*)idx_a.p, (uint64_t*)s_ord.p, n);
-    gather_u64_kernel<<<grid_1d(n), 256, 0, stream>>>((const uint64_t*)rowid.p, (const uint32_t*)idx_a.p, (uint64_t*)s_rowid.p, n);
-    gather_u64_kernel<<<grid_1d(n), 256, 0, stream>>>((const uint64_t*)bits.p, (const uint32_t*)idx_a.p, (uint64_t*)s_bits.p, n);
-    count_launch(5);
     DBX_CUDA_TRY(err, cudaGetLastError());
     return DBX_OK;
   }
 
-  // Cut the candidate list back to the k best and tighten the boundary.
-  int32_t compact() {
-    if (n_cand <= prm.limit) return DBX_OK;
-    DBX_TRY(sort_candidates(n_cand));
+  // rows [off, off + m) in pieces that provably fit the lists; a cut follows every piece
+  int32_t scan_guaranteed(const DevCol& col, int64_t off, int64_t m) {
     const int64_t k = prm.limit;
-    DBX_CUDA_TRY(err, cudaMemcpyAsync(ord.p, s_ord.p, k * 8, cudaMemcpyDeviceToDevice, stream));
-    DBX_CUDA_TRY(err, cudaMemcpyAsync(rowid.p, s_rowid.p, k * 8, cudaMemcpyDeviceToDevice, stream));
-    DBX_CUDA_TRY(err, cudaMemcpyAsync(bits.p, s_bits.p, k * 8, cudaMemcpyDeviceToDevice, stream));
-    DBX_CUDA_TRY(err, cudaMemcpyAsync(host.p, (uint64_t*)s_ord.p + (k - 1), 8, cudaMemcpyDeviceToHost, stream));
-    unsigned long long kk = (unsigned long long)k;
-    DBX_CUDA_TRY(err, cudaMemcpyAsync(counters.p, &kk, 8, cudaMemcpyHostToDevice, stream));
-    DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
-    boundary = *(uint64_t*)host.p;
-    n_cand = k;
+    int64_t done = 0;
+    while (done < m) {
+      int64_t room = cap - std::max(count_ub, null_ub);
+      if (room < cap / 2) { DBX_TRY(launch_cuts(2 * k, rows_seen + off + done)); room = cap - std::max(count_ub, null_ub); }
+      const int64_t piece = std::min(m - done, room);
+      DBX_TRY(launch_scan(col, off + done, piece, rows_seen + off + done));
+      count_ub += piece;
+      if (key_nullable) null_ub += piece;
+      done += piece;
+    }
+    return DBX_OK;
+  }
+
+  int32_t push_topk(const DevCol& col, int64_t n) {
+    const int64_t k = prm.limit;
+    int64_t done = 0;
+    int64_t chunk = std::max<int64_t>(16 * k, 1 << 16);  // warm-up chunks grow geometrically behind cuts
+    while (done < n) {
+      const int64_t seen = rows_seen + done;
+      const int64_t rest = n - done;
+      int64_t room = cap - std::max(count_ub, null_ub);
+      if (room < std::min(rest, chunk)) {  // the host's bounds are pessimistic: let the device cut whatever is really there
+        DBX_TRY(launch_cuts(2 * k, seen));
+        room = cap - std::max(count_ub, null_ub);
+      }
+      if (rest <= room) {  // fits for sure: one launch
+        DBX_TRY(launch_scan(col, done, rest, seen));
+        count_ub += rest;
+        if (key_nullable) null_ub += rest;
+        done = n;
+        // tighten the boundary whenever the rows seen have doubled since the last cut
+        if (rows_seen + n - rows_at_last_cut >= rows_at_last_cut) DBX_TRY(launch_cuts(2 * k, rows_seen + n));
+        break;
+      }
+      if (seen > 0 && (double)rest * (double)k / (double)seen * 4.0 <= (double)(cap - 2 * k)) {
+        // boundary established: ONE optimistic launch over everything left (expected survivors
+        // ~ rest * k / seen), then one check of the overflow flags; on overflow the chunk's appends
+        // are dropped and the range is replayed in pieces that provably fit
+        DBX_TRY(launch_cuts(k, seen));
+        unsigned long long* st = (unsigned long long*)state.p;
+        DBX_CUDA_TRY(err, cudaMemcpyAsync(host.p, st, 8 * ST_WORDS * 2, cudaMemcpyDeviceToHost, stream));
+        DBX_TRY(launch_scan(col, done, rest, seen));
+        DBX_CUDA_TRY(err, cudaMemcpyAsync((char*)host.p + 64, st, 8 * ST_WORDS * 2, cudaMemcpyDeviceToHost, stream));
+        DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
+        const unsigned long long* before = (const unsigned long long*)host.p;
+        const unsigned long long* after = (const unsigned long long*)((char*)host.p + 64);
+        const bool over = after[ST_OVERFLOW] || after[ST_WORDS + ST_OVERFLOW] || (int64_t)after[ST_COUNT] > cap ||
+                          (int64_t)after[ST_WORDS + ST_COUNT] > cap;
+        if (!over) {
+          count_ub = (int64_t)after[ST_COUNT];
+          null_ub = (int64_t)after[ST_WORDS + ST_COUNT];
+          done = n;
+          break;
+        }
+        unsigned long long back[2 * ST_WORDS];
+        memcpy(back, before, sizeof(back));
+        back[ST_OVERFLOW] = back[ST_WORDS + ST_OVERFLOW] = 0;
+        DBX_CUDA_TRY(err, cudaMemcpyAsync(st, back, sizeof(back), cudaMemcpyHostToDevice, stream));
+        DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
+        count_ub = (int64_t)before[ST_COUNT];
+        null_ub = (int64_t)before[ST_WORDS + ST_COUNT];
+        DBX_TRY(scan_guaranteed(col, done, rest));
+        done = n;
+        break;
+      }
+      const int64_t m = std::min<int64_t>({rest, chunk, room});
+      DBX_TRY(launch_scan(col, done, m, seen));
+      count_ub += m;
+      if (key_nullable) null_ub += m;
+      done += m;
+      DBX_TRY(launch_cuts(2 * k, rows_seen + done));
+      chunk *= 8;
+    }
+    return DBX_OK;
+  }
+
+  // grow the full-sort arrays, keeping their contents
+  int32_t sort_reserve(int64_t rows) {
+    if (rows <= s_cap) return DBX_OK;
+    int64_t ncap = std::max<int64_t>(rows, std::max<int64_t>(s_cap * 2, 1 << 20));
+    auto grow = [&](DevBuf& b, size_t elt, bool keep) -> int32_t {
+      DevBuf nb;
+      DBX_CUDA_TRY(err, nb.ensure((size_t)ncap * elt));
+      if (keep && b.p && rows_seen) DBX_CUDA_TRY(err, cudaMemcpyAsync(nb.p, b.p, (size_t)rows_seen * elt, cudaMemcpyDeviceToDevice, stream));
+      DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
+      b = std::move(nb);
+      return DBX_OK;
+    };
+    DBX_TRY(grow(s_ord[0], 8, true));
+    DBX_TRY(grow(s_rid[0], 4, true));
+    DBX_TRY(grow(s_bits, 8, true));
+    s_cap = ncap;
     return DBX_OK;
   }
 
@@ -279,50 +597,20 @@ class TopkOp : public Op {
     const int64_t n = b->num_rows;
     if (n == 0) return DBX_OK;
     if (kc.is_const) { err.set("top-k over a constant key column is not supported"); return DBX_ERR_UNSUPPORTED; }
+    if (kc.validity && !key_nullable) { err.set("push: validity bitmap on a key column declared non-nullable"); return DBX_ERR_INVALID; }
     DevCol col;
     DBX_TRY(stager.begin());
     DBX_TRY(stager.stage(kc, 0, &col));
     DBX_TRY(timing_begin());
-    const int esz = dtype_size(key_dtype);
-    int64_t done = 0;
-    while (done < n) {
-      // a chunk never appends more than it has rows: keep (candidates + chunk) within the list
-      int64_t room = cap - n_cand;
-      if (room < cap / 4) { DBX_TRY(compact()); room = cap - n_cand; }
-      int64_t m = std::min<int64_t>({n - done, next_chunk, kMaxChunk});
-      const bool guaranteed = m <= room;
-      const int64_t nulls_before = n_null_seen;
-      DevCol c = col;
-      c.data = (const char*)col.data + done * esz;
-      if (c.validity) c.vbit_off += done;
-      const bool fast = esz == 8 && !c.validity && ((reinterpret_cast<uintptr_t>(c.data) & 31) == 0);
-      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((m + 1023) / 1024, (int64_t)kNumSMs * 8));
-      if (fast) topk_scan_kernel<true><<<grid, kTopkBlock, 0, stream>>>(c, m, rows_seen + done, cls, prm.asc, boundary, view());
-      else topk_scan_kernel<false><<<grid, kTopkBlock, 0, stream>>>(c, m, rows_seen + done, cls, prm.asc, boundary, view());
+    if (full_sort) {
+      if (rows_seen + n > rs::kMaxRows) { err.set("sort: more than 2^30 - 1 rows are not supported"); return DBX_ERR_UNSUPPORTED; }
+      DBX_TRY(sort_reserve(rows_seen + n));
+      sort_ingest_kernel<<<grid_1d(n), 256, 0, stream>>>(col, n, rows_seen, cls, prm.asc, (uint64_t*)s_ord[0].p, (uint32_t*)s_rid[0].p,
+                                                         (uint64_t*)s_bits.p, (unsigned long long*)state.p + ST_WORDS + ST_COUNT);
       count_launch();
       DBX_CUDA_TRY(err, cudaGetLastError());
-      DBX_CUDA_TRY(err, cudaMemcpyAsync(host.p, counters.p, 16, cudaMemcpyDeviceToHost, stream));
-      DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
-      const int64_t cnt = (int64_t)((unsigned long long*)host.p)[0];
-      n_null_seen = (int64_t)((unsigned long long*)host.p)[1];
-      if (cnt > cap) {  // more survivors than the list holds: drop this chunk's appends, tighten, retry smaller
-        if (guaranteed) { err.set("internal: top-k candidate overflow"); return DBX_ERR_CUDA; }
-        unsigned long long back[2] = {(unsigned long long)n_cand, (unsigned long long)nulls_before};
-        DBX_CUDA_TRY(err, cudaMemcpyAsync(counters.p, back, 16, cudaMemcpyHostToDevice, stream));
-        DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
-        n_null_seen = nulls_before;
-        DBX_TRY(compact());
-        next_chunk = std::max<int64_t>(std::min<int64_t>(m / 4, cap - n_cand), 1024);
-        continue;
-      }
-      n_cand = cnt;
-      done += m;
-      // the boundary tightens as rows are seen: later chunks can be geometrically larger
-      // Cut back after every chunk that left more than 2k candidates: the boundary then reflects
-      // every row seen so far, so the next (8x larger) chunk adds about 8k survivors instead of
-      // overflowing the list and being replayed in smaller pieces.
-      if (n_cand > 2 * prm.limit || n_cand > cap / 2) DBX_TRY(compact());
-      next_chunk = std::min<int64_t>(next_chunk * 8, kMaxChunk);
+    } else {
+      DBX_TRY(push_topk(col, n));
     }
     rows_seen += n;
     DBX_TRY(timing_end());
@@ -330,76 +618,170 @@ class TopkOp : public Op {
     return DBX_OK;
   }
 
-  int32_t finish() override {
-    const int64_t k = prm.limit;
-    DBX_TRY(sort_candidates(n_cand));
-    DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
-    const int64_t n_valid = std::min<int64_t>(n_cand, k);
-    const int64_t n_nulls = std::min<int64_t>(n_null_seen, k);
-    int64_t take_null, take_valid;
-    if (prm.nulls_first) { take_null = n_nulls; take_valid = std::min<int64_t>(k - take_null, n_valid); }
-    else { take_valid = n_valid; take_null = std::min<int64_t>(k - take_valid, n_nulls); }
-    const int64_t n_out = take_null + take_valid;
-    // NULL row ids were appended in arbitrary order: keep the smallest ones (ties by row id)
-    std::vector<uint64_t> null_ids((size_t)n_nulls);
-    if (n_nulls) {
-      DBX_CUDA_TRY(err, cudaMemcpy(null_ids.data(), null_rowid.p, n_nulls * 8, cudaMemcpyDeviceToHost));
-      std::sort(null_ids.begin(), null_ids.end());
-    }
-    std::vector<uint64_t> h_rowid((size_t)n_valid), h_bits((size_t)n_valid);
-    if (n_valid) {
-      DBX_CUDA_TRY(err, cudaMemcpy(h_rowid.data(), s_rowid.p, n_valid * 8, cudaMemcpyDeviceToHost));
-      DBX_CUDA_TRY(err, cudaMemcpy(h_bits.data(), s_bits.p, n_valid * 8, cudaMemcpyDeviceToHost));
-    }
-    // output block: [key (original dtype, nullable), row_id Int64], assembled in pinned memory
+  int32_t dev_alloc(OwnedBlock* ob, size_t bytes, void** p) {
+    DBX_CUDA_TRY(err, pool_alloc(device, stream, bytes ? bytes : 1, p));
+    ob->dev_allocs.push_back(*p);
+    return DBX_OK;
+  }
+
+  int32_t finish_full_sort() {
+    const int64_t n = rows_seen;
     auto ob = std::make_unique<OwnedBlock>();
     ob->device = device;
+    DBX_CUDA_TRY(err, cudaMemcpyAsync(host.p, (unsigned long long*)state.p + ST_WORDS + ST_COUNT, 8, cudaMemcpyDeviceToHost, stream));
+    DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
+    const int64_t n_nulls = (int64_t)*(unsigned long long*)host.p;
+    int buf = 0;
+    if (n > 1) {
+      DBX_CUDA_TRY(err, s_ord[1].ensure((size_t)s_cap * 8));
+      DBX_CUDA_TRY(err, s_rid[1].ensure((size_t)s_cap * 4));
+      DBX_TRY(sorter.sort(err, stream, (uint64_t*)s_ord[0].p, (uint64_t*)s_ord[1].p, (uint32_t*)s_rid[0].p, (uint32_t*)s_rid[1].p, n, 0,
+                          64, n_nulls > 0, prm.nulls_first, n_nulls, &buf));
+    }
+    void *okey = nullptr, *orow = nullptr, *ovb = nullptr, *obits = nullptr;
     const int esz = dtype_size(key_dtype);
-    void *hk = nullptr, *hr = nullptr, *hv = nullptr;
-    DBX_CUDA_TRY(err, pinned_alloc(std::max<int64_t>(1, n_out * esz), &hk));
-    ob->host_allocs.push_back(hk);
-    DBX_CUDA_TRY(err, pinned_alloc(std::max<int64_t>(1, n_out * 8), &hr));
-    ob->host_allocs.push_back(hr);
-    DBX_CUDA_TRY(err, pinned_alloc((size_t)(n_out + 7) / 8 + 1, &hv));
-    ob->host_allocs.push_back(hv);
-    memset(hv, 0, (size_t)(n_out + 7) / 8 + 1);
-    auto put = [&](int64_t o, uint64_t b, uint64_t rid, bool valid) {
-      switch (key_dtype) {
-        case DBX_I8: case DBX_U8: ((uint8_t*)hk)[o] = (uint8_t)b; break;
-        case DBX_I16: case DBX_U16: ((uint16_t*)hk)[o] = (uint16_t)b; break;
-        case DBX_I32: case DBX_U32: ((uint32_t*)hk)[o] = (uint32_t)b; break;
-        case DBX_F32: { double d; memcpy(&d, &b, 8); ((float*)hk)[o] = (float)d; break; }
-        default: ((uint64_t*)hk)[o] = b; break;
-      }
-      ((int64_t*)hr)[o] = (int64_t)rid;
-      if (valid) ((uint8_t*)hv)[o >> 3] |= (uint8_t)(1u << (o & 7));
-    };
-    int64_t o = 0;
-    if (prm.nulls_first) for (int64_t i = 0; i < take_null; ++i) put(o++, 0, null_ids[i], false);
-    for (int64_t i = 0; i < take_valid; ++i) put(o++, h_bits[i], h_rowid[i], true);
-    if (!prm.nulls_first) for (int64_t i = 0; i < take_null; ++i) put(o++, 0, null_ids[i], false);
+    DBX_TRY(dev_alloc(ob.get(), (size_t)n * esz, &okey));
+    DBX_TRY(dev_alloc(ob.get(), (size_t)n * 8, &orow));
+    if (key_nullable) {
+      DBX_TRY(dev_alloc(ob.get(), (size_t)n, &ovb));
+      DBX_TRY(dev_alloc(ob.get(), (size_t)(n + 7) / 8 + 8, &obits));
+    }
+    if (n) {
+      SortEmitArgs ea;
+      ea.rid = (const uint32_t*)s_rid[buf].p; ea.bits = (const uint64_t*)s_bits.p; ea.n = n; ea.dtype = key_dtype;
+      ea.out_key = okey; ea.out_row = (int64_t*)orow; ea.out_valid_bytes = (uint8_t*)ovb;
+      sort_emit_kernel<<<grid_1d(n), 256, 0, stream>>>(ea);
+      count_launch();
+      if (key_nullable) { pack_bits_kernel<<<grid_1d((n + 7) / 8), 256, 0, stream>>>((const uint8_t*)ovb, n, (uint8_t*)obits); count_launch(); }
+      DBX_CUDA_TRY(err, cudaGetLastError());
+    }
+    DBX_CUDA_TRY(err, cudaMemcpyAsync(host.p, sorter.meta.p ? (void*)sorter.fail() : state.p, 4, cudaMemcpyDeviceToHost, stream));
+    DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
+    if (sorter.meta.p && n > 1 && *(unsigned int*)host.p) { err.set("internal: radix sort look-back timed out"); return DBX_ERR_CUDA; }
     dbx_column kcol;
     memset(&kcol, 0, sizeof(kcol));
-    kcol.dtype = key_dtype; kcol.mem = DBX_MEM_HOST; kcol.len = n_out; kcol.data = hk;
-    if (key_nullable) { kcol.validity = (const uint8_t*)hv; kcol.null_count = take_null; }
+    kcol.dtype = key_dtype; kcol.mem = DBX_MEM_DEVICE; kcol.len = n; kcol.data = okey;
+    if (key_nullable) { kcol.validity = (const uint8_t*)obits; kcol.null_count = n_nulls; }
     dbx_column rcol;
     memset(&rcol, 0, sizeof(rcol));
-    rcol.dtype = DBX_I64; rcol.mem = DBX_MEM_HOST; rcol.len = n_out; rcol.data = hr;
+    rcol.dtype = DBX_I64; rcol.mem = DBX_MEM_DEVICE; rcol.len = n; rcol.data = orow;
     ob->cols.push_back(kcol);
     ob->cols.push_back(rcol);
     result = std::move(ob);
     return DBX_OK;
   }
 
-  int32_t pull(int32_t out_mem, dbx_block* out, int32_t* has_block) override {
-    if (!finished) { err.set("pull before finish"); return DBX_ERR_STATE; }
-    if (pulled || !result) { *has_block = 0; return DBX_OK; }
-    if (out_mem != DBX_MEM_HOST) { err.set("top-k results are k rows: host output only"); return DBX_ERR_UNSUPPORTED; }
-    pulled = true;
-    *has_block = 1;
-    return fill_owned_block(result.release(), out);
+  // sort `n` (ord?, rowid, bits?) entries by (ord, rowid) into out_rowid / out_bits
+  int32_t sort_candidates(const uint64_t* c_ord, const uint64_t* c_rowid, const uint64_t* c_bits, int64_t n, uint64_t* out_rowid,
+                          uint64_t* out_bits) {
+    if (n == 0) return DBX_OK;
+    if (n <= 4096) {
+      static std::atomic<bool> attr_set[64];
+      if (!attr_set[device]) {
+        DBX_CUDA_TRY(err, cudaFuncSetAttribute(small_rank_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16));
+        attr_set[device] = true;
+      }
+      small_rank_sort_kernel<<<1, 1024, (size_t)n * 16, stream>>>(c_ord, c_rowid, c_bits, (int)n, out_rowid, out_bits);
+      count_launch();
+      DBX_CUDA_TRY(err, cudaGetLastError());
+      return DBX_OK;
+    }
+    // two stable radix sorts of a permutation: by row id, then by the ordered key
+    DBX_CUDA_TRY(err, f_idx0.ensure(n * 4));
+    DBX_CUDA_TRY(err, f_idx1.ensure(n * 4));
+    DBX_CUDA_TRY(err, f_key0.ensure(n * 8));
+    DBX_CUDA_TRY(err, f_key1.ensure(n * 8));
+    iota_u32_kernel<<<grid_1d(n), 256, 0, stream>>>((uint32_t*)f_idx0.p, n);
+    count_launch();
+    DBX_CUDA_TRY(err, cudaMemcpyAsync(f_key0.p, c_rowid, n * 8, cudaMemcpyDeviceToDevice, stream));
+    int buf = 0;
+    DBX_TRY(sorter.sort(err, stream, (uint64_t*)f_key0.p, (uint64_t*)f_key1.p, (uint32_t*)f_idx0.p, (uint32_t*)f_idx1.p, n, 0, 48, false, 0, 0, &buf));
+    uint32_t* idx = (uint32_t*)(buf ? f_idx1.p : f_idx0.p);
+    uint32_t* idx_other = (uint32_t*)(buf ? f_idx0.p : f_idx1.p);
+    if (c_ord) {
+      uint64_t* kb = (uint64_t*)(buf ? f_key0.p : f_key1.p);  // the buffer the first sort left free
+      uint64_t* kb_other = (uint64_t*)(buf ? f_key1.p : f_key0.p);
+      gather_u64_kernel<<<grid_1d(n), 256, 0, stream>>>(c_ord, idx, kb, n);
+      count_launch();
+      int buf2 = 0;
+      DBX_TRY(sorter.sort(err, stream, kb, kb_other, idx, idx_other, n, 0, 64, false, 0, 0, &buf2));
+      if (buf2) idx = idx_other;
+    }
+    gather_u64_kernel<<<grid_1d(n), 256, 0, stream>>>(c_rowid, idx, out_rowid, n);
+    if (c_bits) gather_u64_kernel<<<grid_1d(n), 256, 0, stream>>>(c_bits, idx, out_bits, n);
+    count_launch(2);
+    DBX_CUDA_TRY(err, cudaGetLastError());
+    return DBX_OK;
   }
+
+  int32_t finish() override {
+    if (full_sort) return finish_full_sort();
+    const int64_t k = prm.limit;
+    DBX_TRY(launch_cuts(k, rows_seen));  // both lists down to <= k entries
+    unsigned long long* st = (unsigned long long*)state.p;
+    DBX_CUDA_TRY(err, cudaMemcpyAsync(host.p, st, 8 * ST_WORDS * 2, cudaMemcpyDeviceToHost, stream));
+    DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
+    const unsigned long long* h = (const unsigned long long*)host.p;
+    if (h[ST_OVERFLOW] || h[ST_WORDS + ST_OVERFLOW]) { err.set("internal: top-k candidate list overflow"); return DBX_ERR_CUDA; }
+    const int64_t n_valid = std::min<int64_t>((int64_t)h[ST_COUNT], k);
+    const int64_t n_nulls = key_nullable ? std::min<int64_t>((int64_t)h[ST_WORDS + ST_COUNT], k) : 0;
+    int64_t take_null, take_valid;
+    if (prm.nulls_first) { take_null = n_nulls; take_valid = std::min<int64_t>(k - take_null, n_valid); }
+    else { take_valid = n_valid; take_null = std::min<int64_t>(k - take_valid, n_nulls); }
+    const int64_t n_out = take_null + take_valid;
+    DBX_CUDA_TRY(err, f_rowid.ensure(std::max<int64_t>(n_valid, 1) * 8));
+    DBX_CUDA_TRY(err, f_bits.ensure(std::max<int64_t>(n_valid, 1) * 8));
+    DBX_TRY(sort_candidates((const uint64_t*)ord.p, (const uint64_t*)rowid.p, (const uint64_t*)bits.p, n_valid, (uint64_t*)f_rowid.p, (uint64_t*)f_bits.p));
+    if (n_nulls) {
+      DBX_CUDA_TRY(err, f_null.ensure(n_nulls * 8));
+      DBX_TRY(sort_candidates(nullptr, (const uint64_t*)null_rowid.p, nullptr, n_nulls, (uint64_t*)f_null.p, nullptr));
+    }
+    // output block: [key (original dtype, nullable), row_id Int64], assembled on the device
+    auto ob = std::make_unique<OwnedBlock>();
+    ob->device = device;
+    const int esz = dtype_size(key_dtype);
+    void *okey = nullptr, *orow = nullptr, *ovb = nullptr, *obits = nullptr;
+    DBX_TRY(dev_alloc(ob.get(), (size_t)n_out * esz, &okey));
+    DBX_TRY(dev_alloc(ob.get(), (size_t)n_out * 8, &orow));
+    DBX_TRY(dev_alloc(ob.get(), (size_t)n_out + 1, &ovb));
+    DBX_TRY(dev_alloc(ob.get(), (size_t)(n_out + 7) / 8 + 8, &obits));
+    if (n_out) {
+      EmitArgs ea;
+      ea.bits = (const uint64_t*)f_bits.p; ea.rowid = (const uint64_t*)f_rowid.p; ea.null_rowid = (const uint64_t*)f_null.p;
+      ea.take_valid = take_valid; ea.take_null = take_null; ea.nulls_first = prm.nulls_first; ea.dtype = key_dtype;
+      ea.out_key = okey; ea.out_row = (int64_t*)orow; ea.out_valid_bytes = (uint8_t*)ovb;
+      topk_emit_kernel<<<grid_1d(n_out), 256, 0, stream>>>(ea);
+      pack_bits_kernel<<<grid_1d((n_out + 7) / 8), 256, 0, stream>>>((const uint8_t*)ovb, n_out, (uint8_t*)obits);
+      count_launch(2);
+      DBX_CUDA_TRY(err, cudaGetLastError());
+    }
+    dbx_column kcol;
+    memset(&kcol, 0, sizeof(kcol));
+    kcol.dtype = key_dtype; kcol.mem = DBX_MEM_DEVICE; kcol.len = n_out; kcol.data = okey;
+    if (key_nullable) { kcol.validity = (const uint8_t*)obits; kcol.null_count = take_null; }
+    dbx_column rcol;
+    memset(&rcol, 0, sizeof(rcol));
+    rcol.dtype = DBX_I64; rcol.mem = DBX_MEM_DEVICE; rcol.len = n_out; rcol.data = orow;
+    ob->cols.push_back(kcol);
+    ob->cols.push_back(rcol);
+    result = std::move(ob);
+    return DBX_OK;
+  }
+
+  int32_t pull(int32_t out_mem, dbx_block* out, int32_t* has_block) override;
 };
+
+}  // namespace dbx
+
+namespace dbx {
+
+int32_t TopkOp::pull(int32_t out_mem, dbx_block* out, int32_t* has_block) {
+  if (!finished) { err.set("pull before finish"); return DBX_ERR_STATE; }
+  if (pulled || !result) { *has_block = 0; return DBX_OK; }
+  pulled = true;
+  *has_block = 1;
+  return pull_owned_block(result, device, stream, err, out_mem, out);
+}
 
 Op* make_topk_op(const dbx_topk_params* p, const int32_t* types, int32_t n, int device, int32_t* st) {
   auto* op = new TopkOp();

@@ -172,3 +172,62 @@ def allreduce_single_state(partial, final, device: int = 0, group=None, out_mem:
     finally:
         check(L.dbx_device_free(device, buf))
     return out[0]
+
+
+def partitioned_hash_join_peer(build: DataBlock, probe: DataBlock, build_key: int, probe_key: int, device: int, rank: int, world: int,
+                               round_rows: int = 32 << 20, out_mem: int = abi.MEM_HOST, group=None, kind: int = abi.JOIN_INNER,
+                               stats: dict = None):
+    """Partitioned hash join with the FUSED shuffle (BASELINE configs[2]): both sides are
+    hash-partitioned by key and stored straight into the owners' HBM over NVLink by one kernel per
+    round (dbx_shuffle_send; no pack pass, no per-column library all-to-all), `round_rows` rows per
+    rank and round; every received region is handed to the local join as a device block.
+    Reference: flight_scatter_hash.rs:86-125 (scatter) + new_hash_join/memory/inner_join.rs:122-262.
+    Returns (joined blocks of this rank, join op, shuffles) — close the shuffles when done."""
+    import time
+    from .exchange import PeerShuffle
+    t = torch.tensor([build.num_rows, probe.num_rows], dtype=torch.int64)
+    if world > 1:
+        if dist.get_backend(group) == "nccl":
+            t = t.to(f"cuda:{device}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    max_build, max_probe = [int(v) for v in t.tolist()]
+    sb = PeerShuffle(device, rank, world, [c.dtype for c in build.columns], build_key, max(1, min(round_rows, max_build)))
+    sp = PeerShuffle(device, rank, world, [c.dtype for c in probe.columns], probe_key, max(1, min(round_rows, max_probe)))
+    if world > 1:
+        sb.connect(group)
+        sp.connect(group)
+    else:
+        sb.connect_local([sb])
+        sp.connect_local([sp])
+    j = HashJoin(schema_types(build), schema_types(probe), build_key, probe_key, device, kind)
+    ms = {"shuffle_send": 0.0, "shuffle_wait": 0.0, "build": 0.0, "probe": 0.0}
+
+    def rounds(shuf, blk, total_max, each):
+        step = max(1, min(round_rows, total_max))
+        for lo in range(0, max(total_max, 1), step):
+            hi = min(blk.num_rows, lo + step)
+            piece = blk.slice(min(lo, blk.num_rows), max(hi, min(lo, blk.num_rows)))
+            shuf.send(piece)
+            got = shuf.recv()
+            lm = shuf.last_ms()
+            ms["shuffle_send"] += lm["send"]
+            ms["shuffle_wait"] += lm["wait"]
+            t0 = time.perf_counter()
+            for b in got:
+                if b.num_rows:
+                    each(b)
+            j.synchronize()  # the regions may be overwritten two sends from now: be done reading them
+            return_ms = (time.perf_counter() - t0) * 1e3
+            yield return_ms
+
+    for m in rounds(sb, build, max_build, j.add_block):
+        ms["build"] += m
+    t0 = time.perf_counter()
+    j.final_build()
+    ms["build"] += (time.perf_counter() - t0) * 1e3
+    outs = []
+    for m in rounds(sp, probe, max_probe, lambda b: outs.extend(j.probe_block(b, out_mem))):
+        ms["probe"] += m
+    if stats is not None:
+        stats.update(ms)
+    return outs, j, (sb, sp)

@@ -128,3 +128,73 @@ class PeerExchange:
             self.close()
         except Exception:
             pass
+
+
+class PeerShuffle:
+    """Hash-partitioned row shuffle over peer memory (include/dbx.h: dbx_shuffle_*): the exchange in
+    front of a partitioned hash join.  `send(block)` partitions a device-resident block by the
+    owner of its key column and stores the rows straight into the owners' HBM over NVLink;
+    `recv()` returns one device-resident block per source rank.  Collective: every rank alternates
+    send / recv the same number of times.  One instance per rank and schema; `connect()` is collective."""
+
+    def __init__(self, device: int, rank: int, world: int, col_types: Sequence[int], key_col: int, region_rows: int):
+        self.device, self.rank, self.world, self.col_types = device, rank, world, list(col_types)
+        self._h = C.c_void_p()
+        self._handle = (C.c_ubyte * 64)()
+        types = (C.c_int32 * len(col_types))(*col_types)
+        st = load().dbx_shuffle_create(device, rank, world, types, len(col_types), key_col, region_rows, C.byref(self._h), self._handle)
+        self._check(st, created=False)
+
+    def _check(self, st, created=True):
+        if st != abi.OK:
+            msg = load().dbx_shuffle_last_error(self._h if created else None)
+            raise DbxError(st, (msg or b"").decode("utf-8", "replace"))
+
+    def connect(self, group=None):
+        handles: List[Optional[bytes]] = [None] * self.world
+        dist.all_gather_object(handles, bytes(self._handle), group=group)
+        blob = b"".join(handles)
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._check(load().dbx_shuffle_connect(self._h, buf, None))
+
+    def connect_local(self, peers: Sequence["PeerShuffle"]):
+        ptrs = (C.c_void_p * self.world)()
+        for i, p in enumerate(peers):
+            base = C.c_void_p()
+            p._check(load().dbx_shuffle_local_buffer(p._h, C.byref(base)))
+            ptrs[i] = base.value
+        self._check(load().dbx_shuffle_connect(self._h, None, ptrs))
+
+    def send(self, block):
+        b, keep = block.as_c()
+        self._check(load().dbx_shuffle_send(self._h, C.byref(b)))
+        self._keep = (block, keep)
+
+    def recv(self):
+        """-> list of `world` device-resident DataBlocks (views into the receive buffer)."""
+        from .block import Column, DataBlock
+        n_cols = len(self.col_types)
+        blocks = (abi.Block * self.world)()
+        cols = (abi.Column * (self.world * n_cols))()
+        self._check(load().dbx_shuffle_recv(self._h, blocks, cols))
+        out = []
+        for r in range(self.world):
+            n = blocks[r].num_rows
+            out.append(DataBlock([Column.device(self.col_types[c], n, cols[r * n_cols + c].data or 0) for c in range(n_cols)], n))
+        return out
+
+    def last_ms(self):
+        a, b = C.c_float(0), C.c_float(0)
+        self._check(load().dbx_shuffle_last_ms(self._h, C.byref(a), C.byref(b)))
+        return {"send": a.value, "wait": b.value}
+
+    def close(self):
+        if self._h:
+            load().dbx_shuffle_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

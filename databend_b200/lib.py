@@ -85,6 +85,18 @@ def load():
         "dbx_op_kernel_ms": (i32, [vp, i32, P(C.c_float)]),
         "dbx_op_inputs_consumed": (i32, [vp]),
         "dbx_agg_exchange_phase_ms": (i32, [vp, P(C.c_float)]),
+        "dbx_shuffle_create": (i32, [i32, i32, i32, P(i32), i32, i32, i64, P(vp), vp]),
+        "dbx_shuffle_local_buffer": (i32, [vp, P(vp)]),
+        "dbx_shuffle_connect": (i32, [vp, vp, P(vp)]),
+        "dbx_shuffle_send": (i32, [vp, P(abi.Block)]),
+        "dbx_shuffle_recv": (i32, [vp, P(abi.Block), P(abi.Column)]),
+        "dbx_shuffle_last_ms": (i32, [vp, P(C.c_float), P(C.c_float)]),
+        "dbx_shuffle_destroy": (i32, [vp]),
+        "dbx_shuffle_last_error": (C.c_char_p, [vp]),
+        "dbx_block_take": (i32, [i32, P(abi.Block), vp, i64, i32, i32, P(abi.Block)]),
+        "dbx_block_take_ranges": (i32, [i32, P(abi.Block), vp, vp, i64, i32, P(abi.Block)]),
+        "dbx_block_scatter": (i32, [i32, P(abi.Block), vp, i32, i32, i32, P(abi.Block)]),
+        "dbx_block_concat": (i32, [i32, P(abi.Block), i32, i32, P(abi.Block)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError = the library does not export a declared symbol

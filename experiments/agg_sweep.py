@@ -66,14 +66,14 @@ def run(name, **env):
 
 
 print(f"rows {rows} keys {n_keys} reps {reps}", flush=True)
-run("plain RED kernel (no pairs), no L2 window", DBX_AGG_BULK=0, DBX_AGG_L2_PERSIST=0)
-run("plain RED kernel (no pairs), L2 window", DBX_AGG_BULK=0)
-run("pairs layout, RED kernel (ring off)", DBX_AGG_RING=0)
+run("plain RED kernel (no pairs), no L2 window", DBX_AGG_L2_PERSIST=0)
+run("plain RED kernel (no pairs), L2 window")
+run("pairs layout, RED kernel (ring off)", DBX_AGG_BULK=1, DBX_AGG_RING=0)
 for lanes in ["00000000", "11111111", "49249249", "55555555", "0000FFFF", "6DB6DB6D", "000FFFFF", "77777777", "00FFFFFF", "FFFFFFFF"]:
-    run(f"ring lanes={lanes} ({bin(int(lanes,16)).count('1')}/32 on TMA)", DBX_AGG_BULK_LANES=lanes)
-run("ring lanes=6DB6DB6D, no L2 window", DBX_AGG_BULK_LANES="6DB6DB6D", DBX_AGG_L2_PERSIST=0)
+    run(f"ring lanes={lanes} ({bin(int(lanes,16)).count('1')}/32 on TMA)", DBX_AGG_BULK=1, DBX_AGG_BULK_LANES=lanes)
+run("ring lanes=6DB6DB6D, no L2 window", DBX_AGG_BULK=1, DBX_AGG_BULK_LANES="6DB6DB6D", DBX_AGG_L2_PERSIST=0)
 for g in [4, 16]:
-    run(f"ring lanes=6DB6DB6D grid {g}/SM", DBX_AGG_BULK_LANES="6DB6DB6D", DBX_AGG_GRID=g)
-run("old bulk path lanes=FFFFFFFF", DBX_AGG_RING=0, DBX_AGG_BULK_OLD=1, DBX_AGG_BULK_LANES="FFFFFFFF")
-run("ring lanes=6DB6DB6D front end only (dbg 2)", DBX_AGG_BULK_LANES="6DB6DB6D", DBX_AGG_DEBUG=2)
-run("ring lanes=6DB6DB6D probe only (dbg 1)", DBX_AGG_BULK_LANES="6DB6DB6D", DBX_AGG_DEBUG=1)
+    run(f"ring lanes=6DB6DB6D grid {g}/SM", DBX_AGG_BULK=1, DBX_AGG_BULK_LANES="6DB6DB6D", DBX_AGG_GRID=g)
+run("old bulk path lanes=FFFFFFFF", DBX_AGG_BULK=1, DBX_AGG_RING=0, DBX_AGG_BULK_OLD=1, DBX_AGG_BULK_LANES="FFFFFFFF")
+run("plain kernel front end only (dbg 2)", DBX_AGG_DEBUG=2)
+run("plain kernel probe only (dbg 1)", DBX_AGG_DEBUG=1)

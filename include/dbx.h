@@ -181,8 +181,10 @@ typedef struct dbx_agg_params {
 } dbx_agg_params;
 
 /* ----------------------------------------------------------------- top-k */
-/* SortColumnDescription{offset, asc, nulls_first} + LimitType::LimitRows(k)
- * (kernels/sort.rs:41-63).  Order: OrderedFloat (NaN greatest, -0 == +0). */
+/* SortColumnDescription{offset, asc, nulls_first} + LimitType::{LimitRows(k), None}
+ * (kernels/sort.rs:41-63).  Order: OrderedFloat (NaN greatest, -0 == +0); ties keep row order.
+ * limit = 0 (LimitType::None) sorts the whole input (device radix sort, up to 2^30 - 1 rows);
+ * 1 <= limit <= 4 Mi runs the streaming top-k.  Result block: [key, row_id Int64]. */
 typedef struct dbx_topk_params {
   int32_t key_col;
   int32_t asc;
@@ -316,6 +318,41 @@ const char* dbx_agg_exchange_last_error(const dbx_agg_exchange* x);
  * (part_offsets is HOST memory, n_parts + 1 entries).  Row order inside a partition is unspecified. */
 int32_t dbx_hash_partition(int32_t device, const dbx_block* block, int32_t key_col, int32_t n_parts,
                            void* const* out_cols, int64_t* part_offsets);
+
+/* Hash-partitioned row shuffle between the GPUs of one box over peer memory — the exchange in
+ * front of a partitioned hash join (flight_scatter_hash.rs:86-125 + the Flight exchange): ONE
+ * kernel partitions a device-resident block by the owner of its key (same owner rule as
+ * dbx_hash_partition / the aggregate exchange) and stores every row straight into the owner's
+ * receive region over NVLink.  Collective protocol: every rank alternates send / recv; recv
+ * returns one device-resident block per source rank (views into the receive buffer, valid until
+ * this rank's next-but-one send); a rank must be done reading them before its next send.
+ * col_types: dbx_dtype per column (fixed-width numeric, not nullable); region_rows: capacity of
+ * one (source, owner) region = the largest block a rank may send. */
+typedef struct dbx_shuffle dbx_shuffle;
+int32_t dbx_shuffle_create(int32_t device, int32_t rank, int32_t n_ranks, const int32_t* col_types, int32_t n_cols, int32_t key_col,
+                           int64_t region_rows, dbx_shuffle** out, void* ipc_handle_out /* 64 bytes, may be NULL */);
+int32_t dbx_shuffle_local_buffer(dbx_shuffle* s, void** base);
+int32_t dbx_shuffle_connect(dbx_shuffle* s, const void* all_handles /* n_ranks x 64 B */, void* const* same_process_ptrs);
+int32_t dbx_shuffle_send(dbx_shuffle* s, const dbx_block* block);
+int32_t dbx_shuffle_recv(dbx_shuffle* s, dbx_block* blocks /* n_ranks */, dbx_column* cols /* n_ranks x n_cols */);
+int32_t dbx_shuffle_last_ms(dbx_shuffle* s, float* send_ms, float* wait_ms);
+int32_t dbx_shuffle_destroy(dbx_shuffle* s);
+const char* dbx_shuffle_last_error(const dbx_shuffle* s);
+
+/* DataBlock kernels (src/query/expression/src/kernels): every column kind libdbx carries
+ * (numeric, Boolean, Vector(Float32), Nullable, Const).  Inputs may live on the host or the
+ * device; outputs are library-owned blocks (dbx_block_release) in `out_mem`.
+ *   take          take.rs:43-60     out row i = block row indices[i]
+ *   take_ranges   take_ranges.rs:40 concatenation of the row ranges [starts[r], starts[r] + lens[r])
+ *   scatter       scatter.rs:21     row i goes to outs[indices[i]], input order kept inside each output
+ *   concat        concat.rs:62      blocks appended in order (Const entries stay Const only when all agree) */
+int32_t dbx_block_take(int32_t device, const dbx_block* block, const uint32_t* indices, int64_t n_indices, int32_t indices_mem,
+                       int32_t out_mem, dbx_block* out);
+int32_t dbx_block_take_ranges(int32_t device, const dbx_block* block, const uint32_t* starts, const uint32_t* lens, int64_t n_ranges,
+                              int32_t out_mem, dbx_block* out);
+int32_t dbx_block_scatter(int32_t device, const dbx_block* block, const uint32_t* indices, int32_t indices_mem, int32_t n_parts,
+                          int32_t out_mem, dbx_block* outs /* n_parts */);
+int32_t dbx_block_concat(int32_t device, const dbx_block* blocks, int32_t n_blocks, int32_t out_mem, dbx_block* out);
 
 /* ScalarFunction::eval replacement for the vector distances (scalars/vector.rs:497-556):
  * out[i] = distance(lhs[i], rhs[i]) row-wise, either side may be const.  f32 result. */

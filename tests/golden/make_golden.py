@@ -107,6 +107,30 @@ kernel = {  # src/query/expression/tests/it/kernel.rs:54-68 + testdata/kernel-pa
         "result": [{"values": [0, 3, 1], "validity": [True, True, True]}, {"values": [10, 13, 11], "validity": [False, False, True]}],
         "src": "kernel.rs:94-108",
     },
+    "concat": [{  # kernel.rs:70-92 (numeric columns 0 and 1), kernel-pass.txt:21-52
+        "blocks": [
+            [{"dtype": "I32", "values": [0, 1, 2, 3, -4]},
+             {"dtype": "U8", "values": [10, 11, 12, 13, 14], "validity": [False, True, False, False, False]}],
+            [{"dtype": "I32", "values": [5, 6]}, {"dtype": "U8", "values": [15, 16], "validity": [False, True]}],
+        ],
+        "result": [{"values": [0, 1, 2, 3, -4, 5, 6], "validity": [True] * 7},
+                   {"values": [10, 11, 12, 13, 14, 15, 16], "validity": [False, True, False, False, False, False, True]}],
+        "src": "kernel.rs:70-92, kernel-pass.txt:21-52",
+    }],
+    "scatter": [{  # kernel.rs:181-196, kernel-pass.txt:211-247
+        "indices": [0, 0, 1, 2, 1],
+        "scatter_size": 3,
+        "columns": [
+            {"dtype": "I32", "values": [0, 1, 2, 3, -4]},
+            {"dtype": "U8", "values": [10, 11, 12, 13, 14], "validity": [False, True, False, False, False]},
+        ],
+        "results": [
+            [{"values": [0, 1], "validity": [True, True]}, {"values": [10, 11], "validity": [False, True]}],
+            [{"values": [2, -4], "validity": [True, True]}, {"values": [12, 14], "validity": [False, False]}],
+            [{"values": [3], "validity": [True]}, {"values": [13], "validity": [False]}],
+        ],
+        "src": "kernel.rs:181-196, kernel-pass.txt:211-247",
+    }],
 }
 
 misc = {

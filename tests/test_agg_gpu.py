@@ -464,6 +464,7 @@ def test_ring_kernel_lane_splits(gpu, monkeypatch, lanes):
     state words updated by TMA bulk reductions on some lanes and by REDs on the others.  Every split
     must give the oracle's result bit for bit (incl. the sentinel-valued key and a ragged tail that
     the generic kernel finishes)."""
+    monkeypatch.setenv("DBX_AGG_BULK", "1")  # the pair layout + ring kernel are opt-in (no gain measured)
     if lanes is not None:
         monkeypatch.setenv("DBX_AGG_BULK_LANES", lanes)
     blk = config2_block(3_000_017, n_keys=70_000)
@@ -471,9 +472,10 @@ def test_ring_kernel_lane_splits(gpu, monkeypatch, lanes):
     run_both(blk, CONFIG2, V_MOD3, device_resident=True)
 
 
-def test_ring_kernel_two_pairs_and_minmax(gpu):
+def test_ring_kernel_two_pairs_and_minmax(gpu, monkeypatch):
     """sum(v), count(*), sum(x), avg(x2), min(v), max(x) over device columns: two pairs (integer and
     f64) go through the bulk path, min/max and the leftovers through REDs."""
+    monkeypatch.setenv("DBX_AGG_BULK", "1")
     rng = np.random.default_rng(3)
     n = 1_500_000
     k = rng.integers(0, 20_000, n).astype(np.int64)
@@ -486,8 +488,7 @@ def test_ring_kernel_two_pairs_and_minmax(gpu):
     run_both(blk, params, None, device_resident=True, split=400_000, n_partials=2)
 
 
-def test_pairs_layout_off_matches(gpu, monkeypatch):
-    monkeypatch.setenv("DBX_AGG_BULK", "0")
+def test_default_red_layout_device_resident(gpu):
     run_both(config2_block(1_200_000, n_keys=30_000), CONFIG2, V_MOD3, device_resident=True)
 
 
@@ -527,3 +528,43 @@ def test_full_size_query_verified(gpu):
     assert v["ok"], v
     assert v["groups"] == v["expected_groups"] == n_keys
     assert v["oracle_subsample"]["bit_exact"]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("device_resident", [False, True])
+def test_float_group_keys(gpu, dtype, device_resident):
+    """GROUP BY a float column (group_hash.rs:599-619, payload_row.rs match on OrderedFloat): rows
+    group by bit pattern, every NaN is ONE group (canonical NaN), -0.0 and +0.0 are separate groups
+    (they hash differently in the reference), +-inf are ordinary keys.  Parity with the oracle."""
+    rng = np.random.default_rng(11)
+    n = 400_000
+    k = (rng.integers(-200, 200, n) / 8.0).astype(dtype)
+    k[rng.random(n) < 0.02] = np.nan
+    k[rng.random(n) < 0.01] = -0.0
+    k[rng.random(n) < 0.005] = np.inf
+    k[rng.random(n) < 0.005] = -np.inf
+    nan2 = np.array([0x7FF8000000000123], dtype=np.uint64).view(np.float64)[0] if dtype == np.float64 else np.array([0x7FC00123], dtype=np.uint32).view(np.float32)[0]
+    k[::1000] = nan2  # a NaN with another payload: same group
+    v = rng.integers(-2**40, 2**40, n).astype(np.int64)
+    x = rng.integers(0, 1 << 20, n).astype(np.float64)
+    blk = DataBlock([Column.from_data(k), Column.from_data(v), Column.from_data(x)])
+    params = AggregatorParams([0], [("sum", 1), ("count", 1), ("avg", 2), ("min", 1)])
+    filt = E.ne(E.col(1) % E.lit(5), E.lit(0))
+    blocks = blk.split_by_rows(150_000)
+    if device_resident:
+        blocks = [DataBlock([to_device(c) for c in b.columns], b.num_rows) for b in blocks]
+    out = filter_group_aggregate(blocks, params, filt, input_types=schema_types(blk), n_partials=2)
+    keys, kvalid, aggs, avalid, _ = oracle().filter_group_agg(blk, params.to_c(filt), threads=4)
+    w = np.uint64 if dtype == np.float64 else np.uint32
+    exp = {int(kb): tuple(a[i].item() for a in aggs) for i, kb in enumerate(keys[0].astype(np.uint64))}
+    gk = out.columns[4].values()
+    assert gk.dtype == dtype
+    got = {int(kb): tuple(out.columns[a].values()[i].item() for a in range(4)) for i, kb in enumerate(gk.view(w).astype(np.uint64))}
+    assert len(got) == out.num_rows, "a group appears twice"
+    assert got.keys() == exp.keys()
+    for kb in exp:
+        assert got[kb] == exp[kb], (hex(kb), got[kb], exp[kb])
+    nan_bits = [kb for kb in got if np.isnan(np.array([kb], dtype=np.uint64).astype(w).view(dtype)[0])]
+    assert len(nan_bits) == 1
+    zero_bits = {int(np.array([z], dtype=dtype).view(w)[0]) for z in (0.0, -0.0)}
+    assert zero_bits <= got.keys()

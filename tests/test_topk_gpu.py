@@ -119,3 +119,97 @@ def test_key_dtypes(gpu, dtype):
         vals = rng.integers(info.min, info.max, n, dtype=nd, endpoint=True)
     for asc in (True, False):
         run_topk(Column.from_data(vals), asc, False, 777, split=64_000)
+
+
+def test_more_nulls_than_k(gpu):
+    """More NULL keys than k (nulls first): the k NULL rows with the SMALLEST row ids are returned,
+    in row order (ties broken by ascending row id, like the oracle) — also across pushes."""
+    rng = np.random.default_rng(17)
+    n = 300_000
+    x = rng.normal(size=n)
+    valid = rng.random(n) > 0.4  # ~120 000 NULLs, k = 500
+    for asc in (True, False):
+        run_topk(Column.from_data(x, validity=valid), asc, True, 500, split=40_000)
+        run_topk(Column.from_data(x, validity=valid), asc, True, 500)
+        run_topk(Column.from_data(x, validity=valid), asc, False, 500, split=40_000)
+
+
+def test_large_k_radix_sort_path(gpu):
+    """k above the one-CTA rank sort (4096): the final order comes from the hand-written radix sort."""
+    x = oracle().synth_fill(3, 99, 0, 0, 2_000_000)
+    x[::7] = x[3]  # heavy ties: the row-id order decides
+    run_topk(Column.from_data(x), True, False, 50_000, split=300_000)
+    run_topk(Column.from_data(x), False, False, 20_000, device_resident=True)
+
+
+def test_small_candidate_list_forces_replay(gpu, monkeypatch):
+    """A candidate list far smaller than the block and adversarial (sorted) input: the optimistic
+    scan overflows, its appends are dropped, and the range is replayed in pieces that fit."""
+    monkeypatch.setenv("DBX_TOPK_CAP", "20000")
+    n = 3_000_000
+    x = np.arange(n, 0, -1).astype(np.float64)  # ASC top-k over descending data: every row beats the boundary
+    run_topk(Column.from_data(x), True, False, 100, device_resident=True)
+    y = oracle().synth_fill(3, 5, 0, 0, n)
+    run_topk(Column.from_data(y), True, False, 100, device_resident=True)
+
+
+def run_sort(col, asc, nulls_first, split=None, device_resident=False):
+    """ORDER BY without LIMIT (limit = 0): the full permutation must equal the oracle's stable sort."""
+    blk = DataBlock([col])
+    op = TransformTopN(0, asc, nulls_first, 0, schema_types(blk))
+    blocks = blk.split_by_rows(split) if split else [blk]
+    for b in blocks:
+        if device_resident:
+            b = DataBlock([to_device(c) for c in b.columns], b.num_rows)
+        op.transform(b)
+    out = op.on_finish()
+    op.close()
+    ref = oracle().topk(col, asc, nulls_first, col.length)
+    np.testing.assert_array_equal(out.columns[1].values(), ref)
+    valid = col.valid_mask()[ref]
+    if col.validity is not None:
+        np.testing.assert_array_equal(out.columns[0].valid_mask(), valid)
+    src, got = col.values()[ref], out.columns[0].values()
+    if src.dtype.kind == "f":
+        w = np.uint64 if src.itemsize == 8 else np.uint32
+        np.testing.assert_array_equal(got[valid].view(w), src[valid].view(w))
+    else:
+        np.testing.assert_array_equal(got[valid], src[valid])
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 4095, 4096, 4097, 100_003, 1_500_000])
+def test_full_sort_f64(gpu, n):
+    x = oracle().synth_fill(3, 31 + n, 0, 0, n)
+    for asc in (True, False):
+        run_sort(Column.from_data(x), asc, False, split=250_000 if n > 250_000 else None)
+
+
+def test_full_sort_adversarial_and_nulls(gpu):
+    rng = np.random.default_rng(21)
+    n = 700_000
+    x = rng.integers(-30, 30, n).astype(np.float64) / 4.0  # heavy ties: stability = row order
+    x[rng.random(n) < 0.01] = np.nan
+    x[rng.random(n) < 0.01] = -0.0
+    x[rng.random(n) < 0.001] = np.inf
+    x[rng.random(n) < 0.001] = -np.inf
+    valid = rng.random(n) > 0.05
+    for asc in (True, False):
+        run_sort(Column.from_data(x), asc, False, split=100_000)
+        for nulls_first in (True, False):
+            run_sort(Column.from_data(x, validity=valid), asc, nulls_first, split=90_000)
+    run_sort(Column.from_data(x), True, False, device_resident=True)
+
+
+@pytest.mark.parametrize("dtype", [abi.I8, abi.I32, abi.I64, abi.U16, abi.U64, abi.F32])
+def test_full_sort_dtypes(gpu, dtype):
+    from databend_b200.block import np_dtype
+    rng = np.random.default_rng(dtype + 100)
+    nd = np_dtype(dtype)
+    n = 300_000
+    if nd.kind == "f":
+        vals = rng.normal(size=n).astype(nd)
+    else:
+        info = np.iinfo(nd)
+        vals = rng.integers(info.min, info.max, n, dtype=nd, endpoint=True)
+    for asc in (True, False):
+        run_sort(Column.from_data(vals), asc, False, split=77_000)
