@@ -231,3 +231,59 @@ def partitioned_hash_join_peer(build: DataBlock, probe: DataBlock, build_key: in
     if stats is not None:
         stats.update(ms)
     return outs, j, (sb, sp)
+
+
+def _dev_tensor(ptr: int, nbytes: int, device: int) -> torch.Tensor:
+    """uint8 view of library-owned device memory (no copy)."""
+    class _H:
+        pass
+    h = _H()
+    h.__cuda_array_interface__ = {"shape": (max(nbytes, 0),), "typestr": "|u1", "data": (ptr, False), "version": 2}
+    return torch.as_tensor(h, device=f"cuda:{device}")
+
+
+def topk_merge_device(local_op: TransformTopN, row_base: int, k: int, final_op: TransformTopN, device: int = 0, group=None) -> DataBlock:
+    """Multi-GPU top-k merge without the host in the data path (non-nullable keys): every rank's
+    sorted top-k stays in HBM (dbx_op_pull with DBX_MEM_DEVICE), keys and GLOBAL row ids are
+    all-gathered as device tensors, and the final TransformTopN consumes the gathered candidates as
+    one device-resident block.  Candidates are concatenated in rank order and each rank's block is
+    already in output order, so equal keys keep ascending global row ids.  Only the k result rows
+    reach the host."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    local_op.finish()
+    b = local_op.pull_c(abi.MEM_DEVICE)
+    n = b.num_rows
+    kcol, rcol = b.cols[0], b.cols[1]
+    esz = np_dtype(kcol.dtype).itemsize
+    if kcol.validity:
+        check(load().dbx_block_release(C.byref(b)))
+        raise ValueError("topk_merge_device: nullable keys take the host merge (topk_merge)")
+    pad_k = torch.zeros(k * esz, dtype=torch.uint8, device=f"cuda:{device}")
+    pad_r = torch.zeros(k, dtype=torch.int64, device=f"cuda:{device}")
+    if n:
+        pad_k[: n * esz] = _dev_tensor(kcol.data, n * esz, device)
+        pad_r[:n] = _dev_tensor(rcol.data, n * 8, device).view(torch.int64) + row_base
+    check(load().dbx_block_release(C.byref(b)))
+    cnt = torch.tensor([n], dtype=torch.int64, device=f"cuda:{device}")
+    if world > 1:
+        gk = torch.empty(world * k * esz, dtype=torch.uint8, device=f"cuda:{device}")
+        gr = torch.empty(world * k, dtype=torch.int64, device=f"cuda:{device}")
+        gc = torch.empty(world, dtype=torch.int64, device=f"cuda:{device}")
+        dist.all_gather_into_tensor(gk, pad_k, group=group)
+        dist.all_gather_into_tensor(gr, pad_r, group=group)
+        dist.all_gather_into_tensor(gc, cnt, group=group)
+        counts = gc.tolist()
+        if all(c == k for c in counts):
+            keys, rows = gk, gr
+        else:  # ragged (a rank with fewer than k rows): compact on the device
+            keys = torch.cat([gk[r * k * esz: r * k * esz + counts[r] * esz] for r in range(world)])
+            rows = torch.cat([gr[r * k: r * k + counts[r]] for r in range(world)])
+    else:
+        keys, rows = pad_k[: n * esz], pad_r[:n]
+    m = rows.numel()
+    torch.cuda.current_stream().synchronize()
+    final_op.reset()
+    final_op.transform(DataBlock([Column.device(kcol.dtype, m, keys.data_ptr())], m))
+    out = final_op.on_finish()
+    pos = torch.from_numpy(out.columns[1].values().astype(np.int64)).to(f"cuda:{device}")
+    return DataBlock([out.columns[0], Column.from_data(rows[pos].cpu().numpy())], out.num_rows)

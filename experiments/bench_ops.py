@@ -23,7 +23,10 @@ from databend_b200.lib import check, load  # noqa: E402
 from databend_b200.transforms import DeviceBuffer, HashJoin, TransformFilter, TransformTopN  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--ops", default="join,topk,filter")
+ap.add_argument("--ops", default="join,topk,sort,filter")
+ap.add_argument("--sort-rows", type=int, default=250_000_000)
+ap.add_argument("--join-shuffle", default="peer", choices=["peer", "nccl"])
+ap.add_argument("--round-rows", type=int, default=32 << 20)
 ap.add_argument("--fact-rows", type=int, default=1_000_000_000)
 ap.add_argument("--dim-rows", type=int, default=10_000_000)
 ap.add_argument("--topk-rows", type=int, default=1_000_000_000)
@@ -83,10 +86,30 @@ if "join" in ops:
     dim = DataBlock([Column.device(abi.I64, nd, dk.ptr), Column.device(abi.I64, nd, dv.ptr)], nd)
     fact = DataBlock([Column.device(abi.I64, nf, fk.ptr), Column.device(abi.I64, nf, fv.ptr)], nf)
     best = None
+    best_stats = None
     for rep in range(a.reps):
         sync_all()
         t0 = time.perf_counter()
         keep = None
+        if world > 1 and a.join_shuffle == "peer":
+            from databend_b200.distributed import partitioned_hash_join_peer
+            st = {}
+            outs, j, shufs = partitioned_hash_join_peer(dim, fact, 0, 0, dev, rank, world, round_rows=a.round_rows, out_mem=abi.MEM_DEVICE, stats=st)
+            out_rows = 0
+            for ob in outs:
+                out_rows += ob.num_rows
+                L.dbx_block_release(C.byref(ob))
+            sync_all()
+            total = time.perf_counter() - t0
+            for s_ in shufs:
+                s_.close()
+            j.close()
+            rec = (max_over_ranks(total), max_over_ranks((st["shuffle_send"] + st["shuffle_wait"]) * 1e-3), max_over_ranks(st["build"] * 1e-3),
+                   max_over_ranks(st["probe"] * 1e-3), max_over_ranks(st["probe"]), out_rows)
+            if best is None or rec[0] < best[0]:
+                best = rec
+                best_stats = {k_: max_over_ranks(v_) for k_, v_ in st.items()}
+            continue
         if world > 1:
             from databend_b200.distributed import shuffle_by_key
             dim_l, k1 = shuffle_by_key(dim, 0, dev)
@@ -130,7 +153,8 @@ if "join" in ops:
           "shuffle_ms": t_shuffle * 1e3, "build_ms": t_build * 1e3, "probe_wall_ms": t_probe * 1e3, "probe_kernel_ms": probe_ms,
           "roofline": {"bound": "hbm", "bytes_per_fact_row": 64, "note": "read fk,fv (16) + table bucket (32-byte sector) + write 4 x 8 (32) = 80 with dk materialised; 56 by SURVEY 8d (3 output columns, dim row gather)",
                        "achieved_GBs_per_gpu": 56.0 * rows_per_gpu / (probe_ms * 1e-3) / 1e9, "peak": HBM, "frac": 56.0 * rows_per_gpu / (probe_ms * 1e-3) / 1e9 / HBM},
-          "parallelism": "single GPU" if world == 1 else f"hash-partition x{world}: dbx_hash_partition + NCCL all-to-all per side and column"})
+          "shuffle_phases_ms": best_stats,
+          "parallelism": "single GPU" if world == 1 else (f"hash-partition x{world}: fused partition + store-to-peer kernel over NVLink (dbx_shuffle), {a.round_rows} rows per rank and round" if a.join_shuffle == "peer" else f"hash-partition x{world}: dbx_hash_partition + NCCL all-to-all per side and column")})
     for b_ in (fk, fv, dk, dv):
         b_.free()
 
@@ -148,13 +172,12 @@ if "topk" in ops:
         sync_all()
         t0 = time.perf_counter()
         op.transform(DataBlock([col], n))
-        k_ms = op.last_kernel_ms()
-        local = op.on_finish()
         if world > 1:
-            from databend_b200.distributed import topk_merge
-            res = topk_merge(local, r0, 1000, True, False, dev, final_op=fop)
+            from databend_b200.distributed import topk_merge_device
+            res = topk_merge_device(op, r0, 1000, fop, dev)
         else:
-            res = local
+            res = op.on_finish()
+        k_ms = op.last_kernel_ms()
         sync_all()
         dt = max_over_ranks(time.perf_counter() - t0)
         if rep and (best is None or dt < best):
@@ -164,7 +187,38 @@ if "topk" in ops:
           "total_ms": best * 1e3, "scan_ms_incl_candidate_cuts": kms, "first_key": float(res.columns[0].values()[0]),
           "roofline": {"bound": "hbm", "bytes_per_row": 8, "achieved_GBs_per_gpu": 8.0 * n / (kms * 1e-3) / 1e9, "peak": HBM,
                        "frac": 8.0 * n / (kms * 1e-3) / 1e9 / HBM},
-          "parallelism": "single GPU" if world == 1 else f"row ranges x{world} + all-gather of 1000 candidates per rank + final top-k"})
+          "parallelism": "single GPU" if world == 1 else f"row ranges x{world} + device all-gather of 1000 candidates per rank + final top-k"})
+    xb.free()
+
+if "sort" in ops and world == 1:
+    # ORDER BY float64 without LIMIT: hand-written onesweep LSD radix sort of (ordered key, row id)
+    n = a.sort_rows
+    xb = fill(3, 13, 0, 0, n)
+    col = Column.device(abi.F64, n, xb.ptr)
+    op = TransformTopN(0, True, False, 0, [abi.F64], dev)
+    best = None
+    for rep in range(a.reps):
+        op.reset()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        op.transform(DataBlock([col], n))
+        op.finish()
+        ob = op.pull_c(abi.MEM_DEVICE)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        first = DeviceBuffer.__new__(DeviceBuffer)
+        first.device, first.nbytes, first.ptr = dev, 16, ob.cols[0].data
+        head = first.download(np.float64, 2)
+        first.ptr = 0
+        L.dbx_block_release(C.byref(ob))
+        if best is None or dt < best:
+            best = dt
+    op.close()
+    # 8 digit passes x (8 + 4 B read + 8 + 4 B written) + one histogram read + ingest/emit
+    emit({"op": "sort", "workload": "ORDER BY float64 (no LIMIT): full device radix sort, keys + row ids out", "rows": n,
+          "rows_per_s": n / best, "total_ms": best * 1e3, "first_keys": [float(head[0]), float(head[1])],
+          "roofline": {"bound": "hbm", "bytes_per_row": 8 * 24 + 8 + 28 + 24, "note": "8 LSD passes x 24 B + histogram 8 B + ingest (8 read, 20 written) + emit (12 + 8 gather read, 16 written)",
+                       "achieved_GBs": (8 * 24 + 8 + 28 + 24 + 12) * n / best / 1e9, "peak": HBM, "frac": (8 * 24 + 8 + 28 + 36) * n / best / 1e9 / HBM}})
     xb.free()
 
 if "filter" in ops and world == 1:
