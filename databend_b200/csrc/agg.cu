@@ -1570,7 +1570,14 @@ int32_t dbx_agg_exchange_scatter(dbx_agg_exchange* x, dbx_op* partial_op) {
   sp.n_ranks = x->n_ranks; sp.rank = x->rank; sp.row_words = x->row_words; sp.parity = (int)(x->epoch & 1);
   sp.clear_src = x->fused_clear ? 1 : 0;
   sp.init = p->plan.init;
-  exchange_scatter_kernel<<<grid_for_entries(sp.src.cap + 2), 256, (size_t)256 * x->row_words * 8, p->stream>>>(sp);
+  {
+    static std::atomic<bool> attr_set[64];
+    if (!attr_set[x->device]) {
+      DBX_CUDA_TRY(x->err, cudaFuncSetAttribute(exchange_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * kScatterSlots * kExchMaxRowWords * 8));
+      attr_set[x->device] = true;
+    }
+  }
+  exchange_scatter_kernel<<<grid_for_entries((sp.src.cap + 2 + kScatterSlots - 1) / kScatterSlots), 256, (size_t)256 * kScatterSlots * x->row_words * 8, p->stream>>>(sp);
   count_launch();
   DBX_CUDA_TRY(x->err, cudaGetLastError());
   if (x->fused_clear) {  // the table is empty again: only the counters are left to reset

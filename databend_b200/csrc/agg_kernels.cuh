@@ -1026,12 +1026,13 @@ __device__ __forceinline__ uint64_t* exchange_region(void* base, int n_ranks, in
 }
 
 constexpr int kExchMaxRowWords = 2 + kMaxWords;
+constexpr int kScatterSlots = 4;  // table slots per thread and step
 __global__ void __launch_bounds__(256) exchange_scatter_kernel(const __grid_constant__ ExchangeScatterParams x) {
-  // Per 256-slot step: count the step's groups per owner, reserve a run in every owner's region
-  // with ONE atomic per owner, lay the rows out owner after owner in shared memory, then copy
-  // each owner's run with consecutive 8-byte stores — NVLink sees full 128-byte lines instead of
-  // scattered 8-byte writes.
-  extern __shared__ __align__(16) uint64_t s_rows[];  // [256][row_words]
+  // Per step of 1024 slots (4 per thread): count the step's groups per owner, reserve a run in every
+  // owner's region with ONE atomic per owner, lay the rows out owner after owner in shared memory,
+  // then copy each owner's run with consecutive 8-byte stores — NVLink sees full 128-byte lines
+  // instead of scattered 8-byte writes, and the barriers are amortised over four slots per thread.
+  extern __shared__ __align__(16) uint64_t s_rows[];  // [1024][row_words]
   __shared__ unsigned int s_cnt[kMaxRanks];
   __shared__ unsigned int s_off[kMaxRanks + 1];
   __shared__ unsigned long long s_base[kMaxRanks];
@@ -1039,21 +1040,30 @@ __global__ void __launch_bounds__(256) exchange_scatter_kernel(const __grid_cons
   const TableDev& src = x.src;
   const int rw = x.row_words;
   const int64_t n_slots = src.cap + 2;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int64_t n_iter = (n_slots + stride - 1) / stride;
-  for (int64_t it = 0; it < n_iter; ++it) {
+  const int64_t step_slots = 256 * kScatterSlots;
+  const int64_t n_steps = (n_slots + step_slots - 1) / step_slots;
+  for (int64_t st = blockIdx.x; st < n_steps; st += gridDim.x) {
     if (threadIdx.x < kMaxRanks) s_cnt[threadIdx.x] = 0;
     __syncthreads();
-    const int64_t i = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint64_t key = kEmptyKey;
-    if (i < n_slots) key = src.keys[i];
-    const bool occ = key != kEmptyKey;
-    const int key_kind = (occ && i >= src.cap) ? (int)(i - src.cap) + 1 : 0;
-    int owner = 0;
-    unsigned int local = 0;
-    if (occ) {
-      owner = owner_of(key, key_kind, x.n_ranks);
-      local = atomicAdd(&s_cnt[owner], 1u);
+    const int64_t i0 = st * step_slots + threadIdx.x;
+    uint64_t key[kScatterSlots];
+    int owner[kScatterSlots];
+    unsigned int local[kScatterSlots];
+#pragma unroll
+    for (int j = 0; j < kScatterSlots; ++j) {
+      const int64_t i = i0 + (int64_t)j * 256;
+      key[j] = i < n_slots ? src.keys[i] : kEmptyKey;
+    }
+#pragma unroll
+    for (int j = 0; j < kScatterSlots; ++j) {
+      const int64_t i = i0 + (int64_t)j * 256;
+      owner[j] = -1;
+      local[j] = 0;
+      if (key[j] != kEmptyKey) {
+        const int key_kind = i >= src.cap ? (int)(i - src.cap) + 1 : 0;
+        owner[j] = owner_of(key[j], key_kind, x.n_ranks);
+        local[j] = atomicAdd(&s_cnt[owner[j]], 1u);
+      }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1064,9 +1074,13 @@ __global__ void __launch_bounds__(256) exchange_scatter_kernel(const __grid_cons
     if (threadIdx.x < x.n_ranks && s_cnt[threadIdx.x])
       s_base[threadIdx.x] = atomicAdd(&x.cursors[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
     __syncthreads();
-    if (occ) {
-      uint64_t* r = s_rows + (size_t)(s_off[owner] + local) * rw;
-      r[0] = key_kind ? 0 : key;
+#pragma unroll
+    for (int j = 0; j < kScatterSlots; ++j) {
+      if (owner[j] < 0) continue;
+      const int64_t i = i0 + (int64_t)j * 256;
+      const int key_kind = i >= src.cap ? (int)(i - src.cap) + 1 : 0;
+      uint64_t* r = s_rows + (size_t)(s_off[owner[j]] + local[j]) * rw;
+      r[0] = key_kind ? 0 : key[j];
       r[1] = (uint64_t)key_kind;
       for (int w = 0; w < src.n_words; ++w) r[2 + w] = *word_ptr(src, i, w);
       if (x.clear_src) {  // the slot is read by this thread only: leave the table ready for the next query

@@ -356,9 +356,9 @@ class JoinOp : public Op {
       DBX_TRY(stager.stage(col, c, &dc));
       GrowCol& g = build[c];
       const size_t need = (size_t)(build_rows + n) * g.size;
-      if (need > g.data.bytes) {  // grow, preserving the rows already appended
+      if (need > g.data.bytes) {  // grow, preserving the rows already appended (the hint avoids re-allocations)
         DevBuf nb;
-        DBX_CUDA_TRY(err, nb.ensure(std::max(need, g.data.bytes * 2)));
+        DBX_CUDA_TRY(err, nb.ensure(std::max({need, g.data.bytes * 2, (size_t)std::max<int64_t>(prm.expected_build_rows, 0) * g.size})));
         if (build_rows) DBX_CUDA_TRY(err, cudaMemcpyAsync(nb.p, g.data.p, (size_t)build_rows * g.size, cudaMemcpyDeviceToDevice, stream));
         DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
         g.data = std::move(nb);
@@ -368,7 +368,7 @@ class JoinOp : public Op {
         const size_t vneed = (size_t)(build_rows + n);
         if (vneed > g.valid_bytes.bytes) {
           DevBuf nb;
-          DBX_CUDA_TRY(err, nb.ensure(std::max(vneed, g.valid_bytes.bytes * 2)));
+          DBX_CUDA_TRY(err, nb.ensure(std::max({vneed, g.valid_bytes.bytes * 2, (size_t)std::max<int64_t>(prm.expected_build_rows, 0)})));
           if (build_rows) DBX_CUDA_TRY(err, cudaMemcpyAsync(nb.p, g.valid_bytes.p, (size_t)build_rows, cudaMemcpyDeviceToDevice, stream));
           DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
           g.valid_bytes = std::move(nb);

@@ -174,40 +174,36 @@ def allreduce_single_state(partial, final, device: int = 0, group=None, out_mem:
     return out[0]
 
 
-def partitioned_hash_join_peer(build: DataBlock, probe: DataBlock, build_key: int, probe_key: int, device: int, rank: int, world: int,
-                               round_rows: int = 32 << 20, out_mem: int = abi.MEM_HOST, group=None, kind: int = abi.JOIN_INNER,
-                               stats: dict = None):
+class PartitionedHashJoin:
     """Partitioned hash join with the FUSED shuffle (BASELINE configs[2]): both sides are
     hash-partitioned by key and stored straight into the owners' HBM over NVLink by one kernel per
     round (dbx_shuffle_send; no pack pass, no per-column library all-to-all), `round_rows` rows per
     rank and round; every received region is handed to the local join as a device block.
     Reference: flight_scatter_hash.rs:86-125 (scatter) + new_hash_join/memory/inner_join.rs:122-262.
-    Returns (joined blocks of this rank, join op, shuffles) — close the shuffles when done."""
-    import time
-    from .exchange import PeerShuffle
-    t = torch.tensor([build.num_rows, probe.num_rows], dtype=torch.int64)
-    if world > 1:
-        if dist.get_backend(group) == "nccl":
-            t = t.to(f"cuda:{device}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-    max_build, max_probe = [int(v) for v in t.tolist()]
-    sb = PeerShuffle(device, rank, world, [c.dtype for c in build.columns], build_key, max(1, min(round_rows, max_build)))
-    sp = PeerShuffle(device, rank, world, [c.dtype for c in probe.columns], probe_key, max(1, min(round_rows, max_probe)))
-    if world > 1:
-        sb.connect(group)
-        sp.connect(group)
-    else:
-        sb.connect_local([sb])
-        sp.connect_local([sp])
-    j = HashJoin(schema_types(build), schema_types(probe), build_key, probe_key, device, kind)
-    ms = {"shuffle_send": 0.0, "shuffle_wait": 0.0, "build": 0.0, "probe": 0.0}
+    The constructor is collective (receive buffers + IPC mapping, once per schema); `run` joins one
+    pair of row-range-sharded tables."""
 
-    def rounds(shuf, blk, total_max, each):
-        step = max(1, min(round_rows, total_max))
+    def __init__(self, build_types: Sequence[int], probe_types: Sequence[int], build_key: int, probe_key: int, device: int, rank: int,
+                 world: int, max_build_rows: int, max_probe_rows: int, round_rows: int = 32 << 20, group=None, kind: int = abi.JOIN_INNER):
+        from .exchange import PeerShuffle
+        self.device, self.rank, self.world, self.round_rows = device, rank, world, round_rows
+        self.build_types, self.probe_types, self.build_key, self.probe_key, self.kind = list(build_types), list(probe_types), build_key, probe_key, kind
+        self.max_build, self.max_probe = max_build_rows, max_probe_rows
+        self.sb = PeerShuffle(device, rank, world, [t & 0xFF for t in build_types], build_key, max(1, min(round_rows, max_build_rows)))
+        self.sp = PeerShuffle(device, rank, world, [t & 0xFF for t in probe_types], probe_key, max(1, min(round_rows, max_probe_rows)))
+        if world > 1:
+            self.sb.connect(group)
+            self.sp.connect(group)
+        else:
+            self.sb.connect_local([self.sb])
+            self.sp.connect_local([self.sp])
+
+    def _rounds(self, shuf, blk, total_max, each, j, ms):
+        import time
+        step = max(1, min(self.round_rows, total_max))
         for lo in range(0, max(total_max, 1), step):
-            hi = min(blk.num_rows, lo + step)
-            piece = blk.slice(min(lo, blk.num_rows), max(hi, min(lo, blk.num_rows)))
-            shuf.send(piece)
+            a = min(lo, blk.num_rows)
+            shuf.send(blk.slice(a, max(min(blk.num_rows, lo + step), a)))
             got = shuf.recv()
             lm = shuf.last_ms()
             ms["shuffle_send"] += lm["send"]
@@ -217,20 +213,45 @@ def partitioned_hash_join_peer(build: DataBlock, probe: DataBlock, build_key: in
                 if b.num_rows:
                     each(b)
             j.synchronize()  # the regions may be overwritten two sends from now: be done reading them
-            return_ms = (time.perf_counter() - t0) * 1e3
-            yield return_ms
+            yield (time.perf_counter() - t0) * 1e3
 
-    for m in rounds(sb, build, max_build, j.add_block):
-        ms["build"] += m
-    t0 = time.perf_counter()
-    j.final_build()
-    ms["build"] += (time.perf_counter() - t0) * 1e3
-    outs = []
-    for m in rounds(sp, probe, max_probe, lambda b: outs.extend(j.probe_block(b, out_mem))):
-        ms["probe"] += m
-    if stats is not None:
-        stats.update(ms)
-    return outs, j, (sb, sp)
+    def run(self, build: DataBlock, probe: DataBlock, out_mem: int = abi.MEM_HOST, stats: dict = None):
+        """-> (joined blocks of this rank, join operator); close the operator when done with the blocks."""
+        import time
+        j = HashJoin(self.build_types, self.probe_types, self.build_key, self.probe_key, self.device, self.kind,
+                     expected_build_rows=int(self.max_build * 1.25) + 1024)
+        ms = {"shuffle_send": 0.0, "shuffle_wait": 0.0, "build": 0.0, "probe": 0.0}
+        for m in self._rounds(self.sb, build, self.max_build, j.add_block, j, ms):
+            ms["build"] += m
+        t0 = time.perf_counter()
+        j.final_build()
+        ms["build"] += (time.perf_counter() - t0) * 1e3
+        outs = []
+        for m in self._rounds(self.sp, probe, self.max_probe, lambda b: outs.extend(j.probe_block(b, out_mem)), j, ms):
+            ms["probe"] += m
+        if stats is not None:
+            stats.update(ms)
+        return outs, j
+
+    def close(self):
+        self.sb.close()
+        self.sp.close()
+
+
+def partitioned_hash_join_peer(build: DataBlock, probe: DataBlock, build_key: int, probe_key: int, device: int, rank: int, world: int,
+                               round_rows: int = 32 << 20, out_mem: int = abi.MEM_HOST, group=None, kind: int = abi.JOIN_INNER,
+                               stats: dict = None):
+    """One-shot form of PartitionedHashJoin (set-up included): returns (joined blocks, join op, [the object to close])."""
+    t = torch.tensor([build.num_rows, probe.num_rows], dtype=torch.int64)
+    if world > 1:
+        if dist.get_backend(group) == "nccl":
+            t = t.to(f"cuda:{device}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    max_build, max_probe = [int(v) for v in t.tolist()]
+    pj = PartitionedHashJoin(schema_types(build), schema_types(probe), build_key, probe_key, device, rank, world, max_build, max_probe,
+                             round_rows, group, kind)
+    outs, j = pj.run(build, probe, out_mem, stats)
+    return outs, j, (pj,)
 
 
 def _dev_tensor(ptr: int, nbytes: int, device: int) -> torch.Tensor:
@@ -254,7 +275,8 @@ def topk_merge_device(local_op: TransformTopN, row_base: int, k: int, final_op: 
     b = local_op.pull_c(abi.MEM_DEVICE)
     n = b.num_rows
     kcol, rcol = b.cols[0], b.cols[1]
-    esz = np_dtype(kcol.dtype).itemsize
+    key_dtype = kcol.dtype  # (the descriptors die with the block below)
+    esz = np_dtype(key_dtype).itemsize
     if kcol.validity:
         check(load().dbx_block_release(C.byref(b)))
         raise ValueError("topk_merge_device: nullable keys take the host merge (topk_merge)")
@@ -283,7 +305,7 @@ def topk_merge_device(local_op: TransformTopN, row_base: int, k: int, final_op: 
     m = rows.numel()
     torch.cuda.current_stream().synchronize()
     final_op.reset()
-    final_op.transform(DataBlock([Column.device(kcol.dtype, m, keys.data_ptr())], m))
+    final_op.transform(DataBlock([Column.device(key_dtype, m, keys.data_ptr())], m))
     out = final_op.on_finish()
     pos = torch.from_numpy(out.columns[1].values().astype(np.int64)).to(f"cuda:{device}")
     return DataBlock([out.columns[0], Column.from_data(rows[pos].cpu().numpy())], out.num_rows)

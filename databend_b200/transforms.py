@@ -313,11 +313,12 @@ class HashJoin(_Op):
     unspecified (compare as multisets)."""
 
     def __init__(self, build_types: Sequence[int], probe_types: Sequence[int], build_key: int, probe_key: int,
-                 device: int = 0, kind: int = abi.JOIN_INNER):
+                 device: int = 0, kind: int = abi.JOIN_INNER, expected_build_rows: int = 0):
         """kind: abi.JOIN_INNER, JOIN_LEFT_SEMI or JOIN_LEFT_ANTI (probe side = left; semi/anti
         emit probe columns only: left_join_semi.rs / left_join_anti.rs)."""
         p = abi.JoinParams()
         p.kind, p.build_key_col, p.probe_key_col, p.n_build_cols = kind, build_key, probe_key, len(build_types)
+        p.expected_build_rows = expected_build_rows
         super().__init__(abi.OP_JOIN, p, list(build_types) + list(probe_types), device)
 
     def add_block(self, block: DataBlock):
