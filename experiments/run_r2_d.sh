@@ -1,0 +1,31 @@
+#!/bin/bash
+# round 2, GPU call D (1 GPU): ncu launch lists of top-k / sort / join, full capture of the agg kernel
+mkdir -p gpurun_out
+NCU="ncu --metrics gpu__time_duration.sum --clock-control none --csv"
+timeout 300 $NCU --log-file gpurun_out/r2d_topk_launches.csv python experiments/bench_ops.py --ops topk --reps 1 > gpurun_out/r2d_topk.log 2>&1
+timeout 300 $NCU --log-file gpurun_out/r2d_sort_launches.csv python experiments/bench_ops.py --ops sort --sort-rows 100000000 --reps 1 > gpurun_out/r2d_sort.log 2>&1
+timeout 400 $NCU --log-file gpurun_out/r2d_join_launches.csv python experiments/bench_ops.py --ops join --fact-rows 250000000 --reps 1 > gpurun_out/r2d_join.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:filter_group_agg -s 4 -c 1 -f -o gpurun_out/r2d_prof_agg python bench.py --no-e2e --no-cpu --no-knn --no-verify --steps 1 --warmup 1 > gpurun_out/r2d_ncu_agg.log 2>&1
+timeout 300 ncu --metrics lts__t_sectors_op_red.sum,lts__t_sectors_op_atom.sum,lts__t_requests_srcunit_tex_op_red.sum,lts__t_sectors_srcunit_tex_op_read.sum,lts__t_sector_hit_rate.pct,lts__t_sectors_op_read.sum,lts__t_sectors_op_write.sum,l1tex__t_set_accesses_pipe_lsu_mem_global_op_red.sum,lts__throughput.avg.pct_of_peak_sustained_elapsed,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:filter_group_agg -s 4 -c 1 --csv --log-file gpurun_out/r2d_agg_red_counters.csv python bench.py --no-e2e --no-cpu --no-knn --no-verify --steps 1 --warmup 1 > gpurun_out/r2d_ncu_agg2.log 2>&1
+python - <<'P'
+import csv, collections
+for name in ["topk", "sort", "join"]:
+    try:
+        rows = list(csv.reader(open(f"gpurun_out/r2d_{name}_launches.csv")))
+    except Exception as e:
+        print(name, e); continue
+    hdr = None
+    agg = collections.OrderedDict()
+    for r in rows:
+        if len(r) > 5 and r[0] == "ID": hdr = r; continue
+        if hdr and len(r) == len(hdr):
+            d = dict(zip(hdr, r))
+            try: v = float(d["Metric Value"].replace(",", ""))
+            except: continue
+            k = d["Kernel Name"][:70]
+            a = agg.setdefault(k, [0, 0.0]); a[0] += 1; a[1] += v
+    print("==", name)
+    for k, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:14]:
+        print(f"{k:70s} n={c:5d} total={t/1e6:9.3f} ms")
+P
+tail -3 gpurun_out/r2d_ncu_agg.log; cat gpurun_out/r2d_agg_red_counters.csv | tail -15
