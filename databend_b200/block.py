@@ -218,8 +218,18 @@ class DataBlock:
         """DataBlock::split_by_rows_no_tail-like helper used by TransformFilter."""
         return [self.slice(s, min(s + max_rows, self.num_rows)) for s in range(0, self.num_rows, max_rows)] or [self]
 
+    def freeze(self) -> "DataBlock":
+        """Build the C descriptors once and reuse them on every as_c() (the block must not change
+        afterwards): what a compiled caller does anyway — only the Python mirror rebuilds them per call."""
+        self._frozen = None
+        self._frozen = self.as_c()
+        return self
+
     def as_c(self):
         """Returns (dbx_block, keepalive)."""
+        fz = getattr(self, "_frozen", None)
+        if fz is not None:
+            return fz
         arr = (abi.Column * max(1, len(self.columns)))()
         for i, c in enumerate(self.columns):
             arr[i] = c.as_c()

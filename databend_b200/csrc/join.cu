@@ -251,6 +251,132 @@ __global__ void __launch_bounds__(kJoinBlock) join_probe_kernel(const __grid_con
   }
 }
 
+// Does any key occur twice on the build side?  One thread per slot walks the rest of the slot's
+// probe sequence (short at load factor <= 0.5).  A build side without duplicates (the usual
+// primary-key dimension table) lets the probe stop at its first match instead of walking on to the
+// next empty entry: one dependent L2 round trip per probe row instead of two or more.
+__global__ void join_dup_check_kernel(const __grid_constant__ JoinTableDev t, unsigned int* dup) {
+  const int64_t mask = t.region - 1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < t.cap; i += (int64_t)gridDim.x * blockDim.x) {
+    const JoinEntry e = t.entries[i];
+    if (e.row1 == 0) continue;
+    const int64_t rb = i & ~mask;
+    int64_t s = (i + 1) & mask;
+    for (;;) {
+      const JoinEntry f = t.entries[rb + s];
+      if (f.row1 == 0) break;
+      if (f.key == e.key) { *dup = 1; break; }
+      s = (s + 1) & mask;
+      if (rb + s == i) break;
+    }
+  }
+}
+
+// probe_block + JoinStream::next fused, two probe rows per thread: both rows' entry loads are in
+// flight together (the probe is bound by dependent L2 round trips, not by bytes).  UNIQUE: the
+// build side has no duplicate keys, so a row's walk ends at its first match.
+template <bool UNIQUE>
+__global__ void __launch_bounds__(kJoinBlock) join_probe2_kernel(const __grid_constant__ JoinProbeParams p) {
+  __shared__ unsigned int s_warp[kJoinBlock / 32];
+  __shared__ unsigned long long s_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t mask = p.table.region - 1;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x * 2;
+  const int64_t n_iter = (p.n_rows + step - 1) / step;
+  const int64_t row_end = p.row_begin + p.n_rows;
+  for (int64_t it = 0; it < n_iter; ++it) {
+    int64_t r[2];
+    r[0] = p.row_begin + it * step + (int64_t)blockIdx.x * blockDim.x * 2 + threadIdx.x;
+    r[1] = r[0] + blockDim.x;
+    bool in_range[2], go[2];
+    uint64_t k[2] = {0, 0};
+    int64_t b0[2] = {0, 0}, rb[2] = {0, 0}, sl[2] = {0, 0};
+    unsigned int n_match[2] = {0, 0};
+    JoinEntry first[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      first[j].key = first[j].row1 = first[j].p0 = first[j].p1 = 0;
+      in_range[j] = r[j] < row_end;
+      go[j] = in_range[j] && !(p.key.validity && !bit_test(p.key.validity, p.key.vbit_off + r[j]));
+      if (go[j]) {
+        k[j] = load_key(p.key, r[j]);
+        b0[j] = join_home(p.table, k[j], &rb[j]);
+        sl[j] = b0[j];
+      }
+    }
+    while (go[0] || go[1]) {  // an empty entry ends a probe sequence
+      JoinEntry e[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        if (go[j]) e[j] = load_entry(p.table.entries + rb[j] + sl[j]);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (!go[j]) continue;
+        if (e[j].row1 == 0) { go[j] = false; continue; }
+        if (e[j].key == k[j]) {
+          if (n_match[j] == 0) first[j] = e[j];
+          ++n_match[j];
+          if (UNIQUE) { go[j] = false; continue; }
+        }
+        sl[j] = (sl[j] + 1) & mask;
+      }
+    }
+    bool outer_null[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      // semi / anti: the probe row itself is the output, at most once (a NULL key counts as no match)
+      if (p.kind == DBX_JOIN_LEFT_SEMI) n_match[j] = n_match[j] ? 1u : 0u;
+      else if (p.kind == DBX_JOIN_LEFT_ANTI) n_match[j] = (in_range[j] && n_match[j] == 0) ? 1u : 0u;
+      outer_null[j] = p.kind == DBX_JOIN_LEFT && in_range[j] && n_match[j] == 0;  // preserved row without a match
+      if (outer_null[j]) n_match[j] = 1;
+    }
+    // block-wide exclusive scan of the match counts -> one reservation per CTA and step
+    const unsigned int mine = n_match[0] + n_match[1];
+    unsigned int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int tot = 0;
+      for (int w = 0; w < kJoinBlock / 32; ++w) { const unsigned int c = s_warp[w]; s_warp[w] = tot; tot += c; }
+      s_base = tot ? atomicAdd(p.cursor, (unsigned long long)tot) : 0ULL;
+    }
+    __syncthreads();
+    int64_t pos = (int64_t)s_base + s_warp[warp] + incl - mine;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (outer_null[j]) {
+        if (pos < p.out_cap) {
+          for (int c = 0; c < p.n_probe_cols; ++c) copy_value(p.probe_cols[c], r[j], pos);
+          for (int c = 0; c < p.n_build_cols; ++c) store_value(p.build_cols[c], 0, false, pos);
+        }
+        ++pos;
+      } else if (n_match[j] && (p.kind == DBX_JOIN_LEFT_SEMI || p.kind == DBX_JOIN_LEFT_ANTI)) {
+        if (pos < p.out_cap)
+          for (int c = 0; c < p.n_probe_cols; ++c) copy_value(p.probe_cols[c], r[j], pos);
+        ++pos;
+      } else if (n_match[j]) {
+        emit_match(p, r[j], first[j], pos++);
+        if (!UNIQUE && n_match[j] > 1) {  // duplicates of the key on the build side: walk again, skip the first
+          int64_t b = b0[j];
+          unsigned int seen = 0;
+          for (;;) {
+            const JoinEntry e = load_entry(p.table.entries + rb[j] + b);
+            if (e.row1 == 0) break;
+            if (e.key == k[j] && seen++ > 0) emit_match(p, r[j], e, pos++);
+            b = (b + 1) & mask;
+          }
+        }
+      }
+    }
+  }
+}
+
 // Pull one table region into L2 with full-line sequential reads before it is probed: the probes
 // themselves would fetch it as scattered 32-byte sectors, which HBM serves an order of magnitude
 // slower than a stream.
@@ -309,6 +435,7 @@ class JoinOp : public Op {
   int n_part = 1;
   int64_t region = 0;
   DevBuf part_counters;
+  bool build_unique = false;  // no key occurs twice on the build side (checked after the build)
   DevBuf part_cols[kMaxJoinCols];
   std::vector<int64_t> part_offs;
   JoinTableDev table_view() const { return JoinTableDev{(JoinEntry*)table_buf.p, table_cap, region, n_part, 0}; }
@@ -443,9 +570,25 @@ class JoinOp : public Op {
       join_build_kernel<<<grid_rows(build_rows), kJoinBlock, 0, stream>>>(key, build_rows, 0, t, ic[0], ic[1]);
       count_launch();
       DBX_CUDA_TRY(err, cudaGetLastError());
+      DBX_CUDA_TRY(err, cudaMemsetAsync(cursor.p, 0, 16, stream));
+      join_dup_check_kernel<<<grid_rows(table_cap), kJoinBlock, 0, stream>>>(t, (unsigned int*)cursor.p + 2);
+      count_launch();
+      DBX_CUDA_TRY(err, cudaGetLastError());
+      DBX_CUDA_TRY(err, cudaMemcpyAsync(host.p, (unsigned int*)cursor.p + 2, 4, cudaMemcpyDeviceToHost, stream));
       DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
+      build_unique = *(unsigned int*)host.p == 0 && !getenv("DBX_JOIN_NO_UNIQUE");
+    } else {
+      build_unique = true;
     }
     return DBX_OK;
+  }
+
+  void launch_probe(const JoinProbeParams& pp, int64_t rows) {
+    static const bool old_probe = getenv("DBX_JOIN_OLD_PROBE") != nullptr;
+    if (old_probe) { join_probe_kernel<<<grid_rows(rows), kJoinBlock, 0, stream>>>(pp); return; }
+    const int grid = grid_rows((rows + 1) / 2);
+    if (build_unique) join_probe2_kernel<true><<<grid, kJoinBlock, 0, stream>>>(pp);
+    else join_probe2_kernel<false><<<grid, kJoinBlock, 0, stream>>>(pp);
   }
 
   // Join::probe_block: join one probe block; the joined block is queued for dbx_op_pull
@@ -542,11 +685,11 @@ class JoinOp : public Op {
               (const char*)table_buf.p + (int64_t)part * bytes, bytes);
           pp.row_begin = part_offs[part];
           pp.n_rows = m;
-          join_probe_kernel<<<grid_rows(m), kJoinBlock, 0, stream>>>(pp);
+          launch_probe(pp, m);
           count_launch(2);
         }
       } else {
-        join_probe_kernel<<<grid_rows(n), kJoinBlock, 0, stream>>>(pp);
+        launch_probe(pp, n);
         count_launch();
       }
       DBX_CUDA_TRY(err, cudaGetLastError());

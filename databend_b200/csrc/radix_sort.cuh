@@ -40,9 +40,16 @@ __global__ void hist_kernel(const uint64_t* __restrict__ keys, int64_t n_host, c
     for (int p = 0; p < 8; ++p) {
       if (p >= n_passes) break;
       const int d = (int)((k >> (begin_bit + 8 * p)) & 255);
-      // warp-aggregated: digits of real columns are often constant across a warp (high bytes)
-      const unsigned peers = __match_any_sync(0xffffffffu, in ? d : 256 + lane) & act;
-      if (in && lane == __ffs(peers) - 1) atomicAdd(&s_h[p][d], (unsigned)__popc(peers));
+      // Digits of real columns are often constant across a warp (high bytes of doubles in [0,1),
+      // sign extension of small integers): one vote tells; only then is the add warp-aggregated.
+      // Random digits take one shared-memory atomic per key (aggregating those costs more than it saves).
+      const int d0 = __shfl_sync(0xffffffffu, d, __ffs(act) - 1);
+      const unsigned same = __ballot_sync(0xffffffffu, in && d == d0);
+      if (same == act) {
+        if (in && lane == __ffs(act) - 1) atomicAdd(&s_h[p][d], (unsigned)__popc(act));
+      } else if (in) {
+        atomicAdd(&s_h[p][d], 1u);
+      }
     }
   }
   __syncthreads();
@@ -90,6 +97,7 @@ __global__ void __launch_bounds__(kThreads) onesweep_kernel(const __grid_constan
   uint32_t(*s_cnt)[kRadix] = reinterpret_cast<uint32_t(*)[kRadix]>(smem + (size_t)kTile * 12);  // [kWarps][256]
   uint32_t* s_start = reinterpret_cast<uint32_t*>(smem + (size_t)kTile * 12 + sizeof(uint32_t) * kWarps * kRadix);  // [256]
   unsigned long long* s_goff = reinterpret_cast<unsigned long long*>(s_start + kRadix);                            // [256]
+  uint32_t* s_count = reinterpret_cast<uint32_t*>(s_goff + kRadix);                                                  // [256] tile counts
   __shared__ unsigned int s_tile;
   __shared__ uint32_t s_wsum[kWarps];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -131,34 +139,15 @@ __global__ void __launch_bounds__(kThreads) onesweep_kernel(const __grid_constan
     __syncwarp();
   }
   __syncthreads();
-  {  // thread d: counts of digit d over the warps -> tile count; chain to the previous tiles
+  {  // thread d: counts of digit d over the warps -> tile count, published for the following tiles
     const int d = tid;
     uint32_t run = 0;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) { const uint32_t c = s_cnt[w][d]; s_cnt[w][d] = run; run += c; }
     const uint32_t count = run;
-    uint32_t excl = 0;
+    s_count[d] = count;
     volatile uint32_t* st = a.status;
-    if (tile == 0) {
-      st[d] = kFlagPrefix | count;
-    } else {
-      st[tile * kRadix + d] = kFlagAgg | count;
-      int64_t t = tile - 1;
-      long long spins = 0;
-      while (true) {
-        const uint32_t s = st[t * kRadix + d];
-        const uint32_t f = s >> 30;
-        if (f == 0) {
-          if (++spins > (1LL << 22)) { atomicExch(a.fail, 1u); break; }  // a few seconds: never a hang
-          continue;
-        }
-        excl += s & kValMask;
-        if (f == 2) break;
-        --t;
-      }
-      st[tile * kRadix + d] = kFlagPrefix | (excl + count);
-    }
-    s_goff[d] = a.base[d] + excl;
+    st[tile * kRadix + d] = (tile == 0 ? kFlagPrefix : kFlagAgg) | count;
     // exclusive scan of `count` over the 256 digits -> start of each digit's run inside the tile
     uint32_t incl = count;
 #pragma unroll
@@ -171,6 +160,64 @@ __global__ void __launch_bounds__(kThreads) onesweep_kernel(const __grid_constan
     uint32_t wbase_sum = 0;
     for (int w = 0; w < warp; ++w) wbase_sum += s_wsum[w];
     s_start[d] = wbase_sum + incl - count;
+  }
+  // Decoupled look-back, warp-parallel: warp w resolves digits [32 w, 32 w + 32), eight at a time;
+  // for one digit the 32 lanes read the status words of the 32 preceding tiles at once, take
+  // everything up to the nearest tile that already published an inclusive prefix, and move one
+  // window further back if there is none.  (A one-thread-per-digit walk costs one dependent L2
+  // round trip per in-flight predecessor: ~20 us per tile with ~300 tiles in flight.)
+  if (tile == 0) {
+    s_goff[tid] = a.base[tid];
+  } else {
+    volatile uint32_t* st = a.status;
+    constexpr int kB = 8;
+    long long spins = 0;
+    for (int i0 = 0; i0 < 32; i0 += kB) {
+      uint32_t excl[kB];
+      int64_t tb[kB];
+      bool done[kB];
+#pragma unroll
+      for (int q = 0; q < kB; ++q) { excl[q] = 0; tb[q] = tile - 1; done[q] = false; }
+      bool all_done = false;
+      while (!all_done) {
+        uint32_t sv[kB];
+#pragma unroll
+        for (int q = 0; q < kB; ++q) {
+          const int64_t t = tb[q] - lane;
+          sv[q] = 2u << 30;  // before tile 0 (or finished): an inclusive prefix of 0
+          if (!done[q] && t >= 0) sv[q] = st[t * kRadix + warp * 32 + i0 + q];
+        }
+        all_done = true;
+#pragma unroll
+        for (int q = 0; q < kB; ++q) {
+          if (done[q]) continue;
+          const uint32_t f = sv[q] >> 30;
+          const unsigned pm = __ballot_sync(0xffffffffu, f == 2);
+          const unsigned zm = __ballot_sync(0xffffffffu, f == 0);
+          const int pidx = pm ? __ffs(pm) - 1 : 32;  // nearest tile with an inclusive prefix
+          const unsigned need = pidx >= 31 ? 0xffffffffu : ((2u << pidx) - 1);
+          if (zm & need) {  // a predecessor in the needed range has not published yet: read the window again
+            all_done = false;
+            continue;
+          }
+          uint32_t v = (lane <= pidx) ? (sv[q] & kValMask) : 0;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          excl[q] += v;
+          if (pm) done[q] = true;
+          else { tb[q] -= 32; all_done = false; }
+        }
+        if (!all_done && ++spins > (1LL << 20)) { atomicExch(a.fail, 1u); break; }  // never a hang
+      }
+      if (lane < kB) {
+        uint32_t e = 0;
+#pragma unroll
+        for (int q = 0; q < kB; ++q) if (lane == q) e = excl[q];
+        const int d = warp * 32 + i0 + lane;
+        st[tile * kRadix + d] = kFlagPrefix | (e + s_count[d]);
+        s_goff[d] = a.base[d] + e;
+      }
+    }
   }
   __syncthreads();
   // reorder through shared memory
@@ -202,7 +249,7 @@ __global__ void __launch_bounds__(kThreads) onesweep_kernel(const __grid_constan
   }
 }
 
-constexpr size_t kSmemBytes = (size_t)kTile * 12 + sizeof(uint32_t) * kWarps * kRadix + sizeof(uint32_t) * kRadix + sizeof(unsigned long long) * kRadix;
+constexpr size_t kSmemBytes = (size_t)kTile * 12 + sizeof(uint32_t) * kWarps * kRadix + sizeof(uint32_t) * kRadix + sizeof(unsigned long long) * kRadix + sizeof(uint32_t) * kRadix;
 }  // namespace rs
 
 // Host driver: sorts n (key, value) pairs by key bits [begin_bit, end_bit) with stable LSD passes,

@@ -104,7 +104,9 @@ __device__ __forceinline__ void cand_append_warp(const CandList& l, bool keep, u
 }
 
 // One pass over `n` rows of the key column.  Only ord <= boundary (read from device memory) can
-// still be in the top k.  FAST: 8-byte column, 32 B aligned, no validity -> one 256-bit load per 4 rows.
+// still be in the top k.  FAST: 8-byte column, 32 B aligned, no validity: a tile is 2048 rows, two
+// 256-bit loads per thread, and the next tile's two loads are issued before this tile is examined
+// (128 B in flight per thread); the grid is exactly the number of resident CTAs.
 template <bool FAST>
 __global__ void __launch_bounds__(256) topk_scan_kernel(const __grid_constant__ DevCol col, int64_t n, int64_t row_base, int cls,
                                                         int asc, const __grid_constant__ CandList cand,
@@ -113,41 +115,50 @@ __global__ void __launch_bounds__(256) topk_scan_kernel(const __grid_constant__ 
   const int lane = threadIdx.x & 31;
   const uint64_t boundary = cand.state[ST_BOUND];
   const uint64_t null_boundary = nulls.rowid ? nulls.state[ST_BOUND] : 0;
-  const int64_t n_tiles = (n + 1023) / 1024;
-  u64x4 next_q;
-  next_q.x = next_q.y = next_q.z = next_q.w = 0;
-  bool have_next = false;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    __syncwarp();
-    const int64_t r0 = tile * 1024 + 4 * (int64_t)threadIdx.x;
-    uint64_t v[4];
-    uint32_t valid = 0, inr = 0;
-    if (FAST && r0 + 4 <= n) {
-      u64x4 q = have_next ? next_q : ld_stream_256((const char*)col.data + r0 * 8);
-      // keep a second tile in flight: one 32-byte load per thread does not cover the HBM latency
-      const int64_t rn = (tile + gridDim.x) * 1024 + 4 * (int64_t)threadIdx.x;
-      have_next = tile + gridDim.x < n_tiles && rn + 4 <= n;
-      if (have_next) next_q = ld_stream_256((const char*)col.data + rn * 8);
-      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-      valid = inr = 0xF;
-    } else {
-      have_next = false;
+  if (FAST) {
+    const int64_t n_tiles = n / 2048;  // whole tiles; the tail goes through the generic loop below
+    const char* base = (const char*)col.data;
+    u64x4 q0, q1;
+    q0.x = q0.y = q0.z = q0.w = q1.x = q1.y = q1.z = q1.w = 0;
+    int64_t tile = blockIdx.x;
+    if (tile < n_tiles) {
+      q0 = ld_stream_256(base + (tile * 2048 + 4 * (int64_t)threadIdx.x) * 8);
+      q1 = ld_stream_256(base + (tile * 2048 + 1024 + 4 * (int64_t)threadIdx.x) * 8);
+    }
+    for (; tile < n_tiles; tile += gridDim.x) {
+      __syncwarp();
+      const u64x4 c0 = q0, c1 = q1;
+      const int64_t nt = tile + gridDim.x;
+      if (nt < n_tiles) {
+        q0 = ld_stream_256(base + (nt * 2048 + 4 * (int64_t)threadIdx.x) * 8);
+        q1 = ld_stream_256(base + (nt * 2048 + 1024 + 4 * (int64_t)threadIdx.x) * 8);
+      }
+      const uint64_t v[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+      uint64_t o[8];
+      bool any = false;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        v[j] = 0;
-        if (r0 + j < n) {
-          inr |= 1u << j;
-          bool ok = !col.validity || bit_test(col.validity, col.vbit_off + r0 + j);
-          if (ok) { v[j] = load_widened(col, r0 + j, pol); valid |= 1u << j; }
-        }
+      for (int j = 0; j < 8; ++j) { o[j] = key_to_ord(v[j], cls, asc != 0); any |= o[j] <= boundary; }
+      if (!__any_sync(0xffffffffu, any)) continue;  // the common case once the boundary is tight
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int64_t r = tile * 2048 + (j >> 2) * 1024 + 4 * (int64_t)threadIdx.x + (j & 3);
+        cand_append_warp(cand, o[j] <= boundary, o[j], (uint64_t)(row_base + r), v[j], lane);
       }
     }
+  }
+  const int64_t first = FAST ? (n / 2048) * 2048 : 0;
+  const int64_t n_tiles = (n - first + 1023) / 1024;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    __syncwarp();
+    const int64_t r0 = first + tile * 1024 + 4 * (int64_t)threadIdx.x;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const bool in = (inr >> j) & 1, ok = (valid >> j) & 1;
-      const uint64_t o = key_to_ord(v[j], cls, asc != 0);
+      const bool in = r0 + j < n;
+      const bool ok = in && (!col.validity || bit_test(col.validity, col.vbit_off + r0 + j));
+      const uint64_t v = ok ? load_widened(col, r0 + j, pol) : 0;
+      const uint64_t o = key_to_ord(v, cls, asc != 0);
       const uint64_t rid = (uint64_t)(row_base + r0 + j);
-      cand_append_warp(cand, in && ok && o <= boundary, o, rid, v[j], lane);
+      cand_append_warp(cand, ok && o <= boundary, o, rid, v, lane);
       if (nulls.rowid) cand_append_warp(nulls, in && !ok && rid <= null_boundary, 0, rid, 0, lane);
     }
   }
@@ -167,9 +178,41 @@ struct CutArgs {
   int64_t k;
   int64_t threshold;
 };
+constexpr int kCutActive = 4096;  // entries of the bucket under examination kept in shared memory
+// bucket that contains the k_rem-th entry of a 256-bin histogram: warp 0, eight bins per lane
+__device__ __forceinline__ void cut_find_bucket(const unsigned int* hist, int64_t k_rem, unsigned int* out3, int tid) {
+  if (tid >= 32) return;
+  unsigned int c[8], sum = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { c[j] = hist[tid * 8 + j]; sum += c[j]; }
+  unsigned int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (tid >= o) incl += up;
+  }
+  unsigned int cum = incl - sum;
+  // the lane whose range [cum, cum + sum) contains the k_rem-th entry (k_rem >= 1)
+  const bool mine = (int64_t)cum < k_rem && k_rem <= (int64_t)cum + sum;
+  const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
+  if (mine) {
+    int b = 0;
+    for (; b < 7; ++b) {
+      if ((int64_t)cum + c[b] >= k_rem) break;
+      cum += c[b];
+    }
+    out3[0] = (unsigned)(tid * 8 + b); out3[1] = cum; out3[2] = c[b];
+  } else if (tid == 31 && (int64_t)total < k_rem) {  // cannot happen (k_rem <= matching entries); keep the state sane
+    out3[0] = 255; out3[1] = total - c[7]; out3[2] = c[7];
+  }
+}
 __global__ void __launch_bounds__(1024) topk_cut_kernel(const __grid_constant__ CutArgs a) {
   __shared__ unsigned int s_hist[256];
-  __shared__ unsigned int s_b, s_cum, s_c, s_out;
+  __shared__ unsigned int s_pick[3];  // bucket, entries before it, entries in it
+  __shared__ unsigned int s_out, s_nact;
+  extern __shared__ __align__(16) uint64_t s_cut_dyn[];  // active set (ord, rowid) once the bucket is small
+  uint64_t* s_ao = s_cut_dyn;
+  uint64_t* s_ar = s_cut_dyn + kCutActive;
   const CandList& l = a.l;
   const int64_t cnt = (int64_t)l.state[ST_COUNT];
   const int64_t n = cnt < l.cap ? cnt : l.cap;
@@ -178,42 +221,104 @@ __global__ void __launch_bounds__(1024) topk_cut_kernel(const __grid_constant__ 
   uint64_t th_hi = 0, th_lo = 0;  // prefix of the threshold key (ord, rowid)
   int64_t k_rem = a.k;
   bool closed = false;
+  bool in_smem = false;   // the entries that still match the prefix sit in s_ao / s_ar
+  int64_t n_act = n;      // entries matching the prefix found so far
   for (int p = l.ord ? 0 : 8; p < 16 && !closed; ++p) {
     if (tid < 256) s_hist[tid] = 0;
+    if (tid == 0) s_nact = 0;
     __syncthreads();
     const int sh = 56 - 8 * (p & 7);
-    for (int64_t i0 = tid - lane; i0 < n; i0 += 1024) {
+    // a bucket that fits is first copied to shared memory (same pass as its histogram)
+    const bool gather = !in_smem && n_act <= kCutActive;
+    const int64_t n_scan = in_smem ? n_act : n;
+    for (int64_t i0 = tid - lane; i0 < n_scan; i0 += 1024) {
       const int64_t i = i0 + lane;
-      bool m = i < n;
+      bool m = i < n_scan;
       int d = 0;
+      uint64_t o = 0, r = 0;
       if (m) {
-        const uint64_t o = l.ord ? l.ord[i] : 0, r = l.rowid[i];
+        if (in_smem) { o = s_ao[i]; r = s_ar[i]; }
+        else { o = l.ord ? l.ord[i] : 0; r = l.rowid[i]; }
         if (p < 8) {
-          m = p == 0 || (o >> (sh + 8)) == (th_hi >> (sh + 8));
+          m = in_smem || p == 0 || (o >> (sh + 8)) == (th_hi >> (sh + 8));
           d = (int)((o >> sh) & 255);
         } else {
-          m = o == th_hi && (p == 8 || (r >> (sh + 8)) == (th_lo >> (sh + 8)));
+          m = in_smem || (o == th_hi && (p == 8 || (r >> (sh + 8)) == (th_lo >> (sh + 8))));
           d = (int)((r >> sh) & 255);
         }
       }
-      const unsigned peers = __match_any_sync(0xffffffffu, m ? d : 256 + lane);
-      if (m && lane == __ffs(peers) - 1) atomicAdd(&s_hist[d], (unsigned)__popc(peers));
-    }
-    __syncthreads();
-    if (tid == 0) {
-      unsigned int cum = 0;
-      int b = 0;
-      for (; b < 255; ++b) {
-        if ((int64_t)cum + s_hist[b] >= k_rem) break;
-        cum += s_hist[b];
+      const unsigned mm = __ballot_sync(0xffffffffu, m);
+      if (!mm) continue;
+      if (gather) {  // (all matching entries of this pass: exactly n_act of them)
+        unsigned int base = 0;
+        if (lane == __ffs(mm) - 1) base = atomicAdd(&s_nact, (unsigned)__popc(mm));
+        base = __shfl_sync(0xffffffffu, base, __ffs(mm) - 1);
+        if (m) {
+          const unsigned int q = base + __popc(mm & ((1u << lane) - 1));
+          if (q < (unsigned)kCutActive) { s_ao[q] = o; s_ar[q] = r; }
+        }
       }
-      s_b = b; s_cum = cum; s_c = s_hist[b];
+      const int d0 = __shfl_sync(0xffffffffu, d, __ffs(mm) - 1);
+      const unsigned same = __ballot_sync(0xffffffffu, m && d == d0);
+      if (same == mm) { if (lane == __ffs(mm) - 1) atomicAdd(&s_hist[d0], (unsigned)__popc(mm)); }
+      else if (m) atomicAdd(&s_hist[d], 1u);
     }
     __syncthreads();
-    const uint64_t b = s_b;
-    if (p < 8) th_hi |= b << sh; else th_lo |= b << sh;
-    k_rem -= s_cum;
-    if ((int64_t)s_c == k_rem) {  // the whole bucket is in: every key with this prefix passes
+    cut_find_bucket(s_hist, k_rem, s_pick, tid);
+    __syncthreads();
+    const uint64_t bkt = s_pick[0];
+    if (p < 8) th_hi |= bkt << sh; else th_lo |= bkt << sh;
+    k_rem -= s_pick[1];
+    if (gather) {
+      // the gathered set matched the OLD prefix; keep only the chosen bucket for the next passes
+      in_smem = true;
+      __syncthreads();
+      // in-place compaction by one warp-strided sweep through a second counter
+      if (tid == 0) s_out = 0;
+      __syncthreads();
+      uint64_t ko[(kCutActive + 1023) / 1024], kr[(kCutActive + 1023) / 1024];
+      bool kk[(kCutActive + 1023) / 1024];
+#pragma unroll
+      for (int t = 0; t < (kCutActive + 1023) / 1024; ++t) {
+        const int64_t i = tid + 1024 * t;
+        kk[t] = false;
+        if (i < n_act) {
+          ko[t] = s_ao[i]; kr[t] = s_ar[i];
+          const int d = p < 8 ? (int)((ko[t] >> sh) & 255) : (int)((kr[t] >> sh) & 255);
+          kk[t] = d == (int)bkt;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int t = 0; t < (kCutActive + 1023) / 1024; ++t) {
+        if (kk[t]) { const unsigned int q = atomicAdd(&s_out, 1u); s_ao[q] = ko[t]; s_ar[q] = kr[t]; }
+      }
+      __syncthreads();
+    } else if (in_smem) {
+      // narrow the shared-memory set to the chosen bucket
+      if (tid == 0) s_out = 0;
+      __syncthreads();
+      uint64_t ko[(kCutActive + 1023) / 1024], kr[(kCutActive + 1023) / 1024];
+      bool kk[(kCutActive + 1023) / 1024];
+#pragma unroll
+      for (int t = 0; t < (kCutActive + 1023) / 1024; ++t) {
+        const int64_t i = tid + 1024 * t;
+        kk[t] = false;
+        if (i < n_act) {
+          ko[t] = s_ao[i]; kr[t] = s_ar[i];
+          const int d = p < 8 ? (int)((ko[t] >> sh) & 255) : (int)((kr[t] >> sh) & 255);
+          kk[t] = d == (int)bkt;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int t = 0; t < (kCutActive + 1023) / 1024; ++t) {
+        if (kk[t]) { const unsigned int q = atomicAdd(&s_out, 1u); s_ao[q] = ko[t]; s_ar[q] = kr[t]; }
+      }
+      __syncthreads();
+    }
+    n_act = s_pick[2];
+    if ((int64_t)s_pick[2] == k_rem) {  // the whole bucket is in: every key with this prefix passes
       const uint64_t low = sh ? ((1ULL << sh) - 1) : 0;
       if (p < 8) { th_hi |= low; th_lo = ~0ULL; } else { th_lo |= low; }
       closed = true;
@@ -277,6 +382,9 @@ __global__ void __launch_bounds__(1024) small_rank_sort_kernel(const uint64_t* o
   }
 }
 
+__global__ void topk_reset_kernel(unsigned long long* state) {
+  if (threadIdx.x < 3 * ST_WORDS) state[threadIdx.x] = (threadIdx.x % ST_WORDS) == ST_BOUND && threadIdx.x < 2 * ST_WORDS ? ~0ULL : 0ULL;
+}
 __global__ void iota_u32_kernel(uint32_t* p, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = (uint32_t)i;
 }
@@ -328,9 +436,11 @@ __global__ void pack_bits_kernel(const uint8_t* bytes, int64_t n, uint8_t* bits)
 // ================================================================ full sort: ingest
 // Appends one chunk of the key column to the (ord, row id | NULL flag, original bits) arrays.
 __global__ void __launch_bounds__(256) sort_ingest_kernel(const __grid_constant__ DevCol col, int64_t n, int64_t row_base, int cls, int asc,
-                                                          uint64_t* ord, uint32_t* rid, uint64_t* bits, unsigned long long* n_null) {
+                                                          uint64_t* ord, uint32_t* rid, uint64_t* bits, unsigned long long* n_null,
+                                                          unsigned long long* inexact) {
   const uint64_t pol = make_policy_evict_first();
   unsigned int nulls = 0;
+  bool lossy = false;  // -0.0 and NaN payloads do not survive key -> ordered image -> key
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const bool ok = !col.validity || bit_test(col.validity, col.vbit_off + i);
     const uint64_t v = ok ? load_widened(col, i, pol) : 0;
@@ -338,14 +448,21 @@ __global__ void __launch_bounds__(256) sort_ingest_kernel(const __grid_constant_
     rid[row_base + i] = (uint32_t)(row_base + i) | (ok ? 0u : 0x80000000u);
     bits[row_base + i] = v;
     nulls += !ok;
+    if (ok && cls == VC_FLT) {
+      const double d = __longlong_as_double((long long)v);
+      lossy |= (d != d && v != 0x7FF8000000000000ULL) || (d == 0.0 && (v >> 63));
+    }
   }
+  if (__any_sync(0xffffffffu, lossy) && (threadIdx.x & 31) == 0) *inexact = 1;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) nulls += __shfl_xor_sync(0xffffffffu, nulls, o);
   if ((threadIdx.x & 31) == 0 && nulls) atomicAdd(n_null, (unsigned long long)nulls);
 }
 struct SortEmitArgs {
   const uint32_t* rid;   // sorted: row id | NULL flag
-  const uint64_t* bits;  // by original row id
+  const uint64_t* bits;  // by original row id; nullptr: invert the sorted ordered images instead (no gather)
+  const uint64_t* ord;   // sorted ordered images
+  int32_t cls, asc;
   int64_t n;
   int32_t dtype;
   void* out_key;
@@ -357,7 +474,15 @@ __global__ void sort_emit_kernel(const __grid_constant__ SortEmitArgs a) {
     const uint32_t r = a.rid[i];
     const uint32_t row = r & 0x7FFFFFFFu;
     const bool is_null = r >> 31;
-    store_narrow_key(a.out_key, i, a.dtype, is_null ? 0 : a.bits[row]);
+    uint64_t b = 0;
+    if (!is_null) {
+      if (a.bits) b = a.bits[row];
+      else {
+        const uint64_t o = a.asc ? a.ord[i] : ~a.ord[i];
+        b = a.cls == VC_FLT ? (uint64_t)__double_as_longlong(ordered_to_f64(o)) : (a.cls == VC_INT ? o ^ 0x8000000000000000ULL : o);
+      }
+    }
+    store_narrow_key(a.out_key, i, a.dtype, b);
     a.out_row[i] = (int64_t)row;
     if (a.out_valid_bytes) a.out_valid_bytes[i] = is_null ? 0 : 1;
   }
@@ -384,6 +509,8 @@ class TopkOp : public Op {
   int64_t count_ub = 0, null_ub = 0;   // upper bounds on the list sizes known to the host without a sync
   int64_t rows_seen = 0;
   int64_t rows_at_last_cut = 0;
+  int scan_ctas_per_sm = 0;
+  DevBuf snap_ord, snap_rowid, snap_bits, snap_null;  // candidate lists as they were before the first optimistic scan of a push
   // ---- full-sort mode
   DevBuf s_ord[2], s_rid[2], s_bits;
   int64_t s_cap = 0;
@@ -403,7 +530,7 @@ class TopkOp : public Op {
     full_sort = p->limit == 0 || p->limit > (1 << 22);  // no LIMIT (or one too large for the candidate list): sort everything
     DBX_TRY(stager.init(dev, stream, &err));
     DBX_CUDA_TRY(err, host.ensure(256));
-    DBX_CUDA_TRY(err, state.ensure(8 * ST_WORDS * 2 + 64));
+    DBX_CUDA_TRY(err, state.ensure(8 * ST_WORDS * 3 + 64));
     if (!full_sort) {
       const int64_t k = p->limit;
       // candidate list: large enough that a whole device-resident column usually fits behind the
@@ -426,10 +553,9 @@ class TopkOp : public Op {
   }
 
   int32_t reset() override {
-    unsigned long long init_state[2 * ST_WORDS] = {0, ~0ULL, 0, 0, 0, ~0ULL, 0, 0};
-    memcpy(host.p, init_state, sizeof(init_state));
-    DBX_CUDA_TRY(err, cudaMemcpyAsync(state.p, host.p, sizeof(init_state), cudaMemcpyHostToDevice, stream));
-    DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
+    topk_reset_kernel<<<1, 32, 0, stream>>>((unsigned long long*)state.p);  // count 0, boundary = everything passes
+    count_launch();
+    DBX_CUDA_TRY(err, cudaGetLastError());
     count_ub = null_ub = 0;
     rows_seen = 0;
     rows_at_last_cut = 0;
@@ -459,14 +585,19 @@ class TopkOp : public Op {
     a.l = cand_list();
     a.alt_ord = (uint64_t*)alt_ord.p; a.alt_rowid = (uint64_t*)alt_rowid.p; a.alt_bits = (uint64_t*)alt_bits.p;
     a.k = prm.limit; a.threshold = threshold;
-    topk_cut_kernel<<<1, 1024, 0, stream>>>(a);
+    static std::atomic<bool> attr_set[64];
+    if (!attr_set[device]) {
+      DBX_CUDA_TRY(err, cudaFuncSetAttribute(topk_cut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCutActive * 16));
+      attr_set[device] = true;
+    }
+    topk_cut_kernel<<<1, 1024, kCutActive * 16, stream>>>(a);
     count_launch();
     if (key_nullable) {
       CutArgs b;
       b.l = null_list();
       b.alt_ord = nullptr; b.alt_rowid = (uint64_t*)alt_null.p; b.alt_bits = nullptr;
       b.k = prm.limit; b.threshold = threshold;
-      topk_cut_kernel<<<1, 1024, 0, stream>>>(b);
+      topk_cut_kernel<<<1, 1024, kCutActive * 16, stream>>>(b);
       count_launch();
     }
     DBX_CUDA_TRY(err, cudaGetLastError());
@@ -482,7 +613,13 @@ class TopkOp : public Op {
     c.data = (const char*)col.data + off * esz;
     if (c.validity) c.vbit_off += off;
     const bool fast = esz == 8 && !c.validity && ((reinterpret_cast<uintptr_t>(c.data) & 31) == 0);
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((m + 1023) / 1024, (int64_t)kNumSMs * 8));
+    if (scan_ctas_per_sm == 0) {
+      int a = 0, b2 = 0;
+      DBX_CUDA_TRY(err, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, topk_scan_kernel<true>, 256, 0));
+      DBX_CUDA_TRY(err, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, topk_scan_kernel<false>, 256, 0));
+      scan_ctas_per_sm = std::max(1, std::min(a, b2));
+    }
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((m + 2047) / 2048, (int64_t)kNumSMs * scan_ctas_per_sm));
     CandList nl = null_list();
     if (!key_nullable) nl.rowid = nullptr;
     if (fast) topk_scan_kernel<true><<<grid, 256, 0, stream>>>(c, m, row_base, cls, prm.asc, cand_list(), nl);
@@ -508,65 +645,73 @@ class TopkOp : public Op {
     return DBX_OK;
   }
 
+  // One pushed block.  Chunks grow geometrically (x8), each followed by a cut that tightens the
+  // device-resident boundary, so a chunk adds about 8k survivors however long the column is.  A
+  // chunk that provably fits the candidate list is "guaranteed"; larger ones are launched
+  // optimistically (expected survivors << capacity) behind a snapshot of the lists, and the
+  // overflow flags are checked ONCE at the end of the push: an overflow restores the snapshot and
+  // replays the range in guaranteed pieces.  No host synchronisation otherwise.
   int32_t push_topk(const DevCol& col, int64_t n) {
     const int64_t k = prm.limit;
     int64_t done = 0;
-    int64_t chunk = std::max<int64_t>(16 * k, 1 << 16);  // warm-up chunks grow geometrically behind cuts
+    int64_t chunk = std::max<int64_t>(8 * k, 1 << 14);
+    bool snap = false;
+    int64_t snap_done = 0, snap_count_ub = 0, snap_null_ub = 0, snap_cut_pos = 0;
+    unsigned long long* st = (unsigned long long*)state.p;
     while (done < n) {
       const int64_t seen = rows_seen + done;
       const int64_t rest = n - done;
       int64_t room = cap - std::max(count_ub, null_ub);
-      if (room < std::min(rest, chunk)) {  // the host's bounds are pessimistic: let the device cut whatever is really there
+      const int64_t m = std::min(rest, chunk);
+      if (room < m && std::max(count_ub, null_ub) > 2 * k) {  // the host's bounds are pessimistic: let the device cut
         DBX_TRY(launch_cuts(2 * k, seen));
         room = cap - std::max(count_ub, null_ub);
       }
-      if (rest <= room) {  // fits for sure: one launch
-        DBX_TRY(launch_scan(col, done, rest, seen));
-        count_ub += rest;
-        if (key_nullable) null_ub += rest;
-        done = n;
-        // tighten the boundary whenever the rows seen have doubled since the last cut
-        if (rows_seen + n - rows_at_last_cut >= rows_at_last_cut) DBX_TRY(launch_cuts(2 * k, rows_seen + n));
-        break;
-      }
-      if (seen > 0 && (double)rest * (double)k / (double)seen * 4.0 <= (double)(cap - 2 * k)) {
-        // boundary established: ONE optimistic launch over everything left (expected survivors
-        // ~ rest * k / seen), then one check of the overflow flags; on overflow the chunk's appends
-        // are dropped and the range is replayed in pieces that provably fit
+      if (m > room && !snap) {  // first optimistic chunk of this push: snapshot the (cut) lists and their state
         DBX_TRY(launch_cuts(k, seen));
-        unsigned long long* st = (unsigned long long*)state.p;
-        DBX_CUDA_TRY(err, cudaMemcpyAsync(host.p, st, 8 * ST_WORDS * 2, cudaMemcpyDeviceToHost, stream));
-        DBX_TRY(launch_scan(col, done, rest, seen));
-        DBX_CUDA_TRY(err, cudaMemcpyAsync((char*)host.p + 64, st, 8 * ST_WORDS * 2, cudaMemcpyDeviceToHost, stream));
-        DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
-        const unsigned long long* before = (const unsigned long long*)host.p;
-        const unsigned long long* after = (const unsigned long long*)((char*)host.p + 64);
-        const bool over = after[ST_OVERFLOW] || after[ST_WORDS + ST_OVERFLOW] || (int64_t)after[ST_COUNT] > cap ||
-                          (int64_t)after[ST_WORDS + ST_COUNT] > cap;
-        if (!over) {
-          count_ub = (int64_t)after[ST_COUNT];
-          null_ub = (int64_t)after[ST_WORDS + ST_COUNT];
-          done = n;
-          break;
+        DBX_CUDA_TRY(err, snap_ord.ensure(k * 8));
+        DBX_CUDA_TRY(err, snap_rowid.ensure(k * 8));
+        DBX_CUDA_TRY(err, snap_bits.ensure(k * 8));
+        DBX_CUDA_TRY(err, cudaMemcpyAsync(snap_ord.p, ord.p, k * 8, cudaMemcpyDeviceToDevice, stream));
+        DBX_CUDA_TRY(err, cudaMemcpyAsync(snap_rowid.p, rowid.p, k * 8, cudaMemcpyDeviceToDevice, stream));
+        DBX_CUDA_TRY(err, cudaMemcpyAsync(snap_bits.p, bits.p, k * 8, cudaMemcpyDeviceToDevice, stream));
+        if (key_nullable) {
+          DBX_CUDA_TRY(err, snap_null.ensure(k * 8));
+          DBX_CUDA_TRY(err, cudaMemcpyAsync(snap_null.p, null_rowid.p, k * 8, cudaMemcpyDeviceToDevice, stream));
         }
-        unsigned long long back[2 * ST_WORDS];
-        memcpy(back, before, sizeof(back));
-        back[ST_OVERFLOW] = back[ST_WORDS + ST_OVERFLOW] = 0;
-        DBX_CUDA_TRY(err, cudaMemcpyAsync(st, back, sizeof(back), cudaMemcpyHostToDevice, stream));
-        DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
-        count_ub = (int64_t)before[ST_COUNT];
-        null_ub = (int64_t)before[ST_WORDS + ST_COUNT];
-        DBX_TRY(scan_guaranteed(col, done, rest));
-        done = n;
-        break;
+        DBX_CUDA_TRY(err, cudaMemcpyAsync(host.p, st, 8 * ST_WORDS * 2, cudaMemcpyDeviceToHost, stream));
+        snap = true;
+        snap_done = done; snap_count_ub = count_ub; snap_null_ub = null_ub; snap_cut_pos = rows_at_last_cut;
       }
-      const int64_t m = std::min<int64_t>({rest, chunk, room});
       DBX_TRY(launch_scan(col, done, m, seen));
       count_ub += m;
       if (key_nullable) null_ub += m;
       done += m;
-      DBX_TRY(launch_cuts(2 * k, rows_seen + done));
+      // cut when the rows seen have doubled since the last cut (always inside a multi-chunk push)
+      if (rows_seen + done - rows_at_last_cut >= rows_at_last_cut || done < n) DBX_TRY(launch_cuts(2 * k, rows_seen + done));
       chunk *= 8;
+    }
+    if (snap) {
+      DBX_CUDA_TRY(err, cudaMemcpyAsync((char*)host.p + 64, st, 8 * ST_WORDS * 2, cudaMemcpyDeviceToHost, stream));
+      DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
+      const unsigned long long* before = (const unsigned long long*)host.p;
+      const unsigned long long* after = (const unsigned long long*)((char*)host.p + 64);
+      if (after[ST_OVERFLOW] || after[ST_WORDS + ST_OVERFLOW]) {
+        // an optimistic chunk did not fit: back to the snapshot, then the same rows in pieces that do
+        unsigned long long back[2 * ST_WORDS];
+        memcpy(back, before, sizeof(back));
+        back[ST_OVERFLOW] = back[ST_WORDS + ST_OVERFLOW] = 0;
+        DBX_CUDA_TRY(err, cudaMemcpyAsync(ord.p, snap_ord.p, k * 8, cudaMemcpyDeviceToDevice, stream));
+        DBX_CUDA_TRY(err, cudaMemcpyAsync(rowid.p, snap_rowid.p, k * 8, cudaMemcpyDeviceToDevice, stream));
+        DBX_CUDA_TRY(err, cudaMemcpyAsync(bits.p, snap_bits.p, k * 8, cudaMemcpyDeviceToDevice, stream));
+        if (key_nullable) DBX_CUDA_TRY(err, cudaMemcpyAsync(null_rowid.p, snap_null.p, k * 8, cudaMemcpyDeviceToDevice, stream));
+        DBX_CUDA_TRY(err, cudaMemcpyAsync(st, back, sizeof(back), cudaMemcpyHostToDevice, stream));
+        DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
+        count_ub = std::min<int64_t>(snap_count_ub, (int64_t)before[ST_COUNT]);
+        null_ub = std::min<int64_t>(snap_null_ub, (int64_t)before[ST_WORDS + ST_COUNT]);
+        rows_at_last_cut = snap_cut_pos;
+        DBX_TRY(scan_guaranteed(col, snap_done, n - snap_done));
+      }
     }
     return DBX_OK;
   }
@@ -606,7 +751,8 @@ class TopkOp : public Op {
       if (rows_seen + n > rs::kMaxRows) { err.set("sort: more than 2^30 - 1 rows are not supported"); return DBX_ERR_UNSUPPORTED; }
       DBX_TRY(sort_reserve(rows_seen + n));
       sort_ingest_kernel<<<grid_1d(n), 256, 0, stream>>>(col, n, rows_seen, cls, prm.asc, (uint64_t*)s_ord[0].p, (uint32_t*)s_rid[0].p,
-                                                         (uint64_t*)s_bits.p, (unsigned long long*)state.p + ST_WORDS + ST_COUNT);
+                                                         (uint64_t*)s_bits.p, (unsigned long long*)state.p + ST_WORDS + ST_COUNT,
+                                                         (unsigned long long*)state.p + ST_WORDS + ST_OVERFLOW);
       count_launch();
       DBX_CUDA_TRY(err, cudaGetLastError());
     } else {
@@ -628,9 +774,10 @@ class TopkOp : public Op {
     const int64_t n = rows_seen;
     auto ob = std::make_unique<OwnedBlock>();
     ob->device = device;
-    DBX_CUDA_TRY(err, cudaMemcpyAsync(host.p, (unsigned long long*)state.p + ST_WORDS + ST_COUNT, 8, cudaMemcpyDeviceToHost, stream));
+    DBX_CUDA_TRY(err, cudaMemcpyAsync(host.p, (unsigned long long*)state.p + ST_WORDS, 8 * ST_WORDS, cudaMemcpyDeviceToHost, stream));
     DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
-    const int64_t n_nulls = (int64_t)*(unsigned long long*)host.p;
+    const int64_t n_nulls = (int64_t)((unsigned long long*)host.p)[ST_COUNT];
+    const bool needs_gather = ((unsigned long long*)host.p)[ST_OVERFLOW] != 0;  // a -0.0 or a NaN with a payload was ingested
     int buf = 0;
     if (n > 1) {
       DBX_CUDA_TRY(err, s_ord[1].ensure((size_t)s_cap * 8));
@@ -648,7 +795,8 @@ class TopkOp : public Op {
     }
     if (n) {
       SortEmitArgs ea;
-      ea.rid = (const uint32_t*)s_rid[buf].p; ea.bits = (const uint64_t*)s_bits.p; ea.n = n; ea.dtype = key_dtype;
+      ea.rid = (const uint32_t*)s_rid[buf].p; ea.bits = needs_gather ? (const uint64_t*)s_bits.p : nullptr; ea.n = n; ea.dtype = key_dtype;
+      ea.ord = (const uint64_t*)s_ord[buf].p; ea.cls = cls; ea.asc = prm.asc;
       ea.out_key = okey; ea.out_row = (int64_t*)orow; ea.out_valid_bytes = (uint8_t*)ovb;
       sort_emit_kernel<<<grid_1d(n), 256, 0, stream>>>(ea);
       count_launch();

@@ -1,0 +1,36 @@
+#!/bin/bash
+# round 2, GPU call E (1 GPU): tests after the sort / top-k / join rework, per-operator numbers, launch lists, agg kernel capture
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -q -m gpu --timeout 600 --maxfail 25 -p no:cacheprovider > gpurun_out/r2e_tests.log 2>&1
+echo "tests rc=$?" >> gpurun_out/r2e_tests.log
+tail -30 gpurun_out/r2e_tests.log
+timeout 600 python experiments/bench_ops.py --reps 2 > gpurun_out/r2e_ops.jsonl 2> gpurun_out/r2e_ops.err
+cut -c1-700 gpurun_out/r2e_ops.jsonl; tail -5 gpurun_out/r2e_ops.err
+NCU="ncu --metrics gpu__time_duration.sum --clock-control none --csv"
+timeout 300 $NCU --log-file gpurun_out/r2e_topk_launches.csv python experiments/bench_ops.py --ops topk --reps 1 > gpurun_out/r2e_topk.log 2>&1
+timeout 300 $NCU --log-file gpurun_out/r2e_sort_launches.csv python experiments/bench_ops.py --ops sort --sort-rows 100000000 --reps 1 > gpurun_out/r2e_sort.log 2>&1
+timeout 400 $NCU --log-file gpurun_out/r2e_join_launches.csv python experiments/bench_ops.py --ops join --fact-rows 250000000 --reps 1 > gpurun_out/r2e_join.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'filter_group_agg_kernel<3, 1' -s 2 -c 1 -f -o gpurun_out/r2e_prof_agg python bench.py --no-e2e --no-cpu --no-knn --no-verify --steps 1 --warmup 1 > gpurun_out/r2e_ncu_agg.log 2>&1
+timeout 300 ncu --metrics lts__t_sectors_op_red.sum,lts__t_sectors_op_atom.sum,lts__t_requests_srcunit_tex_op_red.sum,lts__t_sectors_srcunit_tex_op_read.sum,lts__t_sector_hit_rate.pct,lts__t_sectors_op_read.sum,lts__t_sectors_op_write.sum,l1tex__t_set_accesses_pipe_lsu_mem_global_op_red.sum,lts__throughput.avg.pct_of_peak_sustained_elapsed,dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:'filter_group_agg_kernel<3, 1' -s 2 -c 1 --csv --log-file gpurun_out/r2e_agg_red_counters.csv python bench.py --no-e2e --no-cpu --no-knn --no-verify --steps 1 --warmup 1 > gpurun_out/r2e_ncu_agg2.log 2>&1
+python - <<'P'
+import csv, collections
+for name in ["topk", "sort", "join"]:
+    try:
+        rows = list(csv.reader(open(f"gpurun_out/r2e_{name}_launches.csv")))
+    except Exception as e:
+        print(name, e); continue
+    hdr = None
+    agg = collections.OrderedDict()
+    for r in rows:
+        if len(r) > 5 and r[0] == "ID": hdr = r; continue
+        if hdr and len(r) == len(hdr):
+            d = dict(zip(hdr, r))
+            try: v = float(d["Metric Value"].replace(",", ""))
+            except: continue
+            k = d["Kernel Name"][:70]
+            a = agg.setdefault(k, [0, 0.0]); a[0] += 1; a[1] += v
+    print("==", name)
+    for k, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:12]:
+        print(f"{k:70s} n={c:5d} total={t/1e6:9.3f} ms")
+P
+tail -2 gpurun_out/r2e_ncu_agg.log; cut -d, -f5,9,13,15 gpurun_out/r2e_agg_red_counters.csv | tail -14
