@@ -200,24 +200,23 @@ def run_knn(args, L, dev, rank, world, barrier):
     q_host = Column.vector(qbuf.download(np.float32, nq * dim).reshape(nq, dim))
 
     def search(q):
-        idx, d = op.search(q, k)
         if world == 1:
-            return idx, d
-        # one collective: [nq, k] global row ids and the distance bits, packed into one int64 tensor
-        pack = np.empty((2, nq, k), dtype=np.int64)
-        pack[0] = idx + r0
-        pack[1] = d.view(np.int32)
-        t = torch.from_numpy(pack).to(f"cuda:{dev}", non_blocking=True)
+            return op.search(q, k)
+        # per-rank top-k stays in HBM; ONE collective over [nq, k] global row ids and distance bits
+        idx_t = torch.empty((nq, k), dtype=torch.int64, device=f"cuda:{dev}")
+        d_t = torch.empty((nq, k), dtype=torch.float32, device=f"cuda:{dev}")
+        op.search_into(q, k, idx_t.data_ptr(), d_t.data_ptr())
+        t = torch.stack([idx_t + r0, d_t.view(torch.int32).to(torch.int64)])
         g = torch.empty((world,) + tuple(t.shape), dtype=torch.int64, device=f"cuda:{dev}")
         dist.all_gather_into_tensor(g, t)
         ai = g[:, 0].permute(1, 0, 2).reshape(nq, world * k)
         ad = g[:, 1].permute(1, 0, 2).reshape(nq, world * k).to(torch.int32).view(torch.float32)
-        # merge: ascending (distance, row id); NaN last like OrderedFloat
+        # merge: ascending (distance, row id); NaN last like OrderedFloat.  Ranks hold ascending row
+        # ranges and every rank's list is ordered by (distance, row id), so ONE stable sort by
+        # distance over the rank-major concatenation keeps ascending global row ids inside ties.
         key = torch.where(torch.isnan(ad), torch.full_like(ad, float("inf")), ad)
-        o1 = torch.argsort(ai, dim=1, stable=True)
-        key1, ai1, ad1 = key.gather(1, o1), ai.gather(1, o1), ad.gather(1, o1)
-        o2 = torch.argsort(key1, dim=1, stable=True)[:, :k]
-        return ai1.gather(1, o2).cpu().numpy(), ad1.gather(1, o2).cpu().numpy()
+        o2 = torch.argsort(key, dim=1, stable=True)[:, :k]
+        return ai.gather(1, o2).cpu().numpy(), ad.gather(1, o2).cpu().numpy()
 
     def timed(q, steps, warmup):
         for _ in range(warmup):

@@ -8,8 +8,6 @@
 //   TransformFinalAggregate            .../aggregator/transform_aggregate_final.rs:67-330
 //   FinalSingleStateAggregator         .../aggregator/transform_single_key.rs:190-279
 //   AggregateHashTable                 src/query/expression/src/aggregate/aggregate_hashtable.rs:168-408
-#include <cub/device/device_scan.cuh>
-
 #include <algorithm>
 #include <cstdlib>
 
@@ -1198,6 +1196,52 @@ class AggFinalOp : public Op {
   }
 };
 
+// exclusive prefix sum of the per-tile selection counts: ONE CTA walks the array in chunks of
+// 1024 with a running carry (<= 2 Mi tiles: a few microseconds); offsets[n] = total
+__global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* counts, uint32_t* offsets, int64_t n) {
+  constexpr int kPer = 8;  // consecutive tiles per thread and step
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int64_t i0 = 0; i0 < n; i0 += 1024 * kPer) {
+    const int64_t i = i0 + (int64_t)threadIdx.x * kPer;
+    uint32_t c[kPer], sum = 0;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) { c[j] = i + j < n ? counts[i + j] : 0; sum += c[j]; }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += up;
+      }
+      s_warp[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const uint32_t base = s_carry + (warp ? s_warp[warp - 1] : 0);
+    uint32_t run = base + incl - sum;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      if (i + j < n) offsets[i + j] = run;
+      run += c[j];
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = base + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) offsets[n] = s_carry;
+}
+
 // ================================================================ standalone filter
 // TransformFilter (filter_predicate.rs:35-104): Transform::transform(DataBlock) -> DataBlock, one
 // output block per pushed block, rows in input order.  BlockEntry::Const columns stay const.
@@ -1205,7 +1249,7 @@ class FilterOp : public Op {
  public:
   AggPlan plan;
   Stager stager;
-  DevBuf nibbles, tile_counts, tile_offsets, cub_tmp, dev_total;
+  DevBuf nibbles, tile_counts, tile_offsets, dev_total;
   PinnedBuf host;
   std::vector<std::unique_ptr<OwnedBlock>> out_q;
   size_t out_head = 0;
@@ -1262,9 +1306,6 @@ class FilterOp : public Op {
       DBX_CUDA_TRY(err, nibbles.ensure((size_t)n_tiles * kBlock));
       DBX_CUDA_TRY(err, tile_counts.ensure((size_t)(n_tiles + 1) * 4));
       DBX_CUDA_TRY(err, tile_offsets.ensure((size_t)(n_tiles + 1) * 4));
-      size_t tmp = 0;
-      cub::DeviceScan::ExclusiveSum(nullptr, tmp, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n_tiles, stream);
-      DBX_CUDA_TRY(err, cub_tmp.ensure(tmp + 256));
       AggKernelParams kp;
       memset(&kp, 0, sizeof(kp));
       for (int s = 0; s < plan.n_slots; ++s) kp.cols[s] = pcols[s];
@@ -1284,14 +1325,12 @@ class FilterOp : public Op {
       }
       count_launch();
       DBX_CUDA_TRY(err, cudaGetLastError());
-      tmp = cub_tmp.bytes;
-      DBX_CUDA_TRY(err, cub::DeviceScan::ExclusiveSum(cub_tmp.p, tmp, (const uint32_t*)tile_counts.p, (uint32_t*)tile_offsets.p, (int)n_tiles, stream));
-      count_launch(2);
+      tile_scan_kernel<<<1, 1024, 0, stream>>>((const uint32_t*)tile_counts.p, (uint32_t*)tile_offsets.p, n_tiles);
+      count_launch();
       uint32_t* h = (uint32_t*)host.p;
-      DBX_CUDA_TRY(err, cudaMemcpyAsync(h, (uint32_t*)tile_offsets.p + (n_tiles - 1), 4, cudaMemcpyDeviceToHost, stream));
-      DBX_CUDA_TRY(err, cudaMemcpyAsync(h + 1, (uint32_t*)tile_counts.p + (n_tiles - 1), 4, cudaMemcpyDeviceToHost, stream));
+      DBX_CUDA_TRY(err, cudaMemcpyAsync(h, (uint32_t*)tile_offsets.p + n_tiles, 4, cudaMemcpyDeviceToHost, stream));
       DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
-      total = (int64_t)h[0] + (int64_t)h[1];
+      total = (int64_t)h[0];
       unsigned long long t64 = (unsigned long long)total;
       DBX_CUDA_TRY(err, cudaMemcpyAsync(dev_total.p, &t64, 8, cudaMemcpyHostToDevice, stream));
     }

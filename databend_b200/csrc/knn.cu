@@ -19,15 +19,15 @@
 //      the row-wise function, the bf16 GEMM only decides which rows get that far.
 #include <cuda.h>
 
-#include <cub/device/device_radix_sort.cuh>
-
 #include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <limits>
+#include <vector>
 
 #include "knn_kernels.cuh"
+#include "radix_sort.cuh"
 #include "runtime.h"
 
 namespace dbx {
@@ -40,7 +40,9 @@ inline int grid_1d(int64_t n, int block = 256) {
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 // per query: [start, end) of its run in the sorted candidate keys
-__global__ void seg_bounds_kernel(const uint64_t* keys, int64_t n, int nq, int64_t* seg) {
+// (n_dev != nullptr: the candidate count lives on the device — no host sync in front of the cut)
+__global__ void seg_bounds_kernel(const uint64_t* keys, int64_t n_host, const unsigned long long* n_dev, int nq, int64_t* seg) {
+  const int64_t n = n_dev ? (int64_t)*n_dev : n_host;
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q <= nq; q += gridDim.x * blockDim.x) {
     const uint64_t target = (uint64_t)q << 32;
     int64_t lo = 0, hi = n;
@@ -167,7 +169,13 @@ __global__ void certify_kernel(int kind, int nq, int k, int kk, const int64_t* s
   }
 }
 // exact path: keys of one query's distances to every corpus row
-__global__ void exact_keys_kernel(const float* dist, int64_t n, uint32_t* keys, uint32_t* rows) {
+// After a similarity pass without a host check: a pass that appended more than the list holds is
+// dropped on the device (count back to what it was) and flagged; the host sees the flag at the
+// end of the search and repeats the search with per-pass checks.
+__global__ void knn_post_pass_kernel(unsigned long long* count, const unsigned long long* prev, long long cap, unsigned long long* overflow) {
+  if (threadIdx.x == 0 && (long long)*count > cap) { *count = *prev; *overflow = 1; }
+}
+__global__ void exact_keys_kernel(const float* dist, int64_t n, uint64_t* keys, uint32_t* rows) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     keys[i] = dist_to_ordered32(dist[i]);
     rows[i] = (uint32_t)i;
@@ -183,6 +191,9 @@ __global__ void fill_f32_kernel(float* p, int64_t n, float v) {
 }
 __global__ void iota32_kernel(uint32_t* p, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = (uint32_t)i;
+}
+__global__ void widen_u32_kernel(const uint32_t* src, uint64_t* dst, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
 __global__ void gather_key_kernel(const uint64_t* src, const uint32_t* idx, uint64_t* dst, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[idx[i]];
@@ -245,7 +256,7 @@ struct dbx_knn {
   const float* corpus = nullptr;  // f32 [n, dim] in HBM (borrowed if the caller passed device memory)
   DevBuf corpus_own, corpus_bf16, c_scale;
   // per-search scratch (grow-only)
-  DevBuf q_f32, q_bf16, q_scale, bound, seg, seg_off, cand_key[2], cand_row[2], counters, perm[2], key_tmp, dist, cub_tmp;
+  DevBuf q_f32, q_bf16, q_scale, bound, seg, seg_off, cand_key[2], cand_row[2], counters, perm[2], key_tmp, sort_alt, dist;
   DevBuf out_idx_dev, out_dist_dev, max_norm, flags, ex_dist, ex_key[2], ex_row[2], ex_tmp;
   PinnedBuf host, host_flags;
   int64_t stat_certified = 0, stat_exact = 0, stat_candidates = 0, stat_passes = 0, stat_cluster = 0, stat_grid = 0, stat_us_passes = 0, stat_us_rerank = 0;
@@ -253,6 +264,9 @@ struct dbx_knn {
   int64_t last_gemm_launches = 0;
   float last_gemm_ms = 0.f;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  RadixSorter sorter;
+  std::vector<cudaEvent_t> pass_ev;  // event pairs around the similarity passes of one search
+  ~dbx_knn() { for (cudaEvent_t e : pass_ev) cudaEventDestroy(e); }
 };
 
 // Launch plumbing of the similarity GEMM for a cluster size C in {1,2,4,8}.
@@ -324,25 +338,22 @@ static int32_t knn_exact_query(dbx_knn* h, int q, int k, int kk) {
   const int64_t n = h->n;
   int64_t* oi = (int64_t*)h->out_idx_dev.p + (int64_t)q * k;
   float* od = (float*)h->out_dist_dev.p + (int64_t)q * k;
+  int ex_buf = 0;
   if (n > 0) {
     DBX_CUDA_TRY(err, h->ex_dist.ensure((size_t)n * 4));
     for (int i = 0; i < 2; ++i) {
-      DBX_CUDA_TRY(err, h->ex_key[i].ensure((size_t)n * 4));
+      DBX_CUDA_TRY(err, h->ex_key[i].ensure((size_t)n * 8));
       DBX_CUDA_TRY(err, h->ex_row[i].ensure((size_t)n * 4));
     }
-    size_t tmp = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr,
-                                    (int)n, 0, 32, st);
-    DBX_CUDA_TRY(err, h->ex_tmp.ensure(tmp + 256));
     distance_rows_kernel<<<grid_1d(h->kind == DBX_DIST_COSINE ? n * 8 : n, 128), 128, 0, st>>>(
         h->kind, h->corpus, 0, (const float*)h->q_f32.p + (int64_t)q * h->dim, 1, n, h->dim, nullptr, 0, nullptr, 0, (float*)h->ex_dist.p, nullptr);
-    exact_keys_kernel<<<grid_1d(n), 256, 0, st>>>((const float*)h->ex_dist.p, n, (uint32_t*)h->ex_key[0].p, (uint32_t*)h->ex_row[0].p);
-    tmp = h->ex_tmp.bytes;
-    DBX_CUDA_TRY(err, cub::DeviceRadixSort::SortPairs(h->ex_tmp.p, tmp, (const uint32_t*)h->ex_key[0].p, (uint32_t*)h->ex_key[1].p,
-                                                      (const uint32_t*)h->ex_row[0].p, (uint32_t*)h->ex_row[1].p, (int)n, 0, 32, st));
+    exact_keys_kernel<<<grid_1d(n), 256, 0, st>>>((const float*)h->ex_dist.p, n, (uint64_t*)h->ex_key[0].p, (uint32_t*)h->ex_row[0].p);
+    // stable LSD radix sort on the 32 significant key bits: ties keep ascending row ids
+    DBX_TRY(h->sorter.sort(err, st, (uint64_t*)h->ex_key[0].p, (uint64_t*)h->ex_key[1].p, (uint32_t*)h->ex_row[0].p, (uint32_t*)h->ex_row[1].p, n, 0, 32,
+                           false, 0, 0, &ex_buf));
     count_launch(3);
   }
-  exact_emit_kernel<<<(k + 255) / 256, 256, 0, st>>>((const uint32_t*)h->ex_row[1].p, (const float*)h->ex_dist.p, kk, k, oi, od);
+  exact_emit_kernel<<<(k + 255) / 256, 256, 0, st>>>((const uint32_t*)h->ex_row[ex_buf].p, (const float*)h->ex_dist.p, kk, k, oi, od);
   count_launch();
   DBX_CUDA_TRY(err, cudaGetLastError());
   return DBX_OK;
@@ -454,8 +465,6 @@ int32_t dbx_knn_search(dbx_knn* h, const dbx_column* queries, int32_t k, int32_t
   prep_rows_kernel<<<grid_1d((int64_t)nq_pad * 32), 256, 0, st>>>((const float*)h->q_f32.p, nq_pad, dim, dim_pad, (__nv_bfloat16*)h->q_bf16.p,
                                                                 (float*)h->q_scale.p, h->kind, nullptr);
   count_launch();
-  fill_f32_kernel<<<grid_1d(nq_pad), 256, 0, st>>>((float*)h->bound.p, nq_pad, -std::numeric_limits<float>::infinity());
-  count_launch();
 
   // ---- candidate storage
   const int64_t want_cap = std::max<int64_t>(1 << 22, 4LL * nq * kprime);
@@ -466,16 +475,14 @@ int32_t dbx_knn_search(dbx_knn* h, const dbx_column* queries, int32_t k, int32_t
       DBX_CUDA_TRY(err, h->perm[i].ensure((size_t)want_cap * 4));
     }
     DBX_CUDA_TRY(err, h->key_tmp.ensure((size_t)want_cap * 8));
+    DBX_CUDA_TRY(err, h->sort_alt.ensure((size_t)want_cap * 8));
     DBX_CUDA_TRY(err, h->dist.ensure((size_t)want_cap * 4));
-    size_t tmp = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint32_t*)nullptr,
-                                    (uint32_t*)nullptr, (int)want_cap, 0, 64, st);
-    DBX_CUDA_TRY(err, h->cub_tmp.ensure(tmp + 256));
     h->cand_cap = want_cap;
   }
   const int64_t cap = h->cand_cap;
-  unsigned long long* d_count = (unsigned long long*)h->counters.p;
-  DBX_CUDA_TRY(err, cudaMemsetAsync(d_count, 0, 8, st));
+  unsigned long long* d_count = (unsigned long long*)h->counters.p;  // [0] candidates, [1] count before the pass, [2] overflow flag
+  unsigned long long* d_prev = d_count + 1;
+  unsigned long long* d_over = d_count + 2;
   int cur = 0;           // candidates live in cand_*[cur][0..n_cand)
   int64_t n_cand = 0;
 
@@ -485,21 +492,32 @@ int32_t dbx_knn_search(dbx_knn* h, const dbx_column* queries, int32_t k, int32_t
   int row_bits = 1;
   while (row_bits < 32 && (1LL << row_bits) < h->n) ++row_bits;
   auto t_start = std::chrono::steady_clock::now();
+  // Default: NO host synchronisation between the similarity passes — the candidate count stays on
+  // the device (the cut's radix sort, segment search and copy read it there), passes grow on a
+  // fixed geometric schedule, and a pass that would overflow the candidate list is dropped and
+  // flagged on the device; the flag is read once, before the re-rank, and an overflow repeats the
+  // search with a host check after every pass (DBX_KNN_SYNC=1 forces that mode).
+  bool async_mode = getenv("DBX_KNN_SYNC") == nullptr;
   auto select = [&]() -> int32_t {  // cut every query back to its best k', tighten boundaries
-    if (n_cand == 0) return DBX_OK;
-    size_t tmp = h->cub_tmp.bytes;
-    DBX_CUDA_TRY(err, cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tmp, (const uint64_t*)h->cand_key[cur].p, (uint64_t*)h->cand_key[cur ^ 1].p,
-                                                      (const uint32_t*)h->cand_row[cur].p, (uint32_t*)h->cand_row[cur ^ 1].p, (int)n_cand, 0, key_bits, st));
-    seg_bounds_kernel<<<grid_1d(nq + 1), 256, 0, st>>>((const uint64_t*)h->cand_key[cur ^ 1].p, n_cand, nq, (int64_t*)h->seg.p);
+    if (!async_mode && n_cand == 0) return DBX_OK;
+    const unsigned long long* nd = async_mode ? d_count : nullptr;
+    int rb = 0;
+    DBX_TRY(h->sorter.sort(err, st, (uint64_t*)h->cand_key[cur].p, (uint64_t*)h->cand_key[cur ^ 1].p, (uint32_t*)h->cand_row[cur].p,
+                           (uint32_t*)h->cand_row[cur ^ 1].p, async_mode ? cap : n_cand, 0, key_bits, false, 0, 0, &rb, nd));
+    const int src = rb ? (cur ^ 1) : cur, dst = src ^ 1;
+    seg_bounds_kernel<<<grid_1d(nq + 1), 256, 0, st>>>((const uint64_t*)h->cand_key[src].p, n_cand, nd, nq, (int64_t*)h->seg.p);
     retain_scan_kernel<<<1, 1024, 0, st>>>((const int64_t*)h->seg.p, nq, kprime, (int64_t*)h->seg_off.p, d_count);
-    retain_copy_kernel<<<grid_1d((int64_t)nq * 32), 256, 0, st>>>((const uint64_t*)h->cand_key[cur ^ 1].p, (const uint32_t*)h->cand_row[cur ^ 1].p,
+    retain_copy_kernel<<<grid_1d((int64_t)nq * 32), 256, 0, st>>>((const uint64_t*)h->cand_key[src].p, (const uint32_t*)h->cand_row[src].p,
                                                                  (const int64_t*)h->seg.p, (const int64_t*)h->seg_off.p, nq, kprime,
-                                                                 (uint64_t*)h->cand_key[cur].p, (uint32_t*)h->cand_row[cur].p, (float*)h->bound.p);
-    count_launch(4);
+                                                                 (uint64_t*)h->cand_key[dst].p, (uint32_t*)h->cand_row[dst].p, (float*)h->bound.p);
+    count_launch(3);
     DBX_CUDA_TRY(err, cudaGetLastError());
-    DBX_CUDA_TRY(err, cudaMemcpyAsync(h->host.p, d_count, 8, cudaMemcpyDeviceToHost, st));
-    DBX_CUDA_TRY(err, cudaStreamSynchronize(st));
-    n_cand = (int64_t)*(unsigned long long*)h->host.p;
+    cur = dst;
+    if (!async_mode) {
+      DBX_CUDA_TRY(err, cudaMemcpyAsync(h->host.p, d_count, 8, cudaMemcpyDeviceToHost, st));
+      DBX_CUDA_TRY(err, cudaStreamSynchronize(st));
+      n_cand = (int64_t)*(unsigned long long*)h->host.p;
+    }
     return DBX_OK;
   };
 
@@ -516,73 +534,122 @@ int32_t dbx_knn_search(dbx_knn* h, const dbx_column* queries, int32_t k, int32_t
     DBX_TRY(knn_gemm_prepare(err, cluster, &max_clusters));
     h->stat_cluster = cluster; h->stat_grid = (int64_t)max_clusters * cluster;
   }
-  h->last_gemm_ms = 0.f;
-  h->last_gemm_launches = 0;
-  int64_t done = 0;
-  // first pass: small enough that even "everything passes" fits the candidate list
-  int64_t chunk = std::max<int64_t>(kGemmBN, std::min<int64_t>((cap / 2) / std::max(nq, 1) / kGemmBN * kGemmBN, 1 << 16));
-  while (done < h->n) {
-    const int64_t m = std::min<int64_t>(chunk, h->n - done);
-    KnnGemmParams gp;
-    memset(&gp, 0, sizeof(gp));
-    gp.kind = h->kind; gp.nq = nq; gp.nq_pad = nq_pad; gp.dim_pad = dim_pad; gp.n0 = done; gp.n_rows = m;
-    gp.q_scale = (const float*)h->q_scale.p; gp.c_scale = (const float*)h->c_scale.p; gp.bound = (const float*)h->bound.p;
-    gp.cand_key = (uint64_t*)h->cand_key[cur].p; gp.cand_row = (uint32_t*)h->cand_row[cur].p; gp.cand_count = d_count; gp.cand_cap = cap;
-    DBX_CUDA_TRY(err, cudaEventRecord(h->ev0, st));
-    if (use_ref) {
-      knn_ref_filter_kernel<<<grid_1d((int64_t)nq * m), 256, 0, st>>>((const __nv_bfloat16*)h->q_bf16.p, (const __nv_bfloat16*)h->corpus_bf16.p, gp);
-    } else {
-      const int64_t tiles = ((m + kGemmBN - 1) / kGemmBN) * (nq_pad / (kGemmBM * cluster));
-      const int n_clusters = (int)std::min<int64_t>(tiles, max_clusters);
-      DBX_TRY(knn_gemm_launch(err, cluster, n_clusters, st, tmap_q, tmap_c, gp));
-    }
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    fill_f32_kernel<<<grid_1d(nq_pad), 256, 0, st>>>((float*)h->bound.p, nq_pad, -std::numeric_limits<float>::infinity());
     count_launch();
-    DBX_CUDA_TRY(err, cudaGetLastError());
-    DBX_CUDA_TRY(err, cudaEventRecord(h->ev1, st));
-    DBX_CUDA_TRY(err, cudaMemcpyAsync(h->host.p, d_count, 8, cudaMemcpyDeviceToHost, st));
-    DBX_CUDA_TRY(err, cudaStreamSynchronize(st));
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
-    const int64_t cnt = (int64_t)*(unsigned long long*)h->host.p;
-    if (cnt > cap) {  // more survivors than the list holds: drop this pass, tighten, retry smaller
-      unsigned long long back = (unsigned long long)n_cand;
-      DBX_CUDA_TRY(err, cudaMemcpyAsync(d_count, &back, 8, cudaMemcpyHostToDevice, st));
+    DBX_CUDA_TRY(err, cudaMemsetAsync(d_count, 0, 24, st));
+    cur = 0;
+    n_cand = 0;
+    h->last_gemm_ms = 0.f;
+    h->last_gemm_launches = 0;
+    int64_t done = 0;
+    size_t n_ev = 0;
+    // first pass: small enough that even "everything passes" fits the candidate list
+    int64_t chunk = std::max<int64_t>(kGemmBN, std::min<int64_t>((cap / 2) / std::max(nq, 1) / kGemmBN * kGemmBN, 1 << 16));
+    while (done < h->n) {
+      const int64_t m = std::min<int64_t>(chunk, h->n - done);
+      KnnGemmParams gp;
+      memset(&gp, 0, sizeof(gp));
+      gp.kind = h->kind; gp.nq = nq; gp.nq_pad = nq_pad; gp.dim_pad = dim_pad; gp.n0 = done; gp.n_rows = m;
+      gp.q_scale = (const float*)h->q_scale.p; gp.c_scale = (const float*)h->c_scale.p; gp.bound = (const float*)h->bound.p;
+      gp.cand_key = (uint64_t*)h->cand_key[cur].p; gp.cand_row = (uint32_t*)h->cand_row[cur].p; gp.cand_count = d_count; gp.cand_cap = cap;
+      cudaEvent_t e0 = h->ev0, e1 = h->ev1;
+      if (async_mode) {
+        DBX_CUDA_TRY(err, cudaMemcpyAsync(d_prev, d_count, 8, cudaMemcpyDeviceToDevice, st));
+        while (h->pass_ev.size() < n_ev + 2) {
+          cudaEvent_t e = nullptr;
+          DBX_CUDA_TRY(err, cudaEventCreate(&e));
+          h->pass_ev.push_back(e);
+        }
+        e0 = h->pass_ev[n_ev]; e1 = h->pass_ev[n_ev + 1];
+        n_ev += 2;
+      }
+      DBX_CUDA_TRY(err, cudaEventRecord(e0, st));
+      if (use_ref) {
+        knn_ref_filter_kernel<<<grid_1d((int64_t)nq * m), 256, 0, st>>>((const __nv_bfloat16*)h->q_bf16.p, (const __nv_bfloat16*)h->corpus_bf16.p, gp);
+      } else {
+        const int64_t tiles = ((m + kGemmBN - 1) / kGemmBN) * (nq_pad / (kGemmBM * cluster));
+        const int n_clusters = (int)std::min<int64_t>(tiles, max_clusters);
+        DBX_TRY(knn_gemm_launch(err, cluster, n_clusters, st, tmap_q, tmap_c, gp));
+      }
+      count_launch();
+      DBX_CUDA_TRY(err, cudaGetLastError());
+      DBX_CUDA_TRY(err, cudaEventRecord(e1, st));
+      if (async_mode) {
+        knn_post_pass_kernel<<<1, 32, 0, st>>>(d_count, d_prev, (long long)cap, d_over);
+        count_launch();
+        h->last_gemm_launches += 1;
+        done += m;
+        DBX_TRY(select());
+        chunk = std::min<int64_t>(chunk * 8, 1LL << 24);
+        continue;
+      }
+      DBX_CUDA_TRY(err, cudaMemcpyAsync(h->host.p, d_count, 8, cudaMemcpyDeviceToHost, st));
+      DBX_CUDA_TRY(err, cudaStreamSynchronize(st));
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e0, e1);
+      const int64_t cnt = (int64_t)*(unsigned long long*)h->host.p;
+      if (cnt > cap) {  // more survivors than the list holds: drop this pass, tighten, retry smaller
+        unsigned long long back = (unsigned long long)n_cand;
+        DBX_CUDA_TRY(err, cudaMemcpyAsync(d_count, &back, 8, cudaMemcpyHostToDevice, st));
+        DBX_TRY(select());
+        if (m <= kGemmBN) { err.set("kNN candidate list too small for one GEMM tile"); return DBX_ERR_CUDA; }
+        chunk = std::max<int64_t>(kGemmBN, (m / 4) / kGemmBN * kGemmBN);
+        continue;
+      }
+      h->last_gemm_ms += ms;
+      h->last_gemm_launches += 1;
+      n_cand = cnt;
+      done += m;
       DBX_TRY(select());
-      if (m <= kGemmBN) { err.set("kNN candidate list too small for one GEMM tile"); return DBX_ERR_CUDA; }
-      chunk = std::max<int64_t>(kGemmBN, (m / 4) / kGemmBN * kGemmBN);
-      continue;
+      chunk = std::min<int64_t>(chunk * 8, 1LL << 24);
     }
-    h->last_gemm_ms += ms;
-    h->last_gemm_launches += 1;
     h->stat_passes = h->last_gemm_launches;
-    n_cand = cnt;
-    done += m;
-    DBX_TRY(select());
-    chunk = std::min<int64_t>(chunk * 8, 1LL << 24);
+    if (!async_mode) break;
+    // the one host check of the asynchronous mode
+    DBX_CUDA_TRY(err, cudaMemcpyAsync(h->host.p, d_count, 24, cudaMemcpyDeviceToHost, st));
+    DBX_CUDA_TRY(err, cudaStreamSynchronize(st));
+    n_cand = (int64_t)((unsigned long long*)h->host.p)[0];
+    for (size_t i = 0; i + 1 < n_ev; i += 2) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, h->pass_ev[i], h->pass_ev[i + 1]);
+      h->last_gemm_ms += ms;
+    }
+    if (((unsigned long long*)h->host.p)[2] == 0) break;
+    async_mode = false;  // a pass overflowed the candidate list: once more, with a host check after every pass
   }
 
   auto t_passes = std::chrono::steady_clock::now();
   // ---- exact re-rank of the k' survivors per query, ordered by (distance, row id)
   DBX_CUDA_TRY(err, h->out_idx_dev.ensure((size_t)nq * k * 8));
   DBX_CUDA_TRY(err, h->out_dist_dev.ensure((size_t)nq * k * 4));
+  const uint64_t* final_keys = (const uint64_t*)h->key_tmp.p;
+  const uint32_t* final_perm = (const uint32_t*)h->perm[0].p;
   if (n_cand > 0) {
-    size_t tmp = h->cub_tmp.bytes;
-    // stable pass 1: by row id; stable pass 2: by (query, exact distance)
+    // exact distances, then two stable LSD radix sorts of a permutation: by row id, then by
+    // (query, exact distance) -> ties keep ascending row ids
     rerank_kernel<<<grid_1d(n_cand), 256, 0, st>>>(h->kind, (const float*)h->q_f32.p, h->corpus, dim, (const uint64_t*)h->cand_key[cur].p,
                                                    (const uint32_t*)h->cand_row[cur].p, n_cand, (uint64_t*)h->key_tmp.p, (float*)h->dist.p);
     iota32_kernel<<<grid_1d(n_cand), 256, 0, st>>>((uint32_t*)h->perm[0].p, n_cand);
-    DBX_CUDA_TRY(err, cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tmp, (const uint32_t*)h->cand_row[cur].p, (uint32_t*)h->cand_row[cur ^ 1].p,
-                                                      (const uint32_t*)h->perm[0].p, (uint32_t*)h->perm[1].p, (int)n_cand, 0, row_bits, st));
-    gather_key_kernel<<<grid_1d(n_cand), 256, 0, st>>>((const uint64_t*)h->key_tmp.p, (const uint32_t*)h->perm[1].p, (uint64_t*)h->cand_key[cur ^ 1].p, n_cand);
-    tmp = h->cub_tmp.bytes;
-    DBX_CUDA_TRY(err, cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tmp, (const uint64_t*)h->cand_key[cur ^ 1].p, (uint64_t*)h->key_tmp.p,
-                                                      (const uint32_t*)h->perm[1].p, (uint32_t*)h->perm[0].p, (int)n_cand, 0, key_bits, st));
-    seg_bounds_kernel<<<grid_1d(nq + 1), 256, 0, st>>>((const uint64_t*)h->key_tmp.p, n_cand, nq, (int64_t*)h->seg.p);
-    count_launch(6);
+    uint64_t* ka = (uint64_t*)h->cand_key[cur ^ 1].p;
+    uint64_t* kb = (uint64_t*)h->sort_alt.p;
+    widen_u32_kernel<<<grid_1d(n_cand), 256, 0, st>>>((const uint32_t*)h->cand_row[cur].p, ka, n_cand);
+    count_launch(3);
+    int rb1 = 0, rb2 = 0;
+    DBX_TRY(h->sorter.sort(err, st, ka, kb, (uint32_t*)h->perm[0].p, (uint32_t*)h->perm[1].p, n_cand, 0, row_bits, false, 0, 0, &rb1));
+    uint32_t* p_sorted = (uint32_t*)h->perm[rb1].p;
+    uint32_t* p_other = (uint32_t*)h->perm[rb1 ^ 1].p;
+    gather_key_kernel<<<grid_1d(n_cand), 256, 0, st>>>((const uint64_t*)h->key_tmp.p, p_sorted, ka, n_cand);
+    count_launch();
+    DBX_TRY(h->sorter.sort(err, st, ka, kb, p_sorted, p_other, n_cand, 0, key_bits, false, 0, 0, &rb2));
+    final_keys = rb2 ? kb : ka;
+    final_perm = rb2 ? p_other : p_sorted;
+    seg_bounds_kernel<<<grid_1d(nq + 1), 256, 0, st>>>(final_keys, n_cand, nullptr, nq, (int64_t*)h->seg.p);
+    count_launch();
   } else {
     DBX_CUDA_TRY(err, cudaMemsetAsync(h->seg.p, 0, (size_t)(nq + 2) * 8, st));
   }
-  emit_topk_kernel<<<grid_1d((int64_t)nq * k), 256, 0, st>>>((const uint64_t*)h->key_tmp.p, (const uint32_t*)h->perm[0].p, (const uint32_t*)h->cand_row[cur].p,
+  emit_topk_kernel<<<grid_1d((int64_t)nq * k), 256, 0, st>>>(final_keys, final_perm, (const uint32_t*)h->cand_row[cur].p,
                                                             (const float*)h->dist.p, (const int64_t*)h->seg.p, nq, k, (int64_t*)h->out_idx_dev.p,
                                                             (float*)h->out_dist_dev.p);
   count_launch();

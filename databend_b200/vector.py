@@ -103,6 +103,15 @@ class VectorTopN:
             raise DbxError(st, (msg or b"").decode("utf-8", "replace"))
         return idx, dist
 
+    def search_into(self, queries: Column, k: int, out_idx_dev_ptr: int, out_dist_dev_ptr: int):
+        """Same search, results written to caller-provided DEVICE buffers ([nq, k] int64 row ids and
+        [nq, k] float32 distances): the multi-GPU merge then never leaves HBM."""
+        q = queries.as_c()
+        st = load().dbx_knn_search(self._h, C.byref(q), k, abi.MEM_DEVICE, out_idx_dev_ptr, out_dist_dev_ptr)
+        if st != abi.OK:
+            msg = load().dbx_knn_last_error(self._h)
+            raise DbxError(st, (msg or b"").decode("utf-8", "replace"))
+
     def last_gemm_ms(self) -> Tuple[float, int]:
         ms, n = C.c_float(0), C.c_int64(0)
         load().dbx_knn_last_gemm_ms(self._h, C.byref(ms), C.byref(n))

@@ -10,8 +10,8 @@ NCU="ncu --metrics gpu__time_duration.sum --clock-control none --csv"
 timeout 300 $NCU --log-file gpurun_out/r2e_topk_launches.csv python experiments/bench_ops.py --ops topk --reps 1 > gpurun_out/r2e_topk.log 2>&1
 timeout 300 $NCU --log-file gpurun_out/r2e_sort_launches.csv python experiments/bench_ops.py --ops sort --sort-rows 100000000 --reps 1 > gpurun_out/r2e_sort.log 2>&1
 timeout 400 $NCU --log-file gpurun_out/r2e_join_launches.csv python experiments/bench_ops.py --ops join --fact-rows 250000000 --reps 1 > gpurun_out/r2e_join.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'filter_group_agg_kernel<3, 1' -s 2 -c 1 -f -o gpurun_out/r2e_prof_agg python bench.py --no-e2e --no-cpu --no-knn --no-verify --steps 1 --warmup 1 > gpurun_out/r2e_ncu_agg.log 2>&1
-timeout 300 ncu --metrics lts__t_sectors_op_red.sum,lts__t_sectors_op_atom.sum,lts__t_requests_srcunit_tex_op_red.sum,lts__t_sectors_srcunit_tex_op_read.sum,lts__t_sector_hit_rate.pct,lts__t_sectors_op_read.sum,lts__t_sectors_op_write.sum,l1tex__t_set_accesses_pipe_lsu_mem_global_op_red.sum,lts__throughput.avg.pct_of_peak_sustained_elapsed,dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:'filter_group_agg_kernel<3, 1' -s 2 -c 1 --csv --log-file gpurun_out/r2e_agg_red_counters.csv python bench.py --no-e2e --no-cpu --no-knn --no-verify --steps 1 --warmup 1 > gpurun_out/r2e_ncu_agg2.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'filter_group_agg_kernel<.int.3, .bool.1' -s 2 -c 1 -f -o gpurun_out/r2e_prof_agg python bench.py --no-e2e --no-cpu --no-knn --no-verify --steps 1 --warmup 1 > gpurun_out/r2e_ncu_agg.log 2>&1
+timeout 300 ncu --metrics lts__t_sectors_op_red.sum,lts__t_sectors_op_atom.sum,lts__t_requests_srcunit_tex_op_red.sum,lts__t_sectors_srcunit_tex_op_read.sum,lts__t_sector_hit_rate.pct,lts__t_sectors_op_read.sum,lts__t_sectors_op_write.sum,l1tex__t_set_accesses_pipe_lsu_mem_global_op_red.sum,lts__throughput.avg.pct_of_peak_sustained_elapsed,dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:'filter_group_agg_kernel<.int.3, .bool.1' -s 2 -c 1 --csv --log-file gpurun_out/r2e_agg_red_counters.csv python bench.py --no-e2e --no-cpu --no-knn --no-verify --steps 1 --warmup 1 > gpurun_out/r2e_ncu_agg2.log 2>&1
 python - <<'P'
 import csv, collections
 for name in ["topk", "sort", "join"]:
