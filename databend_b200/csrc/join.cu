@@ -517,7 +517,12 @@ class JoinOp : public Op {
     n_part = 1;
     {
       const int64_t bytes = table_cap * (int64_t)sizeof(JoinEntry);
-      int64_t target = 32LL << 20;  // region size; DBX_JOIN_REGION_BYTES overrides (tests), 0 disables
+      // Radix regions are OFF by default: measured on B200 (profiles/r02_ops_n1_after_rework.jsonl and
+      // call F), 1e9 x 1e7 rows: 39.5 ms without regions vs 50.3 ms with 32 MB regions — once the
+      // probe stops at its first match (unique build keys) one random HBM sector per row costs less
+      // than the extra partition pass over the probe block.  DBX_JOIN_REGION_BYTES=<bytes> turns
+      // them on (tests exercise both).
+      int64_t target = 0;
       if (const char* e = getenv("DBX_JOIN_REGION_BYTES")) target = atoll(e);
       if (target > 0 && bytes > 3 * target) {
         while (n_part < kMaxParts && bytes / n_part > target) n_part *= 2;

@@ -175,6 +175,138 @@ __global__ void certify_kernel(int kind, int nq, int k, int kk, const int64_t* s
 __global__ void knn_post_pass_kernel(unsigned long long* count, const unsigned long long* prev, long long cap, unsigned long long* overflow) {
   if (threadIdx.x == 0 && (long long)*count > cap) { *count = *prev; *overflow = 1; }
 }
+// Per-query cut (per-query candidate lists): ONE CTA per query keeps the k' best of its list —
+// radix select on the 32-bit key image in shared memory — compacts them to the front of the list
+// and tightens the query's boundary to the k'-th best score.  Replaces sort + segment search +
+// scan + copy of the shared-list cut with one launch.
+__global__ void __launch_bounds__(256) knn_cut_perq_kernel(uint64_t* cand_key, uint32_t* cand_row, unsigned int* qcount, int qcap, int kprime,
+                                                           float* bound) {
+  extern __shared__ __align__(16) uint32_t s_dyn[];
+  uint32_t* s_k = s_dyn;          // [qcap] low 32 key bits: ~ordered(score), smaller = better
+  uint32_t* s_r = s_dyn + qcap;   // [qcap] corpus rows
+  __shared__ unsigned int s_hist[256];
+  __shared__ unsigned int s_pick[3];
+  __shared__ unsigned int s_out, s_max;
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const unsigned int cnt = qcount[q];
+  const int n = (int)(cnt < (unsigned)qcap ? cnt : (unsigned)qcap);
+  if (n < kprime) return;  // fewer than k' candidates so far: nothing to cut, the boundary stays
+  uint64_t* kq = cand_key + (size_t)q * qcap;
+  uint32_t* rq = cand_row + (size_t)q * qcap;
+  for (int i = tid; i < n; i += 256) { s_k[i] = (uint32_t)kq[i]; s_r[i] = rq[i]; }
+  if (tid == 0) { s_out = 0; s_max = 0; }
+  __syncthreads();
+  uint32_t th = 0xFFFFFFFFu;  // keep key <= th
+  if (n > kprime) {
+    uint32_t prefix = 0;
+    int k_rem = kprime;
+    bool closed = false;
+    for (int p = 0; p < 4 && !closed; ++p) {
+      s_hist[tid] = 0;
+      __syncthreads();
+      const int sh = 24 - 8 * p;
+      for (int i = tid; i < n; i += 256) {
+        const uint32_t key = s_k[i];
+        if (p == 0 || (key >> (sh + 8)) == (prefix >> (sh + 8))) atomicAdd(&s_hist[(key >> sh) & 255], 1u);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        unsigned int cum = 0;
+        int b = 0;
+        for (; b < 255; ++b) {
+          if ((int)(cum + s_hist[b]) >= k_rem) break;
+          cum += s_hist[b];
+        }
+        s_pick[0] = (unsigned)b; s_pick[1] = cum; s_pick[2] = s_hist[b];
+      }
+      __syncthreads();
+      prefix |= s_pick[0] << sh;
+      k_rem -= (int)s_pick[1];
+      if ((int)s_pick[2] == k_rem) { prefix |= sh ? ((1u << sh) - 1) : 0u; closed = true; }
+      __syncthreads();
+    }
+    th = prefix;
+  }
+  // entries strictly better than the threshold always fit; ties at the threshold fill what is left
+  for (int i = tid; i < n; i += 256) {
+    const uint32_t key = s_k[i];
+    if (key < th || (key == th && n <= kprime)) {
+      const unsigned int pos = atomicAdd(&s_out, 1u);
+      kq[pos] = ((uint64_t)(uint32_t)q << 32) | key;
+      rq[pos] = s_r[i];
+      atomicMax(&s_max, key);
+    }
+  }
+  __syncthreads();
+  if (n > kprime) {
+    for (int i = tid; i < n; i += 256) {
+      const uint32_t key = s_k[i];
+      if (key == th) {
+        const unsigned int pos = atomicAdd(&s_out, 1u);
+        if ((int)pos < kprime) {
+          kq[pos] = ((uint64_t)(uint32_t)q << 32) | key;
+          rq[pos] = s_r[i];
+          atomicMax(&s_max, key);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const unsigned int kept = s_out < (unsigned)kprime ? s_out : (unsigned)kprime;
+    qcount[q] = kept;
+    if ((int)kept == kprime) {  // the k'-th best score so far
+      const uint32_t o = ~s_max;
+      const uint32_t bits = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+      bound[q] = __uint_as_float(bits);
+    }
+  }
+}
+// per-query lists -> one flat list for the re-rank: prefix over min(count, k') (one CTA), then copy
+__global__ void __launch_bounds__(1024) perq_offsets_kernel(const unsigned int* qcount, int nq, int kprime, int64_t* off, unsigned long long* out_count) {
+  __shared__ int64_t s_warp[32];
+  __shared__ int64_t s_carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int q0 = 0; q0 < nq; q0 += 1024) {
+    const int q = q0 + threadIdx.x;
+    const int64_t len = q < nq ? (int64_t)(qcount[q] < (unsigned)kprime ? qcount[q] : (unsigned)kprime) : 0;
+    int64_t incl = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int64_t up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int64_t w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int64_t up = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += up;
+      }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    const int64_t base = s_carry + (warp ? s_warp[warp - 1] : 0);
+    if (q < nq) off[q] = base + incl - len;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = base + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { off[nq] = s_carry; *out_count = (unsigned long long)s_carry; }
+}
+__global__ void perq_flatten_kernel(const uint64_t* keys, const uint32_t* rows, int qcap, const int64_t* off, int nq, uint64_t* out_keys, uint32_t* out_rows) {
+  const int lane = threadIdx.x & 31;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nq; q += n_warps) {
+    const int64_t dst = off[q];
+    const int len = (int)(off[q + 1] - dst);
+    for (int j = lane; j < len; j += 32) { out_keys[dst + j] = keys[(size_t)q * qcap + j]; out_rows[dst + j] = rows[(size_t)q * qcap + j]; }
+  }
+}
 __global__ void exact_keys_kernel(const float* dist, int64_t n, uint64_t* keys, uint32_t* rows) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     keys[i] = dist_to_ordered32(dist[i]);
@@ -256,7 +388,7 @@ struct dbx_knn {
   const float* corpus = nullptr;  // f32 [n, dim] in HBM (borrowed if the caller passed device memory)
   DevBuf corpus_own, corpus_bf16, c_scale;
   // per-search scratch (grow-only)
-  DevBuf q_f32, q_bf16, q_scale, bound, seg, seg_off, cand_key[2], cand_row[2], counters, perm[2], key_tmp, sort_alt, dist;
+  DevBuf q_f32, q_bf16, q_scale, bound, seg, seg_off, cand_key[2], cand_row[2], counters, perm[2], key_tmp, sort_alt, dist, qcount;
   DevBuf out_idx_dev, out_dist_dev, max_norm, flags, ex_dist, ex_key[2], ex_row[2], ex_tmp;
   PinnedBuf host, host_flags;
   int64_t stat_certified = 0, stat_exact = 0, stat_candidates = 0, stat_passes = 0, stat_cluster = 0, stat_grid = 0, stat_us_passes = 0, stat_us_rerank = 0;
@@ -498,7 +630,29 @@ int32_t dbx_knn_search(dbx_knn* h, const dbx_column* queries, int32_t k, int32_t
   // flagged on the device; the flag is read once, before the re-rank, and an overflow repeats the
   // search with a host check after every pass (DBX_KNN_SYNC=1 forces that mode).
   bool async_mode = getenv("DBX_KNN_SYNC") == nullptr;
+  // per-query candidate lists (the asynchronous mode's layout): capacity per query
+  int qcap = (int)std::min<int64_t>(4096, cap / nq_pad / 256 * 256);
+  const bool qcap_forced = getenv("DBX_KNN_QCAP") != nullptr;  // tests: a small capacity forces the overflow fallback
+  if (qcap_forced) qcap = std::min(qcap, std::max(256, atoi(getenv("DBX_KNN_QCAP")) / 256 * 256));
+  bool perq = async_mode && qcap >= 4 * kprime && (qcap >= 1024 || qcap_forced) && !getenv("DBX_KNN_SHARED_LIST") && !getenv("DBX_KNN_REF_GEMM");
+  unsigned int* d_qcount = nullptr;
+  if (perq) {
+    DBX_CUDA_TRY(err, h->qcount.ensure((size_t)nq_pad * 4));
+    d_qcount = (unsigned int*)h->qcount.p;
+    static std::atomic<bool> attr_set[64];
+    if (!attr_set[h->device]) {
+      DBX_CUDA_TRY(err, cudaFuncSetAttribute(knn_cut_perq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 8));
+      attr_set[h->device] = true;
+    }
+  }
   auto select = [&]() -> int32_t {  // cut every query back to its best k', tighten boundaries
+    if (perq) {
+      knn_cut_perq_kernel<<<nq, 256, (size_t)qcap * 8, st>>>((uint64_t*)h->cand_key[0].p, (uint32_t*)h->cand_row[0].p, d_qcount, qcap, kprime,
+                                                            (float*)h->bound.p);
+      count_launch();
+      DBX_CUDA_TRY(err, cudaGetLastError());
+      return DBX_OK;
+    }
     if (!async_mode && n_cand == 0) return DBX_OK;
     const unsigned long long* nd = async_mode ? d_count : nullptr;
     int rb = 0;
@@ -538,6 +692,7 @@ int32_t dbx_knn_search(dbx_knn* h, const dbx_column* queries, int32_t k, int32_t
     fill_f32_kernel<<<grid_1d(nq_pad), 256, 0, st>>>((float*)h->bound.p, nq_pad, -std::numeric_limits<float>::infinity());
     count_launch();
     DBX_CUDA_TRY(err, cudaMemsetAsync(d_count, 0, 24, st));
+    if (perq) DBX_CUDA_TRY(err, cudaMemsetAsync(d_qcount, 0, (size_t)nq_pad * 4, st));
     cur = 0;
     n_cand = 0;
     h->last_gemm_ms = 0.f;
@@ -546,6 +701,7 @@ int32_t dbx_knn_search(dbx_knn* h, const dbx_column* queries, int32_t k, int32_t
     size_t n_ev = 0;
     // first pass: small enough that even "everything passes" fits the candidate list
     int64_t chunk = std::max<int64_t>(kGemmBN, std::min<int64_t>((cap / 2) / std::max(nq, 1) / kGemmBN * kGemmBN, 1 << 16));
+    if (perq) chunk = std::max<int64_t>(kGemmBN, (qcap / 2) / kGemmBN * kGemmBN);  // even "everything passes" fits a query's list
     while (done < h->n) {
       const int64_t m = std::min<int64_t>(chunk, h->n - done);
       KnnGemmParams gp;
@@ -553,9 +709,10 @@ int32_t dbx_knn_search(dbx_knn* h, const dbx_column* queries, int32_t k, int32_t
       gp.kind = h->kind; gp.nq = nq; gp.nq_pad = nq_pad; gp.dim_pad = dim_pad; gp.n0 = done; gp.n_rows = m;
       gp.q_scale = (const float*)h->q_scale.p; gp.c_scale = (const float*)h->c_scale.p; gp.bound = (const float*)h->bound.p;
       gp.cand_key = (uint64_t*)h->cand_key[cur].p; gp.cand_row = (uint32_t*)h->cand_row[cur].p; gp.cand_count = d_count; gp.cand_cap = cap;
+      if (perq) { gp.qcount = d_qcount; gp.qcap = qcap; gp.overflow = d_over; }
       cudaEvent_t e0 = h->ev0, e1 = h->ev1;
       if (async_mode) {
-        DBX_CUDA_TRY(err, cudaMemcpyAsync(d_prev, d_count, 8, cudaMemcpyDeviceToDevice, st));
+        if (!perq) DBX_CUDA_TRY(err, cudaMemcpyAsync(d_prev, d_count, 8, cudaMemcpyDeviceToDevice, st));
         while (h->pass_ev.size() < n_ev + 2) {
           cudaEvent_t e = nullptr;
           DBX_CUDA_TRY(err, cudaEventCreate(&e));
@@ -576,8 +733,10 @@ int32_t dbx_knn_search(dbx_knn* h, const dbx_column* queries, int32_t k, int32_t
       DBX_CUDA_TRY(err, cudaGetLastError());
       DBX_CUDA_TRY(err, cudaEventRecord(e1, st));
       if (async_mode) {
-        knn_post_pass_kernel<<<1, 32, 0, st>>>(d_count, d_prev, (long long)cap, d_over);
-        count_launch();
+        if (!perq) {
+          knn_post_pass_kernel<<<1, 32, 0, st>>>(d_count, d_prev, (long long)cap, d_over);
+          count_launch();
+        }
         h->last_gemm_launches += 1;
         done += m;
         DBX_TRY(select());
@@ -606,6 +765,13 @@ int32_t dbx_knn_search(dbx_knn* h, const dbx_column* queries, int32_t k, int32_t
     }
     h->stat_passes = h->last_gemm_launches;
     if (!async_mode) break;
+    if (perq) {  // per-query lists -> one flat list (cand_*[1]) for the re-rank
+      perq_offsets_kernel<<<1, 1024, 0, st>>>(d_qcount, nq, kprime, (int64_t*)h->seg_off.p, d_count);
+      perq_flatten_kernel<<<grid_1d((int64_t)nq * 32), 256, 0, st>>>((const uint64_t*)h->cand_key[0].p, (const uint32_t*)h->cand_row[0].p, qcap,
+                                                                    (const int64_t*)h->seg_off.p, nq, (uint64_t*)h->cand_key[1].p, (uint32_t*)h->cand_row[1].p);
+      count_launch(2);
+      cur = 1;
+    }
     // the one host check of the asynchronous mode
     DBX_CUDA_TRY(err, cudaMemcpyAsync(h->host.p, d_count, 24, cudaMemcpyDeviceToHost, st));
     DBX_CUDA_TRY(err, cudaStreamSynchronize(st));
@@ -616,7 +782,8 @@ int32_t dbx_knn_search(dbx_knn* h, const dbx_column* queries, int32_t k, int32_t
       h->last_gemm_ms += ms;
     }
     if (((unsigned long long*)h->host.p)[2] == 0) break;
-    async_mode = false;  // a pass overflowed the candidate list: once more, with a host check after every pass
+    async_mode = false;  // a pass overflowed a candidate list: once more, shared list, with a host check after every pass
+    perq = false;
   }
 
   auto t_passes = std::chrono::steady_clock::now();

@@ -188,3 +188,43 @@ def test_knn_tensor_core_pass_matches_cuda_core_reference(gpu, monkeypatch):
     op.close()
     np.testing.assert_array_equal(a[0], b[0])
     assert_f32_bits_equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("mode", ["default", "shared_list", "sync", "tiny_lists"])
+def test_knn_candidate_list_modes(gpu, monkeypatch, mode):
+    """The three ways the candidate lists are run — per-query lists cut by one kernel per pass with
+    no host check (default), one shared list cut by a radix sort without host checks, and the
+    shared list with a host check after every pass — plus per-query lists so small that a pass
+    overflows them (flagged on the device, the search is then repeated in checked mode): all give
+    the oracle's answer."""
+    if mode == "shared_list":
+        monkeypatch.setenv("DBX_KNN_SHARED_LIST", "1")
+    elif mode == "sync":
+        monkeypatch.setenv("DBX_KNN_SYNC", "1")
+    elif mode == "tiny_lists":
+        monkeypatch.setenv("DBX_KNN_QCAP", "256")
+    rng = np.random.default_rng(99)
+    corpus = rng.standard_normal((60_000, 96)).astype(np.float32)
+    queries = rng.standard_normal((130, 96)).astype(np.float32)
+    k = 1 if mode == "tiny_lists" else 10
+    for kind in ("cosine", "l2"):
+        check_knn(kind, corpus, queries, k, device_resident=True)
+
+
+def test_knn_one_million_rows_768(gpu):
+    """configs[4] at 1e6 x 768 (a tenth of the benchmark's corpus): the returned neighbours of a
+    query sample against the oracle's row-wise distances over ALL rows — ranking by (distance,
+    row id) and distances bit for bit."""
+    rng = np.random.default_rng(2024)
+    n, dim, nq, k = 1_000_000, 768, 64, 10
+    corpus = rng.standard_normal((n, dim), dtype=np.float32)
+    queries = rng.standard_normal((nq, dim), dtype=np.float32)
+    op = VectorTopN("cosine_distance", to_device(Column.vector(corpus)))
+    idx, dist = op.search(Column.vector(queries), k)
+    stats = op.stats()
+    op.close()
+    assert stats["certified"] + stats["exact_fallback"] == nq
+    sample = [0, 17, 63]
+    eidx, edist = oracle_knn("cosine", corpus, queries[sample], k)
+    np.testing.assert_array_equal(idx[sample], eidx)
+    assert_f32_bits_equal(dist[sample], edist)
