@@ -262,6 +262,38 @@ __global__ void __launch_bounds__(256) knn_cut_perq_kernel(uint64_t* cand_key, u
     }
   }
 }
+// Shared candidate list (what the similarity GEMM's epilogue appends to, in coalesced bursts) ->
+// per-query lists: every candidate goes to the list of its query (warp-aggregated reservation:
+// consecutive candidates mostly share their query).  Keeps the hot GEMM epilogue untouched and
+// still lets ONE kernel per pass do the cut.
+__global__ void __launch_bounds__(256) perq_distribute_kernel(const uint64_t* keys, const uint32_t* rows, const unsigned long long* n_dev, long long cap,
+                                                              unsigned int* qcount, int qcap, uint64_t* q_keys, uint32_t* q_rows,
+                                                              unsigned long long* overflow) {
+  const long long cnt = (long long)*n_dev;
+  if (cnt > cap) { if (blockIdx.x == 0 && threadIdx.x == 0) *overflow = 1; }  // the shared list itself overflowed in this pass
+  const long long n = cnt < cap ? cnt : cap;
+  const int lane = threadIdx.x & 31;
+  for (long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane; i0 < n; i0 += (long long)gridDim.x * blockDim.x) {
+    const long long i = i0 + lane;
+    const bool in = i < n;
+    const uint64_t key = in ? keys[i] : 0;
+    const uint32_t q = (uint32_t)(key >> 32);
+    const unsigned peers = __match_any_sync(0xffffffffu, in ? q : 0xFFFFFFFFu - (uint32_t)lane);
+    const int leader = __ffs(peers) - 1;
+    unsigned int base = 0;
+    if (in && lane == leader) base = atomicAdd(qcount + q, (unsigned int)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (in) {
+      const unsigned int pos = base + __popc(peers & ((1u << lane) - 1));
+      if ((int)pos < qcap) {
+        q_keys[(size_t)q * qcap + pos] = key;
+        q_rows[(size_t)q * qcap + pos] = rows[i];
+      } else {
+        *overflow = 1;  // never silently: the host repeats the search in checked mode
+      }
+    }
+  }
+}
 // per-query lists -> one flat list for the re-rank: prefix over min(count, k') (one CTA), then copy
 __global__ void __launch_bounds__(1024) perq_offsets_kernel(const unsigned int* qcount, int nq, int kprime, int64_t* off, unsigned long long* out_count) {
   __shared__ int64_t s_warp[32];
@@ -634,7 +666,7 @@ int32_t dbx_knn_search(dbx_knn* h, const dbx_column* queries, int32_t k, int32_t
   int qcap = (int)std::min<int64_t>(4096, cap / nq_pad / 256 * 256);
   const bool qcap_forced = getenv("DBX_KNN_QCAP") != nullptr;  // tests: a small capacity forces the overflow fallback
   if (qcap_forced) qcap = std::min(qcap, std::max(256, atoi(getenv("DBX_KNN_QCAP")) / 256 * 256));
-  bool perq = async_mode && qcap >= 4 * kprime && (qcap >= 1024 || qcap_forced) && !getenv("DBX_KNN_SHARED_LIST") && !getenv("DBX_KNN_REF_GEMM");
+  bool perq = async_mode && qcap >= 4 * kprime && (qcap >= 1024 || qcap_forced) && !getenv("DBX_KNN_SHARED_LIST");
   unsigned int* d_qcount = nullptr;
   if (perq) {
     DBX_CUDA_TRY(err, h->qcount.ensure((size_t)nq_pad * 4));
@@ -646,10 +678,13 @@ int32_t dbx_knn_search(dbx_knn* h, const dbx_column* queries, int32_t k, int32_t
     }
   }
   auto select = [&]() -> int32_t {  // cut every query back to its best k', tighten boundaries
-    if (perq) {
+    if (perq) {  // shared list (cand_*[1], filled by the GEMM) -> per-query lists (cand_*[0]) -> one cut kernel
+      perq_distribute_kernel<<<kNumSMs * 8, 256, 0, st>>>((const uint64_t*)h->cand_key[1].p, (const uint32_t*)h->cand_row[1].p, d_count, (long long)cap,
+                                                          d_qcount, qcap, (uint64_t*)h->cand_key[0].p, (uint32_t*)h->cand_row[0].p, d_over);
+      DBX_CUDA_TRY(err, cudaMemsetAsync(d_count, 0, 8, st));
       knn_cut_perq_kernel<<<nq, 256, (size_t)qcap * 8, st>>>((uint64_t*)h->cand_key[0].p, (uint32_t*)h->cand_row[0].p, d_qcount, qcap, kprime,
                                                             (float*)h->bound.p);
-      count_launch();
+      count_launch(2);
       DBX_CUDA_TRY(err, cudaGetLastError());
       return DBX_OK;
     }
@@ -701,15 +736,14 @@ int32_t dbx_knn_search(dbx_knn* h, const dbx_column* queries, int32_t k, int32_t
     size_t n_ev = 0;
     // first pass: small enough that even "everything passes" fits the candidate list
     int64_t chunk = std::max<int64_t>(kGemmBN, std::min<int64_t>((cap / 2) / std::max(nq, 1) / kGemmBN * kGemmBN, 1 << 16));
-    if (perq) chunk = std::max<int64_t>(kGemmBN, (qcap / 2) / kGemmBN * kGemmBN);  // even "everything passes" fits a query's list
+    if (perq) chunk = std::max<int64_t>(kGemmBN, std::min<int64_t>(chunk, (qcap / 2) / kGemmBN * kGemmBN));  // even "everything passes" fits a query's list
     while (done < h->n) {
       const int64_t m = std::min<int64_t>(chunk, h->n - done);
       KnnGemmParams gp;
       memset(&gp, 0, sizeof(gp));
       gp.kind = h->kind; gp.nq = nq; gp.nq_pad = nq_pad; gp.dim_pad = dim_pad; gp.n0 = done; gp.n_rows = m;
       gp.q_scale = (const float*)h->q_scale.p; gp.c_scale = (const float*)h->c_scale.p; gp.bound = (const float*)h->bound.p;
-      gp.cand_key = (uint64_t*)h->cand_key[cur].p; gp.cand_row = (uint32_t*)h->cand_row[cur].p; gp.cand_count = d_count; gp.cand_cap = cap;
-      if (perq) { gp.qcount = d_qcount; gp.qcap = qcap; gp.overflow = d_over; }
+      gp.cand_key = (uint64_t*)h->cand_key[perq ? 1 : cur].p; gp.cand_row = (uint32_t*)h->cand_row[perq ? 1 : cur].p; gp.cand_count = d_count; gp.cand_cap = cap;
       cudaEvent_t e0 = h->ev0, e1 = h->ev1;
       if (async_mode) {
         if (!perq) DBX_CUDA_TRY(err, cudaMemcpyAsync(d_prev, d_count, 8, cudaMemcpyDeviceToDevice, st));

@@ -227,12 +227,6 @@ struct KnnGemmParams {
   uint32_t* cand_row;    // corpus row
   unsigned long long* cand_count;
   int64_t cand_cap;
-  // per-query candidate lists (qcount != nullptr): list q = cand_key / cand_row [q * qcap, +qcap),
-  // qcount[q] entries appended so far; `overflow` is set when a list is full (never silently)
-  unsigned int* qcount;
-  int32_t qcap;
-  int32_t pad;
-  unsigned long long* overflow;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -498,29 +492,7 @@ knn_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
           }
         }
         pass &= col_mask;
-        if (p.qcount) {
-          // per-query lists: a lane's 32 scores all belong to ITS query, so its survivors go to that
-          // query's own list with one reservation — the cut between passes then needs no sort
-          const int n = __popc(pass);
-          if (n) {
-            const unsigned int base = atomicAdd(p.qcount + q, (unsigned int)n);
-            if ((int)(base + n) <= p.qcap) {
-              uint64_t* kd = p.cand_key + (size_t)q * p.qcap + base;
-              uint32_t* rd = p.cand_row + (size_t)q * p.qcap + base;
-              int w = 0;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if ((pass >> j) & 1) {
-                  kd[w] = ((uint64_t)(uint32_t)q << 32) | (uint64_t)(~f32_to_ordered32(__uint_as_float(v[j])));
-                  rd[w] = (uint32_t)(rbase + j);
-                  ++w;
-                }
-              }
-            } else {
-              *p.overflow = 1;
-            }
-          }
-        } else if (__any_sync(0xffffffffu, pass != 0)) {
+        if (__any_sync(0xffffffffu, pass != 0)) {
           const int n = __popc(pass);
           int incl = n;
 #pragma unroll
