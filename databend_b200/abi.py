@@ -129,6 +129,21 @@ class JoinParams(C.Structure):
     ]
 
 
+EXPR_COLUMN, EXPR_CONST, EXPR_CAST, EXPR_CALL = 0, 1, 2, 3
+(FN_PLUS, FN_MINUS, FN_MULTIPLY, FN_DIVIDE, FN_DIV, FN_MODULO, FN_NEGATE, FN_EQ, FN_NOTEQ, FN_LT, FN_LTE, FN_GT, FN_GTE, FN_AND, FN_OR, FN_NOT,
+ FN_IS_NULL, FN_IS_NOT_NULL) = range(18)
+MAX_EXPR_NODES = 32
+
+
+class ExprNode(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("func", C.c_int32), ("col", C.c_int32), ("cast_to", C.c_int32), ("try_cast", C.c_int32),
+                ("reserved", C.c_int32), ("c", Scalar)]
+
+
+class Expr(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("reserved", C.c_int32), ("nodes", ExprNode * MAX_EXPR_NODES)]
+
+
 # every function include/dbx.h declares (tests check the library exports each one)
 EXPORTS = [
     "dbx_abi_version", "dbx_device_count", "dbx_last_error",
@@ -145,4 +160,5 @@ EXPORTS = [
     "dbx_shuffle_create", "dbx_shuffle_local_buffer", "dbx_shuffle_connect", "dbx_shuffle_send", "dbx_shuffle_recv", "dbx_shuffle_last_ms",
     "dbx_shuffle_destroy", "dbx_shuffle_last_error",
     "dbx_block_take", "dbx_block_take_ranges", "dbx_block_scatter", "dbx_block_concat",
+    "dbx_eval_scalar",
 ]

@@ -97,6 +97,7 @@ def load():
         "dbx_block_take_ranges": (i32, [i32, P(abi.Block), vp, vp, i64, i32, P(abi.Block)]),
         "dbx_block_scatter": (i32, [i32, P(abi.Block), vp, i32, i32, i32, P(abi.Block)]),
         "dbx_block_concat": (i32, [i32, P(abi.Block), i32, i32, P(abi.Block)]),
+        "dbx_eval_scalar": (i32, [i32, P(abi.Expr), P(abi.Block), i32, P(abi.Block), P(i32), P(i64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError = the library does not export a declared symbol

@@ -354,6 +354,41 @@ int32_t dbx_block_scatter(int32_t device, const dbx_block* block, const uint32_t
                           int32_t out_mem, dbx_block* outs /* n_parts */);
 int32_t dbx_block_concat(int32_t device, const dbx_block* blocks, int32_t n_blocks, int32_t out_mem, dbx_block* out);
 
+/* ------------------------------------------------------------ expressions */
+/* Evaluator::run over a block (evaluator.rs:247-465) for numeric / boolean expressions: a postfix
+ * program of column refs, constants, casts and function calls.  Result types follow the
+ * reference's ResultTypeOfBinary rules (arithmetics_type.rs), values its arithmetic (wrapping
+ * integer +,-,*; `/` in Float64 with "divided by zero"; `div` through Float64; modulo in the
+ * LeastSuper type with "Division by zero"; to_<type> casts with "number overflowed", rounding
+ * float -> int like numeric_cast_option = 'rounding'); NULL propagates (passthrough_nullable),
+ * and / or are three-valued.  One fused kernel: inputs read once, one output column written. */
+typedef enum dbx_expr_kind { DBX_EXPR_COLUMN = 0, DBX_EXPR_CONST = 1, DBX_EXPR_CAST = 2, DBX_EXPR_CALL = 3 } dbx_expr_kind;
+typedef enum dbx_func {
+  DBX_FN_PLUS = 0, DBX_FN_MINUS = 1, DBX_FN_MULTIPLY = 2, DBX_FN_DIVIDE = 3, DBX_FN_DIV = 4, DBX_FN_MODULO = 5, DBX_FN_NEGATE = 6,
+  DBX_FN_EQ = 7, DBX_FN_NOTEQ = 8, DBX_FN_LT = 9, DBX_FN_LTE = 10, DBX_FN_GT = 11, DBX_FN_GTE = 12,
+  DBX_FN_AND = 13, DBX_FN_OR = 14, DBX_FN_NOT = 15, DBX_FN_IS_NULL = 16, DBX_FN_IS_NOT_NULL = 17
+} dbx_func;
+typedef struct dbx_expr_node {
+  int32_t kind;     /* dbx_expr_kind */
+  int32_t func;     /* dbx_func (DBX_EXPR_CALL); arguments are the 1 or 2 values below it on the stack */
+  int32_t col;      /* DBX_EXPR_COLUMN: column index in the block */
+  int32_t cast_to;  /* DBX_EXPR_CAST: dbx_dtype */
+  int32_t try_cast; /* DBX_EXPR_CAST: 1 = try_to_<type> (failure gives NULL instead of an error) */
+  int32_t reserved;
+  dbx_scalar c;     /* DBX_EXPR_CONST */
+} dbx_expr_node;
+#define DBX_MAX_EXPR_NODES 32
+typedef struct dbx_expr {
+  int32_t n_nodes;
+  int32_t reserved;
+  dbx_expr_node nodes[DBX_MAX_EXPR_NODES];
+} dbx_expr;
+/* out: library-owned block with ONE column (dbx_block_release); *out_dtype = its dbx_dtype
+ * (| DBX_NULLABLE).  A per-row evaluation error returns DBX_ERR_BAD_ARGUMENTS with the reference's
+ * message in dbx_last_error(NULL) and the first failing row in *first_error_row. */
+int32_t dbx_eval_scalar(int32_t device, const dbx_expr* expr, const dbx_block* block, int32_t out_mem, dbx_block* out,
+                        int32_t* out_dtype, int64_t* first_error_row);
+
 /* ScalarFunction::eval replacement for the vector distances (scalars/vector.rs:497-556):
  * out[i] = distance(lhs[i], rhs[i]) row-wise, either side may be const.  f32 result. */
 int32_t dbx_eval_distance(int32_t kind, int32_t device, const dbx_column* lhs, const dbx_column* rhs,

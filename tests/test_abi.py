@@ -79,6 +79,8 @@ def test_ctypes_mirror_matches_the_header_field_by_field(tmp_path):
         "dbx_agg_params": (abi.AggParams, ["n_group_cols", "group_cols", "n_aggs", "aggs", "filter", "expected_groups"]),
         "dbx_topk_params": (abi.TopkParams, ["key_col", "asc", "nulls_first", "limit"]),
         "dbx_join_params": (abi.JoinParams, ["kind", "build_key_col", "probe_key_col", "n_build_cols", "expected_build_rows"]),
+        "dbx_expr_node": (abi.ExprNode, ["kind", "func", "col", "cast_to", "try_cast", "c"]),
+        "dbx_expr": (abi.Expr, ["n_nodes", "nodes"]),
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "dbx.h")}"', "int main(void) {"]
     for cname, (_, fields) in structs.items():
