@@ -38,6 +38,7 @@ SEEDS = (42, 43, 44)
 N_KEYS = 1_000_000
 BYTES_PER_ROW = 24.0  # three 8-byte columns, each read exactly once
 KERNEL_NAME = "filter_group_agg_kernel<3,FAST=1,INDIRECT=0,BULK=0>"
+KERNEL_NAME_JIT = "dbx_jit_agg_fast (filter_group_agg_body<3,FAST=1> compiled for this plan by NVRTC at operator creation)"
 
 
 def ncu_traffic():
@@ -471,6 +472,7 @@ def run_dbx(args):
 
     state = {"queued": False}
     kernel_ms, phases, step_walls = [], [], []
+    variant = part.kernel_variant()
 
     def step_device(input_blocks, out_mem, prefetch_next):
         """one query: scan (+filter+partial agg) -> exchange -> final -> result block"""
@@ -665,7 +667,7 @@ def run_dbx(args):
         "wall_ms_per_step": wall_ms, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_note": traffic_note,
-                     "achieved_per_launch_bytes": BYTES_PER_ROW * min(n, 1 << 28), "kernel": KERNEL_NAME, "kernel_ms": k_ms,
+                     "achieved_per_launch_bytes": BYTES_PER_ROW * min(n, 1 << 28), "kernel": (KERNEL_NAME_JIT if variant == "specialised" else KERNEL_NAME), "kernel_variant": variant, "kernel_ms": k_ms,
                      "algorithmic_bytes_per_row": BYTES_PER_ROW, "peak_source": peak_src},
         "phases": phase_avg, "verify": verify,
         "cpu_baseline": cpu, "e2e": e2e, "knn": knn,

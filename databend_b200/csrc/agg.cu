@@ -12,6 +12,7 @@
 #include <cstdlib>
 
 #include "agg_kernels.cuh"
+#include "agg_jit.h"
 #include "runtime.h"
 
 namespace dbx {
@@ -525,6 +526,8 @@ class AggPartialOp : public Op {
   bool table_clean = false;  // the exchange scatter left the table empty (fused clear): reset costs no kernel
   void* window_base = nullptr;  // L2 access-policy window currently set on the stream
   size_t window_bytes = 0;
+  AggJitKernels jit;            // kernels compiled for this plan (agg_jit.h); empty: precompiled kernels
+  std::string jit_status = "off";
   ~AggPartialOp() override {
     if (window_base) {  // give the persisting L2 lines back (other operators / the kNN GEMM want the whole L2)
       cudaSetDevice(device);
@@ -544,7 +547,28 @@ class AggPartialOp : public Op {
     else cap = std::max<int64_t>(1024, next_pow2(kDefaultTableBytes / (8 * (1 + plan.n_words)) + 1) / 2);
     initial_cap = cap;
     DBX_TRY(ensure_table());
+    specialise();
     return DBX_OK;
+  }
+
+  const char* kernel_variant() override { return jit_status.c_str(); }
+  // Ask for kernels compiled for this plan (grouped plans without TMA pairs).  Failure is not an
+  // error: the precompiled kernels serve the operator, jit_status says why.
+  void specialise() {
+    const char* e = getenv("DBX_AGG_JIT");
+    if (e && atoi(e) == 0) { jit_status = "off (DBX_AGG_JIT=0)"; return; }
+    if (!plan.grouped || plan.n_pairs > 0) { jit_status = "off (plan shape not specialised)"; return; }
+    StaticPlan sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.n_nodes = plan.n_nodes; sp.n_updates = plan.n_updates; sp.key_slot = plan.key_slot; sp.key_is_float = plan.key_is_float ? 1 : 0;
+    sp.n_key_parts = plan.n_key_parts; sp.debug_flags = plan.debug_flags; sp.n_single = plan.n_words;
+    memcpy(sp.nodes, plan.nodes, sizeof(PredNodeDev) * plan.n_nodes);
+    memcpy(sp.upd, plan.upd, sizeof(UpdateDev) * plan.n_updates);
+    for (int u = 0; u < plan.n_updates; ++u) sp.upd[u].ridx = plan.upd[u].word;  // no pairs: entry index == word index
+    memcpy(sp.key_parts, plan.key_parts, sizeof(plan.key_parts));
+    std::string why;
+    if (agg_jit_get(agg_jit_plan_text(sp), plan.n_slots, &jit, &why)) jit_status = "specialised";
+    else { jit = AggJitKernels(); jit_status = "precompiled kernels (" + why + ")"; }
   }
 
   // Pin the hash table in L2 while the column stream passes through: a persisting access-policy
@@ -669,6 +693,14 @@ class AggPartialOp : public Op {
     int grid = grid_for_rows(kp.n_rows);
     static const int per_sm = getenv("DBX_AGG_GRID") ? atoi(getenv("DBX_AGG_GRID")) : 0;
     if (per_sm > 0) grid = (int)std::max<int64_t>(1, std::min<int64_t>((kp.n_rows + kTileRows - 1) / kTileRows, (int64_t)kNumSMs * per_sm));
+    if (!BULK && !INDIRECT && jit.ok()) {  // same grid, block and shared memory: only the code differs
+      void* args[] = {(void*)&kp};
+      const cudaError_t ce = cudaLaunchKernel((const void*)(FAST ? jit.fast : jit.gen), dim3(grid), dim3(kBlock), args, smem, stream);
+      if (ce == cudaSuccess) { count_launch(); return DBX_OK; }
+      cudaGetLastError();
+      jit = AggJitKernels();
+      jit_status = std::string("precompiled kernels (launch of the specialised kernel failed: ") + cudaGetErrorString(ce) + ")";
+    }
     kern<<<grid, kBlock, smem, stream>>>(kp);
     count_launch();
     DBX_CUDA_TRY(err, cudaGetLastError());

@@ -21,6 +21,21 @@
 
 namespace dbx {
 
+// Plan access.  The precompiled kernels read the plan from the by-value kernel parameters
+// (constant bank).  A run-time specialised build (agg_jit.cu: NVRTC, one compilation per plan
+// shape) defines DBX_JIT and a `__device__ constexpr StaticPlan jit_plan` before including this
+// header: every plan field then is a compile-time constant, the update / predicate loops unroll and
+// the per-row interpretation (op if-chains, slot selects, runtime-shift rotates) folds away.
+#ifdef DBX_JIT
+#define PLN(f) (jit_plan.f)
+#define PLN_TABLE(f) (jit_plan.f)
+#define PLN_UNROLL _Pragma("unroll")
+#else
+#define PLN(f) (p.f)
+#define PLN_TABLE(f) (p.table.f)
+#define PLN_UNROLL
+#endif
+
 constexpr int kBlock = 256;       // threads per CTA
 constexpr int kRowsPerThread = 4; // one 256-bit load per 8-byte column per tile
 constexpr int kTileRows = kBlock * kRowsPerThread;
@@ -195,12 +210,13 @@ __device__ __forceinline__ bool eval_cmp(const PredNodeDev& nd, uint64_t a, uint
 template <int NS>
 __device__ __forceinline__ uint32_t eval_predicate(const AggKernelParams& p, const RowVals (&vals)[NS],
                                                    const uint32_t (&vmask)[NS], uint32_t in_range) {
-  if (p.n_nodes == 0) return in_range;
+  if (PLN(n_nodes) == 0) return in_range;
   uint32_t stack[kRowsPerThread];
 #pragma unroll
   for (int j = 0; j < kRowsPerThread; ++j) stack[j] = 0;
-  for (int n = 0; n < p.n_nodes; ++n) {
-    const PredNodeDev& nd = p.nodes[n];
+  PLN_UNROLL
+  for (int n = 0; n < PLN(n_nodes); ++n) {
+    const PredNodeDev nd = PLN(nodes[n]);
     if (nd.kind == DBX_PRED_CMP) {
       uint32_t lm = pick_mask<NS>(vmask, nd.l_slot);
       uint32_t rm = nd.r_slot >= 0 ? pick_mask<NS>(vmask, nd.r_slot) : 0xF;
@@ -350,17 +366,18 @@ __device__ __forceinline__ void table_phase32(const AggKernelParams& p, const St
   bool key_null = false;
   if (act) {
     if (!FAST) vm = sw.vm[i];
-    if (p.n_key_parts > 1) {  // packed multi-column key; NULLs are encoded inside the key
-      for (int j = 0; j < p.n_key_parts; ++j) {
-        const KeyPartDev kp = p.key_parts[j];
+    if (PLN(n_key_parts) > 1) {  // packed multi-column key; NULLs are encoded inside the key
+      PLN_UNROLL
+      for (int j = 0; j < PLN(n_key_parts); ++j) {
+        const KeyPartDev kp = PLN(key_parts[j]);
         const bool ok = (vm >> kp.slot) & 1;
         if (ok) key |= (sw.val[kp.slot][i] & kp.mask) << kp.shift;
         else key |= 1ULL << kp.null_shift;
       }
     } else {
-      key = sw.val[p.key_slot][i];
-      if (p.key_is_float) key = canonical_float_key(key);
-      key_null = !((vm >> p.key_slot) & 1);
+      key = sw.val[PLN(key_slot)][i];
+      if (PLN(key_is_float)) key = canonical_float_key(key);
+      key_null = !((vm >> PLN(key_slot)) & 1);
     }
   }
   const bool special = key_null || key == kEmptyKey;
@@ -379,11 +396,12 @@ __device__ __forceinline__ void table_phase32(const AggKernelParams& p, const St
     if (slot < 0) {
       unsigned long long idx = atomicAdd(t.n_overflow, 1ULL);
       if (t.overflow_rows) t.overflow_rows[idx] = sw.row[i];
-    } else if (!(p.debug_flags & 1)) {
+    } else if (!(PLN(debug_flags) & 1)) {
       good_slot = slot;
-      uint64_t* row = t.states + t.row_base + slot * t.n_single;
-      for (int u = 0; u < p.n_updates; ++u) {
-        const UpdateDev ud = p.upd[u];
+      uint64_t* row = t.states + t.row_base + slot * PLN_TABLE(n_single);
+      PLN_UNROLL
+      for (int u = 0; u < PLN(n_updates); ++u) {
+        const UpdateDev ud = PLN(upd[u]);
         if (ud.paired) {
           if (!use_bulk) apply_update(ud.op, word_ptr(t, slot, ud.word), sw.val[ud.slot][i], (vm >> ud.slot) & 1);
           continue;
@@ -429,8 +447,8 @@ __device__ __forceinline__ void prefetch_tile(const AggKernelParams& p, int64_t 
   }
 }
 
-template <int NS, bool FAST, bool INDIRECT, bool BULK = false, int MINB = 4>
-__global__ void __launch_bounds__(kBlock, MINB) filter_group_agg_kernel(const __grid_constant__ AggKernelParams p) {
+template <int NS, bool FAST, bool INDIRECT, bool BULK>
+__device__ __forceinline__ void filter_group_agg_body(const AggKernelParams& p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   StageWarp<NS>& sw = reinterpret_cast<StageWarp<NS>*>(smem_raw)[warp];
@@ -458,8 +476,8 @@ __global__ void __launch_bounds__(kBlock, MINB) filter_group_agg_kernel(const __
     uint32_t sel;
     if (FAST) {
       sel = 0xF;
-      if (p.n_nodes) {
-        const PredNodeDev& nd = p.nodes[0];
+      if (PLN(n_nodes)) {
+        const PredNodeDev nd = PLN(nodes[0]);
 #pragma unroll
         for (int j = 0; j < kRowsPerThread; ++j)
           if (!eval_cmp(nd, pick<NS>(vals, nd.l_slot, j), nd.r_const)) sel &= ~(1u << j);
@@ -473,7 +491,7 @@ __global__ void __launch_bounds__(kBlock, MINB) filter_group_agg_kernel(const __
         if (r0 + j < p.n_rows) in_range |= 1u << j;
       sel = eval_predicate<NS>(p, vals, vmask, in_range);
     }
-    if (p.debug_flags & 2) sel = 0;
+    if (PLN(debug_flags) & 2) sel = 0;
     // ballot compaction: append the surviving rows behind the carried-over ones
 #pragma unroll
     for (int j = 0; j < kRowsPerThread; ++j) {
@@ -511,6 +529,14 @@ __global__ void __launch_bounds__(kBlock, MINB) filter_group_agg_kernel(const __
   if (lane == 0 && new_groups) atomicAdd(p.table.n_groups, (unsigned long long)new_groups);
 }
 
+#ifndef DBX_JIT
+template <int NS, bool FAST, bool INDIRECT, bool BULK = false, int MINB = 4>
+__global__ void __launch_bounds__(kBlock, MINB) filter_group_agg_kernel(const __grid_constant__ AggKernelParams p) {
+  filter_group_agg_body<NS, FAST, INDIRECT, BULK>(p);
+}
+#endif
+
+#ifndef DBX_JIT  // everything below is compiled offline only
 // ---------------------------------------------------------------- fused kernel, ring variant
 // Same front end as the FAST kernel above; the table phase differs in how the state words are
 // updated.  The plain kernel is bound by the NUMBER of L2 reduction requests (~150 G RED/s
@@ -1292,5 +1318,7 @@ __global__ void pack_validity_kernel(const uint8_t* bytes, const unsigned long l
     bits[b] = (uint8_t)v;
   }
 }
+
+#endif  // !DBX_JIT
 
 }  // namespace dbx

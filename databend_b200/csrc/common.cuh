@@ -1,5 +1,17 @@
 // common.cuh — shared host/device helpers for libdbx (sm_100a only).
 #pragma once
+#ifdef __CUDACC_RTC__  // run-time specialised kernels (agg_jit.cu): no host headers under NVRTC
+typedef signed char int8_t;
+typedef short int16_t;
+typedef int int32_t;
+typedef long long int64_t;
+typedef unsigned char uint8_t;
+typedef unsigned short uint16_t;
+typedef unsigned int uint32_t;
+typedef unsigned long long uint64_t;
+typedef unsigned long long uintptr_t;
+#define DBX_DEVICE_ONLY 1
+#else
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -7,6 +19,7 @@
 
 #include <atomic>
 #include <string>
+#endif
 
 #include "../../include/dbx.h"
 
@@ -14,6 +27,7 @@ namespace dbx {
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
 
+#ifndef DBX_DEVICE_ONLY
 // ---------------------------------------------------------------- error plumbing
 struct ErrorSink {
   std::string msg;
@@ -40,6 +54,7 @@ extern std::atomic<int64_t> g_launches;        // dbx_kernel_launch_count()
   } while (0)
 
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+#endif  // !DBX_DEVICE_ONLY
 
 // ---------------------------------------------------------------- dtype helpers
 constexpr int kNullableFlag = 0x100;  // OR-ed into input_types[] for Nullable(T) columns
@@ -192,6 +207,7 @@ __device__ __forceinline__ uint64_t f64_to_ordered(double d) {
   uint64_t b = (uint64_t)__double_as_longlong(d);
   return (b & 0x8000000000000000ULL) ? ~b : (b | 0x8000000000000000ULL);
 }
+#ifndef DBX_DEVICE_ONLY
 __host__ __device__ __forceinline__ double ordered_to_f64(uint64_t o) {
   uint64_t b;
   if (o == 0xFFFFFFFFFFFFFFFFULL) b = 0x7FF8000000000000ULL;
@@ -200,6 +216,7 @@ __host__ __device__ __forceinline__ double ordered_to_f64(uint64_t o) {
   memcpy(&d, &b, 8);
   return d;
 }
+#endif
 
 __device__ __forceinline__ bool bit_test(const uint8_t* bits, int64_t i) { return (bits[i >> 3] >> (i & 7)) & 1; }
 

@@ -23,6 +23,7 @@ struct ModMagic {
   int32_t sh1, sh2;
 };
 
+#ifndef DBX_DEVICE_ONLY
 inline ModMagic make_mod_magic(uint64_t d) {
   ModMagic mm;
   mm.d = d;
@@ -34,6 +35,7 @@ inline ModMagic make_mod_magic(uint64_t d) {
   mm.sh2 = l - 1 > 0 ? l - 1 : 0;
   return mm;
 }
+#endif
 
 __host__ __device__ __forceinline__ uint64_t mulhi_u64(uint64_t a, uint64_t b) {
 #ifdef __CUDA_ARCH__
@@ -57,6 +59,7 @@ __host__ __device__ __forceinline__ int64_t smod_magic(int64_t x, const ModMagic
 // Hacker's Delight 10-17): with d = d' 2^k, d' odd and inv = d'^-1 mod 2^64,
 //   d | n  <=>  rotr(n * inv, k) <= floor((2^64 - 1) / d).
 // Used for `x % d = 0` / `x % d <> 0`, the shape the configs filter on.
+#ifndef DBX_DEVICE_ONLY
 inline ModMagic make_div_magic(uint64_t d) {
   ModMagic mm;
   int k = 0;
@@ -70,6 +73,7 @@ inline ModMagic make_div_magic(uint64_t d) {
   mm.d = ~0ULL / d;
   return mm;
 }
+#endif
 __host__ __device__ __forceinline__ bool divisible_magic(uint64_t n, const ModMagic& mm) {
   uint64_t q = n * mm.m;
   q = (q >> mm.sh1) | (mm.sh1 ? (q << (64 - mm.sh1)) : 0);
@@ -180,6 +184,16 @@ struct AggKernelParams {
   // the predicate (key parts + arguments of unpaired updates) and where they are stored in the ring
   int32_t ring_nsv;                 // number of stored slot arrays
   int8_t ring_sidx[kMaxSlots];      // slot -> storage index, -1: not stored
+};
+
+// The plan fields the fused kernels read per row, as ONE constexpr object: a run-time specialised
+// build (agg_jit.cu) emits `__device__ constexpr StaticPlan jit_plan = {...}` from the operator's
+// plan, and agg_kernels.cuh reads `jit_plan.f` where the precompiled kernels read `p.f`.
+struct StaticPlan {
+  int32_t n_nodes, n_updates, key_slot, key_is_float, n_key_parts, debug_flags, n_single;
+  PredNodeDev nodes[DBX_MAX_PRED_NODES];
+  UpdateDev upd[kMaxUpdates];
+  KeyPartDev key_parts[DBX_MAX_GROUP_COLS];
 };
 
 }  // namespace dbx

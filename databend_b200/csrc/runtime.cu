@@ -421,6 +421,11 @@ int32_t dbx_op_kernel_ms(dbx_op* op, int32_t back, float* ms) {
   return DBX_OK;
 }
 int32_t dbx_op_last_kernel_ms(dbx_op* op, float* ms) { return dbx_op_kernel_ms(op, 0, ms); }
+int32_t dbx_op_kernel_variant(dbx_op* op, char* out, int32_t cap) {
+  if (!op || !out || cap <= 0) return DBX_ERR_INVALID;
+  snprintf(out, (size_t)cap, "%s", reinterpret_cast<Op*>(op)->kernel_variant());
+  return DBX_OK;
+}
 int32_t dbx_op_stream(dbx_op* op, void** stream) {
   DBX_OP_ENTER(op);
   *stream = (void*)o->stream;

@@ -120,6 +120,8 @@ class Op {
     DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
     return DBX_OK;
   }
+  // which build of the hot kernel serves this handle ("specialised" / "precompiled kernels (why)")
+  virtual const char* kernel_variant() { return "precompiled kernels"; }
 
   int kind = -1;
   int device = 0;

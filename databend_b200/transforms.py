@@ -170,6 +170,12 @@ class _Op:
         check(load().dbx_op_kernel_ms(self._h, back, C.byref(ms)), self._h)
         return ms.value
 
+    def kernel_variant(self) -> str:
+        """"specialised" (kernel compiled for this plan) or "precompiled kernels (<why>)"."""
+        buf = C.create_string_buffer(2048)
+        check(load().dbx_op_kernel_variant(self._h, buf, 2048), self._h)
+        return buf.value.decode("utf-8", "replace")
+
     def inputs_consumed(self):
         """Block until every pushed block has been read completely (pinned/device inputs may be reused)."""
         check(load().dbx_op_inputs_consumed(self._h), self._h)

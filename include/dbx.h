@@ -38,8 +38,10 @@
 #ifndef DBX_H_
 #define DBX_H_
 
+#ifndef __CUDACC_RTC__ /* run-time compiled kernels get the fixed-width types from common.cuh */
 #include <stddef.h>
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -434,6 +436,14 @@ int32_t dbx_op_last_kernel_ms(dbx_op* op, float* ms);
 /* Same for an earlier push: back = 0 is the last push, 1 the one before, ... (a ring of 8), so
  * the kernel of query i can be read after query i+1 was enqueued without waiting for it. */
 int32_t dbx_op_kernel_ms(dbx_op* op, int32_t back, float* ms);
+/* Which build of the hot kernel serves this handle.  Aggregate operators ask for a kernel compiled
+ * for their plan at create time (NVRTC, sm_100a; cached per plan shape; DBX_AGG_JIT=0 turns it off):
+ * "specialised", or "precompiled kernels (<why>)" when the plan-interpreting kernels serve it.
+ * Results are identical either way. */
+int32_t dbx_op_kernel_variant(dbx_op* op, char* out, int32_t cap);
+/* Compiles the specialised kernels of a canned plan without touching a GPU (is NVRTC usable here?).
+ * DBX_OK, or DBX_ERR_UNSUPPORTED with the reason in msg. */
+int32_t dbx_agg_jit_selftest(char* msg, int32_t msg_cap);
 /* Stream of a handle as a cudaStream_t value (for external event timing). */
 int32_t dbx_op_stream(dbx_op* op, void** stream);
 

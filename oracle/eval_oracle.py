@@ -221,7 +221,8 @@ def eval_row(e, row, col_types, r):
         tm, to = t_super(ta, tb), t_modulo(ta, tb)
         x, y = cast_as(a, ta, tm), cast_as(b, tb, tm)
         if is_float(tm):
-            rem = float(np.fmod(np.float32(x), np.float32(y))) if tm == "F32" else math.fmod(x, y)
+            with np.errstate(invalid="ignore"):  # Rust f32/f64 `%` == C fmodf/fmod (inf % y = NaN)
+                rem = float(np.fmod(np.float32(x), np.float32(y))) if tm == "F32" else float(np.fmod(np.float64(x), np.float64(y)))
         elif is_signed(tm):
             rem = 0 if y == -1 else (abs(x) % abs(y)) * (1 if x >= 0 else -1)  # Rust %: truncated, sign of the dividend
         else:

@@ -99,3 +99,13 @@ def test_ctypes_mirror_matches_the_header_field_by_field(tmp_path):
             assert int(out[f"{cname}.{f}"]) == getattr(ctype, f).offset, f"{cname}.{f}"
     # enum values the Python side hard-codes
     assert (abi.JOIN_INNER, abi.JOIN_LEFT_SEMI, abi.JOIN_LEFT_ANTI, abi.JOIN_LEFT) == (0, 1, 2, 3)
+
+
+def test_runtime_specialisation_compiles_here():
+    """NVRTC is dlopen'ed by libdbx; the specialised aggregate kernels of a canned plan must compile
+    for sm_100a in this image (no GPU involved)."""
+    import ctypes as C
+    from databend_b200.lib import load
+    buf = C.create_string_buffer(4096)
+    rc = load().dbx_agg_jit_selftest(buf, 4096)
+    assert rc == abi.OK, buf.value.decode()

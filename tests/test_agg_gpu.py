@@ -568,3 +568,30 @@ def test_float_group_keys(gpu, dtype, device_resident):
     assert len(nan_bits) == 1
     zero_bits = {int(np.array([z], dtype=dtype).view(w)[0]) for z in (0.0, -0.0)}
     assert zero_bits <= got.keys()
+
+
+def test_specialised_kernels_serve_grouped_plans(gpu, monkeypatch):
+    """Grouped operators run kernels compiled for their plan (NVRTC at create time); the answer is the
+    oracle's with them and with the plan-interpreting precompiled kernels (DBX_AGG_JIT=0) alike, for
+    the benchmark plan, a nullable / min-max / packed-key plan, host blocks and device blocks."""
+    types = [abi.I64, abi.I64, abi.F64]
+    op = TransformPartialAggregate(CONFIG2, types, V_MOD3)
+    assert op.kernel_variant() == "specialised", op.kernel_variant()
+    op.close()
+    blk = config2_block(1_500_000, n_keys=300_000)
+    for jit in ("1", "0"):
+        monkeypatch.setenv("DBX_AGG_JIT", jit)
+        op = TransformPartialAggregate(CONFIG2, types, V_MOD3)
+        assert (op.kernel_variant() == "specialised") == (jit == "1"), op.kernel_variant()
+        op.close()
+        run_both(blk, CONFIG2, V_MOD3, device_resident=True)
+        run_both(blk, CONFIG2, V_MOD3, split=100_000)
+        run_both(blk, CONFIG2, E.and_(E.gt(E.col(1), E.lit(5)), E.ne(E.col(1) % E.lit(7), E.lit(0))), device_resident=True)
+        rng = np.random.default_rng(3)
+        n = 200_000
+        k1 = Column.from_data(rng.integers(0, 50, n).astype(np.int16), validity=rng.random(n) > 0.1)
+        k2 = Column.from_data(rng.integers(0, 9, n).astype(np.uint8))
+        v = Column.from_data(rng.integers(-1000, 1000, n).astype(np.int32), validity=rng.random(n) > 0.2)
+        x = Column.from_data(rng.standard_normal(n))
+        params = AggregatorParams([0, 1], [("sum", 2), ("min", 2), ("max", 3), ("count", 2), ("avg", 3)])
+        run_both(DataBlock([k1, k2, v, x]), params, E.lt(E.col(3), E.lit(1.5)), float_exact=False, rtol=1e-9)
