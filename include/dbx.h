@@ -290,7 +290,7 @@ int32_t dbx_agg_final_merge_rows(dbx_op* final_op, const void* dev_rows, int64_t
 /* Peer-memory exchange of aggregate partials between the GPUs of one box (one process per GPU):
  * the multi-GPU form of the partial -> final shuffle (build_partition_bucket.rs:41-131; between
  * nodes the reference ships AggregateMeta partitions over Arrow Flight,
- * servers/flight/v1/exchange/*).  Every rank creates an exchange (a receive buffer in its HBM),
+ * servers/flight/v1/exchange/...).  Every rank creates an exchange (a receive buffer in its HBM),
  * the 64-byte CUDA-IPC handles are all-gathered by the host (torch.distributed / any transport)
  * and passed to connect; then per query
  *     scatter(partial)  partition + store rows straight into the owners' buffers over NVLink
