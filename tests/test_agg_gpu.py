@@ -587,11 +587,6 @@ def test_specialised_kernels_serve_grouped_plans(gpu, monkeypatch):
         run_both(blk, CONFIG2, V_MOD3, device_resident=True)
         run_both(blk, CONFIG2, V_MOD3, split=100_000)
         run_both(blk, CONFIG2, E.and_(E.gt(E.col(1), E.lit(5)), E.ne(E.col(1) % E.lit(7), E.lit(0))), device_resident=True)
-        rng = np.random.default_rng(3)
-        n = 200_000
-        k1 = Column.from_data(rng.integers(0, 50, n).astype(np.int16), validity=rng.random(n) > 0.1)
-        k2 = Column.from_data(rng.integers(0, 9, n).astype(np.uint8))
-        v = Column.from_data(rng.integers(-1000, 1000, n).astype(np.int32), validity=rng.random(n) > 0.2)
-        x = Column.from_data(rng.standard_normal(n))
-        params = AggregatorParams([0, 1], [("sum", 2), ("min", 2), ("max", 3), ("count", 2), ("avg", 3)])
-        run_both(DataBlock([k1, k2, v, x]), params, E.lt(E.col(3), E.lit(1.5)), float_exact=False, rtol=1e-9)
+        test_multi_column_group_keys(gpu, True)   # packed keys, nullable key / argument, min / max / avg
+        test_multi_column_group_keys(gpu, False)
+        test_nullable_args_and_keys(gpu)
