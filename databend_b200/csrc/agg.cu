@@ -1121,6 +1121,7 @@ class AggFinalOp : public Op {
   int64_t result_capacity = 0;
   int32_t finalize_pass(int64_t capacity, int64_t* ng_out, int64_t* no_out) {
     auto ob = std::make_unique<OwnedBlock>();
+    ob->stream = stream;  // freed in order behind this operator's enqueued work
     ob->device = device;
     const int64_t cap_rows = std::max<int64_t>(capacity, 1);
     const int64_t ng = cap_rows;  // column lengths are patched by finish() once the count is known
@@ -1321,6 +1322,7 @@ class FilterOp : public Op {
     }
     rows_in += n;
     auto ob = std::make_unique<OwnedBlock>();
+    ob->stream = stream;  // freed in order behind this operator's enqueued work
     ob->device = device;
     const int64_t n_tiles = (n + kTileRows - 1) / kTileRows;
     int64_t total = 0;

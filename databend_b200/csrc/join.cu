@@ -461,7 +461,15 @@ class JoinOp : public Op {
     for (int i = 0; i < n_build_cols; ++i) if (dtype_size(build_dtype[i]) == 0) { err.set("join: only fixed-width numeric columns are supported"); return DBX_ERR_UNSUPPORTED; }
     for (int i = 0; i < n_probe_cols; ++i) if (dtype_size(probe_dtype[i]) == 0) { err.set("join: only fixed-width numeric columns are supported"); return DBX_ERR_UNSUPPORTED; }
     // keys of different widths/signedness compare by value: both are widened to 64 bits
-    // (sign-extended if signed), the common super type of the reference's key cast.
+    // (sign-extended if signed), the common super type of the reference's key cast.  The one pair
+    // with no 64-bit super type is (signed, UInt64): the widened images of -1 and 2^64-1 coincide,
+    // so it is refused here (the reference's type checker casts both sides to a wider type first;
+    // a caller wanting that join casts the keys before the operator, as the reference's planner does).
+    {
+      const int bk = build_dtype[p->build_key_col], pk = probe_dtype[p->probe_key_col];
+      const bool bs = dtype_class(bk) == VC_INT, ps = dtype_class(pk) == VC_INT;
+      if ((bk == DBX_U64 && ps) || (pk == DBX_U64 && bs)) { err.set("join: a signed key cannot be compared with a UInt64 key without a cast (no common 64-bit type)"); return DBX_ERR_UNSUPPORTED; }
+    }
     build.resize(n_build_cols);
     for (int i = 0; i < n_build_cols; ++i) { build[i].size = dtype_size(build_dtype[i]); build[i].nullable = build_nullable[i]; }
     DBX_TRY(stager.init(dev, stream, &err));
@@ -630,6 +638,7 @@ class JoinOp : public Op {
     }
     for (int attempt = 0; attempt < 2; ++attempt) {
       auto ob = std::make_unique<OwnedBlock>();
+    ob->stream = stream;  // freed in order behind this operator's enqueued work
       ob->device = device;
       JoinProbeParams pp;
       memset(&pp, 0, sizeof(pp));

@@ -1,6 +1,8 @@
 // runtime.cu — host runtime + the operator-independent part of the C-ABI.
 #include "runtime.h"
 
+#include <set>
+
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -41,12 +43,14 @@ cudaError_t pool_alloc(int device, cudaStream_t stream, size_t bytes, void** out
   }
   return cudaMallocAsync(out, bytes ? bytes : 1, stream);
 }
-void pool_free(int device, void* p) {
+// streams of live operators: a buffer is freed on its producer's stream only while that stream exists
+static std::set<cudaStream_t> g_live_streams;
+void pool_free(int device, void* p, cudaStream_t producer) {
   if (!p) return;
   cudaStream_t s;
   {
     std::lock_guard<std::mutex> lk(g_alloc_mu);
-    s = g_util_stream[device];
+    s = (producer && g_live_streams.count(producer)) ? producer : g_util_stream[device];
   }
   cudaFreeAsync(p, s);
 }
@@ -181,6 +185,7 @@ int32_t Op::base_init(int dev) {
   device = dev;
   DBX_CUDA_TRY(err, cudaSetDevice(device));
   DBX_CUDA_TRY(err, cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  { std::lock_guard<std::mutex> lk(g_alloc_mu); g_live_streams.insert(stream); }
   for (auto& pr : ev_ring)
     for (auto& e : pr) DBX_CUDA_TRY(err, cudaEventCreate(&e));
   return DBX_OK;
@@ -189,7 +194,13 @@ Op::~Op() {
   for (auto& pr : ev_ring)
     for (auto& e : pr)
       if (e) cudaEventDestroy(e);
-  if (stream) cudaStreamDestroy(stream);
+  if (stream) {
+    // blocks this operator produced may outlive it: finish its work first, so that their buffers
+    // can go back to the pool on the utility stream afterwards
+    cudaStreamSynchronize(stream);
+    { std::lock_guard<std::mutex> lk(g_alloc_mu); g_live_streams.erase(stream); }
+    cudaStreamDestroy(stream);
+  }
 }
 int32_t Op::timing_begin() {
   ev_idx += 1;

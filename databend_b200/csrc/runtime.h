@@ -54,7 +54,7 @@ struct PinnedBuf {
 // raised so freed blocks are reused instead of returned to the driver): per-query result and
 // exchange buffers cost microseconds instead of a cudaMalloc/cudaFree round trip.
 cudaError_t pool_alloc(int device, cudaStream_t stream, size_t bytes, void** out);
-void pool_free(int device, void* p);
+void pool_free(int device, void* p, cudaStream_t producer = nullptr);
 // Cached pinned host allocations (cudaMallocHost is milliseconds per call): power-of-two size
 // classes, freed blocks are kept for reuse.
 cudaError_t pinned_alloc(size_t bytes, void** out);
@@ -66,9 +66,14 @@ struct OwnedBlock {
   std::vector<void*> host_allocs;  // pinned_alloc
   std::vector<void*> dev_allocs;   // pool_alloc
   int device = 0;
+  // Stream of the operator that produced the device buffers: they are returned to the pool IN
+  // ORDER behind whatever that stream still has enqueued (a block dropped right after a push may
+  // still be written by the kernels of that push).  Operators that are gone have synchronised
+  // their stream on destruction, and null means "the producer already waited".
+  cudaStream_t stream = nullptr;
   ~OwnedBlock() {
     for (void* p : host_allocs) pinned_free(p);
-    for (void* p : dev_allocs) pool_free(device, p);
+    for (void* p : dev_allocs) pool_free(device, p, stream);
   }
 };
 

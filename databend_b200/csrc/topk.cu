@@ -773,6 +773,7 @@ class TopkOp : public Op {
   int32_t finish_full_sort() {
     const int64_t n = rows_seen;
     auto ob = std::make_unique<OwnedBlock>();
+    ob->stream = stream;  // freed in order behind this operator's enqueued work
     ob->device = device;
     DBX_CUDA_TRY(err, cudaMemcpyAsync(host.p, (unsigned long long*)state.p + ST_WORDS, 8 * ST_WORDS, cudaMemcpyDeviceToHost, stream));
     DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
@@ -886,6 +887,7 @@ class TopkOp : public Op {
     }
     // output block: [key (original dtype, nullable), row_id Int64], assembled on the device
     auto ob = std::make_unique<OwnedBlock>();
+    ob->stream = stream;  // freed in order behind this operator's enqueued work
     ob->device = device;
     const int esz = dtype_size(key_dtype);
     void *okey = nullptr, *orow = nullptr, *ovb = nullptr, *obits = nullptr;

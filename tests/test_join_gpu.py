@@ -210,3 +210,20 @@ def test_left_outer(gpu, monkeypatch):
             valid = np.concatenate([o.columns[ci].valid_mask() for o in outs])
             got_cols.append(Column.from_data(vals, outs[0].columns[ci].dtype, validity=valid))
         np.testing.assert_array_equal(joined_rows_sorted(got_cols), joined_rows_sorted(exp_cols))
+
+
+def test_mixed_width_keys_and_signed_vs_uint64_refused(gpu):
+    """Keys of different widths / signedness compare by VALUE (both widened to 64 bits): Int8 -1
+    matches Int32 -1 and never UInt16 65535; the one pair without a 64-bit super type, signed vs
+    UInt64, is refused (the widened images of -1 and 2^64-1 coincide)."""
+    from databend_b200.lib import DbxError
+    build = DataBlock([Column.from_data(np.array([-1, 5, 127, -128], dtype=np.int8)), Column.from_data(np.arange(4, dtype=np.int64))])
+    probe = DataBlock([Column.from_data(np.array([-1, 5, 255, 127, -128, 65535], dtype=np.int32)), Column.from_data(np.arange(6, dtype=np.float64))])
+    run_join(build, probe, 0, 0)
+    probe_u = DataBlock([Column.from_data(np.array([65535, 5, 255, 127], dtype=np.uint16)), Column.from_data(np.arange(4, dtype=np.float64))])
+    run_join(build, probe_u, 0, 0)
+    b64 = DataBlock([Column.from_data(np.array([-1, 5], dtype=np.int64))])
+    p64 = DataBlock([Column.from_data(np.array([2**64 - 1, 5], dtype=np.uint64))])
+    for a, b in ((b64, p64), (p64, b64)):
+        with pytest.raises(DbxError, match="signed key cannot be compared with a UInt64"):
+            HashJoin(schema_types(a), schema_types(b), 0, 0)
