@@ -1517,6 +1517,203 @@ int32_t dbx_agg_partial_partition(dbx_op* partial_op, int32_t n_parts, void** de
   return DBX_OK;
 }
 
+// ---- spill_schema serde (see the layout comment above rows_to_spill_kernel)
+namespace {
+struct SpillFieldHost { int kind, word, cnt_word, dtype; };
+struct SpillLayout {
+  int n_fields = 0;
+  SpillFieldHost f[dbx::kMaxSpillFields];
+  int arity[DBX_MAX_AGGS] = {};
+};
+int sum_dtype(int arg_dtype) {  // ResultTypeOfUnary::Sum (arithmetics_type.rs:259-267)
+  const int c = dbx::dtype_class(arg_dtype);
+  return c == dbx::VC_FLT ? DBX_F64 : (c == dbx::VC_INT ? DBX_I64 : DBX_U64);
+}
+void spill_layout(const dbx::AggPlan& pl, SpillLayout* L) {
+  using namespace dbx;
+  for (int a = 0; a < pl.params.n_aggs; ++a) {
+    const FinalAgg& fa = pl.fin[a];
+    const int arg_col = pl.params.aggs[a].arg_col;
+    const bool nullable_arg = arg_col >= 0 && pl.col_nullable[arg_col];
+    const int first = L->n_fields;
+    auto add = [&](int kind, int word, int dtype) { L->f[L->n_fields++] = SpillFieldHost{kind, word, fa.cnt_word, dtype}; };
+    switch (fa.kind) {
+      case DBX_AGG_COUNT: add(SPF_CNT, fa.cnt_word, DBX_U64); break;
+      case DBX_AGG_SUM: add(SPF_ACC, fa.acc_word, sum_dtype(fa.arg_dtype)); break;
+      case DBX_AGG_AVG: add(SPF_ACC, fa.acc_word, sum_dtype(fa.arg_dtype)); add(SPF_CNT, fa.cnt_word, DBX_U64); break;
+      default: add(SPF_FLAG, fa.cnt_word, DBX_BOOL); add(SPF_VALUE, fa.acc_word, fa.arg_dtype); break;
+    }
+    if (fa.kind != DBX_AGG_COUNT) {
+      if (nullable_arg) add(SPF_FLAG, fa.cnt_word, DBX_BOOL);  // AggregateNullUnaryAdaptor<true>
+      add(SPF_FLAG, fa.cnt_word, DBX_BOOL);                    // AggregateFunctionOrNullAdaptor
+    }
+    L->arity[a] = L->n_fields - first;
+  }
+}
+}  // namespace
+
+int32_t dbx_agg_partial_serialize(dbx_op* partial_op, int32_t out_mem, dbx_block* out, int32_t* tuple_arity) {
+  using namespace dbx;
+  if (!partial_op || !out || !tuple_arity) return DBX_ERR_INVALID;
+  Op* o = reinterpret_cast<Op*>(partial_op);
+  if (o->kind != DBX_OP_AGG_PARTIAL) { o->err.set("serialize: not a partial aggregate operator"); return DBX_ERR_INVALID; }
+  AggPartialOp* p = static_cast<AggPartialOp*>(o);
+  const AggPlan& pl = p->plan;
+  void* rows = nullptr;
+  int64_t offs[2] = {0, 0};
+  int32_t row_bytes = 0;
+  DBX_TRY(dbx_agg_partial_partition(partial_op, 1, &rows, offs, &row_bytes));
+  const int64_t n = offs[1];
+  struct RowsGuard { int dev; void* p; cudaStream_t s; ~RowsGuard() { pool_free(dev, p, s); } } rows_guard{p->device, rows, p->stream};
+  SpillLayout L;
+  spill_layout(pl, &L);
+  for (int a = 0; a < pl.params.n_aggs; ++a) tuple_arity[a] = L.arity[a];
+  auto ob = std::make_unique<OwnedBlock>();
+  ob->stream = p->stream;
+  ob->device = p->device;
+  const int64_t cap = std::max<int64_t>(n, 1);
+  auto dev_alloc = [&](size_t bytes, void** q) -> int32_t {
+    DBX_CUDA_TRY(p->err, pool_alloc(p->device, p->stream, bytes, q));
+    ob->dev_allocs.push_back(*q);
+    return DBX_OK;
+  };
+  SpillOutParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.n_fields = L.n_fields;
+  sp.row_words = row_bytes / 8;
+  std::vector<uint8_t*> bool_bytes, valid_bytes;  // per output column: byte-per-row staging to pack
+  for (int i = 0; i < L.n_fields; ++i) {
+    const SpillFieldHost& f = L.f[i];
+    const size_t w = f.kind == SPF_FLAG ? 1 : (size_t)dtype_size(f.dtype);
+    void* d = nullptr;
+    DBX_TRY(dev_alloc((size_t)cap * w, &d));
+    sp.f[i] = SpillFieldDev{f.kind, f.word, f.cnt_word, f.dtype, d};
+    dbx_column c;
+    memset(&c, 0, sizeof(c));
+    c.dtype = f.dtype; c.mem = DBX_MEM_DEVICE; c.len = n; c.data = d;
+    ob->cols.push_back(c);
+    bool_bytes.push_back(f.kind == SPF_FLAG ? (uint8_t*)d : nullptr);
+    valid_bytes.push_back(nullptr);
+  }
+  sp.key_dtype = -1;
+  auto add_key = [&](int dt, bool nullable, void** kv, uint8_t** vb) -> int32_t {
+    DBX_TRY(dev_alloc((size_t)cap * dtype_size(dt), kv));
+    *vb = nullptr;
+    if (nullable) DBX_TRY(dev_alloc((size_t)cap, (void**)vb));
+    dbx_column c;
+    memset(&c, 0, sizeof(c));
+    c.dtype = dt; c.mem = DBX_MEM_DEVICE; c.len = n; c.data = *kv; c.null_count = nullable ? -1 : 0;
+    ob->cols.push_back(c);
+    bool_bytes.push_back(nullptr);
+    valid_bytes.push_back(*vb);
+    return DBX_OK;
+  };
+  if (pl.grouped && pl.n_key_parts > 1) {
+    sp.n_key_parts = pl.n_key_parts;
+    memcpy(sp.key_parts, pl.key_parts, sizeof(pl.key_parts));
+    for (int j = 0; j < pl.n_key_parts; ++j) DBX_TRY(add_key(pl.key_parts[j].dtype, pl.key_parts[j].null_shift >= 0, &sp.out_keys[j], &sp.out_keys_valid[j]));
+  } else if (pl.grouped) {
+    sp.key_dtype = pl.key_dtype;
+    DBX_TRY(add_key(pl.key_dtype, pl.key_nullable, &sp.out_key, &sp.out_key_valid));
+  }
+  if (n) {
+    rows_to_spill_kernel<<<grid_for_entries(n), 256, 0, p->stream>>>((const uint64_t*)rows, n, sp);
+    count_launch();
+    DBX_CUDA_TRY(p->err, cudaGetLastError());
+  }
+  for (size_t i = 0; i < ob->cols.size(); ++i) {
+    for (int pass = 0; pass < 2; ++pass) {
+      uint8_t* bytes = pass == 0 ? bool_bytes[i] : valid_bytes[i];
+      if (!bytes) continue;
+      uint8_t* bits = nullptr;
+      DBX_TRY(dev_alloc((size_t)(cap + 7) / 8 + 8, (void**)&bits));
+      if (n) { pack_bytes_kernel<<<grid_for_entries((n + 7) / 8), 256, 0, p->stream>>>(bytes, n, bits); count_launch(); }
+      if (pass == 0) { ob->cols[i].data = bits; ob->cols[i].data_bit_offset = 0; }
+      else { ob->cols[i].validity = bits; ob->cols[i].validity_bit_offset = 0; }
+    }
+  }
+  DBX_CUDA_TRY(p->err, cudaGetLastError());
+  int32_t rc = pull_owned_block(ob, p->device, p->stream, p->err, out_mem, out);
+  if (rc == DBX_OK) out->num_rows = n;
+  return rc;
+}
+
+int32_t dbx_agg_final_merge_serialized(dbx_op* final_op, const dbx_block* block) {
+  using namespace dbx;
+  if (!final_op || !block) return DBX_ERR_INVALID;
+  Op* o = reinterpret_cast<Op*>(final_op);
+  if (o->kind != DBX_OP_AGG_FINAL) { o->err.set("merge_serialized: not a final aggregate operator"); return DBX_ERR_INVALID; }
+  AggFinalOp* f = static_cast<AggFinalOp*>(o);
+  const AggPlan& pl = f->plan;
+  DBX_CUDA_TRY(f->err, cudaSetDevice(f->device));
+  SpillLayout L;
+  spill_layout(pl, &L);
+  const int n_keys = !pl.grouped ? 0 : (pl.n_key_parts > 1 ? pl.n_key_parts : 1);
+  if (block->num_cols != L.n_fields + n_keys) { f->err.set("merge_serialized: block does not have the spill schema's column count"); return DBX_ERR_INVALID; }
+  const int64_t n = block->num_rows;
+  SpillInParams sp;
+  memset(&sp, 0, sizeof(sp));
+  std::vector<DevBuf> owned;
+  for (int c = 0; c < block->num_cols; ++c) {
+    const dbx_column& col = block->cols[c];
+    const int want = c < L.n_fields ? L.f[c].dtype : (pl.n_key_parts > 1 ? pl.key_parts[c - L.n_fields].dtype : pl.key_dtype);
+    if (col.dtype != want || col.len != n || col.is_const) { f->err.set("merge_serialized: column " + std::to_string(c) + " does not match the spill schema"); return DBX_ERR_INVALID; }
+    DevCol& dc = sp.cols[c];
+    dc.dtype = col.dtype;
+    if (col.mem == DBX_MEM_DEVICE) { dc.data = col.data; dc.validity = col.validity; dc.vbit_off = col.validity_bit_offset; dc.dbit_off = col.data_bit_offset; continue; }
+    const bool is_bool = col.dtype == DBX_BOOL;
+    const int64_t b0 = is_bool ? col.data_bit_offset >> 3 : 0;
+    const size_t bytes = is_bool ? (size_t)(((col.data_bit_offset + n + 7) >> 3) - b0) : (size_t)n * dtype_size(col.dtype);
+    owned.emplace_back();
+    DBX_CUDA_TRY(f->err, owned.back().ensure(bytes ? bytes : 1));
+    if (bytes) DBX_CUDA_TRY(f->err, cudaMemcpyAsync(owned.back().p, (const char*)col.data + b0, bytes, cudaMemcpyHostToDevice, f->stream));
+    dc.data = owned.back().p;
+    dc.dbit_off = is_bool ? (col.data_bit_offset & 7) : 0;
+    if (col.validity) {
+      const int64_t v0 = col.validity_bit_offset >> 3, v1 = (col.validity_bit_offset + n + 7) >> 3;
+      owned.emplace_back();
+      DBX_CUDA_TRY(f->err, owned.back().ensure((size_t)std::max<int64_t>(v1 - v0, 1)));
+      if (v1 > v0) DBX_CUDA_TRY(f->err, cudaMemcpyAsync(owned.back().p, col.validity + v0, (size_t)(v1 - v0), cudaMemcpyHostToDevice, f->stream));
+      dc.validity = (const uint8_t*)owned.back().p;
+      dc.vbit_off = col.validity_bit_offset & 7;
+    }
+  }
+  // where each state word comes from: an exact counter beats a flag beats "a group has >= 1 row"
+  sp.n_words = pl.n_words;
+  sp.row_words = 2 + pl.n_words;
+  int rank[kMaxWords];
+  for (int w = 0; w < pl.n_words; ++w) { sp.w[w] = WordSrcDev{WS_CNT_ONE, -1, -1, 0, pl.init.w[w]}; rank[w] = 0; }
+  for (int i = 0; i < L.n_fields; ++i) {
+    const SpillFieldHost& fd = L.f[i];
+    if (fd.kind == SPF_CNT && rank[fd.word] < 3) { sp.w[fd.word] = WordSrcDev{WS_CNT_EXACT, i, -1, 0, pl.init.w[fd.word]}; rank[fd.word] = 3; }
+    else if (fd.kind == SPF_FLAG && rank[fd.word] < 2) { sp.w[fd.word] = WordSrcDev{WS_CNT_FLAG, i, -1, 0, pl.init.w[fd.word]}; rank[fd.word] = 2; }
+  }
+  {
+    int col = 0;
+    for (int a = 0; a < pl.params.n_aggs; ++a) {
+      const int first = col, last = col + L.arity[a] - 1;  // the last field of a non-count tuple is the or-null flag
+      for (; col <= last; ++col) {
+        const SpillFieldHost& fd = L.f[col];
+        if (fd.kind == SPF_ACC) sp.w[fd.word] = WordSrcDev{WS_ACC_RAW, col, last, 0, pl.init.w[fd.word]};
+        else if (fd.kind == SPF_VALUE) sp.w[fd.word] = WordSrcDev{WS_ACC_VALUE, col, first, 0, pl.init.w[fd.word]};
+      }
+    }
+  }
+  sp.key_col = pl.grouped ? L.n_fields : -1;
+  sp.n_key_parts = pl.grouped && pl.n_key_parts > 1 ? pl.n_key_parts : 0;
+  sp.key_is_float = pl.key_is_float ? 1 : 0;
+  memcpy(sp.key_parts, pl.key_parts, sizeof(pl.key_parts));
+  for (int j = 0; j < sp.n_key_parts; ++j) sp.key_parts[j].slot = L.n_fields + j;
+  DevBuf rows;
+  DBX_CUDA_TRY(f->err, rows.ensure((size_t)std::max<int64_t>(n, 1) * sp.row_words * 8));
+  if (n) {
+    spill_to_rows_kernel<<<grid_for_entries(n), 256, 0, f->stream>>>(sp, n, (uint64_t*)rows.p);
+    count_launch();
+    DBX_CUDA_TRY(f->err, cudaGetLastError());
+  }
+  return f->merge_rows(rows.p, n);  // synchronises the stream: the staging buffers can go
+}
+
 int32_t dbx_agg_final_merge_rows(dbx_op* final_op, const void* dev_rows, int64_t n_rows) {
   if (!final_op || (n_rows > 0 && !dev_rows) || n_rows < 0) return DBX_ERR_INVALID;
   Op* f = reinterpret_cast<Op*>(final_op);

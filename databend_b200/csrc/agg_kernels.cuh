@@ -1305,6 +1305,158 @@ __global__ void __launch_bounds__(256) table_finalize_kernel(const __grid_consta
   }
 }
 
+// ---------------------------------------------------------------- spill_schema serde of partial states
+// AggregatorParams::spill_schema (aggregator_params.rs:103-117): one Tuple column `agg_i` per
+// aggregate function holding its serialised state (StateSerde::serialize_type), then the group
+// columns.  The C-ABI carries every tuple FLATTENED into consecutive columns; the fields are
+//   count(..)            [UInt64 count]                                   aggregate_count.rs:170-172
+//   sum(T)               [TSum value]                                     aggregate_sum.rs:155-157
+//   avg(T)               [TSum sum, UInt64 count]                         aggregate_avg.rs:106-111
+//   min(T) / max(T)      [Boolean has_value, T value]                     aggregate_min_max_any.rs:315-321
+// followed, for every function but count, by one Boolean per wrapping adaptor: the null adaptor of a
+// Nullable argument (aggregate_null_adaptor.rs:508-517) and the or-null adaptor every non-count
+// function gets (aggregate_ornull_adaptor.rs:184-190, aggregate_function_factory.rs:219-249); both
+// flags are "a non-NULL input was seen".  Rows come from / go to the fixed-width exchange rows
+// [key][key kind][state words...] (table_partition_scatter_kernel / rows_merge_kernel).
+constexpr int kMaxSpillFields = 5 * DBX_MAX_AGGS;
+enum SpillFieldKind : int32_t { SPF_CNT = 0, SPF_ACC = 1, SPF_FLAG = 2, SPF_VALUE = 3 };
+struct SpillFieldDev {
+  int32_t kind;      // SpillFieldKind
+  int32_t word;      // SPF_ACC / SPF_VALUE: accumulator word; SPF_CNT / SPF_FLAG: counter word
+  int32_t cnt_word;  // word holding the number of non-NULL inputs (gates SPF_VALUE / SPF_ACC defaults)
+  int32_t dtype;     // SPF_VALUE: argument dtype (narrow store, floats leave the ordered image)
+  void* out;         // 8 B per row (CNT / ACC), dtype-wide (VALUE), 1 byte per row (FLAG; packed afterwards)
+};
+struct SpillOutParams {
+  SpillFieldDev f[kMaxSpillFields];
+  int32_t n_fields, row_words;
+  int32_t key_dtype, n_key_parts;  // key_dtype -1: no group columns
+  void* out_key;
+  uint8_t* out_key_valid;
+  KeyPartDev key_parts[DBX_MAX_GROUP_COLS];
+  void* out_keys[DBX_MAX_GROUP_COLS];
+  uint8_t* out_keys_valid[DBX_MAX_GROUP_COLS];
+};
+
+__global__ void __launch_bounds__(256) rows_to_spill_kernel(const uint64_t* rows, int64_t n, const __grid_constant__ SpillOutParams sp) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t* row = rows + r * sp.row_words;
+    const uint64_t key = row[0];
+    const int key_kind = (int)row[1];
+    if (sp.n_key_parts > 1) {
+      const uint64_t kb = key_kind == 1 ? kEmptyKey : key;
+      for (int j = 0; j < sp.n_key_parts; ++j) {
+        const KeyPartDev kp = sp.key_parts[j];
+        const bool is_null = kp.null_shift >= 0 && ((kb >> kp.null_shift) & 1);
+        store_narrow(sp.out_keys[j], r, kp.dtype, is_null ? 0 : ((kb >> kp.shift) & kp.mask));
+        if (sp.out_keys_valid[j]) sp.out_keys_valid[j][r] = is_null ? 0 : 1;
+      }
+    } else if (sp.key_dtype >= 0) {
+      store_narrow(sp.out_key, r, sp.key_dtype, key_kind == 1 ? kEmptyKey : (key_kind == 2 ? 0 : key));
+      if (sp.out_key_valid) sp.out_key_valid[r] = key_kind == 2 ? 0 : 1;
+    }
+    for (int i = 0; i < sp.n_fields; ++i) {
+      const SpillFieldDev& f = sp.f[i];
+      const uint64_t w = row[2 + f.word];
+      const uint64_t cnt = row[2 + f.cnt_word];
+      if (f.kind == SPF_CNT) ((uint64_t*)f.out)[r] = w;
+      else if (f.kind == SPF_ACC) ((uint64_t*)f.out)[r] = cnt ? w : 0;
+      else if (f.kind == SPF_FLAG) ((uint8_t*)f.out)[r] = w ? 1 : 0;
+      else {
+        uint64_t bits = w;
+        if (dtype_class(f.dtype) == VC_FLT) bits = (uint64_t)__double_as_longlong(ordered_to_f64(w));
+        store_narrow(f.out, r, f.dtype, cnt ? bits : 0);
+      }
+    }
+  }
+}
+
+// 64-bit image of row r of a numeric / boolean column as the table kernels widen it
+__device__ __forceinline__ uint64_t column_image(const DevCol& c, int64_t r) {
+  const char* b = (const char*)c.data;
+  switch (c.dtype) {
+    case DBX_I64: case DBX_U64: case DBX_F64: return ((const uint64_t*)b)[r];
+    case DBX_I32: return (uint64_t)(int64_t)((const int32_t*)b)[r];
+    case DBX_U32: return ((const uint32_t*)b)[r];
+    case DBX_F32: return f32_bits_to_f64_bits(((const uint32_t*)b)[r]);
+    case DBX_I16: return (uint64_t)(int64_t)((const int16_t*)b)[r];
+    case DBX_U16: return ((const uint16_t*)b)[r];
+    case DBX_I8: return (uint64_t)(int64_t)((const int8_t*)b)[r];
+    case DBX_U8: return ((const uint8_t*)b)[r];
+    case DBX_BOOL: return (uint64_t)bit_test((const uint8_t*)b, c.dbit_off + r);
+    default: return 0;
+  }
+}
+enum WordSrcMode : int32_t { WS_CNT_EXACT = 0, WS_CNT_FLAG = 1, WS_CNT_ONE = 2, WS_ACC_RAW = 3, WS_ACC_VALUE = 4 };
+struct WordSrcDev {
+  int32_t mode;
+  int32_t col;       // input column of the value (CNT_EXACT / CNT_FLAG / ACC_*)
+  int32_t flag_col;  // ACC_*: Boolean column saying the accumulator holds a value; -1: always
+  int32_t pad;
+  uint64_t init;     // identity of the word (what an accumulator without a value merges as)
+};
+struct SpillInParams {
+  DevCol cols[kMaxSpillFields + DBX_MAX_GROUP_COLS];
+  WordSrcDev w[kMaxWords];
+  int32_t n_words, row_words;
+  int32_t key_col, n_key_parts;  // key_col: first group column; -1: none
+  int32_t key_is_float, pad;
+  KeyPartDev key_parts[DBX_MAX_GROUP_COLS];  // .slot = input column index here
+};
+__global__ void __launch_bounds__(256) spill_to_rows_kernel(const __grid_constant__ SpillInParams sp, int64_t n, uint64_t* rows) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t* row = rows + r * sp.row_words;
+    uint64_t key = 0;
+    int key_kind = 0;
+    if (sp.n_key_parts > 1) {
+      for (int j = 0; j < sp.n_key_parts; ++j) {
+        const KeyPartDev kp = sp.key_parts[j];
+        const DevCol& c = sp.cols[kp.slot];
+        const bool ok = !c.validity || bit_test(c.validity, c.vbit_off + r);
+        if (ok) key |= (column_image(c, r) & kp.mask) << kp.shift;
+        else key |= 1ULL << kp.null_shift;
+      }
+      if (key == kEmptyKey) { key = 0; key_kind = 1; }
+    } else if (sp.key_col >= 0) {
+      const DevCol& c = sp.cols[sp.key_col];
+      const bool ok = !c.validity || bit_test(c.validity, c.vbit_off + r);
+      key = ok ? column_image(c, r) : 0;
+      if (ok && sp.key_is_float) key = canonical_float_key(key);
+      if (!ok) key_kind = 2;
+      else if (key == kEmptyKey) { key = 0; key_kind = 1; }
+    }
+    row[0] = key;
+    row[1] = (uint64_t)key_kind;
+    for (int w = 0; w < sp.n_words; ++w) {
+      const WordSrcDev ws = sp.w[w];
+      uint64_t v;
+      if (ws.mode == WS_CNT_ONE) v = 1;
+      else if (ws.mode == WS_CNT_EXACT) v = column_image(sp.cols[ws.col], r);
+      else if (ws.mode == WS_CNT_FLAG) v = column_image(sp.cols[ws.col], r) ? 1 : 0;
+      else {
+        const bool has = ws.flag_col < 0 || column_image(sp.cols[ws.flag_col], r) != 0;
+        if (!has) v = ws.init;
+        else {
+          v = column_image(sp.cols[ws.col], r);
+          if (ws.mode == WS_ACC_VALUE && dtype_class(sp.cols[ws.col].dtype) == VC_FLT) v = f64_to_ordered(__longlong_as_double((long long)v));
+        }
+      }
+      row[2 + w] = v;
+    }
+  }
+}
+__global__ void pack_bytes_kernel(const uint8_t* bytes, int64_t n, uint8_t* bits) {
+  const int64_t nb = (n + 7) / 8;
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t v = 0;
+    for (int k = 0; k < 8; ++k) {
+      const int64_t i = b * 8 + k;
+      if (i < n && bytes[i]) v |= 1u << k;
+    }
+    bits[b] = (uint8_t)v;
+  }
+}
+
 // bytes (0/1) -> LSB-first bitmap (MutableBitmap layout), one output byte per thread
 __global__ void pack_validity_kernel(const uint8_t* bytes, const unsigned long long* n_dev, int64_t n_max, uint8_t* bits) {
   const int64_t n = min((int64_t)*n_dev, n_max);

@@ -83,6 +83,8 @@ def load():
         "dbx_op_last_kernel_ms": (i32, [vp, P(C.c_float)]),
         "dbx_op_stream": (i32, [vp, P(vp)]),
         "dbx_op_kernel_ms": (i32, [vp, i32, P(C.c_float)]),
+        "dbx_agg_partial_serialize": (i32, [vp, i32, P(abi.Block), P(i32)]),
+        "dbx_agg_final_merge_serialized": (i32, [vp, P(abi.Block)]),
         "dbx_op_inputs_consumed": (i32, [vp]),
         "dbx_op_kernel_variant": (i32, [vp, C.c_char_p, i32]),
         "dbx_agg_jit_selftest": (i32, [C.c_char_p, i32]),

@@ -266,6 +266,15 @@ class TransformPartialAggregate(_Op):
         self.finish()
         return self  # the payload stays in HBM; the handle is the AggregateMeta
 
+    def serialize(self):
+        """The partial's groups in the reference's spill / wire layout (AggregatorParams::spill_schema):
+        (block with every `agg_i` Tuple flattened into consecutive columns followed by the group
+        columns, [arity of agg_0, ...])."""
+        out = abi.Block()
+        arity = (C.c_int32 * abi.MAX_AGGS)()
+        check(load().dbx_agg_partial_serialize(self._h, abi.MEM_HOST, C.byref(out), arity), self._h)
+        return _block_from_c(out, self.device), list(arity[:len(self.params.aggregate_functions)])
+
 
 class TransformFinalAggregate(_Op):
     def __init__(self, params: AggregatorParams, input_types: Sequence[int], device: int = 0):
@@ -276,6 +285,13 @@ class TransformFinalAggregate(_Op):
         """handle_meta -> combine_payload (transform_aggregate_final.rs:201-303)."""
         check(load().dbx_agg_final_merge_partial(self._h, partial.handle), self._h)
         return []
+
+    def merge_serialized(self, block: DataBlock):
+        """Merge a spill-schema block (flattened tuples + group columns) produced by a CPU partial
+        aggregate or by TransformPartialAggregate.serialize() elsewhere."""
+        b, keep = block.as_c()
+        check(load().dbx_agg_final_merge_serialized(self._h, C.byref(b)), self._h)
+        del keep
 
     def merge_rows(self, dev_rows_ptr: int, n_rows: int):
         check(load().dbx_agg_final_merge_rows(self._h, dev_rows_ptr, n_rows), self._h)

@@ -287,6 +287,22 @@ int32_t dbx_agg_partial_partition(dbx_op* partial_op, int32_t n_parts, void** de
 /* AGG_FINAL: merge `n_rows` such rows (device memory, e.g. the all-to-all receive buffer). */
 int32_t dbx_agg_final_merge_rows(dbx_op* final_op, const void* dev_rows, int64_t n_rows);
 
+/* Partial states in the reference's spill / cluster wire layout (AggregatorParams::spill_schema,
+ * aggregator_params.rs:103-117; aggregator/serde/*): one Tuple column `agg_i` per aggregate function
+ * holding its serialised state, then the group columns.  The C-ABI carries each tuple FLATTENED into
+ * consecutive columns — [agg_0.0, agg_0.1, ..., agg_{n-1}.k, group_0, ...] — and reports the arity of
+ * every tuple, so the binding rebuilds Column::Tuple without copying:
+ *   count            (UInt64 count)                          aggregate_count.rs:170
+ *   sum(T)           (Sum<T> value, flags...)                aggregate_sum.rs:155
+ *   avg(T)           (Sum<T> sum, UInt64 count, flags...)    aggregate_avg.rs:106
+ *   min / max(T)     (Boolean has, T value, flags...)        aggregate_min_max_any.rs:315
+ * flags = one Boolean for the null adaptor of a Nullable argument, then one for the or-null adaptor
+ * (aggregate_null_adaptor.rs:508, aggregate_ornull_adaptor.rs:184); Sum<T> = Int64 / UInt64 / Float64.
+ * A GPU partial can so feed the reference's CPU TransformFinalAggregate, and a CPU partial (or a GPU
+ * partial on another node) can feed a GPU final. */
+int32_t dbx_agg_partial_serialize(dbx_op* partial_op, int32_t out_mem, dbx_block* out, int32_t* tuple_arity /* [n_aggs] */);
+int32_t dbx_agg_final_merge_serialized(dbx_op* final_op, const dbx_block* block);
+
 /* Peer-memory exchange of aggregate partials between the GPUs of one box (one process per GPU):
  * the multi-GPU form of the partial -> final shuffle (build_partition_bucket.rs:41-131; between
  * nodes the reference ships AggregateMeta partitions over Arrow Flight,
