@@ -615,7 +615,7 @@ class AggPartialOp : public Op {
   }
 
   int32_t reset() override {
-    if (batch_open) { batch_open = false; batch_rows = 0; DBX_TRY(stager.end()); }
+    if (batch_open) { batch_open = false; batch_rows = 0; DBX_TRY(stager.join_aux()); DBX_TRY(stager.end()); }
     table_ready = false;
     DBX_TRY(ensure_table());
     groups_known = plan.grouped ? 0 : 1;
@@ -859,9 +859,16 @@ class AggPartialOp : public Op {
     }
     return true;
   }
+  // dbx_op_inputs_consumed: copies of a still-open batch run on the stager's auxiliary streams
+  int32_t wait_inputs() override {
+    DBX_TRY(stager.join_aux());
+    DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
+    return DBX_OK;
+  }
   int32_t flush_batch() {
     if (!batch_open) return DBX_OK;
     batch_open = false;
+    DBX_TRY(stager.join_aux());
     if (batch_rows > 0) DBX_TRY(process_rows(batch_cols, batch_rows));
     batch_rows = 0;
     DBX_TRY(stager.end());

@@ -88,11 +88,30 @@ int32_t Stager::init(int device, cudaStream_t stream, ErrorSink* err) {
   stream_ = stream;
   err_ = err;
   for (auto& g : gens_) DBX_CUDA_TRY(*err_, cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
+  if (!getenv("DBX_STAGE_ONE_STREAM")) {
+    for (int i = 0; i < kAux; ++i) {
+      DBX_CUDA_TRY(*err_, cudaStreamCreateWithFlags(&aux_[i], cudaStreamNonBlocking));
+      DBX_CUDA_TRY(*err_, cudaEventCreateWithFlags(&aux_ev_[i], cudaEventDisableTiming));
+    }
+  }
   return DBX_OK;
 }
 Stager::~Stager() {
   for (auto& g : gens_)
     if (g.done) cudaEventDestroy(g.done);
+  for (int i = 0; i < kAux; ++i) {
+    if (aux_[i]) { cudaStreamSynchronize(aux_[i]); cudaStreamDestroy(aux_[i]); }
+    if (aux_ev_[i]) cudaEventDestroy(aux_ev_[i]);
+  }
+}
+int32_t Stager::join_aux() {
+  for (int i = 0; i < kAux; ++i) {
+    if (!aux_used_[i]) continue;
+    aux_used_[i] = false;
+    DBX_CUDA_TRY(*err_, cudaEventRecord(aux_ev_[i], aux_[i]));
+    DBX_CUDA_TRY(*err_, cudaStreamWaitEvent(stream_, aux_ev_[i], 0));
+  }
+  return DBX_OK;
 }
 int32_t Stager::begin() {
   cur_ = (cur_ + 1) % kGenerations;
@@ -166,7 +185,9 @@ int32_t Stager::stage_at(const dbx_column& c, int slot, int64_t row_off, int64_t
     if (row_off != 0) { err_->set("internal: staging buffer too small in the middle of a batch"); return DBX_ERR_INVALID; }
     DBX_CUDA_TRY(*err_, g.data[slot].ensure((size_t)cap_rows * esz));
   }
-  if (c.len) DBX_CUDA_TRY(*err_, cudaMemcpyAsync((char*)g.data[slot].p + (size_t)row_off * esz, c.data, (size_t)c.len * esz, cudaMemcpyHostToDevice, stream_));
+  cudaStream_t cs = stream_;
+  if (aux_[0]) { cs = aux_[slot % kAux]; aux_used_[slot % kAux] = true; }
+  if (c.len) DBX_CUDA_TRY(*err_, cudaMemcpyAsync((char*)g.data[slot].p + (size_t)row_off * esz, c.data, (size_t)c.len * esz, cudaMemcpyHostToDevice, cs));
   h2d_bytes += (size_t)c.len * esz;
   memset(out, 0, sizeof(*out));
   out->dtype = c.dtype;

@@ -91,6 +91,7 @@ class Stager {
   // host) and describe it as a DevCol.  `slot` indexes the per-generation buffers.
   int32_t stage(const dbx_column& c, int slot, DevCol* out);
   // Coalescing of small host blocks: append the column at row `row_off` of a `cap_rows`-row buffer.
+  int32_t join_aux();
   int32_t stage_at(const dbx_column& c, int slot, int64_t row_off, int64_t cap_rows, DevCol* out);
   // Record that all kernels consuming this generation have been enqueued.
   int32_t end();
@@ -106,6 +107,13 @@ class Stager {
   int cur_ = -1;
   int device_ = 0;
   cudaStream_t stream_ = nullptr;
+  // Coalesced small pushes (stage_at) spread their copies over a few auxiliary streams: a 512 KB
+  // transfer leaves the copy engine idle for a few microseconds between descriptors, several
+  // engines in flight keep PCIe busy.  join_aux() makes the operator stream wait for them.
+  static constexpr int kAux = 3;
+  cudaStream_t aux_[kAux] = {};
+  cudaEvent_t aux_ev_[kAux] = {};
+  bool aux_used_[kAux] = {};
   ErrorSink* err_ = nullptr;
 };
 

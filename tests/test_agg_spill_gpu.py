@@ -124,7 +124,7 @@ def test_cpu_partial_states_into_gpu_final(gpu):
     """The states of a CPU partial aggregate (numpy restatement of the reference's serialisation) for
     part A merged into a GPU final that also gets a GPU partial for part B."""
     blk = make_block(150_000, 7)
-    a, b = blk.split_by_rows(60_000)
+    a, b = blk.split_by_rows(75_000)
     flat, arity, okeys = expected_fields(a, [0])
     cols = [Column.from_data(f, abi.BOOL if f.dtype == np.bool_ else None) for f in flat]
     cols.append(Column.from_data(okeys[0][0], validity=okeys[0][1]))
