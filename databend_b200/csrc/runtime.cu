@@ -88,6 +88,7 @@ int32_t Stager::init(int device, cudaStream_t stream, ErrorSink* err) {
   stream_ = stream;
   err_ = err;
   for (auto& g : gens_) DBX_CUDA_TRY(*err_, cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
+  gather_ = !getenv("DBX_STAGE_NO_GATHER");
   if (!getenv("DBX_STAGE_ONE_STREAM")) {
     for (int i = 0; i < kAux; ++i) {
       DBX_CUDA_TRY(*err_, cudaStreamCreateWithFlags(&aux_[i], cudaStreamNonBlocking));
@@ -104,7 +105,33 @@ Stager::~Stager() {
     if (aux_ev_[i]) cudaEventDestroy(aux_ev_[i]);
   }
 }
+// One CTA row (blockIdx.y) per segment, gridDim.x CTAs striding over its 16-byte words.
+__global__ void __launch_bounds__(256) gather_segments_kernel(const Stager::Segment* segs) {
+  const Stager::Segment sg = segs[blockIdx.y];
+  const uint4* src = (const uint4*)sg.src;
+  uint4* dst = (uint4*)sg.dst;
+  const unsigned long long n16 = sg.bytes >> 4;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (unsigned long long)gridDim.x * blockDim.x)
+    dst[i] = __ldcs(src + i);
+  if (blockIdx.x == 0 && threadIdx.x < (sg.bytes & 15)) {  // tail bytes (columns narrower than 16 B per row)
+    const unsigned long long o = (n16 << 4) + threadIdx.x;
+    ((unsigned char*)sg.dst)[o] = ((const unsigned char*)sg.src)[o];
+  }
+}
+
 int32_t Stager::join_aux() {
+  if (!segs_.empty()) {
+    const size_t bytes = segs_.size() * sizeof(Segment);
+    DBX_CUDA_TRY(*err_, seg_host_[cur_].ensure(bytes));
+    DBX_CUDA_TRY(*err_, seg_dev_[cur_].ensure(bytes));
+    memcpy(seg_host_[cur_].p, segs_.data(), bytes);
+    DBX_CUDA_TRY(*err_, cudaMemcpyAsync(seg_dev_[cur_].p, seg_host_[cur_].p, bytes, cudaMemcpyHostToDevice, stream_));
+    const dim3 grid(8, (unsigned)segs_.size());
+    gather_segments_kernel<<<grid, 256, 0, stream_>>>((const Segment*)seg_dev_[cur_].p);
+    count_launch();
+    DBX_CUDA_TRY(*err_, cudaGetLastError());
+    segs_.clear();
+  }
   for (int i = 0; i < kAux; ++i) {
     if (!aux_used_[i]) continue;
     aux_used_[i] = false;
@@ -185,13 +212,21 @@ int32_t Stager::stage_at(const dbx_column& c, int slot, int64_t row_off, int64_t
     if (row_off != 0) { err_->set("internal: staging buffer too small in the middle of a batch"); return DBX_ERR_INVALID; }
     DBX_CUDA_TRY(*err_, g.data[slot].ensure((size_t)cap_rows * esz));
   }
-  cudaStream_t cs = stream_;
-  if (aux_[0]) { cs = aux_[slot % kAux]; aux_used_[slot % kAux] = true; }
-  if (c.len) DBX_CUDA_TRY(*err_, cudaMemcpyAsync((char*)g.data[slot].p + (size_t)row_off * esz, c.data, (size_t)c.len * esz, cudaMemcpyHostToDevice, cs));
   h2d_bytes += (size_t)c.len * esz;
   memset(out, 0, sizeof(*out));
   out->dtype = c.dtype;
   out->data = g.data[slot].p;
+  if (gather_ && c.len && ((uintptr_t)c.data & 15) == 0 && (((size_t)row_off * esz) & 15) == 0 && segs_.size() < 60000) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, c.data) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+      segs_.push_back(Segment{at.devicePointer, (char*)g.data[slot].p + (size_t)row_off * esz, (unsigned long long)c.len * esz});
+      return DBX_OK;
+    }
+    cudaGetLastError();  // pageable memory: the DMA path below
+  }
+  cudaStream_t cs = stream_;
+  if (aux_[0]) { cs = aux_[slot % kAux]; aux_used_[slot % kAux] = true; }
+  if (c.len) DBX_CUDA_TRY(*err_, cudaMemcpyAsync((char*)g.data[slot].p + (size_t)row_off * esz, c.data, (size_t)c.len * esz, cudaMemcpyHostToDevice, cs));
   return DBX_OK;
 }
 int32_t Stager::end() {

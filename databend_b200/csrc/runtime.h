@@ -82,6 +82,7 @@ struct OwnedBlock {
 // a generation is reused only after the event recorded behind its consumer has fired.
 class Stager {
  public:
+  struct Segment { const void* src; void* dst; unsigned long long bytes; };
   static constexpr int kGenerations = 4;
   int32_t init(int device, cudaStream_t stream, ErrorSink* err);
   ~Stager();
@@ -110,6 +111,14 @@ class Stager {
   // Coalesced small pushes (stage_at) spread their copies over a few auxiliary streams: a 512 KB
   // transfer leaves the copy engine idle for a few microseconds between descriptors, several
   // engines in flight keep PCIe busy.  join_aux() makes the operator stream wait for them.
+  // Pinned (mapped) host columns are not copied by the DMA engines at all: stage_at only records
+  // {source, destination, bytes}, and join_aux() launches ONE gather kernel per batch whose CTAs
+  // read the host columns over PCIe with 128-bit loads (gather_segments_kernel) — no per-block
+  // CUDA call is left on the submitting thread.
+  std::vector<Segment> segs_;
+  PinnedBuf seg_host_[kGenerations];
+  DevBuf seg_dev_[kGenerations];
+  bool gather_ = true;
   static constexpr int kAux = 3;
   cudaStream_t aux_[kAux] = {};
   cudaEvent_t aux_ev_[kAux] = {};

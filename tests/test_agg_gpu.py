@@ -590,3 +590,37 @@ def test_specialised_kernels_serve_grouped_plans(gpu, monkeypatch):
         test_multi_column_group_keys(gpu, True)   # packed keys, nullable key / argument, min / max / avg
         test_multi_column_group_keys(gpu, False)
         test_nullable_args_and_keys(gpu)
+
+
+@pytest.mark.parametrize("gather", ["1", "0"])
+def test_small_pinned_host_blocks_gathered_by_the_device(gpu, monkeypatch, gather):
+    """65 536-row blocks in PINNED host memory (the reference's max_block_size): the coalescing
+    stage records the blocks and one gather kernel per batch reads them over PCIe (no per-block
+    copy call); DBX_STAGE_NO_GATHER=1 is the DMA path.  Odd block sizes exercise the 16-byte tail."""
+    import ctypes as C
+    from databend_b200 import lib
+    if gather == "0":
+        monkeypatch.setenv("DBX_STAGE_NO_GATHER", "1")
+    L = lib.load()
+    n = 1_000_003
+    src = config2_block(n, seed=9, n_keys=50_000)
+    ptrs, cols = [], []
+    for c in src.columns:
+        p = C.c_void_p()
+        lib.check(L.dbx_host_alloc(n * 8, C.byref(p)))
+        ptrs.append(p)
+        arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int64 if c.dtype != abi.F64 else C.c_double)), shape=(n,))
+        arr[:] = c.values()
+        cols.append(Column.from_data(arr))
+    pinned = DataBlock(cols, n)
+    try:
+        for split in (65536, 65537, 9999):
+            blocks = pinned.split_by_rows(split)
+            out = filter_group_aggregate(blocks, CONFIG2, V_MOD3, input_types=schema_types(src))
+            ref = oracle().filter_group_agg(src, CONFIG2.to_c(V_MOD3), threads=4)
+            g = sorted_group_result_from_block(out, 3, 1)
+            o = sorted_group_result_from_oracle(ref, [abi.I64])
+            assert_group_results_equal(g, o)
+    finally:
+        for p in ptrs:
+            L.dbx_host_free(p)
