@@ -53,6 +53,7 @@ struct AggPlan {
   bool key_nullable = false;
   bool key_is_float = false;
   int n_key_parts = 0;  // > 1: packed multi-column key
+  int key_words = 1;    // 2: the packed key needs 65..128 bits (HashMethodKeysU128)
   KeyPartDev key_parts[DBX_MAX_GROUP_COLS];
 
   int n_words = 0;
@@ -285,13 +286,16 @@ int32_t build_plan(const dbx_agg_params* p, const int32_t* types, int32_t n_cols
       if (kp.slot < 0) return DBX_ERR_UNSUPPORTED;
       kp.dtype = dt;
       const int w = 8 * dtype_size(dt);
+      const int need = w + (pl->col_nullable[kc] ? 1 : 0);
+      if (bits < 64 && bits + need > 64) bits = 64;  // a field (value + its NULL flag) never straddles the two key words
       kp.shift = bits;
       kp.mask = w == 64 ? ~0ULL : ((1ULL << w) - 1);
       bits += w;
       kp.null_shift = -1;
       if (pl->col_nullable[kc]) kp.null_shift = bits++;
     }
-    if (bits > 64) { err->set("multi-column GROUP BY keys wider than 64 bits (incl. NULL flags) need 128-bit packed keys: not built yet (SURVEY 8f.1)"); return DBX_ERR_UNSUPPORTED; }
+    if (bits > 128) { err->set("multi-column GROUP BY keys wider than 128 bits (incl. NULL flags) need 256-bit or serialised keys: not built (SURVEY 8f.1)"); return DBX_ERR_UNSUPPORTED; }
+    pl->key_words = bits > 64 ? 2 : 1;  // HashMethodKeysU64 / HashMethodKeysU128 (kernels/group_by.rs:66-79)
     pl->n_key_parts = p->n_group_cols;
     pl->key_slot = pl->key_parts[0].slot;
     pl->key_dtype = DBX_U64;
@@ -424,20 +428,22 @@ struct DeviceTable {
   int64_t cap = 0;
   int n_words = 0;
   int n_pairs = 0;
+  int key_words = 1;
   int w_pair[kMaxWords];
   int w_pos[kMaxWords];
 
   unsigned long long* n_groups() const { return (unsigned long long*)counters.p; }
   unsigned long long* n_overflow() const { return (unsigned long long*)counters.p + 1; }
-  size_t bytes() const { return (size_t)(cap + 2) * 8 * (1 + n_words); }
+  size_t bytes() const { return (size_t)(cap + 2) * 8 * (key_words + n_words); }
 
   int32_t create(int64_t capacity, const AggPlan& pl, cudaStream_t stream, ErrorSink* err) {
     cap = capacity < 4 ? 4 : capacity;
     n_words = pl.n_words;
     n_pairs = pl.n_pairs;
+    key_words = pl.key_words;
     memcpy(w_pair, pl.w_pair, sizeof(w_pair));
     memcpy(w_pos, pl.w_pos, sizeof(w_pos));
-    const size_t kbytes = ((size_t)(cap + 2) * 8 + 32 + 255) & ~(size_t)255;
+    const size_t kbytes = ((size_t)(cap + 2) * 8 * key_words + 32 + 255) & ~(size_t)255;
     DBX_CUDA_TRY(*err, mem.ensure(kbytes + (size_t)(cap + 2) * 8 * n_words));
     keys_p = mem.p;
     states_p = (char*)mem.p + kbytes;
@@ -446,7 +452,7 @@ struct DeviceTable {
   }
   int32_t clear(const AggPlan& pl, cudaStream_t stream, ErrorSink* err) {
     DBX_CUDA_TRY(*err, cudaMemsetAsync(counters.p, 0, 64, stream));
-    int64_t total = (cap + 2) * (1 + n_words);
+    int64_t total = (cap + 2) * (key_words + n_words);
     int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)kNumSMs * 16);
     table_init_kernel<<<grid, 256, 0, stream>>>(view(nullptr), pl.init);
     count_launch();
@@ -465,6 +471,7 @@ struct DeviceTable {
     t.states = (uint64_t*)states_p;
     t.cap = cap;
     t.n_words = n_words;
+    t.key_words = key_words;
     // pair arrays first (16-byte aligned: every region has an even number of words), then the
     // unpaired words row-major (one entry per slot, so a row's REDs fall into 1-2 sectors)
     {
@@ -484,7 +491,7 @@ struct DeviceTable {
     t.n_groups = n_groups();
     t.n_overflow = n_overflow();
     t.overflow_rows = overflow_rows;
-    t.probe_limit = (int32_t)std::min<int64_t>(kProbeLimit, cap >> 2);
+    t.probe_limit = (int32_t)std::min<int64_t>(kProbeLimit, cap >> (key_words == 2 ? 1 : 2));
     return t;
   }
   void swap(DeviceTable& o) {
@@ -495,6 +502,7 @@ struct DeviceTable {
     std::swap(cap, o.cap);
     std::swap(n_words, o.n_words);
     std::swap(n_pairs, o.n_pairs);
+    std::swap(key_words, o.key_words);
     std::swap(w_pair, o.w_pair);
     std::swap(w_pos, o.w_pos);
   }
@@ -557,7 +565,7 @@ class AggPartialOp : public Op {
   void specialise() {
     const char* e = getenv("DBX_AGG_JIT");
     if (e && atoi(e) == 0) { jit_status = "off (DBX_AGG_JIT=0)"; return; }
-    if (!plan.grouped || plan.n_pairs > 0) { jit_status = "off (plan shape not specialised)"; return; }
+    if (!plan.grouped || plan.n_pairs > 0 || plan.key_words != 1) { jit_status = "off (plan shape not specialised)"; return; }
     StaticPlan sp;
     memset(&sp, 0, sizeof(sp));
     sp.n_nodes = plan.n_nodes; sp.n_updates = plan.n_updates; sp.key_slot = plan.key_slot; sp.key_is_float = plan.key_is_float ? 1 : 0;
@@ -706,6 +714,33 @@ class AggPartialOp : public Op {
     DBX_CUDA_TRY(err, cudaGetLastError());
     return DBX_OK;
   }
+  template <int NS, bool INDIRECT>
+  int32_t launch_wide(const AggKernelParams& kp) {
+    static std::atomic<bool> attr_set[64];
+    if (device < 0 || device >= 64) { err.set("device index out of range"); return DBX_ERR_INVALID; }
+    const size_t smem = (sizeof(StageWarp<NS>) * kWarpsPerBlock + 15) & ~(size_t)15;
+    if (!attr_set[device]) {
+      DBX_CUDA_TRY(err, cudaFuncSetAttribute(filter_group_agg_wide_kernel<NS, INDIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set[device] = true;
+    }
+    filter_group_agg_wide_kernel<NS, INDIRECT><<<grid_for_rows(kp.n_rows), kBlock, smem, stream>>>(kp);
+    count_launch();
+    DBX_CUDA_TRY(err, cudaGetLastError());
+    return DBX_OK;
+  }
+  template <bool INDIRECT>
+  int32_t launch_wide_ns(const AggKernelParams& kp) {
+    switch (plan.n_slots) {
+      case 1: return launch_wide<1, INDIRECT>(kp);
+      case 2: return launch_wide<2, INDIRECT>(kp);
+      case 3: return launch_wide<3, INDIRECT>(kp);
+      case 4: return launch_wide<4, INDIRECT>(kp);
+      case 5: return launch_wide<5, INDIRECT>(kp);
+      case 6: return launch_wide<6, INDIRECT>(kp);
+      case 7: return launch_wide<7, INDIRECT>(kp);
+      default: return launch_wide<8, INDIRECT>(kp);
+    }
+  }
   template <bool FAST, bool INDIRECT>
   int32_t launch_ns(const AggKernelParams& kp) {
     switch (plan.n_slots) {
@@ -734,6 +769,7 @@ class AggPartialOp : public Op {
     return true;
   }
   int32_t launch_grouped(const AggKernelParams& kp, bool indirect) {
+    if (plan.key_words == 2) return indirect ? launch_wide_ns<true>(kp) : launch_wide_ns<false>(kp);
     if (indirect) return launch_ns<false, true>(kp);
     if (!fast_eligible(kp) || kp.n_rows < kTileRows) return launch_ns<false, false>(kp);
     AggKernelParams a = kp;
@@ -1065,6 +1101,7 @@ class AggFinalOp : public Op {
 
   int32_t merge_rows(const void* dev_rows, int64_t n_rows) {
     if (finished) { err.set("merge after finish"); return DBX_ERR_STATE; }
+    if (plan.key_words != 1) { err.set("128-bit packed group keys: exchange rows carry 64-bit keys only"); return DBX_ERR_UNSUPPORTED; }
     DBX_TRY(ensure_capacity(n_rows));
     if (n_rows == 0) return DBX_OK;
     // no GROUP BY: the rows are per-rank single states (FinalSingleStateAggregator,
@@ -1494,6 +1531,7 @@ int32_t dbx_agg_partial_partition(dbx_op* partial_op, int32_t n_parts, void** de
   Op* o = reinterpret_cast<Op*>(partial_op);
   if (o->kind != DBX_OP_AGG_PARTIAL) { o->err.set("partition: not a partial aggregate operator"); return DBX_ERR_INVALID; }
   AggPartialOp* p = static_cast<AggPartialOp*>(o);
+  if (p->plan.key_words != 1) { p->err.set("128-bit packed group keys: the row exchange / serialisation formats carry 64-bit keys only (single-GPU partial -> final hand-off works)"); return DBX_ERR_UNSUPPORTED; }
   DBX_CUDA_TRY(p->err, cudaSetDevice(p->device));
   DBX_TRY(p->flush_batch());
   DevBuf counts;
@@ -1765,6 +1803,7 @@ int32_t dbx_agg_exchange_create(dbx_op* partial_op, int32_t rank, int32_t n_rank
   if (o->kind != DBX_OP_AGG_PARTIAL) { g_create_error.set("dbx_agg_exchange_create: not a partial aggregate operator"); return DBX_ERR_INVALID; }
   AggPartialOp* p = static_cast<AggPartialOp*>(o);
   if (!p->plan.grouped) { g_create_error.set("dbx_agg_exchange_create: aggregation without GROUP BY has no key to partition by: use dbx_agg_single_allreduce"); return DBX_ERR_UNSUPPORTED; }
+  if (p->plan.key_words != 1) { g_create_error.set("dbx_agg_exchange_create: 128-bit packed group keys are not carried by the exchange rows (64-bit keys only)"); return DBX_ERR_UNSUPPORTED; }
   ErrorSink& err = g_create_error;
   std::unique_ptr<dbx_agg_exchange> x(new dbx_agg_exchange());
   x->device = p->device; x->rank = rank; x->n_ranks = n_ranks; x->row_words = 2 + p->plan.n_words;

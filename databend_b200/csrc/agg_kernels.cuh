@@ -303,6 +303,62 @@ __device__ __noinline__ int64_t find_or_insert_slow(const TableDev& t, uint64_t 
   return -1;
 }
 
+// ---- 128-bit packed keys: slot i holds keys[2 i], keys[2 i + 1]; a bucket is 2 slots = one 32-byte
+// sector = one 256-bit probe; insertion is ONE 128-bit compare-and-swap (atom.cas.b128, sm_90+).
+// The EMPTY pattern is both words == kEmptyKey; a real key equal to it lives in the special slot cap.
+__device__ __forceinline__ uint64_t agg_hash_wide(uint64_t k0, uint64_t k1) {
+  return agg_hash_u64(k0 ^ (agg_hash_u64(k1) + 0x9e3779b97f4a7c15ULL));
+}
+__device__ __forceinline__ void cas_b128(uint64_t* addr, uint64_t c0, uint64_t c1, uint64_t v0, uint64_t v1, uint64_t& o0, uint64_t& o1) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b128 cmp, val, old;\n\t"
+      "mov.b128 cmp, {%2, %3};\n\t"
+      "mov.b128 val, {%4, %5};\n\t"
+      "atom.global.relaxed.gpu.cas.b128 old, [%6], cmp, val;\n\t"
+      "mov.b128 {%0, %1}, old;\n\t"
+      "}"
+      : "=l"(o0), "=l"(o1)
+      : "l"(c0), "l"(c1), "l"(v0), "l"(v1), "l"(addr)
+      : "memory");
+}
+__device__ __forceinline__ int bucket_match_wide(const u64x4& k, uint64_t k0, uint64_t k1) {
+  return (k.x == k0 && k.y == k1) ? 0 : ((k.z == k0 && k.w == k1) ? 1 : -1);
+}
+__device__ __noinline__ int64_t find_or_insert_wide(const TableDev& t, uint64_t k0, uint64_t k1, int64_t b, u64x4 kb, uint32_t& new_groups) {
+  const int64_t nb_mask = (t.cap >> 1) - 1;
+  int probes = 0, retries = 0;
+  while (probes < t.probe_limit) {
+    const int m = bucket_match_wide(kb, k0, k1);
+    if (m >= 0) return 2 * b + m;
+    const int e = (kb.x == kEmptyKey && kb.y == kEmptyKey) ? 0 : ((kb.z == kEmptyKey && kb.w == kEmptyKey) ? 1 : -1);
+    if (e >= 0 && retries < 64) {
+      uint64_t o0, o1;
+      cas_b128(t.keys + 4 * b + 2 * e, kEmptyKey, kEmptyKey, k0, k1, o0, o1);
+      if (o0 == kEmptyKey && o1 == kEmptyKey) { ++new_groups; return 2 * b + e; }
+      if (o0 == k0 && o1 == k1) return 2 * b + e;
+      ++retries;
+      kb = ld_bucket(t.keys + 4 * b);
+      continue;
+    }
+    b = (b + 1) & nb_mask;
+    ++probes;
+    retries = 0;
+    kb = ld_bucket(t.keys + 4 * b);
+  }
+  return -1;
+}
+__device__ __forceinline__ int64_t resolve_slot_wide(const TableDev& t, uint64_t k0, uint64_t k1, uint32_t& new_groups) {
+  if (k0 == kEmptyKey && k1 == kEmptyKey) {  // the key equal to the EMPTY pattern: special slot cap, word 0 is its "present" flag
+    if (atomicExch((unsigned long long*)(t.keys + 2 * t.cap), 1ULL) == kEmptyKey) ++new_groups;
+    return t.cap;
+  }
+  const int64_t b = (int64_t)(agg_hash_wide(k0, k1) & (uint64_t)((t.cap >> 1) - 1));
+  const u64x4 kb = ld_bucket(t.keys + 4 * b);
+  const int m = bucket_match_wide(kb, k0, k1);
+  return m >= 0 ? 2 * b + m : find_or_insert_wide(t, k0, k1, b, kb, new_groups);
+}
+
 __device__ __forceinline__ void apply_update(int op, void* w, uint64_t val, bool valid) {
   if (op == UPD_INC) { red_add_u64(w, 1); return; }
   if (!valid) return;
@@ -353,7 +409,7 @@ __device__ __forceinline__ uint64_t update_contribution(const UpdateDev& ud, uin
   return valid ? val : 0;  // UPD_ADD_INT: two's complement image; UPD_ADD_F64: +0.0 has all-zero bits
 }
 
-template <int NS, bool FAST, bool BULK>
+template <int NS, bool FAST, bool BULK, int KW = 1>
 __device__ __forceinline__ void table_phase32(const AggKernelParams& p, const StageWarp<NS>& sw, int first, int count,
                                               int lane, uint32_t& new_groups, uint64_t* bulk_stage, int& bulk_gen) {
   const TableDev& t = p.table;
@@ -361,12 +417,19 @@ __device__ __forceinline__ void table_phase32(const AggKernelParams& p, const St
   const bool act = lane < count;
   const bool use_bulk = BULK && ((p.bulk_lanes >> lane) & 1);
   int64_t good_slot = -1;
-  uint64_t key = 0;
+  uint64_t key = 0, key_hi = 0;
   uint32_t vm = 0xFF;
   bool key_null = false;
   if (act) {
     if (!FAST) vm = sw.vm[i];
-    if (PLN(n_key_parts) > 1) {  // packed multi-column key; NULLs are encoded inside the key
+    if (KW == 2) {  // 128-bit packed key: a field lives in word (shift >> 6)
+      for (int j = 0; j < p.n_key_parts; ++j) {
+        const KeyPartDev kp = p.key_parts[j];
+        const bool ok = (vm >> kp.slot) & 1;
+        const uint64_t bits = ok ? (sw.val[kp.slot][i] & kp.mask) << (kp.shift & 63) : 1ULL << (kp.null_shift & 63);
+        if ((ok ? kp.shift : kp.null_shift) >> 6) key_hi |= bits; else key |= bits;
+      }
+    } else if (PLN(n_key_parts) > 1) {  // packed multi-column key; NULLs are encoded inside the key
       PLN_UNROLL
       for (int j = 0; j < PLN(n_key_parts); ++j) {
         const KeyPartDev kp = PLN(key_parts[j]);
@@ -380,14 +443,16 @@ __device__ __forceinline__ void table_phase32(const AggKernelParams& p, const St
       key_null = !((vm >> PLN(key_slot)) & 1);
     }
   }
-  const bool special = key_null || key == kEmptyKey;
-  const int64_t b = (int64_t)(agg_hash_u64(key) & (uint64_t)((t.cap >> 2) - 1));
+  const bool special = KW == 2 ? false : (key_null || key == kEmptyKey);
+  const int64_t b = KW == 2 ? 0 : (int64_t)(agg_hash_u64(key) & (uint64_t)((t.cap >> 2) - 1));
   u64x4 kb;
   kb.x = kb.y = kb.z = kb.w = 0;
-  if (act && !special) kb = ld_bucket(t.keys + 4 * b);
+  if (KW == 1 && act && !special) kb = ld_bucket(t.keys + 4 * b);
   if (act) {
     int64_t slot;
-    if (special) {
+    if (KW == 2) {
+      slot = resolve_slot_wide(t, key, key_hi, new_groups);
+    } else if (special) {
       slot = special_slot(t, key_null, new_groups);
     } else {
       int m = bucket_match(kb, key);
@@ -447,7 +512,7 @@ __device__ __forceinline__ void prefetch_tile(const AggKernelParams& p, int64_t 
   }
 }
 
-template <int NS, bool FAST, bool INDIRECT, bool BULK>
+template <int NS, bool FAST, bool INDIRECT, bool BULK, int KW = 1>
 __device__ __forceinline__ void filter_group_agg_body(const AggKernelParams& p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -517,11 +582,11 @@ __device__ __forceinline__ void filter_group_agg_body(const AggKernelParams& p) 
     __syncwarp();
     while (n_staged >= 32) {
       n_staged -= 32;
-      table_phase32<NS, FAST, BULK>(p, sw, n_staged, 32, lane, new_groups, bulk_stage, bulk_gen);
+      table_phase32<NS, FAST, BULK, KW>(p, sw, n_staged, 32, lane, new_groups, bulk_stage, bulk_gen);
     }
   }
   __syncwarp();
-  if (n_staged > 0) table_phase32<NS, FAST, BULK>(p, sw, 0, n_staged, lane, new_groups, bulk_stage, bulk_gen);
+  if (n_staged > 0) table_phase32<NS, FAST, BULK, KW>(p, sw, 0, n_staged, lane, new_groups, bulk_stage, bulk_gen);
   if (BULK) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   // one counter update per warp
 #pragma unroll
@@ -533,6 +598,11 @@ __device__ __forceinline__ void filter_group_agg_body(const AggKernelParams& p) 
 template <int NS, bool FAST, bool INDIRECT, bool BULK = false, int MINB = 4>
 __global__ void __launch_bounds__(kBlock, MINB) filter_group_agg_kernel(const __grid_constant__ AggKernelParams p) {
   filter_group_agg_body<NS, FAST, INDIRECT, BULK>(p);
+}
+// 128-bit packed group keys (two key words per slot): any column layout, direct or replayed rows
+template <int NS, bool INDIRECT>
+__global__ void __launch_bounds__(kBlock, 4) filter_group_agg_wide_kernel(const __grid_constant__ AggKernelParams p) {
+  filter_group_agg_body<NS, false, INDIRECT, false, 2>(p);
 }
 #endif
 
@@ -895,11 +965,12 @@ struct WordInit {
 };
 __global__ void table_init_kernel(const __grid_constant__ TableDev t, const __grid_constant__ WordInit init) {
   const int64_t n_slots = t.cap + 2;
-  const int64_t total = n_slots * (1 + t.n_words);
+  const int64_t n_keys = n_slots * t.key_words;
+  const int64_t total = n_keys + n_slots * t.n_words;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    if (i < n_slots) t.keys[i] = kEmptyKey;
+    if (i < n_keys) t.keys[i] = kEmptyKey;
     else {
-      const int64_t k = i - n_slots;
+      const int64_t k = i - n_keys;
       const int w = (int)(k / n_slots);
       *word_ptr(t, k - w * n_slots, w) = init.w[w];
     }
@@ -929,10 +1000,18 @@ __global__ void table_merge_kernel(const __grid_constant__ TableDev src, const _
   uint32_t new_groups = 0;
   const int64_t n_slots = src.cap + 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (int64_t)gridDim.x * blockDim.x) {
-    uint64_t key = src.keys[i];
-    if (key == kEmptyKey) continue;
-    int key_kind = i >= src.cap ? (int)(i - src.cap) + 1 : 0;
-    int64_t d = resolve_slot(dst, key, key_kind, new_groups);
+    int64_t d;
+    if (src.key_words == 2) {
+      uint64_t k0 = src.keys[2 * i], k1 = src.keys[2 * i + 1];
+      if (i >= src.cap) { if (i > src.cap || k0 == kEmptyKey) continue; k0 = k1 = kEmptyKey; }  // special slot: the EMPTY-pattern key
+      else if (k0 == kEmptyKey && k1 == kEmptyKey) continue;
+      d = resolve_slot_wide(dst, k0, k1, new_groups);
+    } else {
+      uint64_t key = src.keys[i];
+      if (key == kEmptyKey) continue;
+      int key_kind = i >= src.cap ? (int)(i - src.cap) + 1 : 0;
+      d = resolve_slot(dst, key, key_kind, new_groups);
+    }
     if (d < 0) { atomicAdd(dst.n_overflow, 1ULL); continue; }
     for (int w = 0; w < src.n_words; ++w) merge_word(kinds.op[w], word_ptr(dst, d, w), *word_ptr(src, i, w));
   }
@@ -1252,9 +1331,15 @@ __global__ void __launch_bounds__(256) table_finalize_kernel(const __grid_consta
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int64_t it = 0; it < n_iter; ++it) {
     int64_t i = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint64_t key = kEmptyKey;
-    if (i < n_slots) key = src.keys[i];
-    bool occ = key != kEmptyKey;
+    uint64_t key = kEmptyKey, key_hi = kEmptyKey;
+    if (i < n_slots) {
+      if (src.key_words == 2) {
+        key = src.keys[2 * i]; key_hi = src.keys[2 * i + 1];
+        if (i == src.cap && key != kEmptyKey) key = key_hi = kEmptyKey ^ 1;  // occupied marker, values restored below
+        else if (i > src.cap) key = key_hi = kEmptyKey;
+      } else key = src.keys[i];
+    }
+    bool occ = src.key_words == 2 ? !(key == kEmptyKey && key_hi == kEmptyKey) : key != kEmptyKey;
     // output slot allocation: one atomic per CTA and step (warp ballots + an 8-entry scan)
     const unsigned ballot = __ballot_sync(0xffffffffu, occ);
     if (lane == 0) s_warp_cnt[warp] = __popc(ballot);
@@ -1273,10 +1358,12 @@ __global__ void __launch_bounds__(256) table_finalize_kernel(const __grid_consta
     int key_kind = i >= src.cap ? (int)(i - src.cap) + 1 : 0;
     if (fp.n_key_parts > 1) {
       const uint64_t kb = key_kind == 1 ? kEmptyKey : key;
+      const uint64_t kb_hi = key_kind == 1 ? kEmptyKey : key_hi;  // 128-bit keys only
       for (int j = 0; j < fp.n_key_parts; ++j) {
         const KeyPartDev kp = fp.key_parts[j];
-        const bool is_null = kp.null_shift >= 0 && ((kb >> kp.null_shift) & 1);
-        store_narrow(fp.out_keys[j], o, kp.dtype, is_null ? 0 : ((kb >> kp.shift) & kp.mask));
+        const uint64_t w = (kp.shift >> 6) ? kb_hi : kb;
+        const bool is_null = kp.null_shift >= 0 && ((w >> (kp.null_shift & 63)) & 1);
+        store_narrow(fp.out_keys[j], o, kp.dtype, is_null ? 0 : ((w >> (kp.shift & 63)) & kp.mask));
         if (fp.out_keys_valid[j]) fp.out_keys_valid[j][o] = is_null ? 0 : 1;
       }
     } else if (fp.key_dtype >= 0) {

@@ -140,6 +140,8 @@ struct TableDev {
   int32_t n_single;
   int32_t n_words;
   int32_t probe_limit;             // buckets examined before a row is sent to the overflow list
+  int32_t key_words;               // 1: 64-bit keys, buckets of 4; 2: 128-bit packed keys (HashMethodKeysU128,
+                                   // kernels/group_by.rs:66-79): keys[2 i], keys[2 i + 1], buckets of 2 = one sector
   unsigned long long* n_groups;    // device counter: groups inserted so far
   unsigned long long* n_overflow;  // device counter
   uint32_t* overflow_rows;         // rows that could not be placed (nullptr: provably not needed)
@@ -155,8 +157,8 @@ __host__ __device__ __forceinline__ uint64_t* word_ptr(const TableDev& t, int64_
 // NULL value contributes zero value bits, so (NULL, x) and (0, x) stay different groups.
 struct KeyPartDev {
   int32_t slot;        // input slot of the column
-  int32_t shift;       // bit position of the value field
-  int32_t null_shift;  // bit position of the NULL flag, -1: column is not Nullable
+  int32_t shift;       // bit position of the value field (0..127: word = shift >> 6; a field never straddles words)
+  int32_t null_shift;  // bit position of the NULL flag (same word as the value), -1: column is not Nullable
   int32_t dtype;
   uint64_t mask;       // value field mask (unshifted)
 };

@@ -453,9 +453,80 @@ def test_multi_column_group_keys(gpu, device_resident):
 
 def test_multi_column_keys_too_wide_is_loud(gpu):
     from databend_b200.lib import DbxError
-    blk = DataBlock([Column.from_data(np.arange(4, dtype=np.int64)), Column.from_data(np.arange(4, dtype=np.int64))])
-    with pytest.raises(DbxError, match="128-bit"):
-        TransformPartialAggregate(AggregatorParams([0, 1], [("count", None)]), schema_types(blk))
+    cols = [Column.from_data(np.arange(4, dtype=np.int64)) for _ in range(3)]
+    blk = DataBlock(cols)
+    with pytest.raises(DbxError, match="wider than 128 bits"):
+        TransformPartialAggregate(AggregatorParams([0, 1, 2], [("count", None)]), schema_types(blk))
+    # 128 value bits + one NULL flag do not fit either
+    blk2 = DataBlock([cols[0], Column.from_data(np.arange(4, dtype=np.int64), validity=[True, False, True, True])])
+    with pytest.raises(DbxError, match="wider than 128 bits"):
+        TransformPartialAggregate(AggregatorParams([0, 1], [("count", None)]), schema_types(blk2))
+
+
+def _check_multi_key(blk, key_cols, params, filt, key_dtypes, n_partials=1, split=None, device_resident=False, expected_groups=None):
+    blocks = blk.split_by_rows(split) if split else [blk]
+    if device_resident:
+        blocks = [DataBlock([to_device(col) for col in bb.columns], bb.num_rows) for bb in blocks]
+    out = filter_group_aggregate(blocks, params, filt, input_types=schema_types(blk), n_partials=n_partials)
+    keys, kvalid, aggs, avalid, _ = oracle().filter_group_agg(blk, params.to_c(filt), threads=4)
+    exp = _group_dict([k.view(np.int64) for k in keys], kvalid, aggs, avalid)
+    na, nk = len(params.aggregate_functions), len(key_cols)
+    gk = [out.columns[na + j] for j in range(nk)]
+    assert [k.dtype for k in gk] == key_dtypes
+    got = _group_dict([k.values().astype(np.int64) if k.dtype != abi.U64 else k.values().view(np.int64) for k in gk], [k.valid_mask() for k in gk],
+                      [out.columns[i].values() for i in range(na)], [out.columns[i].valid_mask() for i in range(na)])
+    assert got.keys() == exp.keys()
+    for k in exp:
+        assert got[k] == exp[k], (k, got[k], exp[k])
+    if expected_groups is not None:
+        assert len(exp) == expected_groups
+    return exp
+
+
+@pytest.mark.parametrize("device_resident", [False, True])
+def test_wide_128_bit_group_keys(gpu, device_resident):
+    """GROUP BY keys that need 65..128 bits are packed into TWO key words (HashMethodKeysU128,
+    kernels/group_by.rs:66-79): buckets of two 16-byte keys, one 128-bit compare-and-swap per new
+    group.  (Int64, Nullable(Int32), Int16) = 113 bits, with a filter, several partials and host /
+    device blocks; then (Int64, UInt64) = exactly 128 bits including the key whose two words both
+    equal the EMPTY pattern, and a table that has to grow from a tiny size hint."""
+    rng = np.random.default_rng(123)
+    n = 400_000
+    a = rng.integers(-2**62, 2**62, 300).astype(np.int64)[rng.integers(0, 300, n)]
+    b = rng.integers(-4, 4, n).astype(np.int32)
+    c = rng.integers(0, 3, n).astype(np.int16)
+    v = rng.integers(-2**40, 2**40, n).astype(np.int64)
+    x = rng.integers(0, 1 << 20, n).astype(np.float64)
+    blk = DataBlock([Column.from_data(a), Column.from_data(b, validity=rng.random(n) > 0.1), Column.from_data(c), Column.from_data(v),
+                     Column.from_data(x, validity=rng.random(n) > 0.2)])
+    params = AggregatorParams([0, 1, 2], [("sum", 3), ("count", None), ("avg", 4), ("min", 3), ("max", 4)])
+    exp = _check_multi_key(blk, [0, 1, 2], params, E.ne(E.col(3) % E.lit(5), E.lit(0)), [abi.I64, abi.I32, abi.I16],
+                           n_partials=2, split=90_001, device_resident=device_resident)
+    assert any(k[1] is None for k in exp) and any(k[1] == 0 for k in exp)
+    # exactly 128 bits, 200k distinct groups: growth from the default size, the EMPTY-pattern key
+    m = 500_000
+    k0 = rng.integers(0, 200_000, m).astype(np.int64) * 1_000_003
+    k1 = (k0.astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)) ^ np.uint64(12345)
+    k0[:7] = np.int64(-2**63)
+    k1[:7] = np.uint64(2**63)
+    k0[7:9] = np.int64(-2**63)   # same first word, different second word: a different group
+    k1[7:9] = np.uint64(5)
+    blk2 = DataBlock([Column.from_data(k0), Column.from_data(k1), Column.from_data(rng.integers(-100, 100, m).astype(np.int64))])
+    params2 = AggregatorParams([0, 1], [("sum", 2), ("count", None)], expected_groups=64)
+    exp2 = _check_multi_key(blk2, [0, 1], params2, None, [abi.I64, abi.U64], split=65536, device_resident=device_resident)
+    assert exp2[(-2**63, -2**63)][1] == 7 and exp2[(-2**63, 5)][1] == 2
+
+
+def test_wide_keys_do_not_cross_the_row_exchange(gpu):
+    """The exchange / spill rows carry 64-bit keys: asking for them with 128-bit keys is an error, not a wrong answer."""
+    from databend_b200.lib import DbxError
+    blk = DataBlock([Column.from_data(np.arange(10, dtype=np.int64)), Column.from_data(np.arange(10, dtype=np.int64))])
+    part = TransformPartialAggregate(AggregatorParams([0, 1], [("count", None)]), schema_types(blk))
+    part.transform(blk)
+    part.on_finish()
+    with pytest.raises(DbxError, match="128-bit packed group keys"):
+        part.serialize()
+    part.close()
 
 
 @pytest.mark.parametrize("lanes", [None, "FFFFFFFF", "00000000", "55555555", "0000FFFF"])
