@@ -73,6 +73,7 @@ struct AggPlan {
   bool use_ring = true;      // ring kernel for the straight-line case with pairs
   bool l2_persist = true;    // persisting L2 access-policy window over the table
   int debug_flags = 0;
+  bool hot_cache = false;    // per-CTA shared-memory cache of hot groups (skewed keys); DBX_AGG_HOT=0 turns it off
 
   int slot_of(int col, ErrorSink* err) {
     for (int s = 0; s < n_slots; ++s)
@@ -414,6 +415,8 @@ int32_t build_plan(const dbx_agg_params* p, const int32_t* types, int32_t n_cols
   pl->bulk_lanes = getenv("DBX_AGG_BULK_LANES") ? (uint32_t)strtoul(getenv("DBX_AGG_BULK_LANES"), nullptr, 16) : kDefaultBulkLanes;
   pl->use_ring = !(getenv("DBX_AGG_RING") && atoi(getenv("DBX_AGG_RING")) == 0);
   pl->debug_flags = getenv("DBX_AGG_DEBUG") ? atoi(getenv("DBX_AGG_DEBUG")) : 0;
+  pl->hot_cache = pl->grouped && pl->key_words == 1 && pl->n_pairs == 0 && pl->n_words <= kHotWords &&
+                  !(getenv("DBX_AGG_HOT") && atoi(getenv("DBX_AGG_HOT")) == 0);
   pl->l2_persist = !(getenv("DBX_AGG_L2_PERSIST") && atoi(getenv("DBX_AGG_L2_PERSIST")) == 0);
   return DBX_OK;
 }
@@ -516,6 +519,14 @@ inline int64_t next_pow2(int64_t x) {
 
 }  // namespace
 
+// sizeof(StageWarp<NS>) for a run-time slot count
+static size_t kMaxSlotsStageBytes(int ns) {
+  switch (ns) {
+    case 1: return sizeof(StageWarp<1>); case 2: return sizeof(StageWarp<2>); case 3: return sizeof(StageWarp<3>); case 4: return sizeof(StageWarp<4>);
+    case 5: return sizeof(StageWarp<5>); case 6: return sizeof(StageWarp<6>); case 7: return sizeof(StageWarp<7>); default: return sizeof(StageWarp<8>);
+  }
+}
+
 // ================================================================ partial
 class AggPartialOp : public Op {
  public:
@@ -569,14 +580,27 @@ class AggPartialOp : public Op {
     StaticPlan sp;
     memset(&sp, 0, sizeof(sp));
     sp.n_nodes = plan.n_nodes; sp.n_updates = plan.n_updates; sp.key_slot = plan.key_slot; sp.key_is_float = plan.key_is_float ? 1 : 0;
-    sp.n_key_parts = plan.n_key_parts; sp.debug_flags = plan.debug_flags; sp.n_single = plan.n_words;
+    sp.n_key_parts = plan.n_key_parts; sp.debug_flags = plan.debug_flags; sp.n_single = plan.n_words; sp.hot_cache = plan.hot_cache ? 1 : 0;
     memcpy(sp.nodes, plan.nodes, sizeof(PredNodeDev) * plan.n_nodes);
     memcpy(sp.upd, plan.upd, sizeof(UpdateDev) * plan.n_updates);
     for (int u = 0; u < plan.n_updates; ++u) sp.upd[u].ridx = plan.upd[u].word;  // no pairs: entry index == word index
     memcpy(sp.key_parts, plan.key_parts, sizeof(plan.key_parts));
     std::string why;
-    if (agg_jit_get(agg_jit_plan_text(sp), plan.n_slots, &jit, &why)) jit_status = "specialised";
-    else { jit = AggJitKernels(); jit_status = "precompiled kernels (" + why + ")"; }
+    if (!agg_jit_get(agg_jit_plan_text(sp), plan.n_slots, &jit, &why)) { jit = AggJitKernels(); jit_status = "precompiled kernels (" + why + ")"; return; }
+    // the row stages of 5+ slots exceed the 48 KB default: opt the specialised kernels in on this device
+    const size_t smem = (((size_t)(kMaxSlotsStageBytes(plan.n_slots)) * kWarpsPerBlock + 15) & ~(size_t)15) + kHotBytes;
+    cudaError_t ce = cudaSuccess;
+    if (smem > 48 * 1024) {
+      ce = cudaKernelSetAttributeForDevice(jit.fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem, device);
+      if (ce == cudaSuccess) ce = cudaKernelSetAttributeForDevice(jit.gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem, device);
+    }
+    if (ce != cudaSuccess) {
+      cudaGetLastError();
+      jit = AggJitKernels();
+      jit_status = std::string("precompiled kernels (shared-memory opt-in of the specialised kernel failed: ") + cudaGetErrorString(ce) + ")";
+      return;
+    }
+    jit_status = "specialised";
   }
 
   // Pin the hash table in L2 while the column stream passes through: a persisting access-policy
@@ -692,7 +716,7 @@ class AggPartialOp : public Op {
     if (device < 0 || device >= 64) { err.set("device index out of range"); return DBX_ERR_INVALID; }
     const size_t smem_rows = (sizeof(StageWarp<NS>) * kWarpsPerBlock + 15) & ~(size_t)15;
     const size_t smem_bulk = (size_t)kWarpsPerBlock * kBulkGen * kMaxPairs * 32 * 16;
-    const size_t smem = smem_rows + (BULK ? smem_bulk : 0);
+    const size_t smem = smem_rows + (BULK ? smem_bulk : kHotBytes);  // the hot-group cache sits where the bulk staging would
     auto kern = filter_group_agg_kernel<NS, FAST, INDIRECT, BULK, MINB>;
     if (!attr_set[device]) {
       DBX_CUDA_TRY(err, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -931,6 +955,7 @@ class AggPartialOp : public Op {
       ring_ok = safe;  // the ring kernel does not record overflow rows
       if (safe) {
         kp.table = table.view(nullptr);
+        kp.hot_cache = plan.hot_cache ? 1 : 0;  // only when no row can fail to be placed (the cache merges groups, not rows)
         DBX_TRY(launch_grouped(kp, false));
         rows_since_read += m;
         continue;

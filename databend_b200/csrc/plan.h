@@ -186,13 +186,14 @@ struct AggKernelParams {
   // the predicate (key parts + arguments of unpaired updates) and where they are stored in the ring
   int32_t ring_nsv;                 // number of stored slot arrays
   int8_t ring_sidx[kMaxSlots];      // slot -> storage index, -1: not stored
+  int32_t hot_cache;                // 1: per-CTA shared-memory cache of hot groups (skewed keys), flushed at kernel end
 };
 
 // The plan fields the fused kernels read per row, as ONE constexpr object: a run-time specialised
 // build (agg_jit.cu) emits `__device__ constexpr StaticPlan jit_plan = {...}` from the operator's
 // plan, and agg_kernels.cuh reads `jit_plan.f` where the precompiled kernels read `p.f`.
 struct StaticPlan {
-  int32_t n_nodes, n_updates, key_slot, key_is_float, n_key_parts, debug_flags, n_single;
+  int32_t n_nodes, n_updates, key_slot, key_is_float, n_key_parts, debug_flags, n_single, hot_cache;
   PredNodeDev nodes[DBX_MAX_PRED_NODES];
   UpdateDev upd[kMaxUpdates];
   KeyPartDev key_parts[DBX_MAX_GROUP_COLS];

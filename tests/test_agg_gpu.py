@@ -695,3 +695,32 @@ def test_small_pinned_host_blocks_gathered_by_the_device(gpu, monkeypatch, gathe
     finally:
         for p in ptrs:
             L.dbx_host_free(p)
+
+
+@pytest.mark.parametrize("hot", ["1", "0"])
+def test_skewed_keys_hot_group_cache(gpu, monkeypatch, hot):
+    """Heavily skewed keys (P(k) ~ 1/k, one key on half of the rows, and only 3 distinct keys): groups
+    that repeat inside a warp's 32 rows are accumulated in a per-CTA shared-memory cache and merged
+    into the table at the end of the kernel.  Same answer as the oracle with the cache (default) and
+    without it (DBX_AGG_HOT=0), for every update kind (sum / count / avg / min / max, nullable
+    arguments, nullable and sentinel-valued keys), device and host blocks."""
+    if hot == "0":
+        monkeypatch.setenv("DBX_AGG_HOT", "0")
+    rng = np.random.default_rng(11)
+    n = 2_000_000
+    for variant in ("log_uniform", "half_one_key", "three_keys"):
+        if variant == "log_uniform":
+            k = np.minimum((np.exp(rng.random(n) * np.log(1e6)) - 1).astype(np.int64), 999_999)
+        elif variant == "half_one_key":
+            k = np.where(rng.random(n) < 0.5, np.int64(-2**63), rng.integers(0, 100_000, n).astype(np.int64))
+        else:
+            k = rng.integers(0, 3, n).astype(np.int64)
+        kcol = Column.from_data(k, validity=rng.random(n) > 0.02)
+        v = Column.from_data(rng.integers(-2**40, 2**40, n).astype(np.int64), validity=rng.random(n) > 0.25)
+        x = Column.from_data(rng.integers(0, 1 << 20, n).astype(np.float64))
+        f = Column.from_data((rng.integers(-500, 500, n) * 0.25).astype(np.float32), validity=rng.random(n) > 0.5)
+        blk = DataBlock([kcol, v, x, f])
+        params = AggregatorParams([0], [("sum", 1), ("count", None), ("count", 1), ("avg", 2), ("min", 1), ("max", 3), ("min", 3), ("max", 1)])
+        filt = E.ne(E.col(2) % E.lit(7), E.lit(0))
+        run_both(blk, params, filt, device_resident=True)
+        run_both(blk, params, filt, split=300_000, n_partials=2)
