@@ -494,6 +494,8 @@ struct DeviceTable {
     t.n_groups = n_groups();
     t.n_overflow = n_overflow();
     t.overflow_rows = overflow_rows;
+    t.hot_spill = nullptr;
+    t.n_hot_spill = (unsigned long long*)counters.p + 2;
     t.probe_limit = (int32_t)std::min<int64_t>(kProbeLimit, cap >> (key_words == 2 ? 1 : 2));
     return t;
   }
@@ -657,11 +659,14 @@ class AggPartialOp : public Op {
     return DBX_OK;
   }
 
+  unsigned long long hot_spilled = 0;  // read_counters: groups the hot-group caches could not place
+  DevBuf hot_spill;
   int32_t read_counters(unsigned long long* n_groups, unsigned long long* n_overflow) {
-    DBX_CUDA_TRY(err, cudaMemcpyAsync(host_counters.p, table.counters.p, 16, cudaMemcpyDeviceToHost, stream));
+    DBX_CUDA_TRY(err, cudaMemcpyAsync(host_counters.p, table.counters.p, 24, cudaMemcpyDeviceToHost, stream));
     DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
     *n_groups = ((unsigned long long*)host_counters.p)[0];
     *n_overflow = ((unsigned long long*)host_counters.p)[1];
+    hot_spilled = ((unsigned long long*)host_counters.p)[2];
     groups_known = (int64_t)*n_groups;
     rows_since_read = 0;
     return DBX_OK;
@@ -724,7 +729,8 @@ class AggPartialOp : public Op {
     }
     int grid = grid_for_rows(kp.n_rows);
     static const int per_sm = getenv("DBX_AGG_GRID") ? atoi(getenv("DBX_AGG_GRID")) : 0;
-    if (per_sm > 0) grid = (int)std::max<int64_t>(1, std::min<int64_t>((kp.n_rows + kTileRows - 1) / kTileRows, (int64_t)kNumSMs * per_sm));
+    if (per_sm > 0 && !(kp.table.hot_spill && per_sm > 8))  // the spill buffer of the hot-group caches is sized for 8 CTAs per SM
+      grid = (int)std::max<int64_t>(1, std::min<int64_t>((kp.n_rows + kTileRows - 1) / kTileRows, (int64_t)kNumSMs * per_sm));
     if (!BULK && !INDIRECT && jit.ok()) {  // same grid, block and shared memory: only the code differs
       void* args[] = {(void*)&kp};
       const cudaError_t ce = cudaLaunchKernel((const void*)(FAST ? jit.fast : jit.gen), dim3(grid), dim3(kBlock), args, smem, stream);
@@ -962,9 +968,16 @@ class AggPartialOp : public Op {
       }
       DBX_CUDA_TRY(err, ovf[0].ensure((size_t)m * 4));
       kp.table = table.view((uint32_t*)ovf[0].p);
+      if (plan.hot_cache) {  // groups a full table refuses at the end of the kernel come back as rows (merged below)
+        const size_t row_bytes = (size_t)(2 + plan.n_words) * 8;
+        DBX_CUDA_TRY(err, hot_spill.ensure((size_t)kNumSMs * 8 * kHotSlots * row_bytes));
+        kp.table.hot_spill = (uint64_t*)hot_spill.p;
+        kp.hot_cache = 1;
+      }
       DBX_TRY(launch_grouped(kp, false));
       unsigned long long ng = 0, no = 0;
       DBX_TRY(read_counters(&ng, &no));
+      const unsigned long long n_spilled = hot_spilled;
       int cur = 0;
       while (no > 0) {  // rows whose group did not fit: grow and replay just those rows
         int64_t want = next_pow2(std::max<int64_t>(table.cap * 4, 2 * (int64_t)ng));
@@ -978,6 +991,15 @@ class AggPartialOp : public Op {
         DBX_TRY(launch_grouped(kr, true));
         cur ^= 1;
         DBX_TRY(read_counters(&ng, &no));
+      }
+      if (n_spilled) {  // cached groups that found the table full: merge them now that it has room
+        if (((int64_t)ng + (int64_t)n_spilled) * 2 > table.cap) DBX_TRY(grow_to(next_pow2(4 * ((int64_t)ng + (int64_t)n_spilled))));
+        DBX_CUDA_TRY(err, cudaMemsetAsync((unsigned long long*)table.counters.p + 2, 0, 8, stream));
+        rows_merge_kernel<<<grid_for_entries((int64_t)n_spilled), 256, 0, stream>>>((const uint64_t*)hot_spill.p, (int64_t)n_spilled, table.view(nullptr), plan.kinds);
+        count_launch();
+        DBX_CUDA_TRY(err, cudaGetLastError());
+        DBX_TRY(read_counters(&ng, &no));
+        if (no) { err.set("internal: aggregate table overflow while merging cached groups"); return DBX_ERR_CUDA; }
       }
       if ((int64_t)ng * 2 > table.cap) DBX_TRY(grow_to(next_pow2(4 * (int64_t)ng)));
     }

@@ -674,8 +674,14 @@ __device__ __forceinline__ void filter_group_agg_body(const AggKernelParams& p) 
       const u64x4 kb = ld_bucket(t.keys + 4 * b);
       const int m = bucket_match(kb, key);
       const int64_t slot = m >= 0 ? 4 * b + m : find_or_insert_slow(t, key, b, kb, new_groups);
-      if (slot < 0) { atomicAdd(t.n_overflow, 1ULL); continue; }  // cannot happen below the load-factor budget; loud if it does
       const uint64_t* hw = hot + kHotSlots + (size_t)e * kHotWords;
+      if (slot < 0) {  // table full: hand the group to the host, which merges it after growing the table
+        if (!t.hot_spill) { atomicAdd(t.n_overflow, 1ULL); continue; }
+        uint64_t* row = t.hot_spill + atomicAdd(t.n_hot_spill, 1ULL) * (unsigned long long)(2 + t.n_words);
+        row[0] = key; row[1] = 0;
+        for (int w = 0; w < t.n_words; ++w) row[2 + w] = hw[w];
+        continue;
+      }
       PLN_UNROLL
       for (int u = 0; u < PLN(n_updates); ++u) {
         const UpdateDev ud = PLN(upd[u]);

@@ -145,6 +145,10 @@ struct TableDev {
   unsigned long long* n_groups;    // device counter: groups inserted so far
   unsigned long long* n_overflow;  // device counter
   uint32_t* overflow_rows;         // rows that could not be placed (nullptr: provably not needed)
+  // groups of a CTA's hot-group cache that could not be placed when the cache was merged (table full):
+  // exchange-format rows [key][0][words...], merged by the host after the table has grown
+  uint64_t* hot_spill;             // nullptr: a failed merge is counted in n_overflow (cannot happen below the load-factor budget)
+  unsigned long long* n_hot_spill;
 };
 
 __host__ __device__ __forceinline__ uint64_t* word_ptr(const TableDev& t, int64_t slot, int w) {

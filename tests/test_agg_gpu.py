@@ -724,3 +724,8 @@ def test_skewed_keys_hot_group_cache(gpu, monkeypatch, hot):
         filt = E.ne(E.col(2) % E.lit(7), E.lit(0))
         run_both(blk, params, filt, device_resident=True)
         run_both(blk, params, filt, split=300_000, n_partials=2)
+        # a table far too small for the groups: rows overflow and are replayed, cached groups that find
+        # the table full come back as rows and are merged after it has grown
+        tiny = AggregatorParams(params.group_columns, params.aggregate_functions, expected_groups=16)
+        run_both(blk, tiny, filt, device_resident=True)
+        run_both(blk, tiny, filt, split=700_000)
