@@ -90,16 +90,19 @@ class EvalError(DbxError):
         self.row = row
 
 
-def eval_scalar(block: DataBlock, e: SExpr, device: int = 0) -> Tuple[Column, int]:
-    """Evaluator::run(expr) over `block` -> (result column, its dtype | NULLABLE flag)."""
+def eval_scalar(block: DataBlock, e: SExpr, device: int = 0, out_mem: int = abi.MEM_HOST):
+    """Evaluator::run(expr) over `block` -> (result column, its dtype | NULLABLE flag).  With
+    out_mem = MEM_DEVICE the result stays in HBM: (library-owned dbx_block to release, dtype)."""
     from .transforms import _block_from_c
     ce = flatten(e)
     b, keep = block.as_c()
     out = abi.Block()
     odt, erow = C.c_int32(0), C.c_int64(-1)
-    st = load().dbx_eval_scalar(device, C.byref(ce), C.byref(b), abi.MEM_HOST, C.byref(out), C.byref(odt), C.byref(erow))
+    st = load().dbx_eval_scalar(device, C.byref(ce), C.byref(b), out_mem, C.byref(out), C.byref(odt), C.byref(erow))
     if st != abi.OK:
         msg = (load().dbx_last_error(None) or b"").decode("utf-8", "replace")
         raise EvalError(st, msg, erow.value)
+    if out_mem != abi.MEM_HOST:
+        return out, odt.value
     res = _block_from_c(out, device)
     return res.columns[0], odt.value
