@@ -109,6 +109,9 @@ class AggParams(C.Structure):
     ]
 
 
+MAX_SORT_KEYS = 4
+
+
 class TopkParams(C.Structure):
     _fields_ = [
         ("key_col", C.c_int32),
@@ -116,6 +119,10 @@ class TopkParams(C.Structure):
         ("nulls_first", C.c_int32),
         ("reserved", C.c_int32),
         ("limit", C.c_int64),
+        ("n_extra_keys", C.c_int32),
+        ("extra_key_cols", C.c_int32 * (MAX_SORT_KEYS - 1)),
+        ("extra_asc", C.c_int32 * (MAX_SORT_KEYS - 1)),
+        ("extra_nulls_first", C.c_int32 * (MAX_SORT_KEYS - 1)),
     ]
 
 

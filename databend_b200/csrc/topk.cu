@@ -446,17 +446,27 @@ __global__ void __launch_bounds__(256) sort_ingest_kernel(const __grid_constant_
     const uint64_t v = ok ? load_widened(col, i, pol) : 0;
     ord[row_base + i] = ok ? key_to_ord(v, cls, asc != 0) : 0;  // NULL rows: placed by the extra pass on the flag
     rid[row_base + i] = (uint32_t)(row_base + i) | (ok ? 0u : 0x80000000u);
-    bits[row_base + i] = v;
+    if (bits) bits[row_base + i] = v;
     nulls += !ok;
     if (ok && cls == VC_FLT) {
       const double d = __longlong_as_double((long long)v);
       lossy |= (d != d && v != 0x7FF8000000000000ULL) || (d == 0.0 && (v >> 63));
     }
   }
-  if (__any_sync(0xffffffffu, lossy) && (threadIdx.x & 31) == 0) *inexact = 1;
+  if (inexact && __any_sync(0xffffffffu, lossy) && (threadIdx.x & 31) == 0) *inexact = 1;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) nulls += __shfl_xor_sync(0xffffffffu, nulls, o);
   if ((threadIdx.x & 31) == 0 && nulls) atomicAdd(n_null, (unsigned long long)nulls);
+}
+// Multi-column ORDER BY: the keys of column c in the order the less significant columns have
+// established so far (perm = sorted row id | flag of the previous step; nullptr = input order).
+__global__ void __launch_bounds__(256) sort_gather_kernel(const uint64_t* ord_c, const uint32_t* rid_c, const uint32_t* perm, int64_t n,
+                                                          uint64_t* o_ord, uint32_t* o_rid) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t r = perm ? (perm[i] & 0x7FFFFFFFu) : (uint32_t)i;
+    o_ord[i] = ord_c[r];
+    o_rid[i] = r | (rid_c[r] & 0x80000000u);
+  }
 }
 struct SortEmitArgs {
   const uint32_t* rid;   // sorted: row id | NULL flag
@@ -514,6 +524,11 @@ class TopkOp : public Op {
   // ---- full-sort mode
   DevBuf s_ord[2], s_rid[2], s_bits;
   int64_t s_cap = 0;
+  // further sort keys (ORDER BY a, b, ...): ordered images and row id | NULL flag per key, in input order
+  int n_extra = 0;
+  int x_dtype[DBX_MAX_SORT_KEYS - 1] = {}, x_cls[DBX_MAX_SORT_KEYS - 1] = {};
+  bool x_nullable[DBX_MAX_SORT_KEYS - 1] = {};
+  DevBuf x_ord[DBX_MAX_SORT_KEYS - 1], x_rid[DBX_MAX_SORT_KEYS - 1], x_cnt, w_ord[2], w_rid[2];
   std::unique_ptr<OwnedBlock> result;
   bool pulled = false;
 
@@ -528,6 +543,18 @@ class TopkOp : public Op {
     if (dtype_size(key_dtype) == 0) { err.set("top-k: key must be a numeric column"); return DBX_ERR_UNSUPPORTED; }
     cls = key_dtype == DBX_U64 ? VC_UINT : (dtype_class(key_dtype) == VC_FLT ? VC_FLT : VC_INT);
     full_sort = p->limit == 0 || p->limit > (1 << 22);  // no LIMIT (or one too large for the candidate list): sort everything
+    n_extra = p->n_extra_keys;
+    if (n_extra < 0 || n_extra > DBX_MAX_SORT_KEYS - 1) { err.set("sort: at most 4 sort keys"); return DBX_ERR_INVALID; }
+    for (int j = 0; j < n_extra; ++j) {
+      const int c = p->extra_key_cols[j];
+      if (c < 0 || c >= n) { err.set("sort: key column outside the input schema"); return DBX_ERR_INVALID; }
+      x_dtype[j] = types[c] & 0xFF;
+      x_nullable[j] = (types[c] & DBX_NULLABLE) != 0;
+      if (dtype_size(x_dtype[j]) == 0) { err.set("sort: keys must be numeric columns"); return DBX_ERR_UNSUPPORTED; }
+      x_cls[j] = x_dtype[j] == DBX_U64 ? VC_UINT : (dtype_class(x_dtype[j]) == VC_FLT ? VC_FLT : VC_INT);
+    }
+    if (n_extra > 0) full_sort = true;  // several keys: sort everything, LIMIT cuts the sorted result
+    DBX_CUDA_TRY(err, x_cnt.ensure(64));
     DBX_TRY(stager.init(dev, stream, &err));
     DBX_CUDA_TRY(err, host.ensure(256));
     DBX_CUDA_TRY(err, state.ensure(8 * ST_WORDS * 3 + 64));
@@ -555,6 +582,7 @@ class TopkOp : public Op {
   int32_t reset() override {
     topk_reset_kernel<<<1, 32, 0, stream>>>((unsigned long long*)state.p);  // count 0, boundary = everything passes
     count_launch();
+    DBX_CUDA_TRY(err, cudaMemsetAsync(x_cnt.p, 0, 64, stream));
     DBX_CUDA_TRY(err, cudaGetLastError());
     count_ub = null_ub = 0;
     rows_seen = 0;
@@ -731,6 +759,7 @@ class TopkOp : public Op {
     DBX_TRY(grow(s_ord[0], 8, true));
     DBX_TRY(grow(s_rid[0], 4, true));
     DBX_TRY(grow(s_bits, 8, true));
+    for (int j = 0; j < n_extra; ++j) { DBX_TRY(grow(x_ord[j], 8, true)); DBX_TRY(grow(x_rid[j], 4, true)); }
     s_cap = ncap;
     return DBX_OK;
   }
@@ -755,6 +784,17 @@ class TopkOp : public Op {
                                                          (unsigned long long*)state.p + ST_WORDS + ST_OVERFLOW);
       count_launch();
       DBX_CUDA_TRY(err, cudaGetLastError());
+      for (int j = 0; j < n_extra; ++j) {
+        const dbx_column& xc = b->cols[prm.extra_key_cols[j]];
+        if (xc.dtype != x_dtype[j] || xc.len != n || xc.is_const) { err.set("push: sort key column does not match the input schema (constant keys unsupported)"); return DBX_ERR_INVALID; }
+        if (xc.validity && !x_nullable[j]) { err.set("push: validity bitmap on a key column declared non-nullable"); return DBX_ERR_INVALID; }
+        DevCol xcol;
+        DBX_TRY(stager.stage(xc, 1 + j, &xcol));
+        sort_ingest_kernel<<<grid_1d(n), 256, 0, stream>>>(xcol, n, rows_seen, x_cls[j], prm.extra_asc[j], (uint64_t*)x_ord[j].p, (uint32_t*)x_rid[j].p,
+                                                           nullptr, (unsigned long long*)x_cnt.p + j, nullptr);
+        count_launch();
+        DBX_CUDA_TRY(err, cudaGetLastError());
+      }
     } else {
       DBX_TRY(push_topk(col, n));
     }
@@ -780,28 +820,59 @@ class TopkOp : public Op {
     const int64_t n_nulls = (int64_t)((unsigned long long*)host.p)[ST_COUNT];
     const bool needs_gather = ((unsigned long long*)host.p)[ST_OVERFLOW] != 0;  // a -0.0 or a NaN with a payload was ingested
     int buf = 0;
-    if (n > 1) {
+    const uint64_t* sorted_ord = nullptr;
+    const uint32_t* sorted_rid = nullptr;
+    if (n_extra > 0 && n > 1) {
+      // least significant key first; every step is a STABLE sort of (key image, row id) in the order
+      // the previous steps established, so earlier keys dominate and input order breaks the last ties
+      unsigned long long xn[DBX_MAX_SORT_KEYS] = {};
+      DBX_CUDA_TRY(err, cudaMemcpyAsync(xn, x_cnt.p, 8 * (DBX_MAX_SORT_KEYS - 1), cudaMemcpyDeviceToHost, stream));
+      DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
+      for (int i = 0; i < 2; ++i) { DBX_CUDA_TRY(err, w_ord[i].ensure((size_t)n * 8)); DBX_CUDA_TRY(err, w_rid[i].ensure((size_t)n * 4)); }
+      int res = 1;  // which work pair holds the current order (none yet: the first gather goes to pair 0)
+      const uint32_t* perm = nullptr;
+      for (int c = n_extra - 1; c >= -1; --c) {
+        const uint64_t* col_ord = c >= 0 ? (const uint64_t*)x_ord[c].p : (const uint64_t*)s_ord[0].p;
+        const uint32_t* col_rid = c >= 0 ? (const uint32_t*)x_rid[c].p : (const uint32_t*)s_rid[0].p;
+        const int64_t c_nulls = c >= 0 ? (int64_t)xn[c] : n_nulls;
+        const int c_nulls_first = c >= 0 ? prm.extra_nulls_first[c] : prm.nulls_first;
+        const int in = res ^ 1;
+        sort_gather_kernel<<<grid_1d(n), 256, 0, stream>>>(col_ord, col_rid, perm, n, (uint64_t*)w_ord[in].p, (uint32_t*)w_rid[in].p);
+        count_launch();
+        DBX_CUDA_TRY(err, cudaGetLastError());
+        int rb = 0;
+        DBX_TRY(sorter.sort(err, stream, (uint64_t*)w_ord[in].p, (uint64_t*)w_ord[in ^ 1].p, (uint32_t*)w_rid[in].p, (uint32_t*)w_rid[in ^ 1].p, n, 0,
+                            64, c_nulls > 0, c_nulls_first, c_nulls, &rb));
+        res = rb ? (in ^ 1) : in;
+        perm = (const uint32_t*)w_rid[res].p;
+      }
+      sorted_ord = (const uint64_t*)w_ord[res].p;
+      sorted_rid = (const uint32_t*)w_rid[res].p;
+    } else if (n > 1) {
       DBX_CUDA_TRY(err, s_ord[1].ensure((size_t)s_cap * 8));
       DBX_CUDA_TRY(err, s_rid[1].ensure((size_t)s_cap * 4));
       DBX_TRY(sorter.sort(err, stream, (uint64_t*)s_ord[0].p, (uint64_t*)s_ord[1].p, (uint32_t*)s_rid[0].p, (uint32_t*)s_rid[1].p, n, 0,
                           64, n_nulls > 0, prm.nulls_first, n_nulls, &buf));
     }
+    if (!sorted_ord) { sorted_ord = (const uint64_t*)s_ord[buf].p; sorted_rid = (const uint32_t*)s_rid[buf].p; }
+    const int64_t n_in = n;
+    const int64_t n_out = (n_extra > 0 && prm.limit > 0) ? std::min<int64_t>(n_in, prm.limit) : n_in;
     void *okey = nullptr, *orow = nullptr, *ovb = nullptr, *obits = nullptr;
     const int esz = dtype_size(key_dtype);
-    DBX_TRY(dev_alloc(ob.get(), (size_t)n * esz, &okey));
-    DBX_TRY(dev_alloc(ob.get(), (size_t)n * 8, &orow));
+    DBX_TRY(dev_alloc(ob.get(), (size_t)n_out * esz, &okey));
+    DBX_TRY(dev_alloc(ob.get(), (size_t)n_out * 8, &orow));
     if (key_nullable) {
-      DBX_TRY(dev_alloc(ob.get(), (size_t)n, &ovb));
-      DBX_TRY(dev_alloc(ob.get(), (size_t)(n + 7) / 8 + 8, &obits));
+      DBX_TRY(dev_alloc(ob.get(), (size_t)n_out, &ovb));
+      DBX_TRY(dev_alloc(ob.get(), (size_t)(n_out + 7) / 8 + 8, &obits));
     }
-    if (n) {
+    if (n_out) {
       SortEmitArgs ea;
-      ea.rid = (const uint32_t*)s_rid[buf].p; ea.bits = needs_gather ? (const uint64_t*)s_bits.p : nullptr; ea.n = n; ea.dtype = key_dtype;
-      ea.ord = (const uint64_t*)s_ord[buf].p; ea.cls = cls; ea.asc = prm.asc;
+      ea.rid = sorted_rid; ea.bits = needs_gather ? (const uint64_t*)s_bits.p : nullptr; ea.n = n_out; ea.dtype = key_dtype;
+      ea.ord = sorted_ord; ea.cls = cls; ea.asc = prm.asc;
       ea.out_key = okey; ea.out_row = (int64_t*)orow; ea.out_valid_bytes = (uint8_t*)ovb;
-      sort_emit_kernel<<<grid_1d(n), 256, 0, stream>>>(ea);
+      sort_emit_kernel<<<grid_1d(n_out), 256, 0, stream>>>(ea);
       count_launch();
-      if (key_nullable) { pack_bits_kernel<<<grid_1d((n + 7) / 8), 256, 0, stream>>>((const uint8_t*)ovb, n, (uint8_t*)obits); count_launch(); }
+      if (key_nullable) { pack_bits_kernel<<<grid_1d((n_out + 7) / 8), 256, 0, stream>>>((const uint8_t*)ovb, n_out, (uint8_t*)obits); count_launch(); }
       DBX_CUDA_TRY(err, cudaGetLastError());
     }
     DBX_CUDA_TRY(err, cudaMemcpyAsync(host.p, sorter.meta.p ? (void*)sorter.fail() : state.p, 4, cudaMemcpyDeviceToHost, stream));
@@ -809,11 +880,11 @@ class TopkOp : public Op {
     if (sorter.meta.p && n > 1 && *(unsigned int*)host.p) { err.set("internal: radix sort look-back timed out"); return DBX_ERR_CUDA; }
     dbx_column kcol;
     memset(&kcol, 0, sizeof(kcol));
-    kcol.dtype = key_dtype; kcol.mem = DBX_MEM_DEVICE; kcol.len = n; kcol.data = okey;
-    if (key_nullable) { kcol.validity = (const uint8_t*)obits; kcol.null_count = n_nulls; }
+    kcol.dtype = key_dtype; kcol.mem = DBX_MEM_DEVICE; kcol.len = n_out; kcol.data = okey;
+    if (key_nullable) { kcol.validity = (const uint8_t*)obits; kcol.null_count = n_out == n_in ? n_nulls : -1; }
     dbx_column rcol;
     memset(&rcol, 0, sizeof(rcol));
-    rcol.dtype = DBX_I64; rcol.mem = DBX_MEM_DEVICE; rcol.len = n; rcol.data = orow;
+    rcol.dtype = DBX_I64; rcol.mem = DBX_MEM_DEVICE; rcol.len = n_out; rcol.data = orow;
     ob->cols.push_back(kcol);
     ob->cols.push_back(rcol);
     result = std::move(ob);

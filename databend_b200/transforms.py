@@ -313,9 +313,15 @@ class TransformTopN(_Op):
     (kernels/sort.rs:41-63).  The result block is [key column, row_id Int64] in output order; ties
     are broken by ascending row id."""
 
-    def __init__(self, offset: int, asc: bool, nulls_first: bool, limit: int, input_types: Sequence[int], device: int = 0):
+    def __init__(self, offset: int, asc: bool, nulls_first: bool, limit: int, input_types: Sequence[int], device: int = 0,
+                 extra_keys: Sequence[Tuple[int, bool, bool]] = ()):
+        """extra_keys: further SortColumnDescriptions (offset, asc, nulls_first) that break ties of the
+        earlier keys (ORDER BY a, b, c); the result still is [first key column, row_id]."""
         p = abi.TopkParams()
         p.key_col, p.asc, p.nulls_first, p.limit = offset, int(asc), int(nulls_first), limit
+        p.n_extra_keys = len(extra_keys)
+        for i, (c, a, nf) in enumerate(extra_keys):
+            p.extra_key_cols[i], p.extra_asc[i], p.extra_nulls_first[i] = c, int(a), int(nf)
         super().__init__(abi.OP_TOPK, p, input_types, device)
 
     def transform(self, block: DataBlock) -> List[DataBlock]:

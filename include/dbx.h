@@ -187,12 +187,22 @@ typedef struct dbx_agg_params {
  * (kernels/sort.rs:41-63).  Order: OrderedFloat (NaN greatest, -0 == +0); ties keep row order.
  * limit = 0 (LimitType::None) sorts the whole input (device radix sort, up to 2^30 - 1 rows);
  * 1 <= limit <= 4 Mi runs the streaming top-k.  Result block: [key, row_id Int64]. */
+#define DBX_MAX_SORT_KEYS 4
 typedef struct dbx_topk_params {
   int32_t key_col;
   int32_t asc;
   int32_t nulls_first;
   int32_t reserved;
   int64_t limit;
+  /* ORDER BY key_col, extra_key_cols[0], extra_key_cols[1], ... (SortColumnDescription list,
+   * kernels/sort.rs:43-60): ties on the earlier keys are broken by the later ones, each with its own
+   * direction and NULL placement, and finally by input order.  With extra keys the whole input is
+   * sorted on the device (one stable radix sort per key, least significant first) and `limit` > 0
+   * cuts the sorted result.  Result block: [key (first key), row_id Int64] as for one key. */
+  int32_t n_extra_keys; /* 0 .. DBX_MAX_SORT_KEYS - 1 */
+  int32_t extra_key_cols[DBX_MAX_SORT_KEYS - 1];
+  int32_t extra_asc[DBX_MAX_SORT_KEYS - 1];
+  int32_t extra_nulls_first[DBX_MAX_SORT_KEYS - 1];
 } dbx_topk_params;
 
 /* ------------------------------------------------------------------ join */

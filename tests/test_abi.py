@@ -77,7 +77,7 @@ def test_ctypes_mirror_matches_the_header_field_by_field(tmp_path):
         "dbx_predicate": (abi.Predicate, ["n_nodes", "nodes"]),
         "dbx_agg_desc": (abi.AggDesc, ["kind", "arg_col"]),
         "dbx_agg_params": (abi.AggParams, ["n_group_cols", "group_cols", "n_aggs", "aggs", "filter", "expected_groups"]),
-        "dbx_topk_params": (abi.TopkParams, ["key_col", "asc", "nulls_first", "limit"]),
+        "dbx_topk_params": (abi.TopkParams, ["key_col", "asc", "nulls_first", "limit", "n_extra_keys", "extra_key_cols", "extra_asc", "extra_nulls_first"]),
         "dbx_join_params": (abi.JoinParams, ["kind", "build_key_col", "probe_key_col", "n_build_cols", "expected_build_rows"]),
         "dbx_expr_node": (abi.ExprNode, ["kind", "func", "col", "cast_to", "try_cast", "c"]),
         "dbx_expr": (abi.Expr, ["n_nodes", "nodes"]),

@@ -67,3 +67,23 @@ def test_result_type_table():
     assert eo.t_intdiv("U32", "F64") == "I64" and eo.t_intdiv("U8", "U32") == "U32"
     assert eo.t_modulo("I8", "I8") == "I16" and eo.t_modulo("U16", "U8") == "U8" and eo.t_modulo("U8", "I8") == "U8"
     assert eo.t_negate("U8") == "I16" and eo.t_negate("F32") == "F32" and eo.t_negate("U64") == "I64"
+
+
+def test_sort_oracle_matches_reference_golden_permutations():
+    """oracle/sort_oracle.py (multi-column ORDER BY restatement) on the reference's single-key sort
+    goldens (tests/golden/sort.json, from expression/tests/it/sort.rs)."""
+    import numpy as np
+    from oracle import sort_oracle
+    with open(os.path.join(os.path.dirname(GOLD), "sort.json")) as f:
+        cases = json.load(f)["cases"]
+    np_dt = {"I64": np.int64, "F64": np.float64, "I32": np.int32, "U64": np.uint64, "F32": np.float32}
+    for c in cases:
+        vals = c["values"]
+        valid = None
+        if any(v is None for v in vals):
+            valid = [v is not None for v in vals]
+            vals = [0 if v is None else v for v in vals]
+        arr = np.asarray(vals, dtype=np_dt.get(c["dtype"], np.float64))
+        perm = sort_oracle.sort_permutation([(arr, valid, c["asc"], c["nulls_first"])], c["limit"] or 0)
+        if c.get("rows") is not None:
+            assert perm.tolist() == c["rows"], c["src"]

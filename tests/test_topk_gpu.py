@@ -213,3 +213,46 @@ def test_full_sort_dtypes(gpu, dtype):
         vals = rng.integers(info.min, info.max, n, dtype=nd, endpoint=True)
     for asc in (True, False):
         run_sort(Column.from_data(vals), asc, False, split=77_000)
+
+
+@pytest.mark.parametrize("device_resident", [False, True])
+def test_order_by_several_keys(gpu, device_resident):
+    """ORDER BY a [dir] [nulls], b [dir] [nulls], c: ties on the earlier keys are broken by the later
+    ones (each with its own direction and NULL placement) and finally by input order — one stable
+    device radix sort per key, least significant first.  Row ids must equal the oracle's permutation
+    exactly; with a LIMIT the sorted result is cut."""
+    from oracle import sort_oracle
+    rng = np.random.default_rng(31)
+    n = 300_001
+    a = rng.integers(-3, 4, n).astype(np.int8)
+    av = rng.random(n) > 0.1
+    b = np.where(rng.random(n) < 0.05, np.nan, rng.integers(-2, 3, n) * 0.5)
+    b[rng.random(n) < 0.05] = -0.0
+    bv = rng.random(n) > 0.15
+    c = rng.integers(0, 2**64, n, dtype=np.uint64) >> np.uint64(58)
+    d = rng.standard_normal(n)
+    blk = DataBlock([Column.from_data(a, validity=av), Column.from_data(b, validity=bv), Column.from_data(c), Column.from_data(d)])
+    blocks = blk.split_by_rows(70_000)
+    if device_resident:
+        blocks = [DataBlock([to_device(col) for col in bb.columns], bb.num_rows) for bb in blocks]
+    for (asc0, nf0), (asc1, nf1), (asc2, nf2), limit in [((True, False), (False, True), (True, False), 0),
+                                                          ((False, True), (True, False), (False, False), 0),
+                                                          ((True, True), (True, True), (True, True), 1234)]:
+        op = TransformTopN(0, asc0, nf0, limit, schema_types(blk), extra_keys=[(1, asc1, nf1), (2, asc2, nf2)])
+        for bb in blocks:
+            op.transform(bb)
+        out = op.on_finish()
+        op.close()
+        exp = sort_oracle.sort_permutation([(a, av, asc0, nf0), (b, bv, asc1, nf1), (c, None, asc2, nf2)], limit)
+        np.testing.assert_array_equal(out.columns[1].values(), exp)
+        np.testing.assert_array_equal(out.columns[0].valid_mask(), av[exp])
+        np.testing.assert_array_equal(out.columns[0].values()[av[exp]], a[exp][av[exp]])
+    # two keys, second one only: every pair of directions on a float key with NaN / -0
+    for asc1 in (True, False):
+        op = TransformTopN(2, True, False, 0, schema_types(blk), extra_keys=[(1, asc1, False)])
+        for bb in blocks:
+            op.transform(bb)
+        out = op.on_finish()
+        op.close()
+        exp = sort_oracle.sort_permutation([(c, None, True, False), (b, bv, asc1, False)])
+        np.testing.assert_array_equal(out.columns[1].values(), exp)
