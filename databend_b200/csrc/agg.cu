@@ -496,6 +496,7 @@ struct DeviceTable {
     t.overflow_rows = overflow_rows;
     t.hot_spill = nullptr;
     t.n_hot_spill = (unsigned long long*)counters.p + 2;
+    t.n_hot_rows = (unsigned long long*)counters.p + 3;
     t.probe_limit = (int32_t)std::min<int64_t>(kProbeLimit, cap >> (key_words == 2 ? 1 : 2));
     return t;
   }
@@ -641,6 +642,7 @@ class AggPartialOp : public Op {
     if (table.cap != initial_cap || !table.keys_p) DBX_TRY(table.create(initial_cap, plan, stream, &err));
     else if (!table_clean) DBX_TRY(table.clear(plan, stream, &err));
     table_clean = false;
+    hot_absorbed_seen = 0;  // the counters were cleared with the table
     DBX_TRY(apply_l2_window());
     table_ready = true;
     groups_known = plan.grouped ? 0 : 1;
@@ -660,13 +662,26 @@ class AggPartialOp : public Op {
   }
 
   unsigned long long hot_spilled = 0;  // read_counters: groups the hot-group caches could not place
+  bool hot_on = true;                  // adaptive: see read_counters
+  int64_t hot_probe_rows = 0;          // input rows launched with the cache on since the last evaluation
+  unsigned long long hot_absorbed_seen = 0;
+  int64_t hot_launches = 0;
+  bool want_hot() { return plan.hot_cache && (hot_on || (hot_launches++ % 32) == 31); }
   DevBuf hot_spill;
   int32_t read_counters(unsigned long long* n_groups, unsigned long long* n_overflow) {
-    DBX_CUDA_TRY(err, cudaMemcpyAsync(host_counters.p, table.counters.p, 24, cudaMemcpyDeviceToHost, stream));
+    DBX_CUDA_TRY(err, cudaMemcpyAsync(host_counters.p, table.counters.p, 32, cudaMemcpyDeviceToHost, stream));
     DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
     *n_groups = ((unsigned long long*)host_counters.p)[0];
     *n_overflow = ((unsigned long long*)host_counters.p)[1];
     hot_spilled = ((unsigned long long*)host_counters.p)[2];
+    // the hot-group cache pays for itself only on skewed keys: keep it while it absorbs >= 0.5 % of the
+    // rows it saw, turn it off otherwise (uniform keys: +3 % kernel time for nothing); re-probed every 32 launches
+    const unsigned long long absorbed = ((unsigned long long*)host_counters.p)[3];
+    if (hot_probe_rows > 0) {
+      hot_on = (absorbed - std::min(absorbed, hot_absorbed_seen)) * 200 >= (unsigned long long)hot_probe_rows;
+      hot_probe_rows = 0;
+    }
+    hot_absorbed_seen = absorbed;
     groups_known = (int64_t)*n_groups;
     rows_since_read = 0;
     return DBX_OK;
@@ -961,14 +976,15 @@ class AggPartialOp : public Op {
       ring_ok = safe;  // the ring kernel does not record overflow rows
       if (safe) {
         kp.table = table.view(nullptr);
-        kp.hot_cache = plan.hot_cache ? 1 : 0;  // only when no row can fail to be placed (the cache merges groups, not rows)
+        if (want_hot()) { kp.hot_cache = 1; hot_probe_rows += m; }
         DBX_TRY(launch_grouped(kp, false));
         rows_since_read += m;
         continue;
       }
       DBX_CUDA_TRY(err, ovf[0].ensure((size_t)m * 4));
       kp.table = table.view((uint32_t*)ovf[0].p);
-      if (plan.hot_cache) {  // groups a full table refuses at the end of the kernel come back as rows (merged below)
+      if (want_hot()) {  // groups a full table refuses at the end of the kernel come back as rows (merged below)
+        hot_probe_rows += m;
         const size_t row_bytes = (size_t)(2 + plan.n_words) * 8;
         DBX_CUDA_TRY(err, hot_spill.ensure((size_t)kNumSMs * 8 * kHotSlots * row_bytes));
         kp.table.hot_spill = (uint64_t*)hot_spill.p;
@@ -1946,6 +1962,7 @@ int32_t dbx_agg_exchange_scatter(dbx_agg_exchange* x, dbx_op* partial_op) {
   if (x->fused_clear) {  // the table is empty again: only the counters are left to reset
     DBX_CUDA_TRY(x->err, cudaMemsetAsync(p->table.counters.p, 0, 64, p->stream));
     p->table_clean = true;
+    p->hot_absorbed_seen = 0;
   }
   DBX_CUDA_TRY(x->err, cudaEventRecord(x->ev_t[1], p->stream));
   DBX_CUDA_TRY(x->err, cudaEventRecord(x->ev_scatter, p->stream));

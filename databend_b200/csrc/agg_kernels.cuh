@@ -675,6 +675,7 @@ __device__ __forceinline__ void filter_group_agg_body(const AggKernelParams& p) 
       const int m = bucket_match(kb, key);
       const int64_t slot = m >= 0 ? 4 * b + m : find_or_insert_slow(t, key, b, kb, new_groups);
       const uint64_t* hw = hot + kHotSlots + (size_t)e * kHotWords;
+      atomicAdd(t.n_hot_rows, (unsigned long long)hw[0]);  // word 0 = rows of the group
       if (slot < 0) {  // table full: hand the group to the host, which merges it after growing the table
         if (!t.hot_spill) { atomicAdd(t.n_overflow, 1ULL); continue; }
         uint64_t* row = t.hot_spill + atomicAdd(t.n_hot_spill, 1ULL) * (unsigned long long)(2 + t.n_words);

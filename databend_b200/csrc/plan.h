@@ -149,6 +149,7 @@ struct TableDev {
   // exchange-format rows [key][0][words...], merged by the host after the table has grown
   uint64_t* hot_spill;             // nullptr: a failed merge is counted in n_overflow (cannot happen below the load-factor budget)
   unsigned long long* n_hot_spill;
+  unsigned long long* n_hot_rows;  // rows the hot-group caches absorbed (the host turns the cache off when it absorbs next to nothing)
 };
 
 __host__ __device__ __forceinline__ uint64_t* word_ptr(const TableDev& t, int64_t slot, int w) {

@@ -258,7 +258,7 @@ if "eval" in ops and world == 1:
     kb, vb, xb = fill(0, 1, 1_000_000, 0, n), fill(1, 2, 0, 0, n), fill(2, 3, 20, 0, n)
     blk = DataBlock([Column.device(abi.I64, n, kb.ptr), Column.device(abi.I64, n, vb.ptr), Column.device(abi.F64, n, xb.ptr)], n)
     k_, v_, x_ = sx.col(0), sx.col(1), sx.col(2)
-    e = sx.call("and", sx.call("gt", (k_ * v_ + v_) % sx.lit(7, abi.U8), sx.cast(x_ / sx.lit(3, abi.U8), abi.I64)), sx.call("gt", v_, sx.lit(5, abi.I64)))
+    e = sx.call("and", sx.call("gt", sx.cast((k_ * v_ + v_) % sx.lit(7, abi.U8), abi.I64), sx.cast(x_ / sx.lit(3, abi.U8), abi.I64)), sx.call("gt", v_, sx.lit(5, abi.I64)))
     best = None
     for rep in range(a.reps + 2):
         torch.cuda.synchronize()
