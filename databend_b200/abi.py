@@ -167,6 +167,6 @@ EXPORTS = [
     "dbx_shuffle_create", "dbx_shuffle_local_buffer", "dbx_shuffle_connect", "dbx_shuffle_send", "dbx_shuffle_recv", "dbx_shuffle_last_ms",
     "dbx_shuffle_destroy", "dbx_shuffle_last_error",
     "dbx_block_take", "dbx_block_take_ranges", "dbx_block_scatter", "dbx_block_concat",
-    "dbx_eval_scalar", "dbx_op_kernel_variant", "dbx_agg_jit_selftest",
+    "dbx_eval_scalar", "dbx_op_kernel_variant", "dbx_agg_jit_selftest", "dbx_eval_jit_selftest",
     "dbx_agg_partial_serialize", "dbx_agg_final_merge_serialized",
 ]

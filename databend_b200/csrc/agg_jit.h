@@ -26,4 +26,7 @@ std::string agg_jit_plan_text(const StaticPlan& sp);
 // stops after NVRTC (no GPU needed: used by the CPU test-suite); out may then be nullptr.
 bool agg_jit_get(const std::string& plan_text, int n_slots, AggJitKernels* out, std::string* why, bool compile_only = false);
 
+// One kernel of a generated translation unit (see eval.cu): compiled once per distinct source text.
+bool jit_get_kernel(const std::string& source, const char* name, cudaKernel_t* out, std::string* why, bool compile_only = false);
+
 }  // namespace dbx

@@ -88,6 +88,7 @@ def load():
         "dbx_op_inputs_consumed": (i32, [vp]),
         "dbx_op_kernel_variant": (i32, [vp, C.c_char_p, i32]),
         "dbx_agg_jit_selftest": (i32, [C.c_char_p, i32]),
+        "dbx_eval_jit_selftest": (i32, [C.c_char_p, i32]),
         "dbx_agg_exchange_phase_ms": (i32, [vp, P(C.c_float)]),
         "dbx_shuffle_create": (i32, [i32, i32, i32, P(i32), i32, i32, i64, P(vp), vp]),
         "dbx_shuffle_local_buffer": (i32, [vp, P(vp)]),

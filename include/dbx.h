@@ -298,7 +298,7 @@ int32_t dbx_agg_partial_partition(dbx_op* partial_op, int32_t n_parts, void** de
 int32_t dbx_agg_final_merge_rows(dbx_op* final_op, const void* dev_rows, int64_t n_rows);
 
 /* Partial states in the reference's spill / cluster wire layout (AggregatorParams::spill_schema,
- * aggregator_params.rs:103-117; aggregator/serde/*): one Tuple column `agg_i` per aggregate function
+ * aggregator_params.rs:103-117; aggregator/serde/...): one Tuple column `agg_i` per aggregate function
  * holding its serialised state, then the group columns.  The C-ABI carries each tuple FLATTENED into
  * consecutive columns — [agg_0.0, agg_0.1, ..., agg_{n-1}.k, group_0, ...] — and reports the arity of
  * every tuple, so the binding rebuilds Column::Tuple without copying:
@@ -470,6 +470,9 @@ int32_t dbx_op_kernel_variant(dbx_op* op, char* out, int32_t cap);
 /* Compiles the specialised kernels of a canned plan without touching a GPU (is NVRTC usable here?).
  * DBX_OK, or DBX_ERR_UNSUPPORTED with the reason in msg. */
 int32_t dbx_agg_jit_selftest(char* msg, int32_t msg_cap);
+/* Same for the scalar-expression evaluator: generates and compiles the straight-line kernel of a canned
+ * expression (dbx_eval_scalar compiles one per expression shape; DBX_EVAL_JIT=0 keeps the interpreter). */
+int32_t dbx_eval_jit_selftest(char* msg, int32_t msg_cap);
 /* Stream of a handle as a cudaStream_t value (for external event timing). */
 int32_t dbx_op_stream(dbx_op* op, void** stream);
 

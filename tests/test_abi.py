@@ -109,3 +109,5 @@ def test_runtime_specialisation_compiles_here():
     buf = C.create_string_buffer(4096)
     rc = load().dbx_agg_jit_selftest(buf, 4096)
     assert rc == abi.OK, buf.value.decode()
+    rc = load().dbx_eval_jit_selftest(buf, 4096)
+    assert rc == abi.OK, buf.value.decode()
