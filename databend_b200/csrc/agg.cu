@@ -573,7 +573,13 @@ class AggPartialOp : public Op {
     return DBX_OK;
   }
 
-  const char* kernel_variant() override { return jit_status.c_str(); }
+  std::string variant_text;
+  const char* kernel_variant() override {
+    variant_text = jit_status;
+    if (partitioned_chunks || partition_fallbacks)
+      variant_text += "; two-pass (partitioned by table region) chunks: " + std::to_string(partitioned_chunks) + ", one-pass fallbacks (skew): " + std::to_string(partition_fallbacks);
+    return variant_text.c_str();
+  }
   // Ask for kernels compiled for this plan (grouped plans without TMA pairs).  Failure is not an
   // error: the precompiled kernels serve the operator, jit_status says why.
   void specialise() {
@@ -611,6 +617,18 @@ class AggPartialOp : public Op {
   // the window and carry evict_first).  DBX_AGG_L2_PERSIST=0 turns it off.
   int32_t apply_l2_window() {
     if (!plan.l2_persist || !plan.grouped) return DBX_OK;
+    if (part_threshold > 0 && (int64_t)table.bytes() > part_threshold) {
+      // a table beyond L2 is aggregated region by region (partitioned_rows): a window over all of it would
+      // only take capacity away from the region that is being worked on
+      if (window_base) {
+        cudaStreamAttrValue off;
+        memset(&off, 0, sizeof(off));
+        DBX_CUDA_TRY(err, cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &off));
+        DBX_CUDA_TRY(err, cudaCtxResetPersistingL2Cache());
+        window_base = nullptr; window_bytes = 0;
+      }
+      return DBX_OK;
+    }
     if (table.mem.p == window_base && table.bytes() == window_bytes) return DBX_OK;
     window_base = table.mem.p;
     window_bytes = table.bytes();
@@ -746,7 +764,7 @@ class AggPartialOp : public Op {
     static const int per_sm = getenv("DBX_AGG_GRID") ? atoi(getenv("DBX_AGG_GRID")) : 0;
     if (per_sm > 0 && !(kp.table.hot_spill && per_sm > 8))  // the spill buffer of the hot-group caches is sized for 8 CTAs per SM
       grid = (int)std::max<int64_t>(1, std::min<int64_t>((kp.n_rows + kTileRows - 1) / kTileRows, (int64_t)kNumSMs * per_sm));
-    if (!BULK && !INDIRECT && jit.ok()) {  // same grid, block and shared memory: only the code differs
+    if (!BULK && !INDIRECT && jit.ok() && !no_filter_) {  // same grid, block and shared memory: only the code differs
       void* args[] = {(void*)&kp};
       const cudaError_t ce = cudaLaunchKernel((const void*)(FAST ? jit.fast : jit.gen), dim3(grid), dim3(kBlock), args, smem, stream);
       if (ce == cudaSuccess) { count_launch(); return DBX_OK; }
@@ -867,7 +885,7 @@ class AggPartialOp : public Op {
     }
     kp->n_rows = n;
     kp->n_slots = plan.n_slots;
-    kp->n_nodes = plan.n_nodes;
+    kp->n_nodes = no_filter_ ? 0 : plan.n_nodes;  // pass 2 of the partitioned path: the rows are the survivors already
     kp->n_updates = plan.n_updates;
     kp->key_slot = plan.key_slot;
     kp->key_nullable = plan.key_nullable;
@@ -958,17 +976,109 @@ class AggPartialOp : public Op {
   bool no_batching = getenv("DBX_AGG_NO_BATCH") != nullptr;
 
   // the fused kernel(s) over n rows whose needed columns are on the device
+  // ---- two-pass aggregation for tables that do not fit L2 (see filter_partition_kernel)
+  bool no_filter_ = false;
+  DevBuf part_buf[kMaxSlots], part_cnt;
+  PinnedBuf part_host;
+  int64_t part_threshold = getenv("DBX_AGG_PARTITION_BYTES") ? atoll(getenv("DBX_AGG_PARTITION_BYTES")) : (96LL << 20);
+  int64_t part_region_bytes = getenv("DBX_AGG_REGION_BYTES") ? atoll(getenv("DBX_AGG_REGION_BYTES")) : (48LL << 20);
+  int64_t partitioned_chunks = 0, partition_fallbacks = 0;
+  static constexpr int64_t kPartChunkRows = 1LL << 28;
+  bool partition_eligible(const DevCol* cols, int64_t m) const {
+    if (!plan.grouped || plan.key_words != 1 || plan.n_pairs > 0 || part_threshold <= 0) return false;
+    if ((int64_t)table.bytes() <= part_threshold || m < (1 << 16)) return false;
+    // every partition pass pulls its table region into L2 again: worth it only when the rows outweigh the table
+    if (m * 8 * plan.n_slots < 4 * (int64_t)table.bytes() && !getenv("DBX_AGG_PARTITION_ALWAYS")) return false;
+    for (int s = 0; s < plan.n_slots; ++s)
+      if (cols[s].is_const || cols[s].validity) return false;  // the partitions carry value images only
+    return true;
+  }
+  template <int NS>
+  void launch_partition(const AggKernelParams& kp, const PartitionOut& po) {
+    filter_partition_kernel<NS><<<grid_for_rows(kp.n_rows), kBlock, 0, stream>>>(kp, po);
+  }
+  // rows [row0, row0 + m) in two passes; *done = false when a partition overflowed (skewed keys): the caller takes the one-pass path
+  int32_t partitioned_rows(const DevCol* cols, int64_t row0, int64_t m, bool* done) {
+    *done = false;
+    int n_parts = 2;
+    while (n_parts < kMaxPartitions && (int64_t)table.bytes() / n_parts > part_region_bytes) n_parts <<= 1;
+    const int64_t nb = table.cap >> 2;
+    int lg_nb = 0, lg_p = 0;
+    while ((1LL << lg_nb) < nb) ++lg_nb;
+    while ((1 << lg_p) < n_parts) ++lg_p;
+    if (lg_nb < lg_p) return DBX_OK;
+    const int64_t cap_p = ((m / n_parts) * 3 / 2 + 8192 + 3) & ~3LL;  // hash-uniform partitions; skew overflows and falls back
+    AggKernelParams kp;
+    fill_params(&kp, cols, row0, m);
+    PartitionOut po;
+    memset(&po, 0, sizeof(po));
+    for (int s = 0; s < plan.n_slots; ++s) {
+      DBX_CUDA_TRY(err, part_buf[s].ensure((size_t)n_parts * cap_p * 8));
+      po.out[s] = (uint64_t*)part_buf[s].p;
+    }
+    DBX_CUDA_TRY(err, part_cnt.ensure((kMaxPartitions + 1) * 8));
+    DBX_CUDA_TRY(err, part_host.ensure((kMaxPartitions + 1) * 8));
+    DBX_CUDA_TRY(err, cudaMemsetAsync(part_cnt.p, 0, (kMaxPartitions + 1) * 8, stream));
+    po.counts = (unsigned long long*)part_cnt.p; po.cap_p = cap_p; po.nb_mask = (uint64_t)(nb - 1);
+    po.region_shift = lg_nb - lg_p; po.n_parts = n_parts;
+    switch (plan.n_slots) {
+      case 1: launch_partition<1>(kp, po); break; case 2: launch_partition<2>(kp, po); break;
+      case 3: launch_partition<3>(kp, po); break; case 4: launch_partition<4>(kp, po); break;
+      case 5: launch_partition<5>(kp, po); break; case 6: launch_partition<6>(kp, po); break;
+      case 7: launch_partition<7>(kp, po); break; default: launch_partition<8>(kp, po); break;
+    }
+    count_launch();
+    DBX_CUDA_TRY(err, cudaGetLastError());
+    DBX_CUDA_TRY(err, cudaMemcpyAsync(part_host.p, part_cnt.p, (size_t)(n_parts + 1) * 8, cudaMemcpyDeviceToHost, stream));
+    DBX_CUDA_TRY(err, cudaStreamSynchronize(stream));
+    const unsigned long long* hc = (const unsigned long long*)part_host.p;
+    if (hc[n_parts]) { ++partition_fallbacks; return DBX_OK; }
+    no_filter_ = true;
+    int32_t rc = DBX_OK;
+    for (int pi = 0; pi < n_parts && rc == DBX_OK; ++pi) {
+      const int64_t cnt = (int64_t)hc[pi];
+      if (!cnt) continue;
+      DevCol pc[kMaxSlots];
+      for (int s = 0; s < plan.n_slots; ++s) {
+        memset(&pc[s], 0, sizeof(DevCol));
+        pc[s].dtype = DBX_U64;  // 64-bit images as the loads would have widened them
+        pc[s].data = (const char*)part_buf[s].p + (size_t)pi * cap_p * 8;
+      }
+      rc = agg_rows(pc, 0, cnt);
+    }
+    no_filter_ = false;
+    if (rc == DBX_OK) { *done = true; ++partitioned_chunks; }
+    return rc;
+  }
+
   int32_t process_rows(const DevCol* cols, int64_t n) {
     DBX_TRY(timing_begin());
     for (int64_t row0 = 0; row0 < n; row0 += kChunkRows) {
       const int64_t m = std::min(kChunkRows, n - row0);
+      if (partition_eligible(cols, m)) {
+        for (int64_t sub = 0; sub < m; sub += kPartChunkRows) {
+          const int64_t mm = std::min(kPartChunkRows, m - sub);
+          bool done = false;
+          DBX_TRY(partitioned_rows(cols, row0 + sub, mm, &done));
+          if (!done) DBX_TRY(agg_rows(cols, row0 + sub, mm));
+        }
+        continue;
+      }
+      DBX_TRY(agg_rows(cols, row0, m));
+    }
+    DBX_TRY(timing_end());
+    return DBX_OK;
+  }
+  // one chunk through the fused kernel (grouped: with overflow replay and growth)
+  int32_t agg_rows(const DevCol* cols, int64_t row0, int64_t m) {
+    {
       AggKernelParams kp;
       fill_params(&kp, cols, row0, m);
       if (!plan.grouped) {
         kp.table = table.view(nullptr);
         kp.single_state = (unsigned long long*)table.states_p;
         DBX_TRY(launch_single(kp));
-        continue;
+        return DBX_OK;
       }
       // Insertions are provably within the load-factor budget when even "every row is a new
       // group" keeps the table at most half full: no overflow list, no host sync.
@@ -979,7 +1089,7 @@ class AggPartialOp : public Op {
         if (want_hot()) { kp.hot_cache = 1; hot_probe_rows += m; }
         DBX_TRY(launch_grouped(kp, false));
         rows_since_read += m;
-        continue;
+        return DBX_OK;
       }
       DBX_CUDA_TRY(err, ovf[0].ensure((size_t)m * 4));
       kp.table = table.view((uint32_t*)ovf[0].p);
@@ -1019,7 +1129,6 @@ class AggPartialOp : public Op {
       }
       if ((int64_t)ng * 2 > table.cap) DBX_TRY(grow_to(next_pow2(4 * (int64_t)ng)));
     }
-    DBX_TRY(timing_end());
     return DBX_OK;
   }
 

@@ -709,6 +709,80 @@ __global__ void __launch_bounds__(kBlock, 4) filter_group_agg_wide_kernel(const 
 #endif
 
 #ifndef DBX_JIT  // everything below is compiled offline only
+// ---------------------------------------------------------------- pass 1 of the partitioned aggregation
+// Tables larger than L2 (>= ~1.5e6 groups of configs[1]'s shape) turn every reduction into a DRAM
+// round trip (2e6 / 1e7 keys: 28 / 44 ms per 1e9 rows instead of 7.6).  For those the operator makes
+// two passes (SURVEY 3.1's fallback): this kernel filters the rows and scatters the survivors'
+// slot values into P partitions by TABLE REGION — region = the top bits of the row's bucket index —
+// and the fused kernel then aggregates one partition at a time, touching only 1/P of the table, which
+// stays in L2.  The table, the final merge and the exchange are unchanged; only the order in which
+// rows reach the table differs.  Per 1024-row tile a CTA counts its rows per region in shared memory,
+// reserves one run per region with one global atomic each, and writes the rows of a region next to
+// each other (runs of ~sel * 1024 / P rows: full sectors for L2 to combine).
+constexpr int kMaxPartitions = 64;
+struct PartitionOut {
+  uint64_t* out[kMaxSlots];       // per slot: [P][cap_p] 64-bit images
+  unsigned long long* counts;     // [P] rows written per partition; [P] = overflow flag
+  int64_t cap_p;
+  uint64_t nb_mask;               // (cap >> 2) - 1
+  int32_t region_shift;           // region = (hash & nb_mask) >> region_shift
+  int32_t n_parts;
+};
+template <int NS>
+__global__ void __launch_bounds__(kBlock, 4) filter_partition_kernel(const __grid_constant__ AggKernelParams p, const __grid_constant__ PartitionOut po) {
+  __shared__ unsigned int s_cnt[kMaxPartitions];
+  __shared__ unsigned long long s_base[kMaxPartitions];
+  const int64_t n_tiles = (p.n_rows + kTileRows - 1) / kTileRows;
+  const uint64_t pol = make_policy_evict_first();
+  RowVals vals[NS];
+  uint32_t vmask[NS];
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    if (threadIdx.x < kMaxPartitions) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t tile_base = tile * kTileRows;
+    const int64_t r0 = tile_base + (int64_t)kRowsPerThread * threadIdx.x;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) load_slot<false>(p.cols[s], tile_base, p.n_rows, nullptr, pol, vals[s], vmask[s]);
+    uint32_t in_range = 0;
+#pragma unroll
+    for (int j = 0; j < kRowsPerThread; ++j)
+      if (r0 + j < p.n_rows) in_range |= 1u << j;
+    const uint32_t sel = eval_predicate<NS>(p, vals, vmask, in_range);
+    int region[kRowsPerThread];
+    unsigned int rank[kRowsPerThread];
+#pragma unroll
+    for (int j = 0; j < kRowsPerThread; ++j) {
+      region[j] = 0; rank[j] = 0;
+      if ((sel >> j) & 1) {
+        uint64_t key = 0;
+        if (p.n_key_parts > 1) {
+          for (int k = 0; k < p.n_key_parts; ++k) { const KeyPartDev kp = p.key_parts[k]; key |= (pick<NS>(vals, kp.slot, j) & kp.mask) << kp.shift; }
+        } else {
+          key = pick<NS>(vals, p.key_slot, j);
+          if (p.key_is_float) key = canonical_float_key(key);
+        }
+        region[j] = key == kEmptyKey ? 0 : (int)((agg_hash_u64(key) & po.nb_mask) >> po.region_shift);
+        rank[j] = atomicAdd(&s_cnt[region[j]], 1u);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < po.n_parts) {
+      const unsigned int c = s_cnt[threadIdx.x];
+      s_base[threadIdx.x] = c ? atomicAdd(&po.counts[threadIdx.x], (unsigned long long)c) : 0ULL;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kRowsPerThread; ++j) {
+      if (!((sel >> j) & 1)) continue;
+      const unsigned long long pos = s_base[region[j]] + rank[j];
+      if (pos >= (unsigned long long)po.cap_p) { po.counts[po.n_parts] = 1; continue; }  // the host falls back to the one-pass path
+#pragma unroll
+      for (int s = 0; s < NS; ++s) po.out[s][(size_t)region[j] * po.cap_p + pos] = vals[s].v[j];
+    }
+    __syncthreads();  // s_cnt / s_base are reused by the next tile
+  }
+}
+
 // ---------------------------------------------------------------- fused kernel, ring variant
 // Same front end as the FAST kernel above; the table phase differs in how the state words are
 // updated.  The plain kernel is bound by the NUMBER of L2 reduction requests (~150 G RED/s
