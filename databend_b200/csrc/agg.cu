@@ -995,7 +995,13 @@ class AggPartialOp : public Op {
   }
   template <int NS>
   void launch_partition(const AggKernelParams& kp, const PartitionOut& po) {
-    filter_partition_kernel<NS><<<grid_for_rows(kp.n_rows), kBlock, 0, stream>>>(kp, po);
+    static std::atomic<bool> attr_set[64];
+    const size_t smem = (size_t)(NS + 1) * kTileRows * 8;
+    if (device >= 0 && device < 64 && !attr_set[device]) {
+      cudaFuncSetAttribute(filter_partition_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      attr_set[device] = true;
+    }
+    filter_partition_kernel<NS><<<grid_for_rows(kp.n_rows), kBlock, smem, stream>>>(kp, po);
   }
   // rows [row0, row0 + m) in two passes; *done = false when a partition overflowed (skewed keys): the caller takes the one-pass path
   int32_t partitioned_rows(const DevCol* cols, int64_t row0, int64_t m, bool* done) {

@@ -730,7 +730,12 @@ struct PartitionOut {
 };
 template <int NS>
 __global__ void __launch_bounds__(kBlock, 4) filter_partition_kernel(const __grid_constant__ AggKernelParams p, const __grid_constant__ PartitionOut po) {
+  // dynamic shared memory: [NS][kTileRows] staged slot values ordered by region, then [kTileRows] destinations
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* stage = reinterpret_cast<uint64_t*>(smem_raw);
+  unsigned long long* dst = reinterpret_cast<unsigned long long*>(smem_raw) + (size_t)NS * kTileRows;
   __shared__ unsigned int s_cnt[kMaxPartitions];
+  __shared__ unsigned int s_off[kMaxPartitions + 1];
   __shared__ unsigned long long s_base[kMaxPartitions];
   const int64_t n_tiles = (p.n_rows + kTileRows - 1) / kTileRows;
   const uint64_t pol = make_policy_evict_first();
@@ -770,16 +775,33 @@ __global__ void __launch_bounds__(kBlock, 4) filter_partition_kernel(const __gri
       const unsigned int c = s_cnt[threadIdx.x];
       s_base[threadIdx.x] = c ? atomicAdd(&po.counts[threadIdx.x], (unsigned long long)c) : 0ULL;
     }
+    if (threadIdx.x == 0) {
+      unsigned int acc = 0;
+      for (int r = 0; r < po.n_parts; ++r) { s_off[r] = acc; acc += s_cnt[r]; }
+      s_off[po.n_parts] = acc;
+    }
     __syncthreads();
+    // stage the surviving rows in region order, with the global position of each
 #pragma unroll
     for (int j = 0; j < kRowsPerThread; ++j) {
       if (!((sel >> j) & 1)) continue;
+      const unsigned int li = s_off[region[j]] + rank[j];
       const unsigned long long pos = s_base[region[j]] + rank[j];
-      if (pos >= (unsigned long long)po.cap_p) { po.counts[po.n_parts] = 1; continue; }  // the host falls back to the one-pass path
+      if (pos >= (unsigned long long)po.cap_p) { po.counts[po.n_parts] = 1; dst[li] = ~0ULL; }  // the host falls back to the one-pass path
+      else dst[li] = (unsigned long long)region[j] * (unsigned long long)po.cap_p + pos;
 #pragma unroll
-      for (int s = 0; s < NS; ++s) po.out[s][(size_t)region[j] * po.cap_p + pos] = vals[s].v[j];
+      for (int s = 0; s < NS; ++s) stage[(size_t)s * kTileRows + li] = vals[s].v[j];
     }
-    __syncthreads();  // s_cnt / s_base are reused by the next tile
+    __syncthreads();
+    // copy out: consecutive staged rows of a region go to consecutive addresses (whole sectors per warp)
+    const unsigned int n_sel = s_off[po.n_parts];
+    for (unsigned int li = threadIdx.x; li < n_sel; li += kBlock) {
+      const unsigned long long d = dst[li];
+      if (d == ~0ULL) continue;
+#pragma unroll
+      for (int s = 0; s < NS; ++s) po.out[s][d] = stage[(size_t)s * kTileRows + li];
+    }
+    __syncthreads();  // shared buffers are reused by the next tile
   }
 }
 
