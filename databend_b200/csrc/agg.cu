@@ -993,6 +993,33 @@ class AggPartialOp : public Op {
       if (cols[s].is_const || cols[s].validity) return false;  // the partitions carry value images only
     return true;
   }
+  bool region_window_on = false;
+  void region_window(void* base, size_t bytes) {  // best effort: a failure only costs speed
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
+    cudaStreamAttrValue av;
+    memset(&av, 0, sizeof(av));
+    if (base && bytes && max_persist > 0 && max_window > 0) {
+      const size_t win = std::min<size_t>(bytes, (size_t)max_window);
+      static std::atomic<size_t> limit_set[64];
+      const size_t want = std::min<size_t>(win, (size_t)max_persist);
+      if (device >= 0 && device < 64 && limit_set[device] < want) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want); limit_set[device] = want; }
+      av.accessPolicyWindow.base_ptr = base;
+      av.accessPolicyWindow.num_bytes = win;
+      av.accessPolicyWindow.hitRatio = win <= want ? 1.0f : (float)want / (float)win;
+      av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      av.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+      region_window_on = true;
+    } else if (!region_window_on) {
+      return;
+    } else {
+      region_window_on = false;
+    }
+    cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av);
+    if (!region_window_on) cudaCtxResetPersistingL2Cache();
+    cudaGetLastError();
+  }
   template <int NS>
   void launch_partition(const AggKernelParams& kp, const PartitionOut& po) {
     static std::atomic<bool> attr_set[64];
@@ -1041,9 +1068,16 @@ class AggPartialOp : public Op {
     if (hc[n_parts]) { ++partition_fallbacks; return DBX_OK; }
     no_filter_ = true;
     int32_t rc = DBX_OK;
+    const int64_t cap_at_start = table.cap;
     for (int pi = 0; pi < n_parts && rc == DBX_OK; ++pi) {
       const int64_t cnt = (int64_t)hc[pi];
       if (!cnt) continue;
+      // keep the state words of THIS region in L2 while its rows stream through (they take the reductions;
+      // the key buckets are read with evict-last hints)
+      if (plan.l2_persist && table.cap == cap_at_start) {
+        const int64_t slots = table.cap / n_parts;
+        region_window((char*)table.states_p + (size_t)pi * slots * plan.n_words * 8, (size_t)slots * plan.n_words * 8);
+      }
       DevCol pc[kMaxSlots];
       for (int s = 0; s < plan.n_slots; ++s) {
         memset(&pc[s], 0, sizeof(DevCol));
@@ -1053,6 +1087,7 @@ class AggPartialOp : public Op {
       rc = agg_rows(pc, 0, cnt);
     }
     no_filter_ = false;
+    region_window(nullptr, 0);
     if (rc == DBX_OK) { *done = true; ++partitioned_chunks; }
     return rc;
   }
