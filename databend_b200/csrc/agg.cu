@@ -522,6 +522,8 @@ inline int64_t next_pow2(int64_t x) {
 
 }  // namespace
 
+static std::atomic<size_t> g_persist_limit[64];  // cudaLimitPersistingL2CacheSize as last set, per device
+
 // sizeof(StageWarp<NS>) for a run-time slot count
 static size_t kMaxSlotsStageBytes(int ns) {
   switch (ns) {
@@ -637,11 +639,10 @@ class AggPartialOp : public Op {
     DBX_CUDA_TRY(err, cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device));
     if (max_persist <= 0 || max_window <= 0) return DBX_OK;
     const size_t bytes = std::min<size_t>(table.bytes() + 512, (size_t)max_window);
-    static std::atomic<size_t> limit_set[64];
     const size_t want = std::min<size_t>(bytes, (size_t)max_persist);
-    if (limit_set[device] < want) {
+    if (g_persist_limit[device] < want) {  // the set-aside only ever grows (it is a device-wide limit shared by all operators)
       DBX_CUDA_TRY(err, cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
-      limit_set[device] = want;
+      g_persist_limit[device] = want;
     }
     cudaStreamAttrValue av;
     memset(&av, 0, sizeof(av));
@@ -1002,9 +1003,8 @@ class AggPartialOp : public Op {
     memset(&av, 0, sizeof(av));
     if (base && bytes && max_persist > 0 && max_window > 0) {
       const size_t win = std::min<size_t>(bytes, (size_t)max_window);
-      static std::atomic<size_t> limit_set[64];
       const size_t want = std::min<size_t>(win, (size_t)max_persist);
-      if (device >= 0 && device < 64 && limit_set[device] < want) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want); limit_set[device] = want; }
+      if (device >= 0 && device < 64 && g_persist_limit[device] < want) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want); g_persist_limit[device] = want; }
       av.accessPolicyWindow.base_ptr = base;
       av.accessPolicyWindow.num_bytes = win;
       av.accessPolicyWindow.hitRatio = win <= want ? 1.0f : (float)want / (float)win;
