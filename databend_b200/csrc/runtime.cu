@@ -504,6 +504,7 @@ int32_t dbx_op_inputs_consumed(dbx_op* op) {
 }
 int32_t dbx_op_synchronize(dbx_op* op) {
   DBX_OP_ENTER(op);
+  DBX_TRY(o->wait_inputs());  // reads recorded but not yet enqueued (coalesced small pushes) first: the header promises them consumed
   DBX_CUDA_TRY(o->err, cudaStreamSynchronize(o->stream));
   return DBX_OK;
 }
