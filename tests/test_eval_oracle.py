@@ -87,3 +87,50 @@ def test_sort_oracle_matches_reference_golden_permutations():
         perm = sort_oracle.sort_permutation([(arr, valid, c["asc"], c["nulls_first"])], c["limit"] or 0)
         if c.get("rows") is not None:
             assert perm.tolist() == c["rows"], c["src"]
+
+
+def test_spill_oracle_states_finalize_to_the_c_oracle_results():
+    """oracle/spill_oracle.py (serialised partial states, restated from the reference's StateSerde) has no
+    reference golden; this ties it to the pinned C oracle instead: finalising its states (sum, count,
+    sum / count, min / max with the NULL flags) must give exactly the C oracle's final results."""
+    import numpy as np
+    from databend_b200 import abi
+    from databend_b200.block import Column, DataBlock
+    from databend_b200.transforms import AggregatorParams
+    from oracle import oracle as orc
+    from oracle import spill_oracle
+    rng = np.random.default_rng(4)
+    n = 50_000
+    k = rng.integers(-3, 200, n).astype(np.int32)
+    kv = rng.random(n) > 0.05
+    v = rng.integers(-10**6, 10**6, n).astype(np.int64)
+    vv = rng.random(n) > 0.3
+    x = rng.integers(0, 1 << 20, n).astype(np.float64)
+    f = (rng.integers(-500, 500, n) * 0.25).astype(np.float32)
+    fv = rng.random(n) > 0.5
+    blk = DataBlock([Column.from_data(k, validity=kv), Column.from_data(v, validity=vv), Column.from_data(x), Column.from_data(f, validity=fv)])
+    kinds = ["sum", "count", "count", "avg", "min", "max", "avg"]
+    args = [1, None, 1, 2, 1, 3, 3]
+    params = AggregatorParams([0], list(zip(kinds, args)))
+    cols = {1: (v, vv), 2: (x, None), 3: (f, fv)}
+    fields, arity, okeys = spill_oracle.group_states([(k, kv)], [None if a is None else cols[a] for a in args], kinds)
+    keys, kvalid, aggs, avalid, _ = orc.filter_group_agg(blk, params.to_c(None), threads=2)
+    exp = {}
+    for i in range(len(aggs[0])):
+        key = int(keys[0].view(np.int64)[i]) if kvalid[0][i] else None
+        exp[key] = [(aggs[a][i].item() if avalid[a][i] else None) for a in range(len(kinds))]
+    assert len(okeys[0][0]) == len(exp)
+    for g in range(len(okeys[0][0])):
+        key = int(okeys[0][0][g]) if okeys[0][1][g] else None
+        got = []
+        for a, kind in enumerate(kinds):
+            fs = [fld[g] for fld in fields[a]]
+            if kind == "count":
+                got.append(int(fs[0]))
+            elif kind == "sum":
+                got.append(fs[0].item() if fs[-1] else None)
+            elif kind == "avg":
+                got.append(float(np.float64(fs[0]) / np.float64(fs[1])) if fs[-1] else None)
+            else:
+                got.append(fs[1].item() if fs[0] else None)
+        assert got == exp[key], (key, got, exp[key])
