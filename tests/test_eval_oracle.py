@@ -134,3 +134,25 @@ def test_spill_oracle_states_finalize_to_the_c_oracle_results():
             else:
                 got.append(fs[1].item() if fs[0] else None)
         assert got == exp[key], (key, got, exp[key])
+
+
+def test_expression_builder_flattens_to_postfix():
+    """Host logic of databend_b200/scalar_expr.py (no GPU): operator overloads build the tree, flatten()
+    emits the postfix program the C-ABI takes, oversized trees and unknown functions are refused."""
+    from databend_b200 import abi, scalar_expr as sx
+    from databend_b200.lib import DbxError
+    e = sx.call("and", sx.call("gt", sx.cast((sx.col(0) * sx.col(1) + sx.col(1)) % sx.lit(7, abi.U8), abi.I64), sx.lit(3, abi.I64)), sx.call("not", sx.call("is_null", sx.col(2))))
+    prog = sx.flatten(e)
+    kinds = [prog.nodes[i].kind for i in range(prog.n_nodes)]
+    funcs = [prog.nodes[i].func for i in range(prog.n_nodes) if prog.nodes[i].kind == abi.EXPR_CALL]
+    assert kinds == [abi.EXPR_COLUMN, abi.EXPR_COLUMN, abi.EXPR_CALL, abi.EXPR_COLUMN, abi.EXPR_CALL, abi.EXPR_CONST, abi.EXPR_CALL, abi.EXPR_CAST,
+                     abi.EXPR_CONST, abi.EXPR_CALL, abi.EXPR_COLUMN, abi.EXPR_CALL, abi.EXPR_CALL, abi.EXPR_CALL]
+    assert funcs == [abi.FN_MULTIPLY, abi.FN_PLUS, abi.FN_MODULO, abi.FN_GT, abi.FN_IS_NULL, abi.FN_NOT, abi.FN_AND]
+    assert prog.nodes[7].cast_to == abi.I64 and prog.nodes[5].c.dtype == abi.U8 and prog.nodes[5].c.v.u64 == 7
+    big = sx.col(0)
+    for _ in range(abi.MAX_EXPR_NODES):
+        big = big + sx.col(0)
+    with pytest.raises(DbxError, match="too large"):
+        sx.flatten(big)
+    with pytest.raises(DbxError, match="not built"):
+        sx.call("sqrt", sx.col(0))
